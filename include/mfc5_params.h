@@ -1,0 +1,88 @@
+/* mfc5_params.h -- the parameter contract of the 5-equation RHS hot path.
+ *
+ * One plain-C struct carrying every case.py / namelist parameter that reaches the hot path
+ * (SURVEY.md Appendix C).  It is shared by the product library (include/mfc5.h, CUDA) and by the
+ * CPU oracle (oracle/mfc5_oracle.h, test infrastructure).  Field names follow the reference's
+ * namelist names (src/simulation/m_global_parameters.fpp:330-420, m_start_up.fpp:81-130).
+ *
+ * Variable ordering (reference m_global_parameters_common.fpp:125-141), 0-based here:
+ *   [0, NF)            partial densities  alpha_k rho_k       (cont)
+ *   [NF, NF+ND)        momenta (cons) / velocities (prim)     (mom)
+ *   E = NF+ND          total energy (cons) / pressure (prim)
+ *   (E, E+NF]          volume fractions alpha_k               (adv)
+ *   sys_size N = 2*NF + ND + 1
+ */
+#ifndef MFC5_PARAMS_H
+#define MFC5_PARAMS_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MFC5_MAX_FLUIDS 4
+#define MFC5_MAX_EQ (2 * MFC5_MAX_FLUIDS + 4)
+
+/* Boundary-condition codes, reference src/common/m_constants.fpp:97-113.  A value >= 0 in bc[][]
+ * means "processor boundary, value = neighbour rank" (m_mpi_common.fpp:1496-1509). */
+enum {
+    MFC5_BC_PERIODIC = -1,
+    MFC5_BC_REFLECTIVE = -2,
+    MFC5_BC_GHOST_EXTRAP = -3,
+    MFC5_BC_RIEMANN_EXTRAP = -4,
+    MFC5_BC_CHAR_SLIP_WALL = -5,
+    MFC5_BC_CHAR_NR_SUB_BUFFER = -6,
+    MFC5_BC_CHAR_NR_SUB_INFLOW = -7,
+    MFC5_BC_CHAR_NR_SUB_OUTFLOW = -8,
+    MFC5_BC_CHAR_FF_SUB_OUTFLOW = -9,
+    MFC5_BC_CHAR_CP_SUB_OUTFLOW = -10,
+    MFC5_BC_CHAR_SUP_INFLOW = -11,
+    MFC5_BC_CHAR_SUP_OUTFLOW = -12,
+    MFC5_BC_SLIP_WALL = -15,
+    MFC5_BC_NO_SLIP_WALL = -16,
+    MFC5_BC_DIRICHLET = -17
+};
+
+typedef struct mfc5_params {
+    /* grid extents of THIS rank: cells-1 per direction, n = 0 / p = 0 collapse dimensions */
+    int m, n, p;
+    int num_fluids;
+    int model_eqns;      /* must be 2 (5-equation) */
+    /* reconstruction */
+    int weno_order;      /* 1, 3 or 5 */
+    int mapped_weno;     /* WENO-M (Henrick) */
+    int wenoz;           /* WENO-Z (Borges) ; neither => WENO-JS */
+    int null_weights;
+    double weno_eps;
+    /* Riemann solver */
+    int riemann_solver;  /* 1 = HLL, 2 = HLLC */
+    int hll_u_interface; /* HLL alpha transport "method 2" */
+    int avg_state;       /* 1 = Roe, 2 = arithmetic */
+    int wave_speeds;     /* 1 = direct, 2 = pressure based */
+    int mpp_lim;
+    int mixture_err;
+    /* time stepping */
+    int time_stepper;    /* 1, 2, 3 (TVD RK order) */
+    double dt;
+    /* boundary conditions: bc[dir][0] = %beg, bc[dir][1] = %end */
+    int bc[3][2];
+    double bc_vb[3][3];  /* bc_<dir>%vb1..3 : wall velocity on the beg side */
+    double bc_ve[3][3];  /* bc_<dir>%ve1..3 */
+    /* GRCBC inputs (m_cbc.fpp:300-321) */
+    int grcbc_in[3], grcbc_out[3], grcbc_vel_out[3];
+    double vel_in[3][3], vel_out[3][3];
+    double pres_in[3], pres_out[3];
+    double alpha_rho_in[3][MFC5_MAX_FLUIDS], alpha_in[3][MFC5_MAX_FLUIDS];
+    /* stiffened-gas EOS in the reference's form: gamma = 1/(g-1), pi_inf = g*pinf/(g-1) */
+    double fluid_gamma[MFC5_MAX_FLUIDS];
+    double fluid_pi_inf[MFC5_MAX_FLUIDS];
+    double fluid_qv[MFC5_MAX_FLUIDS];
+    /* product-side knobs (ignored by the oracle) */
+    int device;          /* CUDA device ordinal */
+    int fast_math;       /* 0: reference operation order; 1: division-light WENO weights */
+    int reserved[6];
+} mfc5_params;
+
+#ifdef __cplusplus
+}
+#endif
+#endif

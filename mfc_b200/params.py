@@ -1,0 +1,160 @@
+"""ctypes mirror of ``include/mfc5_params.h`` and the case.py -> ``mfc5_params`` translation.
+
+The keys accepted are the reference's own namelist names (``m``, ``weno_order``, ``bc_x%beg``,
+``fluid_pp(1)%gamma`` ...; reference ``src/simulation/m_start_up.fpp:81-130``), with defaults as in
+``src/simulation/m_global_parameters.fpp:330-420`` and named enums as in
+``toolchain/mfc/params/definitions.py:299-359``.  Parameters that would leave the 5-equation
+inviscid envelope are rejected.
+"""
+import ctypes as C
+
+MAX_FLUIDS = 4
+
+_NAMED = {
+    "model_eqns": {"gamma_law": 1, "5eq": 2, "6eq": 3},
+    "riemann_solver": {"hll": 1, "hllc": 2, "hlld": 4, "lax_friedrichs": 5},
+    "time_stepper": {"rk1": 1, "rk2": 2, "rk3": 3},
+    "wave_speeds": {"direct": 1, "pressure": 2},
+    "avg_state": {"roe": 1, "arithmetic": 2},
+    "recon_type": {"weno": 1, "muscl": 2},
+}
+
+
+class Mfc5Params(C.Structure):
+    _fields_ = [
+        ("m", C.c_int), ("n", C.c_int), ("p", C.c_int),
+        ("num_fluids", C.c_int), ("model_eqns", C.c_int),
+        ("weno_order", C.c_int), ("mapped_weno", C.c_int), ("wenoz", C.c_int), ("null_weights", C.c_int),
+        ("weno_eps", C.c_double),
+        ("riemann_solver", C.c_int), ("hll_u_interface", C.c_int), ("avg_state", C.c_int),
+        ("wave_speeds", C.c_int), ("mpp_lim", C.c_int), ("mixture_err", C.c_int),
+        ("time_stepper", C.c_int),
+        ("dt", C.c_double),
+        ("bc", (C.c_int * 2) * 3),
+        ("bc_vb", (C.c_double * 3) * 3), ("bc_ve", (C.c_double * 3) * 3),
+        ("grcbc_in", C.c_int * 3), ("grcbc_out", C.c_int * 3), ("grcbc_vel_out", C.c_int * 3),
+        ("vel_in", (C.c_double * 3) * 3), ("vel_out", (C.c_double * 3) * 3),
+        ("pres_in", C.c_double * 3), ("pres_out", C.c_double * 3),
+        ("alpha_rho_in", (C.c_double * MAX_FLUIDS) * 3), ("alpha_in", (C.c_double * MAX_FLUIDS) * 3),
+        ("fluid_gamma", C.c_double * MAX_FLUIDS), ("fluid_pi_inf", C.c_double * MAX_FLUIDS),
+        ("fluid_qv", C.c_double * MAX_FLUIDS),
+        ("device", C.c_int), ("fast_math", C.c_int), ("reserved", C.c_int * 6),
+    ]
+
+    @property
+    def num_dims(self):
+        return 1 + (self.n > 0) + (self.p > 0)
+
+    @property
+    def sys_size(self):
+        return 2 * self.num_fluids + self.num_dims + 1
+
+    @property
+    def buff_size(self):
+        # src/common/m_helper_basic.fpp:127-132 (inviscid WENO)
+        return (self.weno_order - 1) // 2 + 2
+
+    def copy(self):
+        q = Mfc5Params()
+        C.memmove(C.byref(q), C.byref(self), C.sizeof(Mfc5Params))
+        return q
+
+
+def _logical(v):
+    if isinstance(v, str):
+        return 1 if v.strip().upper() in ("T", ".TRUE.", "TRUE") else 0
+    return 1 if v else 0
+
+
+def _val(case, key, default=None):
+    v = case.get(key, default)
+    if isinstance(v, str) and key in _NAMED:
+        v = _NAMED[key].get(v, v)
+    return v
+
+
+_UNSUPPORTED_TRUE = [
+    "alt_soundspeed", "viscous", "surface_tension", "bubbles_euler", "bubbles_lagrange", "qbmm", "hypoelasticity",
+    "hyperelasticity", "mhd", "relativity", "chemistry", "igr", "ib", "cyl_coord", "acoustic_source", "relax",
+    "mp_weno", "teno", "cfl_adap_dt", "cfl_const_dt", "cont_damage", "hyper_cleaning",
+]
+
+
+class UnsupportedCase(ValueError):
+    """Raised (like the reference's ``@:PROHIBIT`` / ``s_mpi_abort``) for cases outside the envelope."""
+
+
+def params_from_case(case, device=0, fast_math=0):
+    """Translate a case dictionary (what a reference ``case.py`` prints) into ``Mfc5Params``."""
+    for k in _UNSUPPORTED_TRUE:
+        if _logical(case.get(k, "F")):
+            raise UnsupportedCase(f"{k}=T is outside the 5-equation inviscid hot path")
+    if int(_val(case, "low_Mach", 0) or 0) != 0:
+        raise UnsupportedCase("low_Mach != 0 is not supported")
+    ic = case.get("int_comp", 0)
+    if (_logical(ic) if isinstance(ic, str) else int(ic or 0) != 0):
+        raise UnsupportedCase("interface compression is not supported")
+    P = Mfc5Params()
+    P.m, P.n, P.p = int(case["m"]), int(case.get("n", 0)), int(case.get("p", 0))
+    P.num_fluids = int(case["num_fluids"])
+    P.model_eqns = int(_val(case, "model_eqns"))
+    if P.model_eqns != 2:
+        raise UnsupportedCase("only model_eqns = 2 (5-equation) is on the hot path")
+    if P.num_fluids > MAX_FLUIDS:
+        raise UnsupportedCase(f"num_fluids > {MAX_FLUIDS}")
+    if int(_val(case, "recon_type", 1)) != 1:
+        raise UnsupportedCase("only recon_type = weno")
+    P.weno_order = int(case["weno_order"])
+    if P.weno_order not in (1, 3, 5):
+        raise UnsupportedCase("weno_order must be 1, 3 or 5")
+    P.mapped_weno = _logical(case.get("mapped_weno", "F"))
+    P.wenoz = _logical(case.get("wenoz", "F"))
+    P.null_weights = _logical(case.get("null_weights", "F"))
+    P.weno_eps = float(case.get("weno_eps", 1e-16))
+    P.riemann_solver = int(_val(case, "riemann_solver"))
+    if P.riemann_solver not in (1, 2):
+        raise UnsupportedCase("riemann_solver must be HLL (1) or HLLC (2)")
+    P.hll_u_interface = _logical(case.get("hll_u_interface", "F"))
+    P.avg_state = int(_val(case, "avg_state", 2))
+    P.wave_speeds = int(_val(case, "wave_speeds", 1))
+    P.mpp_lim = _logical(case.get("mpp_lim", "F"))
+    P.mixture_err = _logical(case.get("mixture_err", "F"))
+    P.time_stepper = int(_val(case, "time_stepper", 3))
+    P.dt = float(case["dt"])
+    nd = P.num_dims
+    for d, x in enumerate("xyz"):
+        if d >= nd:
+            continue
+        P.bc[d][0] = int(case[f"bc_{x}%beg"])
+        P.bc[d][1] = int(case[f"bc_{x}%end"])
+        for a in range(3):
+            P.bc_vb[d][a] = float(case.get(f"bc_{x}%vb{a + 1}", 0.0))
+            P.bc_ve[d][a] = float(case.get(f"bc_{x}%ve{a + 1}", 0.0))
+            P.vel_in[d][a] = float(case.get(f"bc_{x}%vel_in({a + 1})", 0.0))
+            P.vel_out[d][a] = float(case.get(f"bc_{x}%vel_out({a + 1})", 0.0))
+        P.grcbc_in[d] = _logical(case.get(f"bc_{x}%grcbc_in", "F"))
+        P.grcbc_out[d] = _logical(case.get(f"bc_{x}%grcbc_out", "F"))
+        P.grcbc_vel_out[d] = _logical(case.get(f"bc_{x}%grcbc_vel_out", "F"))
+        P.pres_in[d] = float(case.get(f"bc_{x}%pres_in", 0.0))
+        P.pres_out[d] = float(case.get(f"bc_{x}%pres_out", 0.0))
+        for f in range(P.num_fluids):
+            P.alpha_rho_in[d][f] = float(case.get(f"bc_{x}%alpha_rho_in({f + 1})", 0.0))
+            P.alpha_in[d][f] = float(case.get(f"bc_{x}%alpha_in({f + 1})", 0.0))
+    for f in range(P.num_fluids):
+        P.fluid_gamma[f] = float(case[f"fluid_pp({f + 1})%gamma"])
+        P.fluid_pi_inf[f] = float(case.get(f"fluid_pp({f + 1})%pi_inf", 0.0))
+        P.fluid_qv[f] = float(case.get(f"fluid_pp({f + 1})%qv", 0.0))
+    P.device = device
+    P.fast_math = fast_math
+    check_params(P)
+    return P
+
+
+def check_params(P):
+    """Run-time checks of the reference: src/simulation/m_checker.fpp:52-69 (cells per rank)."""
+    need = 5 * P.weno_order if P.weno_order > 1 else 1
+    for s, name in ((P.m, "m"), (P.n, "n"), (P.p, "p")):
+        if s > 0 and s + 1 < need:
+            raise UnsupportedCase(f"{name}+1 must be >= num_stcls_min*weno_order = {need}")
+    if P.mapped_weno and P.wenoz:
+        raise UnsupportedCase("mapped_weno and wenoz are mutually exclusive")

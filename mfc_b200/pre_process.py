@@ -1,0 +1,196 @@
+"""Minimal pre_process: grid generation and patch initial conditions.
+
+Restates, for the 5-equation model only:
+  * ``s_generate_serial_grid``  (reference ``src/pre_process/m_grid.f90:33-170``): uniform grid and the
+    ``cosh`` stretching loops;
+  * the patch geometries used by the in-scope cases: line segment (1), circle (2), rectangle (3),
+    sphere (8), cuboid (9) with ``alter_patch`` (``src/pre_process/m_icpp_patches.fpp:165,286,591,
+    939,1008``; inside tests ``src/common/m_patch_geometries.fpp:24-69``), no smoothing;
+  * ``s_assign_patch_species_primitive_variables`` with ``eta = 1``
+    (``src/pre_process/m_assign_variables.fpp:208-510``);
+  * ``s_convert_primitive_to_conservative_variables`` (``src/common/m_variables_conversion.fpp:722-950``).
+"""
+import math
+
+import numpy as np
+
+from .params import _logical
+
+
+def _domain(case, x):
+    return float(case[f"{x}_domain%beg"]), float(case[f"{x}_domain%end"])
+
+
+def generate_grid_1d(case, x, ncells_m1, beg=None, end=None, glb=None):
+    """Cell boundaries ``s_cb[-1..s]`` (returned as array of length s+2) for direction ``x``.
+
+    ``beg``/``end`` override the (rank-local) domain bounds; ``glb`` = (beg, end) of the global domain
+    (used for the stretching normalisation, m_grid.f90:51)."""
+    dbeg, dend = _domain(case, x)
+    if beg is None:
+        beg, end = dbeg, dend
+    if glb is None:
+        glb = (dbeg, dend)
+    s = ncells_m1
+    cb = np.empty(s + 2)
+    dx = (end - beg) / float(s + 1)
+    for i in range(0, s + 1):
+        cb[i] = beg + dx * float(i)  # x_cb(i-1)
+    cb[s + 1] = end
+    if _logical(case.get(f"stretch_{x}", "F")):
+        length = abs(glb[1] - glb[0])
+        a = float(case[f"a_{x}"])
+        xa = float(case[f"{x}_a"]) / length
+        xb = float(case[f"{x}_b"]) / length
+        cb = cb / length
+        for _ in range(int(case.get(f"loops_{x}", 1))):
+            for i in range(s + 2):
+                cb[i] = cb[i] / a * (a + math.log(math.cosh(a * (cb[i] - xa))) + math.log(math.cosh(a * (cb[i] - xb)))
+                                     - 2.0 * math.log(math.cosh(a * (xb - xa) / 2.0)))
+        cb = cb * length
+    return cb
+
+
+def cell_centers(cb, stretched, beg, s):
+    """x_cc as pre_process computes it (m_grid.f90:43-44 uniform, :63 stretched)."""
+    if stretched:
+        return (cb[1:] + cb[:-1]) / 2.0
+    dx = (cb[-1] - beg) / float(s + 1) if False else None
+    return None
+
+
+def generate_grid(case, local=None):
+    """Return ([x_cb, y_cb, z_cb], [x_cc, y_cc, z_cc]) for the (possibly rank-local) block.
+
+    ``local`` = optional list per direction of (s_local, beg, end) from ``decomp``."""
+    m, n, p = int(case["m"]), int(case.get("n", 0)), int(case.get("p", 0))
+    cbs, ccs = [], []
+    for d, (x, s) in enumerate(zip("xyz", (m, n, p))):
+        if d > 0 and s == 0:
+            cbs.append(None)
+            ccs.append(np.zeros(1))
+            continue
+        if local is not None:
+            s, beg, end = local[d]
+        else:
+            beg, end = _domain(case, x)
+        cb = generate_grid_1d(case, x, s, beg, end)
+        if _logical(case.get(f"stretch_{x}", "F")):
+            cc = (cb[1:] + cb[:-1]) / 2.0
+        else:
+            dx = (end - beg) / float(s + 1)
+            cc = np.array([beg + 5.0e-1 * dx * float(2 * i + 1) for i in range(s + 1)])
+        cbs.append(cb)
+        ccs.append(cc)
+    return cbs, ccs
+
+
+def _patch(case, i, key, default=None):
+    return case.get(f"patch_icpp({i})%{key}", default)
+
+
+def initial_condition(case, ccs):
+    """Primitive then conservative variables, arrays [N][nz][ny][nx] -> returned as (N, nz, ny, nx)."""
+    nf = int(case["num_fluids"])
+    nx, ny, nz = len(ccs[0]), len(ccs[1]), len(ccs[2])
+    nd = 1 + (ny > 1) + (nz > 1)
+    N = 2 * nf + nd + 1
+    iE = nf + nd
+    prim = np.zeros((N, nz, ny, nx))
+    pid = np.zeros((nz, ny, nx), dtype=np.int64)
+    X = ccs[0][None, None, :]
+    Y = ccs[1][None, :, None]
+    Z = ccs[2][:, None, None]
+    for ip in range(1, int(case["num_patches"]) + 1):
+        geom = int(_patch(case, ip, "geometry"))
+        if _logical(_patch(case, ip, "smoothen", "F")):
+            raise NotImplementedError("patch smoothing")
+        if _patch(case, ip, "hcid") is not None:
+            raise NotImplementedError("hard-coded patches")
+        xc = float(_patch(case, ip, "x_centroid", 0.0))
+        yc = float(_patch(case, ip, "y_centroid", 0.0))
+        zc = float(_patch(case, ip, "z_centroid", 0.0))
+        if geom == 1:
+            lx = float(_patch(case, ip, "length_x"))
+            inside = ((xc - 0.5 * lx) <= X) & ((xc + 0.5 * lx) >= X) & (Y == Y) & (Z == Z)
+        elif geom in (3, 9):
+            lx = float(_patch(case, ip, "length_x"))
+            ly = float(_patch(case, ip, "length_y"))
+            inside = (-0.5 * lx <= X - xc) & (0.5 * lx >= X - xc) & (-0.5 * ly <= Y - yc) & (0.5 * ly >= Y - yc)
+            if nd == 3:
+                lz = float(_patch(case, ip, "length_z"))
+                inside = inside & (-0.5 * lz <= Z - zc) & (0.5 * lz >= Z - zc)
+            else:
+                inside = inside & (Z == Z)
+        elif geom == 2:
+            r = float(_patch(case, ip, "radius"))
+            inside = ((X - xc) ** 2 + (Y - yc) ** 2 <= r ** 2) & (Z == Z)
+        elif geom == 8:
+            r = float(_patch(case, ip, "radius"))
+            inside = (X - xc) ** 2 + (Y - yc) ** 2 + (Z - zc) ** 2 <= r ** 2
+        else:
+            raise NotImplementedError(f"patch geometry {geom}")
+        inside = np.broadcast_to(inside, pid.shape)
+        # alter_patch(0) defaults to T, alter_patch(j>0) to F unless given (m_global_parameters.fpp pre_process)
+        allowed = np.zeros(ip, dtype=bool)
+        allowed[0] = True
+        for jp in range(1, ip):
+            allowed[jp] = _logical(_patch(case, ip, f"alter_patch({jp})", "F"))
+        # patch 1 may always write (nothing there yet); later patches overwrite only where allowed
+        if ip > 1:
+            pass
+        mask = inside & allowed[pid]
+        for f in range(nf):
+            prim[f][mask] = float(_patch(case, ip, f"alpha_rho({f + 1})"))
+            prim[iE + 1 + f][mask] = float(_patch(case, ip, f"alpha({f + 1})"))
+        for a in range(nd):
+            prim[nf + a][mask] = float(_patch(case, ip, f"vel({a + 1})", 0.0))
+        prim[iE][mask] = float(_patch(case, ip, "pres"))
+        pid[mask] = ip
+    return prim, prim_to_cons(case, prim, nf, nd)
+
+
+def prim_to_cons(case, prim, nf, nd):
+    mpp = _logical(case.get("mpp_lim", "F"))
+    gam = [float(case[f"fluid_pp({f + 1})%gamma"]) for f in range(nf)]
+    pinf = [float(case.get(f"fluid_pp({f + 1})%pi_inf", 0.0)) for f in range(nf)]
+    qvs = [float(case.get(f"fluid_pp({f + 1})%qv", 0.0)) for f in range(nf)]
+    iE = nf + nd
+    arho = [prim[f].copy() for f in range(nf)]
+    alf = [prim[iE + 1 + f].copy() for f in range(nf)]
+    if mpp:
+        for _ in range(2):  # s_compute_species_fraction + mixture kernel both limit
+            s = np.zeros_like(alf[0])
+            for f in range(nf):
+                arho[f] = np.maximum(0.0, arho[f])
+                alf[f] = np.minimum(np.maximum(0.0, alf[f]), 1.0)
+                s = s + alf[f]
+            for f in range(nf):
+                alf[f] = alf[f] / np.maximum(s, 1e-16)
+    rho = np.zeros_like(prim[0]); g = np.zeros_like(rho); pi = np.zeros_like(rho); qv = np.zeros_like(rho)
+    for f in range(nf):
+        rho = rho + arho[f]
+        g = g + alf[f] * gam[f]
+        pi = pi + alf[f] * pinf[f]
+        qv = qv + arho[f] * qvs[f]
+    cons = prim.copy()
+    dyn = np.zeros_like(rho)
+    for a in range(nd):
+        cons[nf + a] = rho * prim[nf + a]
+        dyn = dyn + cons[nf + a] * prim[nf + a] / 2.0
+    cons[iE] = g * prim[iE] + dyn + pi + qv
+    return cons
+
+
+def dirichlet_buffers(P, prim):
+    """Face values for BC -17: what pre_process packs from the initial primitive field
+    (reference ``src/common/m_boundary_io.fpp:271-330``).  Returns {(dir, side): array [N][t2][t1]}."""
+    out = {}
+    for d in range(P.num_dims):
+        for side in range(2):
+            if P.bc[d][side] != -17:
+                continue
+            ax = 3 - d  # prim is (N, z, y, x)
+            idx = 0 if side == 0 else prim.shape[ax] - 1
+            out[(d, side)] = np.ascontiguousarray(np.take(prim, idx, axis=ax))
+    return out

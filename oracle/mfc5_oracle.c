@@ -1,0 +1,1086 @@
+/* mfc5_oracle.c -- CPU ORACLE (TEST INFRASTRUCTURE ONLY; see mfc5_oracle.h).
+ *
+ * Unfused, array-for-array restatement of the reference's arithmetic, in the reference's
+ * operation order.  Every routine cites the reference lines it follows (paths relative to
+ * MFlowCode/MFC @ 0b234b19).  Build: oracle/Makefile (-O2 -ffp-contract=off so results do not
+ * depend on FMA contraction).
+ */
+#include "mfc5_oracle.h"
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+#define SGM_EPS 1.e-16 /* src/common/m_constants.fpp:16 */
+#define MAXF MFC5_MAX_FLUIDS
+#define MAXN MFC5_MAX_EQ
+
+struct orc_state {
+    mfc5_params P;
+    int nd, nf, N, b, polyn, ns; /* ns = weno_num_stencils + 1 */
+    int s[3];                    /* m, n, p */
+    int off[3], ext[3];
+    long stride[3], fsz;
+    int iE, iadv, imom;
+    /* grid: scb[d][i], i in [-1-b, s+b]; ds[d][i], i in [-b, s+b] (pointers pre-offset) */
+    double *scb_store[3], *ds_store[3];
+    double *scb[3], *ds[3];
+    /* WENO tables, index j in [-b+polyn, s+b-polyn] -> slot j + b (m_weno.fpp:170-893) */
+    double *cL[3], *cR[3], *dL[3], *dR[3], *bt[3];
+    int uniform[3];
+    /* CBC coefficients per (dir, side) (m_cbc.fpp:327-408) */
+    double fd[3][2][8], pi[3][2][2][3], cds[3][2][8], Del[3];
+    /* fields */
+    double *q1, *q2, *prim, *rhs, *vL, *vR, *flux, *fsrc;
+    /* Dirichlet (-17) face values, bc_buffers of m_boundary_common.fpp:46-65: [v][t2][t1] over the transverse interior */
+    double* dirich[3][2];
+};
+
+static inline long IDX(const orc_state* S, int i, int j, int k) {
+    return (long)(i + S->off[0]) + (long)S->ext[0] * ((long)(j + S->off[1]) + (long)S->ext[1] * (long)(k + S->off[2]));
+}
+static inline double sq(double x) { return x * x; }
+static inline double dmin(double a, double b) { return a < b ? a : b; }
+static inline double dmax(double a, double b) { return a > b ? a : b; }
+/* Fortran sign(a, b): |a| with the sign of b (b = +0 -> +, b = -0 -> -) */
+static inline double fsign(double a, double b) { return copysign(fabs(a), b); }
+
+int orc_num_threads(void) {
+#ifdef _OPENMP
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}
+
+orc_state* orc_create(const mfc5_params* P) {
+    orc_state* S = (orc_state*)calloc(1, sizeof(orc_state));
+    S->P = *P;
+    S->s[0] = P->m; S->s[1] = P->n; S->s[2] = P->p;
+    S->nd = 1 + (P->n > 0) + (P->p > 0);
+    S->nf = P->num_fluids;
+    S->N = 2 * S->nf + S->nd + 1;
+    S->polyn = (P->weno_order - 1) / 2;
+    S->ns = S->polyn + 1;
+    /* buff_size = weno_polyn + 2 for inviscid WENO: src/common/m_helper_basic.fpp:127-132 */
+    S->b = S->polyn + 2;
+    for (int d = 0; d < 3; d++) {
+        S->off[d] = (d < S->nd) ? S->b : 0;
+        S->ext[d] = S->s[d] + 1 + 2 * S->off[d];
+    }
+    S->stride[0] = 1; S->stride[1] = S->ext[0]; S->stride[2] = (long)S->ext[0] * S->ext[1];
+    S->fsz = (long)S->ext[0] * S->ext[1] * S->ext[2];
+    S->imom = S->nf; S->iE = S->nf + S->nd; S->iadv = S->iE + 1;
+    size_t nb = (size_t)S->N * S->fsz * sizeof(double);
+    S->q1 = (double*)calloc(1, nb); S->q2 = (double*)calloc(1, nb); S->prim = (double*)calloc(1, nb);
+    S->rhs = (double*)calloc(1, nb); S->vL = (double*)calloc(1, nb); S->vR = (double*)calloc(1, nb);
+    S->flux = (double*)calloc(1, nb); S->fsrc = (double*)calloc(1, (size_t)MAXF * S->fsz * sizeof(double));
+    return S;
+}
+
+void orc_destroy(orc_state* S) {
+    if (!S) return;
+    for (int d = 0; d < 3; d++) {
+        free(S->scb_store[d]); free(S->ds_store[d]);
+        free(S->cL[d]); free(S->cR[d]); free(S->dL[d]); free(S->dR[d]); free(S->bt[d]);
+    }
+    for (int d = 0; d < 3; d++) { free(S->dirich[d][0]); free(S->dirich[d][1]); }
+    free(S->q1); free(S->q2); free(S->prim); free(S->rhs); free(S->vL); free(S->vR); free(S->flux); free(S->fsrc);
+    free(S);
+}
+int orc_sys_size(const orc_state* S) { return S->N; }
+int orc_buff_size(const orc_state* S) { return S->b; }
+
+/* ---------------------------------------------------------------------------------------------
+ * Grid ghost metrics: src/common/m_boundary_common.fpp:404-466 (physical BCs),
+ * src/common/m_mpi_common.fpp:1745-1796 (processor boundaries); interior widths as
+ * src/simulation/m_start_up.fpp:190-191.
+ * ------------------------------------------------------------------------------------------- */
+void orc_set_grid(orc_state* S, int d, const double* s_cb_in, const double* gbeg, const double* gend) {
+    int s = S->s[d], b = S->b;
+    S->scb_store[d] = (double*)calloc((size_t)(s + 2 + 2 * b), sizeof(double));
+    S->ds_store[d] = (double*)calloc((size_t)(s + 1 + 2 * b), sizeof(double));
+    double* cb = S->scb_store[d] + 1 + b; /* cb[-1-b .. s+b] */
+    double* w = S->ds_store[d] + b;       /* w[-b .. s+b] */
+    S->scb[d] = cb; S->ds[d] = w;
+    for (int i = -1; i <= s; i++) cb[i] = s_cb_in[i + 1];
+    for (int i = 0; i <= s; i++) w[i] = cb[i] - cb[i - 1];
+    int bcb = S->P.bc[d][0], bce = S->P.bc[d][1];
+    for (int i = 1; i <= b; i++) {
+        if (bcb >= 0) w[-i] = gbeg[b - i]; /* neighbour's last b widths, increasing index */
+        else {
+            int src = (bcb == MFC5_BC_PERIODIC) ? s - i + 1 : (bcb == MFC5_BC_REFLECTIVE) ? i - 1 : 0;
+            w[-i] = w[src];
+        }
+    }
+    for (int i = 1; i <= b; i++) {
+        if (bce >= 0) w[s + i] = gend[i - 1];
+        else {
+            int src = (bce == MFC5_BC_PERIODIC) ? i - 1 : (bce == MFC5_BC_REFLECTIVE) ? s - i + 1 : s;
+            w[s + i] = w[src];
+        }
+    }
+    for (int i = 1; i <= b; i++) cb[-1 - i] = cb[-i] - w[-i];
+    for (int i = 1; i <= b; i++) cb[s + i] = cb[s + i - 1] + w[s + i];
+}
+
+/* ---------------------------------------------------------------------------------------------
+ * WENO coefficient tables: src/simulation/m_weno.fpp:196-215 (WENO3), :233-341 (WENO5),
+ * null_weights :219-229,345-361, uniform-grid detection :869-879.
+ * ------------------------------------------------------------------------------------------- */
+static void weno_coefficients(orc_state* S, int d) {
+    int s = S->s[d], b = S->b, pn = S->polyn, ns = S->ns;
+    int nslot = s + 1 + 2 * b;
+    S->cL[d] = (double*)calloc((size_t)nslot * ns * (pn > 0 ? pn : 1), sizeof(double));
+    S->cR[d] = (double*)calloc((size_t)nslot * ns * (pn > 0 ? pn : 1), sizeof(double));
+    S->dL[d] = (double*)calloc((size_t)nslot * ns, sizeof(double));
+    S->dR[d] = (double*)calloc((size_t)nslot * ns, sizeof(double));
+    S->bt[d] = (double*)calloc((size_t)nslot * ns * 3, sizeof(double));
+    const double* scb = S->scb[d];
+#define C(k) scb[i + (k)]
+#define CL(j, q, r) S->cL[d][(((j) + b) * ns + (q)) * pn + (r)]
+#define CR(j, q, r) S->cR[d][(((j) + b) * ns + (q)) * pn + (r)]
+#define DL(q, j) S->dL[d][((j) + b) * ns + (q)]
+#define DR(q, j) S->dR[d][((j) + b) * ns + (q)]
+#define BT(j, q, r) S->bt[d][(((j) + b) * ns + (q)) * 3 + (r)]
+    int bcb = S->P.bc[d][0], bce = S->P.bc[d][1];
+    if (S->P.weno_order == 3) {
+        for (int i = -b - 1 + pn; i <= s + b - 1 - pn; i++) {
+            int j = i + 1;
+            CR(j, 0, 0) = (C(0) - C(1)) / (C(0) - C(2));
+            CR(j, 1, 0) = (C(0) - C(1)) / (C(-1) - C(1));
+            CL(j, 0, 0) = -CR(j, 0, 0);
+            CL(j, 1, 0) = -CR(j, 1, 0);
+            DR(0, j) = (C(-1) - C(1)) / (C(-1) - C(2));
+            DL(0, j) = (C(-1) - C(0)) / (C(-1) - C(2));
+            DR(1, j) = 1.0 - DR(0, j);
+            DL(1, j) = 1.0 - DL(0, j);
+            BT(j, 0, 0) = 4.0 * sq(C(0) - C(1)) / sq(C(0) - C(2));
+            BT(j, 1, 0) = 4.0 * sq(C(0) - C(1)) / sq(C(-1) - C(1));
+        }
+        if (S->P.null_weights) {
+            if (bcb == MFC5_BC_RIEMANN_EXTRAP) { DR(1, 0) = 0; DR(0, 0) = 1; DL(1, 0) = 0; DL(0, 0) = 1; }
+            if (bce == MFC5_BC_RIEMANN_EXTRAP) { DR(0, s) = 0; DR(1, s) = 1; DL(0, s) = 0; DL(1, s) = 1; }
+        }
+    } else if (S->P.weno_order == 5) {
+        for (int i = -b - 1 + pn; i <= s + b - 1 - pn; i++) {
+            int j = i + 1;
+            CR(j, 0, 0) = ((C(0) - C(1)) * (C(1) - C(2))) / ((C(0) - C(3)) * (C(3) - C(1)));
+            CR(j, 1, 0) = ((C(-1) - C(1)) * (C(1) - C(0))) / ((C(-1) - C(2)) * (C(2) - C(0)));
+            CR(j, 1, 1) = ((C(0) - C(1)) * (C(1) - C(2))) / ((C(-1) - C(1)) * (C(-1) - C(2)));
+            CR(j, 2, 1) = ((C(0) - C(1)) * (C(1) - C(-1))) / ((C(-2) - C(0)) * (C(-2) - C(1)));
+            CL(j, 0, 0) = ((C(1) - C(0)) * (C(0) - C(2))) / ((C(0) - C(3)) * (C(3) - C(1)));
+            CL(j, 1, 0) = ((C(0) - C(-1)) * (C(0) - C(1))) / ((C(-1) - C(2)) * (C(0) - C(2)));
+            CL(j, 1, 1) = ((C(1) - C(0)) * (C(0) - C(2))) / ((C(-1) - C(1)) * (C(-1) - C(2)));
+            CL(j, 2, 1) = ((C(-1) - C(0)) * (C(0) - C(1))) / ((C(-2) - C(0)) * (C(-2) - C(1)));
+
+            CR(j, 0, 1) = ((C(0) - C(2)) + (C(1) - C(3))) / ((C(0) - C(2)) * (C(0) - C(3))) * ((C(0) - C(1)));
+            CR(j, 2, 0) = ((C(-2) - C(1)) + (C(-1) - C(1))) / ((C(-1) - C(1)) * (C(1) - C(-2))) * ((C(1) - C(0)));
+            CL(j, 0, 1) = ((C(0) - C(2)) + (C(0) - C(3))) / ((C(0) - C(2)) * (C(0) - C(3))) * ((C(1) - C(0)));
+            CL(j, 2, 0) = ((C(-2) - C(0)) + (C(-1) - C(1))) / ((C(-2) - C(1)) * (C(1) - C(-1))) * ((C(0) - C(1)));
+
+            DR(0, j) = ((C(-2) - C(1)) * (C(1) - C(-1))) / ((C(-2) - C(3)) * (C(3) - C(-1)));
+            DR(2, j) = ((C(1) - C(2)) * (C(1) - C(3))) / ((C(-2) - C(2)) * (C(-2) - C(3)));
+            DL(0, j) = ((C(-2) - C(0)) * (C(0) - C(-1))) / ((C(-2) - C(3)) * (C(3) - C(-1)));
+            DL(2, j) = ((C(0) - C(2)) * (C(0) - C(3))) / ((C(-2) - C(2)) * (C(-2) - C(3)));
+            DR(1, j) = 1.0 - DR(0, j) - DR(2, j);
+            DL(1, j) = 1.0 - DL(0, j) - DL(2, j);
+
+            BT(j, 0, 0) = 4.0 * sq(C(0) - C(1)) * (10.0 * sq(C(1) - C(0)) + (C(1) - C(0)) * (C(2) - C(1)) + sq(C(2) - C(1))) /
+                          (sq(C(0) - C(3)) * sq(C(1) - C(3)));
+            BT(j, 0, 1) = 4.0 * sq(C(0) - C(1)) *
+                          (19.0 * sq(C(1) - C(0)) - (C(1) - C(0)) * (C(3) - C(1)) +
+                           2.0 * (C(2) - C(0)) * ((C(2) - C(0)) + (C(3) - C(1)))) /
+                          ((C(0) - C(2)) * sq(C(0) - C(3)) * (C(3) - C(1)));
+            BT(j, 0, 2) = 4.0 * sq(C(0) - C(1)) *
+                          (10.0 * sq(C(1) - C(0)) + (C(1) - C(0)) * ((C(2) - C(0)) + (C(3) - C(1))) +
+                           sq((C(2) - C(0)) + (C(3) - C(1)))) /
+                          (sq(C(0) - C(2)) * sq(C(0) - C(3)));
+            BT(j, 1, 0) = 4.0 * sq(C(0) - C(1)) * (10.0 * sq(C(1) - C(0)) + sq(C(0) - C(-1)) + (C(0) - C(-1)) * (C(1) - C(0))) /
+                          (sq(C(-1) - C(2)) * sq(C(0) - C(2)));
+            BT(j, 1, 1) = 4.0 * sq(C(0) - C(1)) *
+                          ((C(0) - C(1)) * ((C(0) - C(-1)) + 20.0 * (C(1) - C(0))) +
+                           (2.0 * (C(0) - C(-1)) + (C(1) - C(0))) * (C(2) - C(0))) /
+                          ((C(1) - C(-1)) * sq(C(-1) - C(2)) * (C(2) - C(0)));
+            BT(j, 1, 2) = 4.0 * sq(C(0) - C(1)) * (10.0 * sq(C(1) - C(0)) + (C(1) - C(0)) * (C(2) - C(1)) + sq(C(2) - C(1))) /
+                          (sq(C(-1) - C(1)) * sq(C(-1) - C(2)));
+            BT(j, 2, 0) = 4.0 * sq(C(0) - C(1)) *
+                          (12.0 * sq(C(1) - C(0)) + sq((C(0) - C(-2)) + (C(0) - C(-1))) +
+                           3.0 * ((C(0) - C(-2)) + (C(0) - C(-1))) * (C(1) - C(0))) /
+                          (sq(C(-2) - C(1)) * sq(C(-1) - C(1)));
+            BT(j, 2, 1) = 4.0 * sq(C(0) - C(1)) *
+                          (19.0 * sq(C(1) - C(0)) + ((C(0) - C(-2)) * (C(0) - C(1))) +
+                           2.0 * (C(1) - C(-1)) * ((C(0) - C(-2)) + (C(1) - C(-1)))) /
+                          ((C(-2) - C(0)) * sq(C(-2) - C(1)) * (C(1) - C(-1)));
+            BT(j, 2, 2) = 4.0 * sq(C(0) - C(1)) * (10.0 * sq(C(1) - C(0)) + sq(C(0) - C(-1)) + (C(0) - C(-1)) * (C(1) - C(0))) /
+                          (sq(C(-2) - C(0)) * sq(C(-2) - C(1)));
+        }
+        if (S->P.null_weights) {
+            if (bcb == MFC5_BC_RIEMANN_EXTRAP) {
+                DR(1, 0) = 0; DR(2, 0) = 0; DR(0, 0) = 1; DL(1, 0) = 0; DL(2, 0) = 0; DL(0, 0) = 1;
+                DR(2, 1) = 0; { double t = DR(0, 1) + DR(1, 1) + DR(2, 1); for (int q = 0; q < 3; q++) DR(q, 1) /= t; }
+                DL(2, 1) = 0; { double t = DL(0, 1) + DL(1, 1) + DL(2, 1); for (int q = 0; q < 3; q++) DL(q, 1) /= t; }
+            }
+            if (bce == MFC5_BC_RIEMANN_EXTRAP) {
+                DR(0, s - 1) = 0; { double t = DR(0, s - 1) + DR(1, s - 1) + DR(2, s - 1); for (int q = 0; q < 3; q++) DR(q, s - 1) /= t; }
+                DL(0, s - 1) = 0; { double t = DL(0, s - 1) + DL(1, s - 1) + DL(2, s - 1); for (int q = 0; q < 3; q++) DL(q, s - 1) /= t; }
+                DR(0, s) = 0; DR(1, s) = 0; DR(2, s) = 1; DL(0, s) = 0; DL(1, s) = 0; DL(2, s) = 1;
+            }
+        }
+    }
+    /* uniform-grid detection, m_weno.fpp:869-879 (epsilon(h0) = 2^-52) */
+    S->uniform[d] = 1;
+    if (s > 0) {
+        double h0 = (scb[s] - scb[0]) / (double)s;
+        for (int i = 0; i <= s - 1; i++)
+            if (fabs((scb[i + 1] - scb[i]) - h0) > sqrt(2.220446049250313e-16) * fabs(h0)) { S->uniform[d] = 0; break; }
+    }
+#undef C
+}
+
+/* CBC coefficients: src/simulation/m_cbc.fpp:327-408 (fd_coef, pi_coef), :410-461 (ds), Del :312-313 */
+static void cbc_coefficients(orc_state* S, int d, int side) {
+    int s = S->s[d], b = S->b;
+    double* ds = S->cds[d][side];
+    for (int i = 0; i <= b; i++) ds[i] = side == 0 ? S->ds[d][i] : S->ds[d][s - i];
+    double scb[10];
+    scb[0] = 0.0;
+    for (int i = 0; i <= b; i++) scb[i + 1] = scb[i] + ds[i];
+    double* fd = S->fd[d][side];
+    for (int i = 0; i < 8; i++) fd[i] = 0.0;
+    if (S->P.weno_order == 1) {
+        fd[0] = -2.0 / (ds[0] + ds[1]);
+        fd[1] = -fd[0];
+    } else if (S->P.weno_order == 3) {
+        fd[0] = -6.0 / (3.0 * ds[0] + 2.0 * ds[1] - ds[2]);
+        fd[1] = -4.0 * fd[0] / 3.0;
+        fd[2] = fd[0] / 3.0;
+        S->pi[d][side][0][0] = (scb[0] - scb[1]) / (scb[0] - scb[2]);
+    } else {
+        fd[0] = -50.0 / (25.0 * ds[0] + 2.0 * ds[1] - 1.e1 * ds[2] + 1.e1 * ds[3] - 3.0 * ds[4]);
+        fd[1] = -48.0 * fd[0] / 25.0;
+        fd[2] = 36.0 * fd[0] / 25.0;
+        fd[3] = -16.0 * fd[0] / 25.0;
+        fd[4] = 3.0 * fd[0] / 25.0;
+        double(*pi)[3] = S->pi[d][side];
+        pi[0][0] = ((scb[0] - scb[1]) * (scb[1] - scb[2]) * (scb[1] - scb[3])) /
+                   ((scb[1] - scb[4]) * (scb[4] - scb[0]) * (scb[4] - scb[2]));
+        pi[0][1] = ((scb[1] - scb[0]) * (scb[1] - scb[2]) *
+                    ((scb[1] - scb[3]) * (scb[1] - scb[3]) - (scb[0] - scb[4]) * ((scb[3] - scb[1]) + (scb[4] - scb[1])))) /
+                   ((scb[0] - scb[3]) * (scb[1] - scb[3]) * (scb[0] - scb[4]) * (scb[1] - scb[4]));
+        pi[0][2] = (scb[1] - scb[0]) *
+                   ((scb[1] - scb[2]) * (scb[1] - scb[3]) + ((scb[0] - scb[2]) + (scb[1] - scb[3])) * (scb[0] - scb[4])) /
+                   ((scb[2] - scb[0]) * (scb[0] - scb[3]) * (scb[0] - scb[4]));
+        pi[1][0] = ((scb[0] - scb[2]) * (scb[2] - scb[1]) * (scb[2] - scb[3])) /
+                   ((scb[2] - scb[4]) * (scb[4] - scb[0]) * (scb[4] - scb[1]));
+        pi[1][1] = ((scb[0] - scb[2]) * (scb[1] - scb[2]) *
+                    ((scb[1] - scb[3]) * (scb[2] - scb[3]) + (scb[0] - scb[4]) * ((scb[1] - scb[3]) + (scb[2] - scb[4])))) /
+                   ((scb[0] - scb[3]) * (scb[1] - scb[3]) * (scb[0] - scb[4]) * (scb[1] - scb[4]));
+        pi[1][2] = ((scb[1] - scb[2]) * (scb[2] - scb[3]) * (scb[2] - scb[4])) /
+                   ((scb[0] - scb[2]) * (scb[0] - scb[3]) * (scb[0] - scb[4]));
+    }
+}
+
+static int is_cbc(int bc) { return bc <= MFC5_BC_CHAR_SLIP_WALL && bc >= MFC5_BC_CHAR_SUP_OUTFLOW; }
+
+void orc_finalize_setup(orc_state* S) {
+    for (int d = 0; d < S->nd; d++) {
+        if (S->P.weno_order > 1) weno_coefficients(S, d);
+        /* Del_in = Del_out = maxval(d<xyz>) over the ghosted array, m_cbc.fpp:312-313 */
+        double mx = S->ds[d][-S->b];
+        for (int i = -S->b; i <= S->s[d] + S->b; i++) mx = dmax(mx, S->ds[d][i]);
+        S->Del[d] = mx;
+        for (int side = 0; side < 2; side++)
+            if (is_cbc(S->P.bc[d][side])) cbc_coefficients(S, d, side);
+    }
+}
+
+/* --------------------------------------------------------------------------------------------- */
+static void copy_interior(const orc_state* S, const double* src_packed, double* dst_field, int to_field) {
+    int nx = S->s[0] + 1, ny = S->s[1] + 1, nz = S->s[2] + 1;
+    long ncell = (long)nx * ny * nz;
+    for (int v = 0; v < S->N; v++)
+        for (int k = 0; k < nz; k++)
+            for (int j = 0; j < ny; j++)
+                for (int i = 0; i < nx; i++) {
+                    long a = v * ncell + ((long)k * ny + j) * nx + i;
+                    long f = v * S->fsz + IDX(S, i, j, k);
+                    if (to_field) dst_field[f] = src_packed[a];
+                    else ((double*)src_packed)[a] = dst_field[f];
+                }
+}
+void orc_set_cons(orc_state* S, const double* q) { copy_interior(S, q, S->q1, 1); }
+void orc_get_cons(const orc_state* S, double* q) { copy_interior(S, q, S->q1, 0); }
+void orc_get_prim(const orc_state* S, double* q) { copy_interior(S, q, S->prim, 0); }
+void orc_get_rhs(const orc_state* S, double* q) { copy_interior(S, q, S->rhs, 0); }
+
+/* mixture rule shared by cons->prim, CBC and ICFL:
+ * s_compute_species_fraction (m_variables_conversion.fpp:1140-1188) followed by
+ * s_convert_species_to_mixture_variables_kernel (:198-270); with mpp_lim the clamp/renormalise is
+ * applied by BOTH routines, in place. `passes` = 2 for callers that go through both. */
+static void mixture(const orc_state* S, double* arho, double* alf, int passes, double* rho, double* gam, double* pinf, double* qv) {
+    int nf = S->nf;
+    if (S->P.mpp_lim) {
+        for (int pass = 0; pass < passes; pass++) {
+            double sum = 0.0;
+            for (int i = 0; i < nf; i++) {
+                arho[i] = dmax(0.0, arho[i]);
+                alf[i] = dmin(dmax(0.0, alf[i]), 1.0);
+                sum = sum + alf[i];
+            }
+            for (int i = 0; i < nf; i++) alf[i] = alf[i] / dmax(sum, SGM_EPS);
+        }
+    }
+    double r = 0, g = 0, pi = 0, q = 0;
+    for (int i = 0; i < nf; i++) {
+        r = r + arho[i];
+        g = g + alf[i] * S->P.fluid_gamma[i];
+        pi = pi + alf[i] * S->P.fluid_pi_inf[i];
+        q = q + arho[i] * S->P.fluid_qv[i];
+    }
+    *rho = r; *gam = g; *pinf = pi; *qv = q;
+}
+
+/* s_compute_speed_of_sound, 5-eq non-bubble branch: m_variables_conversion.fpp:1248-1260 */
+static double sound_speed(const orc_state* S, double rho, double gam, double H, double vel_sum, double qv) {
+    double c = (H - 5.e-1 * vel_sum - qv / rho) / gam;
+    if (S->P.mixture_err && c < 0.0) return 100.0 * SGM_EPS;
+    return sqrt(c);
+}
+
+/* s_convert_conservative_to_primitive_variables: m_variables_conversion.fpp:459-717, on idwint
+ * (m_rhs.fpp:641).  The simulation enables enforce_density_floor (m_start_up.fpp:823). */
+void orc_cons2prim(orc_state* S) {
+    int nf = S->nf, nd = S->nd;
+#pragma omp parallel for collapse(2)
+    for (int k = 0; k <= S->s[2]; k++)
+        for (int j = 0; j <= S->s[1]; j++)
+            for (int i = 0; i <= S->s[0]; i++) {
+                long c = IDX(S, i, j, k);
+                double arho[MAXF], alf[MAXF], rho, gam, pinf, qv;
+                for (int f = 0; f < nf; f++) {
+                    arho[f] = S->q1[f * S->fsz + c];
+                    alf[f] = S->q1[(S->iadv + f) * S->fsz + c];
+                }
+                mixture(S, arho, alf, 2, &rho, &gam, &pinf, &qv);
+                for (int f = 0; f < nf; f++) S->prim[f * S->fsz + c] = S->q1[f * S->fsz + c];
+                rho = dmax(rho, SGM_EPS);
+                double dyn = 0.0;
+                for (int a = 0; a < nd; a++) {
+                    long v = (S->imom + a) * S->fsz + c;
+                    S->prim[v] = S->q1[v] / rho;
+                    dyn = dyn + 5.e-1 * S->q1[v] * S->prim[v];
+                }
+                /* s_compute_pressure: m_variables_conversion.fpp:99 */
+                S->prim[S->iE * S->fsz + c] = (S->q1[S->iE * S->fsz + c] - dyn - pinf - qv) / gam;
+                for (int f = 0; f < nf; f++) S->prim[(S->iadv + f) * S->fsz + c] = S->q1[(S->iadv + f) * S->fsz + c];
+            }
+}
+
+/* ---------------------------------------------------------------------------------------------
+ * Ghost-cell fill of the primitive variables for one (direction, side):
+ * s_populate_bc_direction m_boundary_common.fpp:120-187 with the per-cell kernels of
+ * m_boundary_primitives.fpp: extrapolation :27-111 (codes -3..-12 and -17 without bc_io),
+ * symmetry :114-335, periodic :338-494, slip wall :552-701, no-slip wall :704-874.
+ * Transverse extents: x faces interior; y faces span x ghosts; z faces span x and y ghosts (:143-149).
+ * ------------------------------------------------------------------------------------------- */
+void orc_bc_fill(orc_state* S, int d, int side) {
+    int bc = S->P.bc[d][side];
+    if (bc >= 0) return;
+    int b = S->b, s = S->s[d];
+    int lo[3] = {0, 0, 0}, hi[3] = {S->s[0], S->s[1], S->s[2]};
+    for (int e = 0; e < d; e++) { lo[e] = -S->off[e]; hi[e] = S->s[e] + S->off[e]; }
+    lo[d] = hi[d] = 0;
+    const double* wv = side == 0 ? S->P.bc_vb[d] : S->P.bc_ve[d];
+    for (int k = lo[2]; k <= hi[2]; k++)
+        for (int j = lo[1]; j <= hi[1]; j++)
+            for (int i = lo[0]; i <= hi[0]; i++) {
+                int ijk[3] = {i, j, k};
+                for (int l = 1; l <= b; l++) {
+                    int g = side == 0 ? -l : s + l;             /* ghost index */
+                    int edge = side == 0 ? 0 : s;               /* boundary cell */
+                    int mir = side == 0 ? l - 1 : s - (l - 1);  /* mirror cell */
+                    int per = side == 0 ? s - (l - 1) : l - 1;  /* periodic image */
+                    ijk[d] = g; long cg = IDX(S, ijk[0], ijk[1], ijk[2]);
+                    ijk[d] = edge; long ce = IDX(S, ijk[0], ijk[1], ijk[2]);
+                    ijk[d] = mir; long cm = IDX(S, ijk[0], ijk[1], ijk[2]);
+                    ijk[d] = per; long cp = IDX(S, ijk[0], ijk[1], ijk[2]);
+                    for (int v = 0; v < S->N; v++) {
+                        double* f = S->prim + v * S->fsz;
+                        int a = v - S->imom; /* velocity component if 0 <= a < nd */
+                        switch (bc) {
+                        case MFC5_BC_PERIODIC: f[cg] = f[cp]; break;
+                        case MFC5_BC_REFLECTIVE: f[cg] = (a == d) ? -f[cm] : f[cm]; break;
+                        case MFC5_BC_SLIP_WALL: f[cg] = (a == d) ? -f[cm] + 2.0 * wv[d] : f[ce]; break;
+                        case MFC5_BC_NO_SLIP_WALL: f[cg] = (a >= 0 && a < S->nd) ? -f[cm] + 2.0 * wv[a] : f[ce]; break;
+                        case MFC5_BC_DIRICHLET:
+                            if (S->dirich[d][side]) { /* s_dirichlet, m_boundary_primitives.fpp:877-969 */
+                                int t1 = d == 0 ? 1 : 0, t2 = d == 2 ? 1 : 2;
+                                int n1 = S->s[t1] + 1, n2 = S->s[t2] + 1;
+                                int a1 = ijk[t1], a2 = ijk[t2];
+                                if (a1 < 0 || a1 >= n1 || a2 < 0 || a2 >= n2) f[cg] = 0.0; /* never packed by pre_process */
+                                else f[cg] = S->dirich[d][side][((long)v * n2 + a2) * n1 + a1];
+                            } else f[cg] = f[ce];
+                            break;
+                        default: f[cg] = f[ce]; break; /* -3 .. -12 */
+                        }
+                    }
+                }
+            }
+}
+
+/* Dirichlet buffers: what pre_process packs from the initial primitive field
+ * (src/common/m_boundary_io.fpp:271-330) and the simulation reads back (bc_io). */
+void orc_set_dirichlet(orc_state* S, int d, int side, const double* buf) {
+    int t1 = d == 0 ? 1 : 0, t2 = d == 2 ? 1 : 2;
+    long n = (long)S->N * (S->s[t1] + 1) * (S->s[t2] + 1);
+    free(S->dirich[d][side]);
+    S->dirich[d][side] = (double*)malloc(n * sizeof(double));
+    memcpy(S->dirich[d][side], buf, n * sizeof(double));
+}
+
+/* Halo slabs for processor boundaries (bc >= 0): the b interior layers next to `side` are what the
+ * neighbour on that side needs; extents as m_mpi_common.fpp:574-588,620-804 (y spans x ghosts,
+ * z spans x and y ghosts).  Buffer order: var fastest is irrelevant here (both ends are ours):
+ * (v, k, j, i) with i fastest. */
+static void halo_bounds(const orc_state* S, int d, int lo[3], int hi[3]) {
+    for (int e = 0; e < 3; e++) { lo[e] = 0; hi[e] = S->s[e]; }
+    for (int e = 0; e < d; e++) { lo[e] = -S->off[e]; hi[e] = S->s[e] + S->off[e]; }
+}
+int orc_halo_count(const orc_state* S, int d) {
+    int lo[3], hi[3]; halo_bounds(S, d, lo, hi);
+    long n = S->N * (long)S->b;
+    for (int e = 0; e < 3; e++) if (e != d) n *= (hi[e] - lo[e] + 1);
+    return (int)n;
+}
+static void halo_copy(orc_state* S, int d, int first, double* buf, int pack) {
+    int lo[3], hi[3]; halo_bounds(S, d, lo, hi);
+    lo[d] = first; hi[d] = first + S->b - 1;
+    long a = 0;
+    for (int v = 0; v < S->N; v++)
+        for (int k = lo[2]; k <= hi[2]; k++)
+            for (int j = lo[1]; j <= hi[1]; j++)
+                for (int i = lo[0]; i <= hi[0]; i++, a++) {
+                    double* f = S->prim + v * S->fsz + IDX(S, i, j, k);
+                    if (pack) buf[a] = *f; else *f = buf[a];
+                }
+}
+void orc_halo_pack(const orc_state* S, int d, int side, double* buf) {
+    halo_copy((orc_state*)S, d, side == 0 ? 0 : S->s[d] - S->b + 1, buf, 1);
+}
+void orc_halo_unpack(orc_state* S, int d, int side, const double* buf) {
+    halo_copy(S, d, side == 0 ? -S->b : S->s[d] + 1, (double*)buf, 0);
+}
+
+/* ---------------------------------------------------------------------------------------------
+ * WENO reconstruction along direction d: s_weno, m_weno.fpp:1007-1085 (WENO3), :1098-1239 (WENO5),
+ * :952-993 (order 1).  vL = left-boundary value of cell j, vR = right-boundary value.  Only cells
+ * -1..s+1 along the sweep and the transverse interior are consumed by the Riemann solver
+ * (m_rhs.fpp:1020-1027), so only those are computed.
+ * ------------------------------------------------------------------------------------------- */
+static void weno_dir(orc_state* S, int d) {
+    int b = S->b, pn = S->polyn, ns = S->ns;
+    long sd = S->stride[d];
+    int lo[3] = {0, 0, 0}, hi[3] = {S->s[0], S->s[1], S->s[2]};
+    lo[d] = -1; hi[d] = S->s[d] + 1;
+    const double eps = S->P.weno_eps;
+    const int mapped = S->P.mapped_weno, wz = S->P.wenoz;
+#pragma omp parallel for collapse(2)
+    for (int k = lo[2]; k <= hi[2]; k++)
+        for (int j = lo[1]; j <= hi[1]; j++)
+            for (int i = lo[0]; i <= hi[0]; i++) {
+                int ijk[3] = {i, j, k};
+                int jc = ijk[d];
+                long c = IDX(S, i, j, k);
+                for (int v = 0; v < S->N; v++) {
+                    const double* f = S->prim + v * S->fsz + c;
+                    double* oL = S->vL + v * S->fsz + c;
+                    double* oR = S->vR + v * S->fsz + c;
+                    if (pn == 0) { *oL = f[0]; *oR = f[0]; continue; }
+                    double dvd[4], poly[3], beta[3], alpha[3], omega[3], tau = 0.0;
+                    const double* dl = &S->dL[d][(jc + b) * ns];
+                    const double* dr = &S->dR[d][(jc + b) * ns];
+                    const double* cl = &S->cL[d][(jc + b) * ns * pn];
+                    const double* cr = &S->cR[d][(jc + b) * ns * pn];
+                    const double* bt = &S->bt[d][(jc + b) * ns * 3];
+                    double vp0 = f[0];
+                    if (pn == 1) {
+                        double vm1 = f[-sd], vp1 = f[sd];
+                        double d0 = vp1 - vp0, dm1 = vp0 - vm1; /* dvd(0), dvd(-1) */
+                        beta[0] = bt[0 * 3 + 0] * d0 * d0 + eps;
+                        beta[1] = bt[1 * 3 + 0] * dm1 * dm1 + eps;
+                        for (int sideLR = 0; sideLR < 2; sideLR++) {
+                            const double* dd = sideLR == 0 ? dl : dr;
+                            const double* cc = sideLR == 0 ? cl : cr;
+                            poly[0] = vp0 + cc[0 * pn + 0] * d0;
+                            poly[1] = vp0 + cc[1 * pn + 0] * dm1;
+                            if (mapped) {
+                                for (int q = 0; q < 2; q++) alpha[q] = dd[q] / (beta[q] * beta[q]);
+                                double sum = alpha[0] + alpha[1];
+                                for (int q = 0; q < 2; q++) omega[q] = alpha[q] / sum;
+                                for (int q = 0; q < 2; q++)
+                                    alpha[q] = (dd[q] * (1.0 + dd[q] - 3.0 * omega[q]) + omega[q] * omega[q]) *
+                                               (omega[q] / (dd[q] * dd[q] + omega[q] * (1.0 - 2.0 * dd[q])));
+                            } else if (wz) {
+                                if (sideLR == 0) tau = fabs(beta[1] - beta[0]);
+                                for (int q = 0; q < 2; q++) alpha[q] = dd[q] * (1.0 + tau / beta[q]);
+                            } else {
+                                for (int q = 0; q < 2; q++) alpha[q] = dd[q] / (beta[q] * beta[q]);
+                            }
+                            double sum = alpha[0] + alpha[1];
+                            omega[0] = alpha[0] / sum; omega[1] = alpha[1] / sum;
+                            double val = omega[0] * poly[0] + omega[1] * poly[1];
+                            if (sideLR == 0) *oL = val; else *oR = val;
+                        }
+                    } else {
+                        double vm1 = f[-sd], vm2 = f[-2 * sd], vp1 = f[sd], vp2 = f[2 * sd];
+                        double d1 = vp2 - vp1, d0 = vp1 - vp0, dm1 = vp0 - vm1, dm2 = vm1 - vm2;
+                        dvd[0] = d1; dvd[1] = d0; dvd[2] = dm1; dvd[3] = dm2;
+                        (void)dvd;
+                        if (S->uniform[d]) {
+                            beta[0] = 13.0 / 12.0 * sq(d1 - d0) + 0.25 * sq(d1 - 3.0 * d0) + eps;
+                            beta[1] = 13.0 / 12.0 * sq(d0 - dm1) + 0.25 * sq(d0 + dm1) + eps;
+                            beta[2] = 13.0 / 12.0 * sq(dm1 - dm2) + 0.25 * sq(3.0 * dm1 - dm2) + eps;
+                        } else {
+                            beta[0] = bt[0] * d1 * d1 + bt[1] * d1 * d0 + bt[2] * d0 * d0 + eps;
+                            beta[1] = bt[3] * d0 * d0 + bt[4] * d0 * dm1 + bt[5] * dm1 * dm1 + eps;
+                            beta[2] = bt[6] * dm1 * dm1 + bt[7] * dm1 * dm2 + bt[8] * dm2 * dm2 + eps;
+                        }
+                        for (int sideLR = 0; sideLR < 2; sideLR++) {
+                            const double* dd = sideLR == 0 ? dl : dr;
+                            const double* cc = sideLR == 0 ? cl : cr;
+                            poly[0] = vp0 + cc[0 * pn + 0] * d1 + cc[0 * pn + 1] * d0;
+                            poly[1] = vp0 + cc[1 * pn + 0] * d0 + cc[1 * pn + 1] * dm1;
+                            poly[2] = vp0 + cc[2 * pn + 0] * dm1 + cc[2 * pn + 1] * dm2;
+                            if (mapped) {
+                                for (int q = 0; q < 3; q++) alpha[q] = dd[q] / (beta[q] * beta[q]);
+                                double sum = alpha[0] + alpha[1] + alpha[2];
+                                for (int q = 0; q < 3; q++) omega[q] = alpha[q] / sum;
+                                for (int q = 0; q < 3; q++)
+                                    alpha[q] = (dd[q] * (1.0 + dd[q] - 3.0 * omega[q]) + omega[q] * omega[q]) *
+                                               (omega[q] / (dd[q] * dd[q] + omega[q] * (1.0 - 2.0 * dd[q])));
+                            } else if (wz) {
+                                if (sideLR == 0) tau = fabs(beta[2] - beta[0]);
+                                for (int q = 0; q < 3; q++) alpha[q] = dd[q] * (1.0 + (tau / beta[q]));
+                            } else {
+                                for (int q = 0; q < 3; q++) alpha[q] = dd[q] / (beta[q] * beta[q]);
+                            }
+                            omega[0] = alpha[0] / (alpha[0] + alpha[1] + alpha[2]);
+                            omega[1] = alpha[1] / (alpha[0] + alpha[1] + alpha[2]);
+                            omega[2] = alpha[2] / (alpha[0] + alpha[1] + alpha[2]);
+                            double val = omega[0] * poly[0] + omega[1] * poly[1] + omega[2] * poly[2];
+                            if (sideLR == 0) *oL = val; else *oR = val;
+                        }
+                    }
+                }
+            }
+}
+
+/* ---------------------------------------------------------------------------------------------
+ * Riemann solvers on faces -1..s of direction d (face j = right face of cell j):
+ *   left state  = right-boundary value of cell j   (the solver's qL_prim_rs(j),   = S->vR[j])
+ *   right state = left-boundary value of cell j+1  (the solver's qR_prim_rs(j+1), = S->vL[j+1])
+ * (argument swap at m_rhs.fpp:1031-1033).  BC -4: m_riemann_state.fpp:149-206.
+ * HLLC: m_riemann_solver_hllc.fpp:878-1332 (5-eq pure-fluid emission).
+ * HLL : m_riemann_solver_hll.fpp:128-576.
+ * Averages: include/inline_riemann.fpp:1-30.
+ * ------------------------------------------------------------------------------------------- */
+static void riemann_dir(orc_state* S, int d) {
+    int nf = S->nf, nd = S->nd;
+    long sd = S->stride[d];
+    int lo[3] = {0, 0, 0}, hi[3] = {S->s[0], S->s[1], S->s[2]};
+    lo[d] = -1;
+    const mfc5_params* P = &S->P;
+    int didx[3];
+    didx[0] = d;
+    if (d == 0) { didx[1] = 1; didx[2] = 2; } else if (d == 1) { didx[1] = 0; didx[2] = 2; } else { didx[1] = 0; didx[2] = 1; }
+    const int hllc = P->riemann_solver == 2;
+#pragma omp parallel for collapse(2)
+    for (int k = lo[2]; k <= hi[2]; k++)
+        for (int j = lo[1]; j <= hi[1]; j++)
+            for (int i = lo[0]; i <= hi[0]; i++) {
+                int ijk[3] = {i, j, k};
+                int jf = ijk[d];
+                long c = IDX(S, i, j, k);
+                double qL[MAXN], qR[MAXN];
+                for (int v = 0; v < S->N; v++) {
+                    qL[v] = S->vR[v * S->fsz + c];
+                    qR[v] = S->vL[v * S->fsz + c + sd];
+                }
+                if (P->bc[d][0] == MFC5_BC_RIEMANN_EXTRAP && jf == -1)
+                    for (int v = 0; v < S->N; v++) qL[v] = qR[v];
+                if (P->bc[d][1] == MFC5_BC_RIEMANN_EXTRAP && jf == S->s[d])
+                    for (int v = 0; v < S->N; v++) qR[v] = qL[v];
+
+                double vel_L[3] = {0, 0, 0}, vel_R[3] = {0, 0, 0}, vel_L_rms = 0, vel_R_rms = 0;
+                for (int a = 0; a < nd; a++) {
+                    vel_L[a] = qL[S->imom + a]; vel_R[a] = qR[S->imom + a];
+                    vel_L_rms = vel_L_rms + vel_L[a] * vel_L[a];
+                    vel_R_rms = vel_R_rms + vel_R[a] * vel_R[a];
+                }
+                double pres_L = qL[S->iE], pres_R = qR[S->iE];
+                double arho_L[MAXF], arho_R[MAXF], alf_L[MAXF], alf_R[MAXF];
+                if (hllc) {
+                    /* in-place limiter on the face buffers: hllc.fpp:938-958 */
+                    if (P->mpp_lim) {
+                        double sL = 0, sR = 0;
+                        for (int f = 0; f < nf; f++) {
+                            qL[f] = dmax(0.0, qL[f]);
+                            qL[S->iadv + f] = dmin(dmax(0.0, qL[S->iadv + f]), 1.0);
+                            qR[f] = dmax(0.0, qR[f]);
+                            qR[S->iadv + f] = dmin(dmax(0.0, qR[S->iadv + f]), 1.0);
+                            sL = sL + qL[S->iadv + f];
+                            sR = sR + qR[S->iadv + f];
+                        }
+                        for (int f = 0; f < nf; f++) {
+                            qL[S->iadv + f] = qL[S->iadv + f] / dmax(sL, SGM_EPS);
+                            qR[S->iadv + f] = qR[S->iadv + f] / dmax(sR, SGM_EPS);
+                        }
+                    }
+                    for (int f = 0; f < nf; f++) {
+                        arho_L[f] = qL[f]; arho_R[f] = qR[f];
+                        alf_L[f] = qL[S->iadv + f]; alf_R[f] = qR[S->iadv + f];
+                    }
+                } else {
+                    /* HLL clamps local copies only: hll.fpp:187-200 */
+                    for (int f = 0; f < nf; f++) {
+                        arho_L[f] = qL[f]; arho_R[f] = qR[f];
+                        alf_L[f] = qL[S->iadv + f]; alf_R[f] = qR[S->iadv + f];
+                    }
+                    if (P->mpp_lim) {
+                        double sL = 0, sR = 0;
+                        for (int f = 0; f < nf; f++) {
+                            arho_L[f] = dmax(0.0, arho_L[f]);
+                            alf_L[f] = dmin(dmax(0.0, alf_L[f]), 1.0);
+                            sL = sL + alf_L[f];
+                            arho_R[f] = dmax(0.0, arho_R[f]);
+                            alf_R[f] = dmin(dmax(0.0, alf_R[f]), 1.0);
+                            sR = sR + alf_R[f];
+                        }
+                        for (int f = 0; f < nf; f++) {
+                            alf_L[f] = alf_L[f] / dmax(sL, SGM_EPS);
+                            alf_R[f] = alf_R[f] / dmax(sR, SGM_EPS);
+                        }
+                    }
+                }
+                /* s_accumulate_mixture_properties: m_riemann_state.fpp:1036-1058 */
+                double rho_L = 0, gamma_L = 0, pi_inf_L = 0, qv_L = 0, rho_R = 0, gamma_R = 0, pi_inf_R = 0, qv_R = 0;
+                for (int f = 0; f < nf; f++) {
+                    rho_L = rho_L + arho_L[f];
+                    gamma_L = gamma_L + alf_L[f] * P->fluid_gamma[f];
+                    pi_inf_L = pi_inf_L + alf_L[f] * P->fluid_pi_inf[f];
+                    qv_L = qv_L + arho_L[f] * P->fluid_qv[f];
+                }
+                for (int f = 0; f < nf; f++) {
+                    rho_R = rho_R + arho_R[f];
+                    gamma_R = gamma_R + alf_R[f] * P->fluid_gamma[f];
+                    pi_inf_R = pi_inf_R + alf_R[f] * P->fluid_pi_inf[f];
+                    qv_R = qv_R + arho_R[f] * P->fluid_qv[f];
+                }
+                double E_L = gamma_L * pres_L + pi_inf_L + 5.e-1 * rho_L * vel_L_rms + qv_L;
+                double E_R = gamma_R * pres_R + pi_inf_R + 5.e-1 * rho_R * vel_R_rms + qv_R;
+                double H_L = (E_L + pres_L) / rho_L;
+                double H_R = (E_R + pres_R) / rho_R;
+                /* average state */
+                double rho_avg, vel_avg_rms, H_avg, gamma_avg, qv_avg;
+                if (P->avg_state == 1) {
+                    rho_avg = sqrt(rho_L * rho_R);
+                    vel_avg_rms = 0.0;
+                    for (int a = 0; a < nd; a++)
+                        vel_avg_rms = vel_avg_rms + sq(sqrt(rho_L) * vel_L[a] + sqrt(rho_R) * vel_R[a]) / sq(sqrt(rho_L) + sqrt(rho_R));
+                    H_avg = (sqrt(rho_L) * H_L + sqrt(rho_R) * H_R) / (sqrt(rho_L) + sqrt(rho_R));
+                    gamma_avg = (sqrt(rho_L) * gamma_L + sqrt(rho_R) * gamma_R) / (sqrt(rho_L) + sqrt(rho_R));
+                    vel_avg_rms = sq(sqrt(rho_L) * vel_L[0] + sqrt(rho_R) * vel_R[0]) / sq(sqrt(rho_L) + sqrt(rho_R));
+                    qv_avg = (sqrt(rho_L) * qv_L + sqrt(rho_R) * qv_R) / (sqrt(rho_L) + sqrt(rho_R));
+                } else {
+                    rho_avg = 5.e-1 * (rho_L + rho_R);
+                    vel_avg_rms = 0.0;
+                    for (int a = 0; a < nd; a++) vel_avg_rms = vel_avg_rms + sq(5.e-1 * (vel_L[a] + vel_R[a]));
+                    H_avg = 5.e-1 * (H_L + H_R);
+                    gamma_avg = 5.e-1 * (gamma_L + gamma_R);
+                    qv_avg = 5.e-1 * (qv_L + qv_R);
+                }
+                double c_L = sound_speed(S, rho_L, gamma_L, H_L, vel_L_rms, qv_L);
+                double c_R = sound_speed(S, rho_R, gamma_R, H_R, vel_R_rms, qv_R);
+                double c_avg = sound_speed(S, rho_avg, gamma_avg, H_avg, vel_avg_rms, qv_avg);
+                double uL = vel_L[d], uR = vel_R[d];
+                double s_L, s_R, s_S;
+                if (P->wave_speeds == 1) {
+                    s_L = dmin(uL - c_L, uR - c_R);
+                    s_R = dmax(uR + c_R, uL + c_L);
+                    s_S = (pres_R - pres_L + rho_L * uL * (s_L - uL) - rho_R * uR * (s_R - uR)) / (rho_L * (s_L - uL) - rho_R * (s_R - uR));
+                } else {
+                    double pres_SL = 5.e-1 * (pres_L + pres_R + rho_avg * c_avg * (uL - uR));
+                    double pres_SR = pres_SL;
+                    double Ms_L = dmax(1.0, sqrt(1.0 + ((5.e-1 + gamma_L) / (1.0 + gamma_L)) * (pres_SL / pres_L - 1.0) * pres_L /
+                                                           ((pres_L + pi_inf_L / (1.0 + gamma_L)))));
+                    double Ms_R = dmax(1.0, sqrt(1.0 + ((5.e-1 + gamma_R) / (1.0 + gamma_R)) * (pres_SR / pres_R - 1.0) * pres_R /
+                                                           ((pres_R + pi_inf_R / (1.0 + gamma_R)))));
+                    s_L = uL - c_L * Ms_L;
+                    s_R = uR + c_R * Ms_R;
+                    s_S = 5.e-1 * ((uL + uR) + (pres_L - pres_R) / (rho_avg * c_avg));
+                }
+                double s_M = dmin(0.0, s_L), s_P = dmax(0.0, s_R);
+                const double pcorr = 0.0; /* low_Mach = 0 */
+                double F[MAXN], Fsrc[MAXF];
+                for (int f = 0; f < MAXF; f++) Fsrc[f] = 0.0;
+                if (hllc) {
+                    double xi_L = (s_L - uL) / dmin(s_L - s_S, -SGM_EPS);
+                    double xi_R = (s_R - uR) / dmax(s_R - s_S, SGM_EPS);
+                    double xi_L_m1 = (s_S - uL) / dmin(s_L - s_S, -SGM_EPS);
+                    double xi_R_m1 = (s_S - uR) / dmax(s_R - s_S, SGM_EPS);
+                    double xi_M = (5.e-1 + fsign(5.e-1, s_S));
+                    double xi_P = (5.e-1 - fsign(5.e-1, s_S));
+                    for (int f = 0; f < nf; f++)
+                        F[f] = xi_M * qL[f] * (uL + s_M * xi_L_m1) + xi_P * qR[f] * (uR + s_P * xi_R_m1);
+                    for (int ii = 0; ii < nd; ii++) {
+                        int a = didx[ii];
+                        if (a >= nd) continue;
+                        double flg = (a == d) ? 1.0 : 0.0;
+                        F[S->imom + a] = xi_M * (rho_L * (uL * vel_L[a] + s_M * (flg * s_L + (1.0 - flg) * vel_L[a]) * xi_L_m1) + flg * (pres_L)) +
+                                         xi_P * (rho_R * (uR * vel_R[a] + s_P * (flg * s_R + (1.0 - flg) * vel_R[a]) * xi_R_m1) + flg * (pres_R)) +
+                                         (s_M / s_L) * (s_P / s_R) * flg * pcorr;
+                    }
+                    F[S->iE] = xi_M * (uL * (E_L + pres_L) + s_M * (E_L * xi_L_m1 + xi_L * (s_S - uL) * (rho_L * s_S + pres_L / (s_L - uL)))) +
+                               xi_P * (uR * (E_R + pres_R) + s_P * (E_R * xi_R_m1 + xi_R * (s_S - uR) * (rho_R * s_S + pres_R / (s_R - uR)))) +
+                               (s_M / s_L) * (s_P / s_R) * pcorr * s_S;
+                    for (int f = 0; f < nf; f++)
+                        F[S->iadv + f] = xi_M * qL[S->iadv + f] * (uL + s_M * xi_L_m1) + xi_P * qR[S->iadv + f] * (uR + s_P * xi_R_m1);
+                    /* vel_src for the normal direction -> flux_src(adv%beg): hllc.fpp:1319-1332 */
+                    Fsrc[0] = xi_M * (uL + 1.0 * s_M * xi_L_m1) + xi_P * (uR + 1.0 * s_P * xi_R_m1);
+                } else {
+                    for (int f = 0; f < nf; f++)
+                        F[f] = (s_M * arho_R[f] * uR - s_P * arho_L[f] * uL + s_M * s_P * (arho_L[f] - arho_R[f])) / (s_M - s_P);
+                    for (int ii = 0; ii < nd; ii++) {
+                        int a = didx[ii];
+                        if (a >= nd) continue;
+                        double flg = (a == d) ? 1.0 : 0.0;
+                        F[S->imom + a] = (s_M * (rho_R * uR * vel_R[a] + flg * pres_R) - s_P * (rho_L * uL * vel_L[a] + flg * pres_L) +
+                                          s_M * s_P * (rho_L * vel_L[a] - rho_R * vel_R[a])) / (s_M - s_P) +
+                                         (s_M / s_L) * (s_P / s_R) * pcorr * (vel_R[a] - vel_L[a]);
+                    }
+                    F[S->iE] = (s_M * uR * (E_R + pres_R) - s_P * uL * (E_L + pres_L) + s_M * s_P * (E_L - E_R)) / (s_M - s_P) +
+                               (s_M / s_L) * (s_P / s_R) * pcorr * (vel_R_rms - vel_L_rms) / 2.0;
+                    if (!P->hll_u_interface) {
+                        for (int f = 0; f < nf; f++) {
+                            F[S->iadv + f] = (qL[S->iadv + f] - qR[S->iadv + f]) * s_M * s_P / (s_M - s_P);
+                            Fsrc[f] = (s_M * qR[S->iadv + f] - s_P * qL[S->iadv + f]) / (s_M - s_P);
+                        }
+                    } else {
+                        for (int f = 0; f < nf; f++) {
+                            double aL = qL[S->iadv + f], aR = qR[S->iadv + f];
+                            if (0.0 <= s_L) F[S->iadv + f] = aL * uL;
+                            else if (s_R <= 0.0) F[S->iadv + f] = aR * uR;
+                            else F[S->iadv + f] = (s_R * aL * uL - s_L * aR * uR + s_L * s_R * (aR - aL)) / (s_R - s_L);
+                        }
+                        if (0.0 <= s_L) Fsrc[0] = uL;
+                        else if (s_R <= 0.0) Fsrc[0] = uR;
+                        else Fsrc[0] = (s_R * uL - s_L * uR) / (s_R - s_L);
+                    }
+                }
+                for (int v = 0; v < S->N; v++) S->flux[v * S->fsz + c] = F[v];
+                for (int f = 0; f < nf; f++) S->fsrc[f * S->fsz + c] = Fsrc[f];
+            }
+}
+
+/* ---------------------------------------------------------------------------------------------
+ * Characteristic boundary conditions on one (direction, side): s_cbc m_cbc.fpp:464-927 with
+ * s_initialize_cbc :930-1182 (load + sign flips), s_finalize_cbc :1185-1345 (store),
+ * s_convert_primitive_to_flux_variables m_variables_conversion.fpp:952-1135, wave amplitudes
+ * m_compute_cbc.fpp:136-365.  Rewrites flux / flux_src on the boundary face and, for WENO3/5, the
+ * first 1/2 interior faces.
+ * ------------------------------------------------------------------------------------------- */
+static void cbc_dir_side(orc_state* S, int d, int side) {
+    const mfc5_params* P = &S->P;
+    int nf = S->nf, nd = S->nd, N = S->N, b = S->b, s = S->s[d];
+    int bc = P->bc[d][side];
+    long sd = S->stride[d];
+    const double sgn = side == 0 ? 1.0 : -1.0; /* sign(1, -cbc_loc) */
+    const int hll1 = (P->riemann_solver == 1 && !P->hll_u_interface);
+    const double* fd = S->fd[d][side];
+    const double(*pi)[3] = S->pi[d][side];
+    const double ds0 = S->cds[d][side][0];
+    int lo[3] = {0, 0, 0}, hi[3] = {S->s[0], S->s[1], S->s[2]};
+    lo[d] = hi[d] = 0;
+    int didx[3];
+    didx[0] = d;
+    if (d == 0) { didx[1] = 1; didx[2] = 2; } else if (d == 1) { didx[1] = 0; didx[2] = 2; } else { didx[1] = 0; didx[2] = 1; }
+    int nface = S->P.weno_order == 5 ? 2 : (S->P.weno_order == 3 ? 1 : 0); /* interpolated interior faces */
+    for (int k = lo[2]; k <= hi[2]; k++)
+        for (int j = lo[1]; j <= hi[1]; j++)
+            for (int i = lo[0]; i <= hi[0]; i++) {
+                int ijk[3] = {i, j, k};
+                ijk[d] = 0;
+                long base = IDX(S, ijk[0], ijk[1], ijk[2]); /* cell 0 along d */
+                /* local layers jl = 0..b -> global cell (side==0 ? jl : s - jl) */
+                double q[8][MAXN], Fc[8][MAXN], Fs[8][MAXF];
+                for (int jl = 0; jl <= b; jl++) {
+                    long c = base + sd * (side == 0 ? jl : s - jl);
+                    for (int v = 0; v < N; v++) q[jl][v] = S->prim[v * S->fsz + c];
+                    q[jl][S->imom + d] = q[jl][S->imom + d] * sgn;
+                }
+                /* local flux slots jl = -1..nface-1 -> global face (side==0 ? jl : s-1-jl) */
+                double fl[4][MAXN], fsl[4][MAXF]; /* index jl+1 */
+                if (nface == 0) {
+                    long c = base + sd * (side == 0 ? 0 : s - 1);
+                    for (int v = 0; v < N; v++) fl[1][v] = S->flux[v * S->fsz + c] * (v == S->imom + d ? 1.0 : sgn);
+                    for (int f = 0; f < nf; f++) fsl[1][f] = S->fsrc[f * S->fsz + c] * (hll1 ? 1.0 : sgn);
+                }
+                /* cell-centre fluxes of the b+1 layers */
+                for (int jl = 0; jl <= b && nface > 0; jl++) {
+                    double arho[MAXF], alf[MAXF], vel[3] = {0, 0, 0}, vsum = 0, rho, gam, pinf, qv;
+                    for (int f = 0; f < nf; f++) { arho[f] = q[jl][f]; alf[f] = q[jl][S->iadv + f]; }
+                    for (int a = 0; a < nd; a++) { vel[a] = q[jl][S->imom + a]; }
+                    for (int a = 0; a < nd; a++) vsum = vsum + vel[a] * vel[a];
+                    double pres = q[jl][S->iE];
+                    mixture(S, arho, alf, 1, &rho, &gam, &pinf, &qv);
+                    double E = gam * pres + pinf + 5.e-1 * rho * vsum + qv;
+                    for (int f = 0; f < nf; f++) Fc[jl][f] = arho[f] * vel[d];
+                    for (int ii = 0; ii < nd; ii++) {
+                        int a = didx[ii];
+                        if (a >= nd) continue;
+                        Fc[jl][S->imom + a] = rho * vel[d] * vel[a] + pres * (a == d ? 1.0 : 0.0);
+                    }
+                    Fc[jl][S->iE] = vel[d] * (E + pres);
+                    if (hll1) {
+                        for (int f = 0; f < nf; f++) { Fc[jl][S->iadv + f] = 0.0; Fs[jl][f] = alf[f]; }
+                    } else {
+                        for (int f = 0; f < nf; f++) { Fc[jl][S->iadv + f] = vel[d] * alf[f]; Fs[jl][f] = vel[d]; }
+                    }
+                }
+                if (nface == 1) {
+                    for (int v = 0; v < N; v++) fl[1][v] = Fc[0][v] + pi[0][0] * (Fc[1][v] - Fc[0][v]);
+                    for (int f = 0; f < nf; f++) fsl[1][f] = Fs[0][f] + (Fs[1][f] - Fs[0][f]) * pi[0][0];
+                } else if (nface == 2) {
+                    for (int jl = 0; jl <= 1; jl++) {
+                        for (int v = 0; v < N; v++)
+                            fl[jl + 1][v] = Fc[jl][v] + pi[jl][0] * (Fc[3][v] - Fc[2][v]) + pi[jl][1] * (Fc[2][v] - Fc[1][v]) +
+                                            pi[jl][2] * (Fc[1][v] - Fc[0][v]);
+                        for (int f = 0; f < nf; f++)
+                            fsl[jl + 1][f] = Fs[jl][f] + (Fs[3][f] - Fs[2][f]) * pi[jl][0] + (Fs[2][f] - Fs[1][f]) * pi[jl][1] +
+                                             (Fs[1][f] - Fs[0][f]) * pi[jl][2];
+                    }
+                }
+                /* FD of the primitive variables at layer 0 and the LODI system */
+                double arho[MAXF], adv[MAXF], vel[3] = {0, 0, 0}, vel_K_sum = 0, rho, gam, pinf, qv;
+                for (int f = 0; f < nf; f++) arho[f] = q[0][f];
+                for (int a = 0; a < nd; a++) vel[a] = q[0][S->imom + a];
+                for (int a = 0; a < nd; a++) vel_K_sum = vel_K_sum + vel[a] * vel[a];
+                double pres = q[0][S->iE];
+                for (int f = 0; f < nf; f++) adv[f] = q[0][S->iadv + f];
+                mixture(S, arho, adv, 1, &rho, &gam, &pinf, &qv);
+                double mf[MAXF];
+                for (int f = 0; f < nf; f++) mf[f] = arho[f] / rho;
+                double E = gam * pres + pinf + 5.e-1 * rho * vel_K_sum;
+                double H = (E + pres) / rho;
+                double c = sound_speed(S, rho, gam, H, vel_K_sum, qv);
+                double darho_ds[MAXF], dvel_ds[3] = {0, 0, 0}, dpres_ds = 0, dadv_ds[MAXF];
+                for (int f = 0; f < nf; f++) { darho_ds[f] = 0; dadv_ds[f] = 0; }
+                for (int jl = 0; jl <= b; jl++) {
+                    for (int f = 0; f < nf; f++) darho_ds[f] = q[jl][f] * fd[jl] + darho_ds[f];
+                    for (int a = 0; a < nd; a++) dvel_ds[a] = q[jl][S->imom + a] * fd[jl] + dvel_ds[a];
+                    dpres_ds = q[jl][S->iE] * fd[jl] + dpres_ds;
+                    for (int f = 0; f < nf; f++) dadv_ds[f] = q[jl][S->iadv + f] * fd[jl] + dadv_ds[f];
+                }
+                double lambda[3] = {vel[d] - c, vel[d], vel[d] + c};
+                double Ma = vel[d] / c;
+                double L[MAXN];
+                for (int v = 0; v < N; v++) L[v] = 0.0;
+                const int last = N - 1;
+                /* index map (0-based): L[0]; L[1..nf] density; L[nf+1..nf+nd-1] transverse velocity;
+                 * L[iE..N-2] advection; L[N-1]. */
+#define L1_BASE (lambda[0] * (dpres_ds - rho * c * dvel_ds[d]))
+#define FILL_ALL(fac, l2)                                                                              \
+    do {                                                                                               \
+        for (int f = 0; f < nf; f++) L[1 + f] = (fac) * (l2) * (c * c * darho_ds[f] - mf[f] * dpres_ds); \
+        for (int ii = 1; ii < nd; ii++) L[S->imom + ii] = (fac) * (l2) * dvel_ds[didx[ii]];             \
+        for (int f = 0; f < nf; f++) L[S->iE + f] = (fac) * (l2) * dadv_ds[f];                          \
+    } while (0)
+                switch (bc) {
+                case MFC5_BC_CHAR_SLIP_WALL:
+                    L[0] = L1_BASE; L[last] = L[0]; break;
+                case MFC5_BC_CHAR_NR_SUB_BUFFER: {
+                    double lf = (5.e-1 - 5.e-1 * fsign(1.0, lambda[0]));
+                    L[0] = lf * lambda[0] * (dpres_ds - rho * c * dvel_ds[d]);
+                    lf = (5.e-1 - 5.e-1 * fsign(1.0, lambda[1]));
+                    FILL_ALL(lf, lambda[1]);
+                    lf = (5.e-1 - 5.e-1 * fsign(1.0, lambda[2]));
+                    L[last] = lf * lambda[2] * (dpres_ds + rho * c * dvel_ds[d]);
+                } break;
+                case MFC5_BC_CHAR_NR_SUB_INFLOW:
+                    L[0] = L1_BASE;
+                    if (P->grcbc_in[d]) {
+                        for (int f = 0; f < nf; f++)
+                            L[1 + f] = pow(c, 3.0) * Ma * (arho[f] - P->alpha_rho_in[d][f]) / S->Del[d] - c * Ma * (pres - P->pres_in[d]) / S->Del[d];
+                        if (nd > 1) {
+                            L[S->imom + 1] = c * Ma * (vel[didx[1]] - P->vel_in[d][didx[1]]) / S->Del[d];
+                            if (nd > 2) L[S->imom + 2] = c * Ma * (vel[didx[2]] - P->vel_in[d][didx[2]]) / S->Del[d];
+                        }
+                        for (int f = 0; f < nf; f++) L[S->iE + f] = c * Ma * (adv[f] - P->alpha_in[d][f]) / S->Del[d];
+                        L[last] = rho * sq(c) * (1.0 + Ma) * (vel[d] + P->vel_in[d][d] * (side == 0 ? -1.0 : 1.0)) / S->Del[d] +
+                                  c * (1.0 + Ma) * (pres - P->pres_in[d]) / S->Del[d];
+                    }
+                    break;
+                case MFC5_BC_CHAR_NR_SUB_OUTFLOW:
+                    L[0] = L1_BASE; FILL_ALL(1.0, lambda[1]); L[last] = 0.0;
+                    if (P->grcbc_out[d]) {
+                        L[last] = c * (1.0 - Ma) * (pres - P->pres_out[d]) / S->Del[d];
+                        if (P->grcbc_vel_out[d])
+                            L[last] = L[last] + rho * sq(c) * (1.0 - Ma) * (vel[d] + P->vel_out[d][d] * (side == 0 ? -1.0 : 1.0)) / S->Del[d];
+                    }
+                    break;
+                case MFC5_BC_CHAR_FF_SUB_OUTFLOW:
+                    L[0] = L1_BASE; FILL_ALL(1.0, lambda[1]); L[last] = L[0] + 2.0 * rho * c * lambda[1] * dvel_ds[d]; break;
+                case MFC5_BC_CHAR_CP_SUB_OUTFLOW:
+                    L[0] = L1_BASE; FILL_ALL(1.0, lambda[1]); L[last] = -L[0]; break;
+                case MFC5_BC_CHAR_SUP_INFLOW: break;
+                case MFC5_BC_CHAR_SUP_OUTFLOW:
+                    L[0] = L1_BASE; FILL_ALL(1.0, lambda[1]); L[last] = lambda[2] * (dpres_ds + rho * c * dvel_ds[d]); break;
+                }
+                double dpres_dt = -5.e-1 * (L[last] + L[0]);
+                double darho_dt[MAXF], dvel_dt[3] = {0, 0, 0}, dadv_dt[MAXF];
+                for (int f = 0; f < nf; f++) darho_dt[f] = -(L[1 + f] - mf[f] * dpres_dt) / (c * c);
+                for (int ii = 0; ii < nd; ii++) {
+                    int a = didx[ii];
+                    if (a >= nd) continue;
+                    double flg = (a == d) ? 1.0 : 0.0;
+                    dvel_dt[a] = flg * (L[0] - L[last]) / (2.0 * rho * c) + (flg - 1.0) * L[S->imom + ii];
+                }
+                double vel_dv_dt_sum = 0.0;
+                for (int a = 0; a < nd; a++) vel_dv_dt_sum = vel_dv_dt_sum + vel[a] * dvel_dt[a];
+                for (int f = 0; f < nf; f++) dadv_dt[f] = -L[S->iE + f];
+                double drho_dt = 0, dgamma_dt = 0, dpi_inf_dt = 0, dqv_dt = 0;
+                for (int f = 0; f < nf; f++) {
+                    drho_dt = drho_dt + darho_dt[f];
+                    dgamma_dt = dgamma_dt + dadv_dt[f] * P->fluid_gamma[f];
+                    dpi_inf_dt = dpi_inf_dt + dadv_dt[f] * P->fluid_pi_inf[f];
+                    dqv_dt = dqv_dt + darho_dt[f] * P->fluid_qv[f];
+                }
+                for (int f = 0; f < nf; f++) fl[0][f] = fl[1][f] + ds0 * darho_dt[f];
+                for (int a = 0; a < nd; a++) fl[0][S->imom + a] = fl[1][S->imom + a] + ds0 * (vel[a] * drho_dt + rho * dvel_dt[a]);
+                fl[0][S->iE] = fl[1][S->iE] + ds0 * (pres * dgamma_dt + gam * dpres_dt + dpi_inf_dt + dqv_dt + rho * vel_dv_dt_sum +
+                                                    5.e-1 * drho_dt * vel_K_sum);
+                if (hll1) {
+                    for (int f = 0; f < nf; f++) fl[0][S->iadv + f] = 0.0;
+                    for (int f = 0; f < nf; f++)
+                        fsl[0][f] = 1.0 / dmax(fabs(vel[d]), SGM_EPS) * fsign(1.0, vel[d]) *
+                                    (fl[1][S->iadv + f] + vel[d] * fsl[1][f] + ds0 * dadv_dt[f]);
+                } else {
+                    for (int f = 0; f < nf; f++) fl[0][S->iadv + f] = fl[1][S->iadv + f] + ds0 * dadv_dt[f];
+                    for (int f = 0; f < nf; f++) fsl[0][f] = fsl[1][f];
+                }
+                /* store back with the sign conventions of s_finalize_cbc */
+                for (int jl = -1; jl <= nface - 1; jl++) {
+                    long cf = base + sd * (side == 0 ? jl : s - 1 - jl);
+                    for (int v = 0; v < N; v++) S->flux[v * S->fsz + cf] = fl[jl + 1][v] * (v == S->imom + d ? 1.0 : sgn);
+                    if (hll1) for (int f = 0; f < nf; f++) S->fsrc[f * S->fsz + cf] = fsl[jl + 1][f];
+                    else S->fsrc[cf] = fsl[jl + 1][0] * sgn;
+                }
+            }
+#undef L1_BASE
+#undef FILL_ALL
+}
+
+/* flux difference + advection source: m_rhs.fpp:1107-1120 (x, assigns), :1183-1196 (y), :1345-1358 (z),
+ * alpha source m_rhs.fpp:1440-1458 (HLL method 1), :1474-1488 (u-interface). */
+static void flux_difference(orc_state* S, int d) {
+    long sd = S->stride[d];
+    int nf = S->nf;
+    const int alpha_iface = (S->P.riemann_solver == 1 && !S->P.hll_u_interface);
+#pragma omp parallel for collapse(2)
+    for (int k = 0; k <= S->s[2]; k++)
+        for (int j = 0; j <= S->s[1]; j++)
+            for (int i = 0; i <= S->s[0]; i++) {
+                int ijk[3] = {i, j, k};
+                long c = IDX(S, i, j, k);
+                double inv_ds = 1.0 / S->ds[d][ijk[d]];
+                for (int v = 0; v < S->N; v++) {
+                    double f1 = S->flux[v * S->fsz + c - sd], f2 = S->flux[v * S->fsz + c];
+                    if (d == 0) S->rhs[v * S->fsz + c] = inv_ds * (f1 - f2);
+                    else S->rhs[v * S->fsz + c] = S->rhs[v * S->fsz + c] + inv_ds * (f1 - f2);
+                }
+                for (int f = 0; f < nf; f++) {
+                    long v = (S->iadv + f) * S->fsz + c;
+                    if (alpha_iface) {
+                        double coeff = S->prim[(S->imom + d) * S->fsz + c];
+                        double f1 = S->fsrc[f * S->fsz + c - sd], f2 = S->fsrc[f * S->fsz + c];
+                        S->rhs[v] = S->rhs[v] + inv_ds * coeff * (f1 - f2);
+                    } else {
+                        double coeff = S->q1[v];
+                        double f1 = S->fsrc[c], f2 = S->fsrc[c - sd];
+                        S->rhs[v] = S->rhs[v] + inv_ds * coeff * (f1 - f2);
+                    }
+                }
+            }
+}
+
+void orc_sweeps(orc_state* S) {
+    for (int d = 0; d < S->nd; d++) {
+        weno_dir(S, d);
+        riemann_dir(S, d);
+        for (int side = 0; side < 2; side++)
+            if (is_cbc(S->P.bc[d][side])) cbc_dir_side(S, d, side);
+        flux_difference(S, d);
+    }
+}
+
+/* s_tvd_rk update: m_time_steppers.fpp:421-432 (coefficients), :486-507 (update) */
+void orc_rk_update(orc_state* S, int stage, double dt) {
+    static const double rk3[3][4] = {{1, 0, 1, 1}, {1, 3, 1, 4}, {2, 1, 2, 3}};
+    static const double rk2[2][4] = {{1, 0, 1, 1}, {1, 1, 1, 2}};
+    static const double rk1[1][4] = {{1, 0, 1, 1}};
+    const double* rk = S->P.time_stepper == 3 ? rk3[stage - 1] : S->P.time_stepper == 2 ? rk2[stage - 1] : rk1[0];
+    int nstage = S->P.time_stepper;
+#pragma omp parallel for collapse(2)
+    for (int v = 0; v < S->N; v++)
+        for (int k = 0; k <= S->s[2]; k++)
+            for (int j = 0; j <= S->s[1]; j++)
+                for (int i = 0; i <= S->s[0]; i++) {
+                    long a = v * S->fsz + IDX(S, i, j, k);
+                    if (stage == 1 && nstage > 1) S->q2[a] = S->q1[a];
+                    double q2 = nstage > 1 ? S->q2[a] : S->q1[a];
+                    S->q1[a] = (rk[0] * S->q1[a] + rk[1] * q2 + rk[2] * dt * S->rhs[a]) / rk[3];
+                }
+}
+
+void orc_compute_rhs(orc_state* S) {
+    orc_cons2prim(S);
+    for (int d = 0; d < S->nd; d++) { orc_bc_fill(S, d, 0); orc_bc_fill(S, d, 1); }
+    orc_sweeps(S);
+}
+
+void orc_tvd_rk_step(orc_state* S, double dt) {
+    for (int st = 1; st <= S->P.time_stepper; st++) {
+        orc_compute_rhs(S);
+        orc_rk_update(S, st, dt);
+    }
+}
+
+/* ICFL: m_data_output.fpp:159-224 with s_compute_enthalpy (m_sim_helpers.fpp:45-105) and
+ * s_compute_stability_from_dt (:108-130); uses the primitive variables of the last RHS evaluation. */
+double orc_icfl_max(orc_state* S, double dt) {
+    int nf = S->nf, nd = S->nd;
+    double mx = 0.0;
+    for (int k = 0; k <= S->s[2]; k++)
+        for (int j = 0; j <= S->s[1]; j++)
+            for (int i = 0; i <= S->s[0]; i++) {
+                long c = IDX(S, i, j, k);
+                double arho[MAXF], alf[MAXF], rho, gam, pinf, qv, vel[3] = {0, 0, 0}, vs = 0;
+                for (int f = 0; f < nf; f++) { arho[f] = S->prim[f * S->fsz + c]; alf[f] = S->prim[(S->iadv + f) * S->fsz + c]; }
+                mixture(S, arho, alf, 2, &rho, &gam, &pinf, &qv);
+                for (int a = 0; a < nd; a++) vel[a] = S->prim[(S->imom + a) * S->fsz + c];
+                for (int a = 0; a < nd; a++) vs = vs + vel[a] * vel[a];
+                double pres = S->prim[S->iE * S->fsz + c];
+                double E = gam * pres + pinf + 5.e-1 * rho * vs + qv;
+                double H = (E + pres) / rho;
+                double cs = sound_speed(S, rho, gam, H, vs, qv);
+                double icfl;
+                if (nd == 3) icfl = dt / dmin(dmin(S->ds[0][i] / (fabs(vel[0]) + cs), S->ds[1][j] / (fabs(vel[1]) + cs)), S->ds[2][k] / (fabs(vel[2]) + cs));
+                else if (nd == 2) icfl = dt / dmin(S->ds[0][i] / (fabs(vel[0]) + cs), S->ds[1][j] / (fabs(vel[1]) + cs));
+                else icfl = (dt / S->ds[0][i]) * (fabs(vel[0]) + cs);
+                if (icfl > mx || icfl != icfl) mx = icfl;
+            }
+    return mx;
+}

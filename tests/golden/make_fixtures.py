@@ -1,0 +1,100 @@
+#!/usr/bin/env python3
+"""Regenerate tests/golden/ fixtures from the read-only reference tree (run in the build container only).
+
+What it does (nothing here is copied reference *source*; goldens are test data):
+  1. expands the reference's own test-case generator (toolchain/mfc/test/cases.py:list_cases, with
+     the optional third-party modules it imports stubbed out) to obtain the
+     full parameter dictionary of every case whose UUID is inside the hot-path envelope
+     (SURVEY.md section 4), and writes them to cases.json;
+  2. converts tests/<UUID>/golden.txt (one line per D/*.dat file: name + values,
+     toolchain/mfc/packer/pack.py:117-158) into a compressed <UUID>.npz of float64 arrays.
+
+Usage:  python tests/golden/make_fixtures.py [/root/reference]
+"""
+import json
+import os
+import re
+import sys
+import types
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF = sys.argv[1] if len(sys.argv) > 1 else "/root/reference"
+
+# UUIDs inside the 5-eq / WENO{3,5}{JS,M,Z} / HLL|HLLC / RK3 envelope
+UUIDS = """
+D79C3E6F 8A59E8E6 2AB32975 70DAE9E8 3AE495F4 5EC236F2 48CCE072 AED93D34 C5B79059 727F72ED A60691E7 3FC6FC4A
+2FD933A2 ED728400 9D92767D 63CD6ADF
+55533234 EAA53889 D972BA0F 20AE0551 A6E65782 4129A23A E84967E7 5F877BC9 16C03D8E B96AC58F 8FDEE23A BF46F657
+4D7926CD 98081DA3 10DBA76B 212401B4 EB6687AB
+6FC6A809 09DAFEBA 6B4B738B F99FBB36 E09A12D9 5010B814 730DFD6D ABAC3AE3 C93BE9B5 D0045756 557FF170 61FFF3D3
+6249EDDE 8BCBAED8 9DCBE54F 0BDC8E40 38C2159F D7107B89
+2A5CFF02 F9850EA5 16A922E4 7789B55A 9090FC4B 677DAA82
+EA9C3FA3 A21CF713 39816683 9EF5305B 31742FC7 D6415F48
+4B7FC359 BB0418CD EFDCFF72 35231DF8 5F099890 04E1CB26
+5527832F 4AEF478A 32D0F235 18BDCBC8 F97573DB F4F6AC27 1E738705 0879E062 83EFC30C 1CCA82F5 3A8359F6 6D24B115
+461DCB09 C4907722
+7374E266 3BFEAC19 FBF808BE 3B414AF0 3C00B89D 345A94C0 16FBF4C8 DC9CB97E A5C93D62 A6AC2E06 5781A4C2 645A26E3
+FC4D07B6 F0F175B2 AE3ECF01
+9ACD5174 73B0539E 2A523AC1 C06849AD AB0BE4E4 C36F18FB C4A2FAA3 851F7AE2 BD8004FF 758D0268 AACF1BC5 B33E256A
+B8F5F1C8 A0B82851 C7B686C0
+0FCCE9F1 8C7AA13B CE232828
+05D092C5 59C3F366 B49877F3 1A379909 C3A4DBAE
+BCA926AC 24FD489A B5F0C655 82152069 BCB15E8E 02D1E522
+""".split()
+
+
+def expand_cases():
+    sys.dont_write_bytecode = True
+    for name in ["fastjsonschema", "mako", "mako.template", "mako.lookup", "cantera", "pyrometheus"]:
+        sys.modules[name] = types.ModuleType(name)
+    sys.modules["fastjsonschema"].compile = lambda *a, **k: (lambda x: x)
+    sys.modules["fastjsonschema"].JsonSchemaException = Exception
+    sys.modules["mako.template"].Template = object
+    sys.modules["mako.lookup"].TemplateLookup = object
+    sys.path.insert(0, os.path.join(REF, "toolchain"))
+    cwd = os.getcwd()
+    os.chdir(REF)
+    try:
+        from mfc.test.cases import list_cases  # noqa
+
+        out = {}
+        for b in list_cases():
+            try:
+                c = b.to_case()
+            except Exception:  # example cases needing cantera etc. -- none in scope
+                continue
+            u = c.get_uuid()
+            if u in UUIDS:
+                tol = c.override_tol
+                if tol is None:
+                    tol = 1e-3 if "Example" in c.trace else 1e-12
+                out[u] = dict(trace=c.trace, ppn=c.ppn, tol=tol, params=c.params)
+    finally:
+        os.chdir(cwd)
+    return out
+
+
+def convert_golden(uuid):
+    arrs = {}
+    with open(os.path.join(REF, "tests", uuid, "golden.txt")) as f:
+        for line in f:
+            parts = line.split()
+            if not parts:
+                continue
+            key = re.sub(r"^D/", "", parts[0]).replace(".dat", "")
+            arrs[key] = np.array([float(x) for x in parts[1:]], dtype=np.float64)
+    np.savez_compressed(os.path.join(HERE, uuid + ".npz"), **arrs)
+    return len(arrs)
+
+
+if __name__ == "__main__":
+    cases = expand_cases()
+    missing = [u for u in UUIDS if u not in cases]
+    assert not missing, missing
+    with open(os.path.join(HERE, "cases.json"), "w") as f:
+        json.dump(cases, f, indent=1, sort_keys=True)
+    for u in UUIDS:
+        n = convert_golden(u)
+        print(u, cases[u]["trace"], n)

@@ -1,0 +1,48 @@
+"""Pins the CPU oracle against the reference's own golden regression files.
+
+Every case inside the hot-path envelope (124 single-rank cases here, the 2-rank
+cases are in test_decomp_gloo.py) is run from its regenerated initial condition for its 50 steps and
+compared with ``tests/<UUID>/golden.txt`` of the reference using the reference's own rule and
+tolerance (toolchain/mfc/packer/tol.py:10-20; 1e-12, 1e-3 for examples).
+"""
+import numpy as np
+import pytest
+
+from golden_util import CASES, compare, golden, golden_field, setup_case
+from mfc_b200 import driver
+from oracle_lib import Oracle
+
+SINGLE = sorted(u for u in CASES if CASES[u]["ppn"] == 1)
+
+
+def run_oracle(uuid, omp=False):
+    case, P, cbs, cons, dbuf = setup_case(uuid)
+    o = Oracle(P, cbs, omp=omp)
+    for (d, side), buf in dbuf.items():
+        o.set_dirichlet(d, side, buf)
+    o.set_cons(cons)
+    driver.run(o, case)
+    return case, cons, o.get_cons()
+
+
+@pytest.mark.parametrize("uuid", SINGLE)
+def test_golden(uuid):
+    is3d = int(CASES[uuid]["params"].get("p", 0)) > 0
+    case, cons0, q = run_oracle(uuid, omp=is3d)
+    g = golden(uuid)
+    shape = q.shape[1:]
+    nstep = int(case["t_step_stop"])
+    tol = CASES[uuid]["tol"]
+    for v in range(q.shape[0]):
+        # the regenerated initial condition must reproduce the golden's own step-0 lines
+        ok0, a0, _ = compare(cons0[v], golden_field(g, "cons", v + 1, 0, 0, shape), 1e-13)
+        assert ok0, f"{uuid} IC var {v + 1}: max abs err {a0:.3e}"
+        ok, a, w = compare(q[v], golden_field(g, "cons", v + 1, 0, nstep, shape), tol)
+        assert ok, f"{uuid} ({CASES[uuid]['trace']}) var {v + 1}: worst min(abs,rel) err {w:.3e} > {tol}"
+
+
+def test_omp_build_is_bitwise_identical():
+    """The OpenMP/-O3 build used for timing must give the same bits as the scalar build."""
+    _, _, a = run_oracle("A6AC2E06", omp=False)
+    _, _, b = run_oracle("A6AC2E06", omp=True)
+    assert np.array_equal(a, b)
