@@ -1,0 +1,705 @@
+// mfc5.cu -- C ABI of libmfc5.so (include/mfc5.h): device state, table set-up, stage orchestration.
+//
+// One RK stage (reference s_compute_rhs m_rhs.fpp:574-902 + RK update m_time_steppers.fpp:486-507):
+//   k_cons2prim -> [k_bc_fill | halo exchange] per direction -> per direction { k_cbc ; fused sweep }
+// with the RK update fused into the last sweep.  There is no CPU fallback: every entry point fails
+// loudly if CUDA is unavailable.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/mfc5.h"
+#define MFC5_HOST_TU
+#include "mfc5_host.cuh"
+
+using namespace mfc5;
+
+static thread_local std::string g_err;
+static int fail(const std::string& m) { g_err = m; return -1; }
+#define CK(call)                                                                                         \
+    do {                                                                                                 \
+        cudaError_t e_ = (call);                                                                         \
+        if (e_ != cudaSuccess) return fail(std::string(#call) + ": " + cudaGetErrorString(e_));          \
+    } while (0)
+
+// ---- NCCL, loaded lazily so single-GPU use has no dependency on it --------------------------------
+typedef struct ncclComm* ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId;
+struct NcclApi {
+    void* lib = nullptr;
+    int (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    int (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    int (*CommDestroy)(ncclComm_t) = nullptr;
+    int (*Send)(const void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    int (*Recv)(void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    int (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+};
+static NcclApi g_nccl;
+static int nccl_load() {
+    if (g_nccl.lib) return 0;
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char* n : names) {
+        g_nccl.lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+        if (g_nccl.lib) break;
+    }
+    if (!g_nccl.lib) return fail("cannot dlopen libnccl.so.2");
+#define SYM(f, name) *(void**)(&g_nccl.f) = dlsym(g_nccl.lib, name); if (!g_nccl.f) return fail("missing NCCL symbol " name)
+    SYM(GetUniqueId, "ncclGetUniqueId");
+    SYM(CommInitRank, "ncclCommInitRank");
+    SYM(CommDestroy, "ncclCommDestroy");
+    SYM(Send, "ncclSend");
+    SYM(Recv, "ncclRecv");
+    SYM(AllReduce, "ncclAllReduce");
+    SYM(GroupStart, "ncclGroupStart");
+    SYM(GroupEnd, "ncclGroupEnd");
+    SYM(GetErrorString, "ncclGetErrorString");
+#undef SYM
+    return 0;
+}
+#define NK(call)                                                                                          \
+    do {                                                                                                  \
+        int r_ = (call);                                                                                  \
+        if (r_ != 0) return fail(std::string(#call) + ": " + g_nccl.GetErrorString(r_));                  \
+    } while (0)
+enum { NCCL_FLOAT64 = 8, NCCL_UINT64 = 5, NCCL_SUM = 0, NCCL_MAX = 2, NCCL_MIN = 3 };
+
+// ---- handle ---------------------------------------------------------------------------------------
+struct mfc5_handle {
+    mfc5_params P;
+    int nd, nf, N, b, pn, ns;
+    int s[3];
+    int ox, oy, oz;
+    long long px, ey, ez, fs;
+    double* d_q[2] = {nullptr, nullptr};
+    double *d_prim = nullptr, *d_rhs = nullptr;
+    int cur = 0;
+    // host grid (ghosted): scb[d][i + 1 + b], ds[d][i + b]
+    std::vector<double> scb[3], ds[3];
+    bool grid_set[3] = {false, false, false};
+    bool setup = false;
+    double* d_tab[3][6] = {};  // cL cR dL dR bt ds
+    int uniform[3] = {1, 1, 1};
+    CbcCoef cbc[3][2];
+    double* d_cbcbuf[3][2] = {};
+    double* d_dirich[3][2] = {};
+    long long plane[3];
+    cudaStream_t st = nullptr, st_comm = nullptr;
+    cudaEvent_t ev_stage[4] = {}, ev_sw[3][2] = {}, ev_comm = nullptr, ev_comp = nullptr;
+    unsigned long long* d_red = nullptr;
+    long long launches = 0;
+    float sweep_ms[3] = {-1, -1, -1};
+    DevP D;
+    // multi-GPU
+    ncclComm_t comm = nullptr;
+    int rank = 0, nranks = 1;
+    double* d_send[3][2] = {};
+    double* d_recv[3][2] = {};
+    // graph replay of a whole step, keyed by (cur, dt)
+    cudaGraphExec_t gexec[2] = {nullptr, nullptr};
+    double gdt[2] = {0, 0};
+};
+
+static bool is_cbc(int bc) { return bc <= MFC5_BC_CHAR_SLIP_WALL && bc >= MFC5_BC_CHAR_SUP_OUTFLOW; }
+
+extern "C" const char* mfc5_last_error(void) { return g_err.c_str(); }
+extern "C" const char* mfc5_version(void) { return "mfc5-b200 0.1 (sm_100a, fp64)"; }
+extern "C" int mfc5_sys_size(const mfc5_handle* h) { return h->N; }
+extern "C" int mfc5_buff_size(const mfc5_handle* h) { return h->b; }
+extern "C" long long mfc5_kernel_launches(const mfc5_handle* h) { return h->launches; }
+extern "C" double mfc5_last_sweep_ms(const mfc5_handle* h, int dir) { return (dir >= 0 && dir < 3) ? h->sweep_ms[dir] : -1.0; }
+extern "C" void* mfc5_compute_stream(const mfc5_handle* h) { return (void*)h->st; }
+
+extern "C" int mfc5_create(const mfc5_params* p, mfc5_handle** out) {
+    if (!p || !out) return fail("null argument");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(std::string("no CUDA device available (libmfc5 has no CPU fallback): ") + cudaGetErrorString(e));
+    if (p->model_eqns != 2) return fail("only model_eqns = 2 (5-equation model) is supported");
+    if (p->num_fluids < 1 || p->num_fluids > 3) return fail("num_fluids must be 1..3");
+    if (p->weno_order != 1 && p->weno_order != 3 && p->weno_order != 5) return fail("weno_order must be 1, 3 or 5");
+    if (p->riemann_solver != 1 && p->riemann_solver != 2) return fail("riemann_solver must be 1 (HLL) or 2 (HLLC)");
+    if (p->mapped_weno && p->wenoz) return fail("mapped_weno and wenoz are mutually exclusive");
+    if (p->time_stepper < 1 || p->time_stepper > 3) return fail("time_stepper must be 1..3");
+    if (p->m < 0 || p->n < 0 || p->p < 0 || (p->n == 0 && p->p > 0)) return fail("invalid m, n, p");
+    // m_checker.fpp:52-69: at least num_stcls_min*weno_order cells per direction
+    const int need = p->weno_order > 1 ? 5 * p->weno_order : 1;
+    const int ss[3] = {p->m, p->n, p->p};
+    for (int d = 0; d < 3; d++)
+        if ((d == 0 || ss[d] > 0) && ss[d] + 1 < need) return fail("too few cells for the WENO stencil (m_checker.fpp:52-69)");
+    mfc5_handle* h = new mfc5_handle();
+    h->P = *p;
+    h->s[0] = p->m; h->s[1] = p->n; h->s[2] = p->p;
+    h->nd = 1 + (p->n > 0) + (p->p > 0);
+    h->nf = p->num_fluids;
+    h->N = 2 * h->nf + h->nd + 1;
+    h->pn = (p->weno_order - 1) / 2;
+    h->ns = h->pn + 1;
+    h->b = h->pn + 2;  // m_helper_basic.fpp:127-132
+    for (int d = 0; d < h->nd; d++)
+        for (int sd = 0; sd < 2; sd++)
+            if (is_cbc(p->bc[d][sd]) && p->weno_order == 1) { delete h; return fail("characteristic BCs need weno_order >= 3"); }
+    CK(cudaSetDevice(p->device));
+    // HBM layout: SoA, x contiguous; interior x = 0 sits on a 128-byte boundary
+    h->ox = 16; h->oy = h->nd > 1 ? h->b : 0; h->oz = h->nd > 2 ? h->b : 0;
+    h->px = ((h->ox + h->s[0] + 1 + h->b + 15) / 16) * 16;
+    h->ey = h->s[1] + 1 + 2 * h->oy;
+    h->ez = h->s[2] + 1 + 2 * h->oz;
+    h->fs = h->px * h->ey * h->ez;
+    const size_t nb = (size_t)h->N * h->fs * sizeof(double);
+    CK(cudaMalloc(&h->d_q[0], nb)); CK(cudaMalloc(&h->d_q[1], nb));
+    CK(cudaMalloc(&h->d_prim, nb)); CK(cudaMalloc(&h->d_rhs, nb));
+    CK(cudaMemset(h->d_q[0], 0, nb)); CK(cudaMemset(h->d_q[1], 0, nb));
+    CK(cudaMemset(h->d_prim, 0, nb)); CK(cudaMemset(h->d_rhs, 0, nb));
+    CK(cudaMalloc(&h->d_red, 4 * sizeof(unsigned long long)));
+    int lo, hi;
+    CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    CK(cudaStreamCreateWithPriority(&h->st, cudaStreamNonBlocking, lo));
+    CK(cudaStreamCreateWithPriority(&h->st_comm, cudaStreamNonBlocking, hi));
+    for (auto& ev : h->ev_stage) CK(cudaEventCreate(&ev));
+    for (int d = 0; d < 3; d++) for (int k = 0; k < 2; k++) CK(cudaEventCreate(&h->ev_sw[d][k]));
+    CK(cudaEventCreateWithFlags(&h->ev_comm, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&h->ev_comp, cudaEventDisableTiming));
+    *out = h;
+    return 0;
+}
+
+extern "C" int mfc5_destroy(mfc5_handle* h) {
+    if (!h) return 0;
+    cudaSetDevice(h->P.device);
+    cudaDeviceSynchronize();
+    for (int i = 0; i < 2; i++) { cudaFree(h->d_q[i]); if (h->gexec[i]) cudaGraphExecDestroy(h->gexec[i]); }
+    cudaFree(h->d_prim); cudaFree(h->d_rhs); cudaFree(h->d_red);
+    for (int d = 0; d < 3; d++) {
+        for (int k = 0; k < 6; k++) cudaFree(h->d_tab[d][k]);
+        for (int k = 0; k < 2; k++) { cudaFree(h->d_cbcbuf[d][k]); cudaFree(h->d_dirich[d][k]); cudaFree(h->d_send[d][k]); cudaFree(h->d_recv[d][k]); }
+        for (int k = 0; k < 2; k++) cudaEventDestroy(h->ev_sw[d][k]);
+    }
+    for (auto& ev : h->ev_stage) cudaEventDestroy(ev);
+    cudaEventDestroy(h->ev_comm); cudaEventDestroy(h->ev_comp);
+    if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
+    cudaStreamDestroy(h->st); cudaStreamDestroy(h->st_comm);
+    delete h;
+    return 0;
+}
+
+// ---- grid ghost metrics: m_boundary_common.fpp:404-466, m_mpi_common.fpp:1745-1796 ------------------
+extern "C" int mfc5_set_grid(mfc5_handle* h, int d, const double* s_cb, const double* gbeg, const double* gend) {
+    if (!h || d < 0 || d >= h->nd || !s_cb) return fail("mfc5_set_grid: bad argument");
+    const int s = h->s[d], b = h->b;
+    h->scb[d].assign(s + 2 + 2 * b, 0.0);
+    h->ds[d].assign(s + 1 + 2 * b, 0.0);
+    double* cb = h->scb[d].data() + 1 + b;
+    double* w = h->ds[d].data() + b;
+    for (int i = -1; i <= s; i++) cb[i] = s_cb[i + 1];
+    for (int i = 0; i <= s; i++) w[i] = cb[i] - cb[i - 1];  // m_start_up.fpp:190
+    const int bcb = h->P.bc[d][0], bce = h->P.bc[d][1];
+    if ((bcb >= 0 && !gbeg) || (bce >= 0 && !gend)) return fail("mfc5_set_grid: neighbour cell widths required on processor boundaries");
+    for (int i = 1; i <= b; i++) {
+        if (bcb >= 0) w[-i] = gbeg[b - i];
+        else w[-i] = w[bcb == MFC5_BC_PERIODIC ? s - i + 1 : bcb == MFC5_BC_REFLECTIVE ? i - 1 : 0];
+        if (bce >= 0) w[s + i] = gend[i - 1];
+        else w[s + i] = w[bce == MFC5_BC_PERIODIC ? i - 1 : bce == MFC5_BC_REFLECTIVE ? s - i + 1 : s];
+    }
+    for (int i = 1; i <= b; i++) cb[-1 - i] = cb[-i] - w[-i];
+    for (int i = 1; i <= b; i++) cb[s + i] = cb[s + i - 1] + w[s + i];
+    h->grid_set[d] = true;
+    h->setup = false;
+    return 0;
+}
+
+// ---- WENO tables: s_compute_weno_coefficients, m_weno.fpp:196-215 (order 3), :233-341 (order 5) -----
+static void weno_tables(const mfc5_handle* h, int d, std::vector<double> (&tab)[5], int& uniform) {
+    const int s = h->s[d], b = h->b, pn = h->pn, ns = h->ns;
+    const int nslot = s + 1 + 2 * b;
+    const int pr = pn > 0 ? pn : 1;
+    tab[0].assign((size_t)nslot * ns * pr, 0.0);  // cL
+    tab[1].assign((size_t)nslot * ns * pr, 0.0);  // cR
+    tab[2].assign((size_t)nslot * ns, 0.0);       // dL
+    tab[3].assign((size_t)nslot * ns, 0.0);       // dR
+    tab[4].assign((size_t)nslot * ns * 3, 0.0);   // beta
+    const double* x = h->scb[d].data() + 1 + b;
+    auto q2 = [](double v) { return v * v; };
+    auto CL = [&](int j, int q, int r) -> double& { return tab[0][((size_t)(j + b) * ns + q) * pr + r]; };
+    auto CR = [&](int j, int q, int r) -> double& { return tab[1][((size_t)(j + b) * ns + q) * pr + r]; };
+    auto DL = [&](int q, int j) -> double& { return tab[2][(size_t)(j + b) * ns + q]; };
+    auto DR = [&](int q, int j) -> double& { return tab[3][(size_t)(j + b) * ns + q]; };
+    auto BT = [&](int j, int q, int r) -> double& { return tab[4][((size_t)(j + b) * ns + q) * 3 + r]; };
+    const int bcb = h->P.bc[d][0], bce = h->P.bc[d][1];
+    if (h->P.weno_order == 3) {
+        for (int i = -b - 1 + pn; i <= s + b - 1 - pn; i++) {
+            const int j = i + 1;
+            const double xm = x[i - 1], x0 = x[i], x1 = x[i + 1], x2 = x[i + 2];
+            CR(j, 0, 0) = (x0 - x1) / (x0 - x2);
+            CR(j, 1, 0) = (x0 - x1) / (xm - x1);
+            CL(j, 0, 0) = -CR(j, 0, 0);
+            CL(j, 1, 0) = -CR(j, 1, 0);
+            DR(0, j) = (xm - x1) / (xm - x2);
+            DL(0, j) = (xm - x0) / (xm - x2);
+            DR(1, j) = 1.0 - DR(0, j);
+            DL(1, j) = 1.0 - DL(0, j);
+            BT(j, 0, 0) = 4.0 * q2(x0 - x1) / q2(x0 - x2);
+            BT(j, 1, 0) = 4.0 * q2(x0 - x1) / q2(xm - x1);
+        }
+        if (h->P.null_weights) {  // m_weno.fpp:219-229
+            if (bcb == MFC5_BC_RIEMANN_EXTRAP) { DR(1, 0) = 0; DR(0, 0) = 1; DL(1, 0) = 0; DL(0, 0) = 1; }
+            if (bce == MFC5_BC_RIEMANN_EXTRAP) { DR(0, s) = 0; DR(1, s) = 1; DL(0, s) = 0; DL(1, s) = 1; }
+        }
+    } else if (h->P.weno_order == 5) {
+        for (int i = -b - 1 + pn; i <= s + b - 1 - pn; i++) {
+            const int j = i + 1;
+            const double a = x[i - 2], bb = x[i - 1], c = x[i], e = x[i + 1], f = x[i + 2], g = x[i + 3];
+            // a = s_cb(i-2), bb = s_cb(i-1), c = s_cb(i), e = s_cb(i+1), f = s_cb(i+2), g = s_cb(i+3)
+            CR(j, 0, 0) = ((c - e) * (e - f)) / ((c - g) * (g - e));
+            CR(j, 1, 0) = ((bb - e) * (e - c)) / ((bb - f) * (f - c));
+            CR(j, 1, 1) = ((c - e) * (e - f)) / ((bb - e) * (bb - f));
+            CR(j, 2, 1) = ((c - e) * (e - bb)) / ((a - c) * (a - e));
+            CL(j, 0, 0) = ((e - c) * (c - f)) / ((c - g) * (g - e));
+            CL(j, 1, 0) = ((c - bb) * (c - e)) / ((bb - f) * (c - f));
+            CL(j, 1, 1) = ((e - c) * (c - f)) / ((bb - e) * (bb - f));
+            CL(j, 2, 1) = ((bb - c) * (c - e)) / ((a - c) * (a - e));
+            CR(j, 0, 1) = ((c - f) + (e - g)) / ((c - f) * (c - g)) * ((c - e));
+            CR(j, 2, 0) = ((a - e) + (bb - e)) / ((bb - e) * (e - a)) * ((e - c));
+            CL(j, 0, 1) = ((c - f) + (c - g)) / ((c - f) * (c - g)) * ((e - c));
+            CL(j, 2, 0) = ((a - c) + (bb - e)) / ((a - e) * (e - bb)) * ((c - e));
+            DR(0, j) = ((a - e) * (e - bb)) / ((a - g) * (g - bb));
+            DR(2, j) = ((e - f) * (e - g)) / ((a - f) * (a - g));
+            DL(0, j) = ((a - c) * (c - bb)) / ((a - g) * (g - bb));
+            DL(2, j) = ((c - f) * (c - g)) / ((a - f) * (a - g));
+            DR(1, j) = 1.0 - DR(0, j) - DR(2, j);
+            DL(1, j) = 1.0 - DL(0, j) - DL(2, j);
+            const double h4 = 4.0 * q2(c - e);
+            BT(j, 0, 0) = h4 * (10.0 * q2(e - c) + (e - c) * (f - e) + q2(f - e)) / (q2(c - g) * q2(e - g));
+            BT(j, 0, 1) = h4 * (19.0 * q2(e - c) - (e - c) * (g - e) + 2.0 * (f - c) * ((f - c) + (g - e))) /
+                          ((c - f) * q2(c - g) * (g - e));
+            BT(j, 0, 2) = h4 * (10.0 * q2(e - c) + (e - c) * ((f - c) + (g - e)) + q2((f - c) + (g - e))) / (q2(c - f) * q2(c - g));
+            BT(j, 1, 0) = h4 * (10.0 * q2(e - c) + q2(c - bb) + (c - bb) * (e - c)) / (q2(bb - f) * q2(c - f));
+            BT(j, 1, 1) = h4 * ((c - e) * ((c - bb) + 20.0 * (e - c)) + (2.0 * (c - bb) + (e - c)) * (f - c)) /
+                          ((e - bb) * q2(bb - f) * (f - c));
+            BT(j, 1, 2) = h4 * (10.0 * q2(e - c) + (e - c) * (f - e) + q2(f - e)) / (q2(bb - e) * q2(bb - f));
+            BT(j, 2, 0) = h4 * (12.0 * q2(e - c) + q2((c - a) + (c - bb)) + 3.0 * ((c - a) + (c - bb)) * (e - c)) /
+                          (q2(a - e) * q2(bb - e));
+            BT(j, 2, 1) = h4 * (19.0 * q2(e - c) + ((c - a) * (c - e)) + 2.0 * (e - bb) * ((c - a) + (e - bb))) /
+                          ((a - c) * q2(a - e) * (e - bb));
+            BT(j, 2, 2) = h4 * (10.0 * q2(e - c) + q2(c - bb) + (c - bb) * (e - c)) / (q2(a - c) * q2(a - e));
+        }
+        if (h->P.null_weights) {  // m_weno.fpp:345-361
+            auto renorm = [&](bool right, int j) {
+                double t = 0;
+                for (int q = 0; q < 3; q++) t += right ? DR(q, j) : DL(q, j);
+                for (int q = 0; q < 3; q++) { if (right) DR(q, j) /= t; else DL(q, j) /= t; }
+            };
+            if (bcb == MFC5_BC_RIEMANN_EXTRAP) {
+                DR(1, 0) = 0; DR(2, 0) = 0; DR(0, 0) = 1; DL(1, 0) = 0; DL(2, 0) = 0; DL(0, 0) = 1;
+                DR(2, 1) = 0; renorm(true, 1);
+                DL(2, 1) = 0; renorm(false, 1);
+            }
+            if (bce == MFC5_BC_RIEMANN_EXTRAP) {
+                DR(0, s - 1) = 0; renorm(true, s - 1);
+                DL(0, s - 1) = 0; renorm(false, s - 1);
+                DR(0, s) = 0; DR(1, s) = 0; DR(2, s) = 1; DL(0, s) = 0; DL(1, s) = 0; DL(2, s) = 1;
+            }
+        }
+    }
+    uniform = 1;  // m_weno.fpp:869-879
+    if (s > 0) {
+        const double h0 = (x[s] - x[0]) / (double)s;
+        for (int i = 0; i <= s - 1; i++)
+            if (std::fabs((x[i + 1] - x[i]) - h0) > std::sqrt(2.220446049250313e-16) * std::fabs(h0)) { uniform = 0; break; }
+    }
+}
+
+// ---- CBC coefficients: s_compute_cbc_coefficients m_cbc.fpp:327-408 ----------------------------------
+static void cbc_tables(mfc5_handle* h, int d, int side) {
+    const int s = h->s[d], b = h->b;
+    const double* w = h->ds[d].data() + b;
+    CbcCoef& K = h->cbc[d][side];
+    std::memset(&K, 0, sizeof(K));
+    double ds[8], x[10];
+    for (int i = 0; i <= b; i++) ds[i] = side == 0 ? w[i] : w[s - i];
+    x[0] = 0.0;
+    for (int i = 0; i <= b; i++) x[i + 1] = x[i] + ds[i];
+    if (h->P.weno_order == 3) {
+        K.fd[0] = -6.0 / (3.0 * ds[0] + 2.0 * ds[1] - ds[2]);
+        K.fd[1] = -4.0 * K.fd[0] / 3.0;
+        K.fd[2] = K.fd[0] / 3.0;
+        K.pi[0][0] = (x[0] - x[1]) / (x[0] - x[2]);
+    } else {
+        K.fd[0] = -50.0 / (25.0 * ds[0] + 2.0 * ds[1] - 1.e1 * ds[2] + 1.e1 * ds[3] - 3.0 * ds[4]);
+        K.fd[1] = -48.0 * K.fd[0] / 25.0;
+        K.fd[2] = 36.0 * K.fd[0] / 25.0;
+        K.fd[3] = -16.0 * K.fd[0] / 25.0;
+        K.fd[4] = 3.0 * K.fd[0] / 25.0;
+        K.pi[0][0] = ((x[0] - x[1]) * (x[1] - x[2]) * (x[1] - x[3])) / ((x[1] - x[4]) * (x[4] - x[0]) * (x[4] - x[2]));
+        K.pi[0][1] = ((x[1] - x[0]) * (x[1] - x[2]) * ((x[1] - x[3]) * (x[1] - x[3]) - (x[0] - x[4]) * ((x[3] - x[1]) + (x[4] - x[1])))) /
+                     ((x[0] - x[3]) * (x[1] - x[3]) * (x[0] - x[4]) * (x[1] - x[4]));
+        K.pi[0][2] = (x[1] - x[0]) * ((x[1] - x[2]) * (x[1] - x[3]) + ((x[0] - x[2]) + (x[1] - x[3])) * (x[0] - x[4])) /
+                     ((x[2] - x[0]) * (x[0] - x[3]) * (x[0] - x[4]));
+        K.pi[1][0] = ((x[0] - x[2]) * (x[2] - x[1]) * (x[2] - x[3])) / ((x[2] - x[4]) * (x[4] - x[0]) * (x[4] - x[1]));
+        K.pi[1][1] = ((x[0] - x[2]) * (x[1] - x[2]) * ((x[1] - x[3]) * (x[2] - x[3]) + (x[0] - x[4]) * ((x[1] - x[3]) + (x[2] - x[4])))) /
+                     ((x[0] - x[3]) * (x[1] - x[3]) * (x[0] - x[4]) * (x[1] - x[4]));
+        K.pi[1][2] = ((x[1] - x[2]) * (x[2] - x[3]) * (x[2] - x[4])) / ((x[0] - x[2]) * (x[0] - x[3]) * (x[0] - x[4]));
+    }
+    K.ds0 = ds[0];
+    double mx = w[-b];  // Del = maxval(d<xyz>) over the ghosted array, m_cbc.fpp:312-313
+    for (int i = -b; i <= s + b; i++) mx = std::fmax(mx, w[i]);
+    K.Del = mx;
+    for (int a = 0; a < 3; a++) { K.vel_in[a] = h->P.vel_in[d][a]; K.vel_out[a] = h->P.vel_out[d][a]; }
+    K.pres_in = h->P.pres_in[d]; K.pres_out = h->P.pres_out[d];
+    for (int f = 0; f < MFC5_MAX_FLUIDS; f++) { K.arho_in[f] = h->P.alpha_rho_in[d][f]; K.alf_in[f] = h->P.alpha_in[d][f]; }
+    K.grcbc_in = h->P.grcbc_in[d]; K.grcbc_out = h->P.grcbc_out[d]; K.grcbc_vel_out = h->P.grcbc_vel_out[d];
+}
+
+static int upload(double** dptr, const std::vector<double>& v) {
+    if (*dptr) cudaFree(*dptr);
+    *dptr = nullptr;
+    CK(cudaMalloc(dptr, std::max<size_t>(v.size(), 1) * sizeof(double)));
+    if (!v.empty()) CK(cudaMemcpy(*dptr, v.data(), v.size() * sizeof(double), cudaMemcpyHostToDevice));
+    return 0;
+}
+
+extern "C" int mfc5_finalize_setup(mfc5_handle* h) {
+    if (!h) return fail("null handle");
+    CK(cudaSetDevice(h->P.device));
+    for (int d = 0; d < h->nd; d++)
+        if (!h->grid_set[d]) return fail("mfc5_finalize_setup: grid not set for every direction");
+    DevP& D = h->D;
+    std::memset(&D, 0, sizeof(D));
+    for (int d = 0; d < 3; d++) D.s[d] = h->s[d];
+    D.nd = h->nd; D.nf = h->nf; D.N = h->N; D.b = h->b; D.pn = h->pn; D.ns = h->ns;
+    D.wo = h->P.weno_order; D.wv = h->P.mapped_weno ? 1 : (h->P.wenoz ? 2 : 0); D.rs = h->P.riemann_solver;
+    D.hll_u = h->P.hll_u_interface; D.avg = h->P.avg_state; D.ws = h->P.wave_speeds; D.mpp = h->P.mpp_lim;
+    D.mixerr = h->P.mixture_err; D.fast = h->P.fast_math;
+    D.sy = h->px; D.sz = h->px * h->ey; D.fs = h->fs;
+    D.base = h->ox + h->oy * D.sy + h->oz * D.sz;
+    D.eps = h->P.weno_eps;
+    for (int f = 0; f < MFC5_MAX_FLUIDS; f++) { D.gam[f] = h->P.fluid_gamma[f]; D.pinf[f] = h->P.fluid_pi_inf[f]; D.qv[f] = h->P.fluid_qv[f]; }
+    const bool hll1 = (D.rs == 1 && !D.hll_u);
+    D.nface = h->P.weno_order == 5 ? 2 : 1;
+    D.ncbc_comp = h->N + (hll1 ? h->nf : 1);
+    for (int d = 0; d < h->nd; d++) {
+        std::vector<double> tab[5];
+        int uni = 1;
+        weno_tables(h, d, tab, uni);
+        h->uniform[d] = uni;
+        for (int k = 0; k < 5; k++) if (upload(&h->d_tab[d][k], tab[k])) return -1;
+        if (upload(&h->d_tab[d][5], h->ds[d])) return -1;
+        D.T[d].cL = h->d_tab[d][0]; D.T[d].cR = h->d_tab[d][1]; D.T[d].dL = h->d_tab[d][2]; D.T[d].dR = h->d_tab[d][3];
+        D.T[d].bt = h->d_tab[d][4]; D.T[d].ds = h->d_tab[d][5]; D.T[d].uniform = uni;
+        const int t1 = d == 0 ? 1 : 0, t2 = d == 2 ? 1 : 2;
+        h->plane[d] = (long long)(h->s[t1] + 1) * (h->s[t2] + 1);
+        for (int sd = 0; sd < 2; sd++) {
+            D.bc[d][sd] = h->P.bc[d][sd];
+            D.cbc_on[d][sd] = is_cbc(h->P.bc[d][sd]);
+            if (D.cbc_on[d][sd]) {
+                cbc_tables(h, d, sd);
+                if (h->d_cbcbuf[d][sd]) cudaFree(h->d_cbcbuf[d][sd]);
+                CK(cudaMalloc(&h->d_cbcbuf[d][sd], (size_t)(D.nface + 1) * D.ncbc_comp * h->plane[d] * sizeof(double)));
+            }
+            D.cbcbuf[d][sd] = h->d_cbcbuf[d][sd];
+            D.dirich[d][sd] = h->d_dirich[d][sd];
+        }
+        for (int a = 0; a < 3; a++) { D.vb[d][a] = h->P.bc_vb[d][a]; D.ve[d][a] = h->P.bc_ve[d][a]; }
+    }
+    D.chunk = 32;
+    if (const char* e = getenv("MFC5_CHUNK")) D.chunk = std::max(1, atoi(e));
+    // small grids: shorten the marching chunks so the grid still fills the machine
+    if (h->nd > 1) {
+        const long long plane = (long long)(h->s[0] + 1) * (h->nd > 2 ? (long long)(h->s[1] + 1) : 1);
+        while (D.chunk > 8 && plane * ((h->s[h->nd - 1] + D.chunk) / D.chunk) < 148LL * 1024) D.chunk /= 2;
+    }
+    h->setup = true;
+    for (int i = 0; i < 2; i++) if (h->gexec[i]) { cudaGraphExecDestroy(h->gexec[i]); h->gexec[i] = nullptr; }
+    return 0;
+}
+
+extern "C" int mfc5_set_dirichlet(mfc5_handle* h, int d, int side, const double* values) {
+    if (!h || d < 0 || d >= h->nd || side < 0 || side > 1 || !values) return fail("mfc5_set_dirichlet: bad argument");
+    CK(cudaSetDevice(h->P.device));
+    const int t1 = d == 0 ? 1 : 0, t2 = d == 2 ? 1 : 2;
+    const size_t n = (size_t)h->N * (h->s[t1] + 1) * (h->s[t2] + 1);
+    if (h->d_dirich[d][side]) cudaFree(h->d_dirich[d][side]);
+    CK(cudaMalloc(&h->d_dirich[d][side], n * sizeof(double)));
+    CK(cudaMemcpy(h->d_dirich[d][side], values, n * sizeof(double), cudaMemcpyHostToDevice));
+    h->D.dirich[d][side] = h->d_dirich[d][side];
+    return 0;
+}
+
+// ---- host <-> device field copies ------------------------------------------------------------------
+static int copy_fields(mfc5_handle* h, double* dev, const double* const* hostc, double* const* hostm, int ghosted, bool to_dev) {
+    CK(cudaSetDevice(h->P.device));
+    CK(cudaStreamSynchronize(h->st));
+    const int gx = ghosted ? h->b : 0, gy = (ghosted && h->nd > 1) ? h->b : 0, gz = (ghosted && h->nd > 2) ? h->b : 0;
+    // host extents
+    const size_t hx = h->s[0] + 1 + 2 * gx, hy = h->s[1] + 1 + 2 * gy, hz = h->s[2] + 1 + 2 * gz;
+    // copy region: upload -> interior only; download -> everything the host array holds
+    const int cgx = to_dev ? 0 : gx, cgy = to_dev ? 0 : gy, cgz = to_dev ? 0 : gz;
+    const size_t wx = h->s[0] + 1 + 2 * cgx, wy = h->s[1] + 1 + 2 * cgy, wz = h->s[2] + 1 + 2 * cgz;
+    for (int v = 0; v < h->N; v++) {
+        cudaMemcpy3DParms p = {};
+        double* hp = to_dev ? const_cast<double*>(hostc[v]) : hostm[v];
+        if (!hp) return fail("null field pointer");
+        cudaPitchedPtr hptr = make_cudaPitchedPtr(hp, hx * sizeof(double), hx, hy);
+        cudaPitchedPtr dptr = make_cudaPitchedPtr(dev + (size_t)v * h->fs, h->px * sizeof(double), h->px, h->ey);
+        cudaPos hpos = make_cudaPos((gx - cgx) * sizeof(double), gy - cgy, gz - cgz);
+        cudaPos dpos = make_cudaPos((h->ox - cgx) * sizeof(double), h->oy - cgy, h->oz - cgz);
+        p.extent = make_cudaExtent(wx * sizeof(double), wy, wz);
+        if (to_dev) { p.srcPtr = hptr; p.srcPos = hpos; p.dstPtr = dptr; p.dstPos = dpos; p.kind = cudaMemcpyHostToDevice; }
+        else { p.srcPtr = dptr; p.srcPos = dpos; p.dstPtr = hptr; p.dstPos = hpos; p.kind = cudaMemcpyDeviceToHost; }
+        CK(cudaMemcpy3D(&p));
+    }
+    return 0;
+}
+
+extern "C" int mfc5_upload_cons(mfc5_handle* h, const double* const* q, int ghosted) {
+    if (!h || !q) return fail("mfc5_upload_cons: null argument");
+    return copy_fields(h, h->d_q[h->cur], q, nullptr, ghosted, true);
+}
+extern "C" int mfc5_download_cons(mfc5_handle* h, double* const* q, int ghosted) {
+    if (!h || !q) return fail("mfc5_download_cons: null argument");
+    return copy_fields(h, h->d_q[h->cur], nullptr, q, ghosted, false);
+}
+extern "C" int mfc5_download_prim(mfc5_handle* h, double* const* q, int ghosted) {
+    if (!h || !q) return fail("mfc5_download_prim: null argument");
+    return copy_fields(h, h->d_prim, nullptr, q, ghosted, false);
+}
+extern "C" int mfc5_download_rhs(mfc5_handle* h, double* const* q, int ghosted) {
+    if (!h || !q) return fail("mfc5_download_rhs: null argument");
+    return copy_fields(h, h->d_rhs, nullptr, q, ghosted, false);
+}
+
+// ---- stage orchestration ---------------------------------------------------------------------------
+template <typename F>
+static int by_shape(const mfc5_handle* h, F&& f) {
+    switch (h->nf * 10 + h->nd) {
+    case 11: f(std::integral_constant<int, 1>(), std::integral_constant<int, 1>()); return 0;
+    case 12: f(std::integral_constant<int, 1>(), std::integral_constant<int, 2>()); return 0;
+    case 13: f(std::integral_constant<int, 1>(), std::integral_constant<int, 3>()); return 0;
+    case 21: f(std::integral_constant<int, 2>(), std::integral_constant<int, 1>()); return 0;
+    case 22: f(std::integral_constant<int, 2>(), std::integral_constant<int, 2>()); return 0;
+    case 23: f(std::integral_constant<int, 2>(), std::integral_constant<int, 3>()); return 0;
+    case 31: f(std::integral_constant<int, 3>(), std::integral_constant<int, 1>()); return 0;
+    case 32: f(std::integral_constant<int, 3>(), std::integral_constant<int, 2>()); return 0;
+    case 33: f(std::integral_constant<int, 3>(), std::integral_constant<int, 3>()); return 0;
+    }
+    return fail("unsupported (num_fluids, num_dims)");
+}
+
+static unsigned grid_for(long long n, int block) { return (unsigned)std::min<long long>((n + block - 1) / block, 148LL * 16); }
+
+static int halo_count(const mfc5_handle* h, int d) {
+    long long n = (long long)h->N * h->b;
+    for (int e = 0; e < 3; e++) {
+        if (e == d) continue;
+        n *= (e < d) ? (h->s[e] + 1 + 2 * (e < h->nd ? h->b : 0)) : (h->s[e] + 1);
+    }
+    return (int)n;
+}
+
+// ghost fill of one direction: physical BCs locally, processor boundaries by NCCL send/recv of packed
+// faces (replaces s_mpi_sendrecv_variables_buffers, m_mpi_common.fpp:549-1070)
+static int fill_direction(mfc5_handle* h, const DevP& D, int d) {
+    const int t1 = d == 0 ? 1 : 0, t2 = d == 2 ? 1 : 2;
+    long long n1 = h->s[t1] + 1, n2 = h->s[t2] + 1;
+    if (t1 < d) n1 += 2 * h->b;
+    if (t2 < d && t2 < h->nd) n2 += 2 * h->b;
+    const long long tot = n1 * n2 * h->N;
+    bool any_nb = false;
+    for (int sd = 0; sd < 2; sd++) {
+        if (h->P.bc[d][sd] < 0) {
+            k_bc_fill<<<grid_for(tot, 256), 256, 0, h->st>>>(D, d, sd);
+            h->launches++;
+        } else any_nb = true;
+    }
+    if (any_nb) {
+        if (!h->comm) return fail("processor boundary (bc >= 0) but mfc5_comm_init was not called");
+        const int cnt = halo_count(h, d);
+        for (int sd = 0; sd < 2; sd++) {
+            if (h->P.bc[d][sd] < 0) continue;
+            if (!h->d_send[d][sd]) {
+                CK(cudaMalloc(&h->d_send[d][sd], (size_t)cnt * sizeof(double)));
+                CK(cudaMalloc(&h->d_recv[d][sd], (size_t)cnt * sizeof(double)));
+            }
+            k_halo_copy<<<grid_for(cnt, 256), 256, 0, h->st>>>(D, d, sd == 0 ? 0 : h->s[d] - h->b + 1, h->d_send[d][sd], 1);
+            h->launches++;
+        }
+        NK(g_nccl.GroupStart());
+        // sends low face then high face; receives in the opposite order so that the pairing is also
+        // right when both neighbours are the same rank (periodic direction split over 2 ranks)
+        for (int sd = 0; sd < 2; sd++)
+            if (h->P.bc[d][sd] >= 0) NK(g_nccl.Send(h->d_send[d][sd], cnt, NCCL_FLOAT64, h->P.bc[d][sd], h->comm, h->st));
+        for (int sd = 1; sd >= 0; sd--)
+            if (h->P.bc[d][sd] >= 0) NK(g_nccl.Recv(h->d_recv[d][sd], cnt, NCCL_FLOAT64, h->P.bc[d][sd], h->comm, h->st));
+        NK(g_nccl.GroupEnd());
+        for (int sd = 0; sd < 2; sd++) {
+            if (h->P.bc[d][sd] < 0) continue;
+            k_halo_copy<<<grid_for(cnt, 256), 256, 0, h->st>>>(D, d, sd == 0 ? -h->b : h->s[d] + 1, h->d_recv[d][sd], 0);
+            h->launches++;
+        }
+    }
+    return 0;
+}
+
+static int launch_sweep(mfc5_handle* h, const DevP& D, int dir) {
+    bool ok = false;
+    if (!getenv("MFC5_NO_OPT")) ok = launch_sweep_opt(D, dir, h->st);
+    if (!ok) ok = launch_sweep_generic_nf1(D, dir, h->st) || launch_sweep_generic_nf2(D, dir, h->st) || launch_sweep_generic_nf3(D, dir, h->st);
+    if (!ok) return fail("no sweep kernel for this configuration");
+    h->launches++;
+    return 0;
+}
+
+// one RHS evaluation (+ fused RK update when do_rk): q1 = state read, q2 = stage-1 copy, qout = target
+static int run_stage(mfc5_handle* h, const double* q1, const double* q2, double* qout, int do_rk, const double rk[4], double dt, bool timed) {
+    DevP D = h->D;
+    D.prim = h->d_prim; D.primw = h->d_prim; D.q1 = q1; D.q2 = q2; D.qout = qout; D.rhs = h->d_rhs;
+    D.rk0 = rk[0]; D.rk1 = rk[1]; D.rk2 = rk[2]; D.rk3 = rk[3]; D.dt = dt; D.do_rk = do_rk;
+    const long long ncell = (long long)(h->s[0] + 1) * (h->s[1] + 1) * (h->s[2] + 1);
+    int rc = by_shape(h, [&](auto nf, auto nd) {
+        k_cons2prim<decltype(nf)::value, decltype(nd)::value><<<grid_for(ncell, 256), 256, 0, h->st>>>(D);
+    });
+    if (rc) return rc;
+    h->launches++;
+    for (int d = 0; d < h->nd; d++)
+        if (fill_direction(h, D, d)) return -1;
+    for (int d = 0; d < h->nd; d++) {
+        for (int sd = 0; sd < 2; sd++) {
+            if (!D.cbc_on[d][sd]) continue;
+            const CbcCoef K = h->cbc[d][sd];
+            by_shape(h, [&](auto nf, auto nd) {
+                k_cbc<decltype(nf)::value, decltype(nd)::value><<<(unsigned)((h->plane[d] + 127) / 128), 128, 0, h->st>>>(D, K, d, sd);
+            });
+            h->launches++;
+        }
+        if (timed) CK(cudaEventRecord(h->ev_sw[d][0], h->st));
+        if (launch_sweep(h, D, d)) return -1;
+        if (timed) CK(cudaEventRecord(h->ev_sw[d][1], h->st));
+    }
+    CK(cudaGetLastError());
+    return 0;
+}
+
+static const double RK3[3][4] = {{1, 0, 1, 1}, {1, 3, 1, 4}, {2, 1, 2, 3}};  // m_time_steppers.fpp:421-432
+static const double RK2[2][4] = {{1, 0, 1, 1}, {1, 1, 1, 2}};
+static const double RK1[1][4] = {{1, 0, 1, 1}};
+
+// enqueue one full step on h->st.  Ping-pong: stage 1 reads A (which thereby *is* q_cons_ts(2)) and
+// writes B; later stages update B in place.  For time_stepper = 1 the update is in place.
+static int enqueue_step(mfc5_handle* h, double dt, bool timed) {
+    const int ns = h->P.time_stepper;
+    double* A = h->d_q[h->cur];
+    double* B = ns > 1 ? h->d_q[h->cur ^ 1] : A;
+    for (int st = 1; st <= ns; st++) {
+        const double* rk = ns == 3 ? RK3[st - 1] : ns == 2 ? RK2[st - 1] : RK1[0];
+        const double* q1 = st == 1 ? A : B;
+        if (timed) CK(cudaEventRecord(h->ev_stage[st - 1], h->st));
+        if (run_stage(h, q1, A, B, 1, rk, dt, timed && st == ns)) return -1;
+    }
+    if (timed) CK(cudaEventRecord(h->ev_stage[ns], h->st));
+    if (ns > 1) h->cur ^= 1;
+    return 0;
+}
+
+extern "C" int mfc5_compute_rhs(mfc5_handle* h) {
+    if (!h || !h->setup) return fail("mfc5_compute_rhs: handle not set up");
+    CK(cudaSetDevice(h->P.device));
+    const double rk[4] = {1, 0, 1, 1};
+    if (run_stage(h, h->d_q[h->cur], h->d_q[h->cur], h->d_q[h->cur], 0, rk, 0.0, false)) return -1;
+    CK(cudaStreamSynchronize(h->st));
+    return 0;
+}
+
+extern "C" int mfc5_tvd_rk(mfc5_handle* h, double dt, double* stage_time_min) {
+    if (!h || !h->setup) return fail("mfc5_tvd_rk: handle not set up");
+    CK(cudaSetDevice(h->P.device));
+    if (enqueue_step(h, dt, true)) return -1;
+    CK(cudaStreamSynchronize(h->st));
+    const int ns = h->P.time_stepper;
+    for (int st = 0; st < ns; st++) {
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, h->ev_stage[st], h->ev_stage[st + 1]));
+        if (stage_time_min) {
+            const double t = ms * 1e-3;
+            *stage_time_min = (*stage_time_min <= 0.0) ? t : std::min(*stage_time_min, t);
+        }
+    }
+    for (int d = 0; d < h->nd; d++) CK(cudaEventElapsedTime(&h->sweep_ms[d], h->ev_sw[d][0], h->ev_sw[d][1]));
+    return 0;
+}
+
+extern "C" int mfc5_tvd_rk_n(mfc5_handle* h, double dt, int nsteps) {
+    if (!h || !h->setup) return fail("mfc5_tvd_rk_n: handle not set up");
+    CK(cudaSetDevice(h->P.device));
+    for (int i = 0; i < nsteps; i++)
+        if (enqueue_step(h, dt, false)) return -1;
+    return 0;
+}
+
+extern "C" int mfc5_sync(mfc5_handle* h) {
+    if (!h) return fail("null handle");
+    CK(cudaSetDevice(h->P.device));
+    CK(cudaStreamSynchronize(h->st));
+    CK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int mfc5_reduce(mfc5_handle* h, int what, double dt, double* out) {
+    if (!h || !h->setup || !out) return fail("mfc5_reduce: bad argument");
+    if (what < 0 || what > 2) return fail("mfc5_reduce: what must be 0, 1 or 2");
+    CK(cudaSetDevice(h->P.device));
+    // primitive variables of the current state
+    DevP D = h->D;
+    D.prim = h->d_prim; D.primw = h->d_prim; D.q1 = h->d_q[h->cur]; D.q2 = D.q1; D.qout = nullptr; D.rhs = h->d_rhs;
+    const long long ncell = (long long)(h->s[0] + 1) * (h->s[1] + 1) * (h->s[2] + 1);
+    const unsigned long long init[4] = {0ull, 0x7FEFFFFFFFFFFFFFull, 0ull, 0ull};
+    CK(cudaMemcpyAsync(h->d_red, init, sizeof(init), cudaMemcpyHostToDevice, h->st));
+    int rc = by_shape(h, [&](auto nf, auto nd) {
+        k_cons2prim<decltype(nf)::value, decltype(nd)::value><<<grid_for(ncell, 256), 256, 0, h->st>>>(D);
+        k_reduce<decltype(nf)::value, decltype(nd)::value><<<grid_for(ncell, 256), 256, 0, h->st>>>(D, dt, h->d_red);
+    });
+    if (rc) return rc;
+    h->launches += 2;
+    if (h->comm) {
+        NK(g_nccl.AllReduce(h->d_red + 0, h->d_red + 0, 1, NCCL_FLOAT64, NCCL_MAX, h->comm, h->st));
+        NK(g_nccl.AllReduce(h->d_red + 1, h->d_red + 1, 1, NCCL_FLOAT64, NCCL_MIN, h->comm, h->st));
+        NK(g_nccl.AllReduce(h->d_red + 2, h->d_red + 2, 1, NCCL_UINT64, NCCL_SUM, h->comm, h->st));
+    }
+    unsigned long long res[4];
+    CK(cudaMemcpyAsync(res, h->d_red, sizeof(res), cudaMemcpyDeviceToHost, h->st));
+    CK(cudaStreamSynchronize(h->st));
+    if (what == 2) { *out = (double)res[2]; return 0; }
+    double v;
+    std::memcpy(&v, &res[what], sizeof(double));
+    if (what == 0 && res[2] > 0) v = NAN;  // a NaN ICFL must not be hidden by fmax
+    *out = v;
+    return 0;
+}
+
+// ---- multi-GPU ---------------------------------------------------------------------------------------
+extern "C" int mfc5_nccl_unique_id(char id_out[128]) {
+    if (nccl_load()) return -1;
+    ncclUniqueId id;
+    NK(g_nccl.GetUniqueId(&id));
+    std::memcpy(id_out, id.internal, 128);
+    return 0;
+}
+
+extern "C" int mfc5_comm_init(mfc5_handle* h, const char id_in[128], int rank, int nranks) {
+    if (!h) return fail("null handle");
+    if (nccl_load()) return -1;
+    CK(cudaSetDevice(h->P.device));
+    ncclUniqueId id;
+    std::memcpy(id.internal, id_in, 128);
+    NK(g_nccl.CommInitRank(&h->comm, nranks, id, rank));
+    h->rank = rank; h->nranks = nranks;
+    return 0;
+}

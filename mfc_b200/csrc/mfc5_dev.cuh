@@ -1,0 +1,358 @@
+// mfc5_dev.cuh -- device-side numerics of the fused 5-equation sweep (sm_100a, FP64).
+//
+// Per-cell / per-face arithmetic written in the reference's operation order (file:line cited at
+// each routine; paths relative to MFlowCode/MFC @ 0b234b19).  Everything is templated on the
+// compile-time shape <NF fluids, ND dims, DIR sweep direction> so the per-thread state lives in
+// registers; WENO order / variant / Riemann solver are template parameters where a specialised
+// ("case-optimised") kernel exists and run-time (-1) in the generic kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+#include "../../include/mfc5_params.h"
+
+#define MFC5_SGM_EPS 1.e-16  // reference src/common/m_constants.fpp:16
+
+namespace mfc5 {
+
+struct DirTables {
+    // WENO tables of one direction, index j in [-b+polyn, s+b-polyn] -> slot (j + b)
+    // (reference src/simulation/m_weno.fpp:170-893)
+    const double* cL;  // [slot][q][r]  poly_coef_cbL
+    const double* cR;  // [slot][q][r]  poly_coef_cbR
+    const double* dL;  // [slot][q]     d_cbL
+    const double* dR;  // [slot][q]     d_cbR
+    const double* bt;  // [slot][q][3]  beta_coef
+    const double* ds;  // cell widths, index i in [-b, s+b] -> slot (i + b)
+    int uniform;       // uniform_grid(dir), m_weno.fpp:869-879
+};
+
+// Everything a kernel needs, passed by value (__grid_constant__).
+struct DevP {
+    int s[3];          // m, n, p
+    int nd, nf, N, b, pn, ns;
+    int wo, wv, rs;    // weno_order; variant 0 JS / 1 M / 2 Z; riemann_solver 1 HLL / 2 HLLC
+    int hll_u, avg, ws, mpp, mixerr, fast;
+    long long sy, sz, fs, base;  // strides (x stride = 1), field size, offset of cell (0,0,0)
+    double eps;
+    double gam[MFC5_MAX_FLUIDS], pinf[MFC5_MAX_FLUIDS], qv[MFC5_MAX_FLUIDS];
+    DirTables T[3];
+    int bc[3][2];
+    double vb[3][3], ve[3][3];
+    // characteristic BC replacement fluxes, [slot 0..nface][comp 0..N-1 flux, N.. src][plane]
+    int cbc_on[3][2];
+    int nface, ncbc_comp;
+    double* cbcbuf[3][2];
+    const double* dirich[3][2];
+    // per launch
+    const double* prim;
+    double* primw;
+    const double* q1;   // conservative state read by this stage
+    const double* q2;   // stage-1 copy (q_cons_ts(2))
+    double* qout;       // where the fused RK update writes
+    double* rhs;
+    double rk0, rk1, rk2, rk3, dt;
+    int do_rk;
+    int chunk;          // marching chunk length of the y/z sweeps
+};
+
+__device__ __forceinline__ double sq(double x) { return x * x; }
+__device__ __forceinline__ double fsign(double a, double b) { return copysign(fabs(a), b); }
+
+// -------------------------------------------------------------------------------------------------
+// WENO reconstruction of one variable in one cell: left- and right-boundary values.
+// reference: s_weno, src/simulation/m_weno.fpp:1007-1085 (WENO3), :1098-1239 (WENO5), :952-993 (1).
+// f[0..4] = v(j-2..j+2).  WO / WV < 0: read from P (generic kernels).
+// -------------------------------------------------------------------------------------------------
+template <int WO, int WV>
+__device__ __forceinline__ void weno_edges(const DevP& P, const DirTables& T, int slot, const double f0, const double f1,
+                                           const double f2, const double f3, const double f4, double& eL, double& eR) {
+    const int wo = (WO < 0) ? P.wo : WO;
+    const int wv = (WV < 0) ? P.wv : WV;
+    const double eps = P.eps;
+    if (wo == 1) { eL = f2; eR = f2; return; }
+    if (wo == 3) {
+        const double* cl = T.cL + slot * 2;
+        const double* cr = T.cR + slot * 2;
+        const double* dl = T.dL + slot * 2;
+        const double* dr = T.dR + slot * 2;
+        const double* bt = T.bt + slot * 6;
+        const double vp0 = f2;
+        const double d0 = f3 - f2, dm1 = f2 - f1;
+        const double b0 = __ldg(bt + 0) * d0 * d0 + eps;
+        const double b1 = __ldg(bt + 3) * dm1 * dm1 + eps;
+        double tau = 0.0;
+        if (wv == 2) tau = fabs(b1 - b0);
+#pragma unroll
+        for (int side = 0; side < 2; side++) {
+            const double* dd = side == 0 ? dl : dr;
+            const double* cc = side == 0 ? cl : cr;
+            const double dd0 = __ldg(dd + 0), dd1 = __ldg(dd + 1);
+            const double p0 = vp0 + __ldg(cc + 0) * d0;
+            const double p1 = vp0 + __ldg(cc + 1) * dm1;
+            double a0, a1;
+            if (wv == 1) {
+                a0 = dd0 / (b0 * b0);
+                a1 = dd1 / (b1 * b1);
+                const double sum = a0 + a1;
+                const double w0 = a0 / sum, w1 = a1 / sum;
+                a0 = (dd0 * (1.0 + dd0 - 3.0 * w0) + w0 * w0) * (w0 / (dd0 * dd0 + w0 * (1.0 - 2.0 * dd0)));
+                a1 = (dd1 * (1.0 + dd1 - 3.0 * w1) + w1 * w1) * (w1 / (dd1 * dd1 + w1 * (1.0 - 2.0 * dd1)));
+            } else if (wv == 2) {
+                a0 = dd0 * (1.0 + tau / b0);
+                a1 = dd1 * (1.0 + tau / b1);
+            } else {
+                a0 = dd0 / (b0 * b0);
+                a1 = dd1 / (b1 * b1);
+            }
+            const double sum = a0 + a1;
+            const double w0 = a0 / sum, w1 = a1 / sum;
+            const double val = w0 * p0 + w1 * p1;
+            if (side == 0) eL = val; else eR = val;
+        }
+        return;
+    }
+    // WENO5
+    {
+        const double* cl = T.cL + slot * 6;
+        const double* cr = T.cR + slot * 6;
+        const double* dl = T.dL + slot * 3;
+        const double* dr = T.dR + slot * 3;
+        const double* bt = T.bt + slot * 9;
+        const double vp0 = f2;
+        const double d1 = f4 - f3, d0 = f3 - f2, dm1 = f2 - f1, dm2 = f1 - f0;
+        double b0, b1, b2;
+        if (T.uniform) {
+            b0 = 13.0 / 12.0 * sq(d1 - d0) + 0.25 * sq(d1 - 3.0 * d0) + eps;
+            b1 = 13.0 / 12.0 * sq(d0 - dm1) + 0.25 * sq(d0 + dm1) + eps;
+            b2 = 13.0 / 12.0 * sq(dm1 - dm2) + 0.25 * sq(3.0 * dm1 - dm2) + eps;
+        } else {
+            b0 = __ldg(bt + 0) * d1 * d1 + __ldg(bt + 1) * d1 * d0 + __ldg(bt + 2) * d0 * d0 + eps;
+            b1 = __ldg(bt + 3) * d0 * d0 + __ldg(bt + 4) * d0 * dm1 + __ldg(bt + 5) * dm1 * dm1 + eps;
+            b2 = __ldg(bt + 6) * dm1 * dm1 + __ldg(bt + 7) * dm1 * dm2 + __ldg(bt + 8) * dm2 * dm2 + eps;
+        }
+        double tau = 0.0;
+        if (wv == 2) tau = fabs(b2 - b0);
+#pragma unroll
+        for (int side = 0; side < 2; side++) {
+            const double* dd = side == 0 ? dl : dr;
+            const double* cc = side == 0 ? cl : cr;
+            const double dd0 = __ldg(dd + 0), dd1 = __ldg(dd + 1), dd2 = __ldg(dd + 2);
+            const double p0 = vp0 + __ldg(cc + 0) * d1 + __ldg(cc + 1) * d0;
+            const double p1 = vp0 + __ldg(cc + 2) * d0 + __ldg(cc + 3) * dm1;
+            const double p2 = vp0 + __ldg(cc + 4) * dm1 + __ldg(cc + 5) * dm2;
+            double a0, a1, a2;
+            if (wv == 1) {
+                a0 = dd0 / (b0 * b0);
+                a1 = dd1 / (b1 * b1);
+                a2 = dd2 / (b2 * b2);
+                const double sum = a0 + a1 + a2;
+                const double w0 = a0 / sum, w1 = a1 / sum, w2 = a2 / sum;
+                a0 = (dd0 * (1.0 + dd0 - 3.0 * w0) + w0 * w0) * (w0 / (dd0 * dd0 + w0 * (1.0 - 2.0 * dd0)));
+                a1 = (dd1 * (1.0 + dd1 - 3.0 * w1) + w1 * w1) * (w1 / (dd1 * dd1 + w1 * (1.0 - 2.0 * dd1)));
+                a2 = (dd2 * (1.0 + dd2 - 3.0 * w2) + w2 * w2) * (w2 / (dd2 * dd2 + w2 * (1.0 - 2.0 * dd2)));
+            } else if (wv == 2) {
+                a0 = dd0 * (1.0 + (tau / b0));
+                a1 = dd1 * (1.0 + (tau / b1));
+                a2 = dd2 * (1.0 + (tau / b2));
+            } else {
+                a0 = dd0 / (b0 * b0);
+                a1 = dd1 / (b1 * b1);
+                a2 = dd2 / (b2 * b2);
+            }
+            const double sum = a0 + a1 + a2;
+            const double w0 = a0 / sum, w1 = a1 / sum, w2 = a2 / sum;
+            const double val = w0 * p0 + w1 * p1 + w2 * p2;
+            if (side == 0) eL = val; else eR = val;
+        }
+    }
+}
+
+// s_compute_speed_of_sound, 5-eq branch: src/common/m_variables_conversion.fpp:1248-1260
+__device__ __forceinline__ double sound_speed(const DevP& P, double rho, double gam, double H, double vel_sum, double qv) {
+    const double c = (H - 5.e-1 * vel_sum - qv / rho) / gam;
+    if (P.mixerr && c < 0.0) return 100.0 * MFC5_SGM_EPS;
+    return sqrt(c);
+}
+
+// -------------------------------------------------------------------------------------------------
+// One Riemann problem on a face normal to DIR.
+// qL = right-boundary value of the left cell, qR = left-boundary value of the right cell.
+// HLLC: src/simulation/m_riemann_solver_hllc.fpp:878-1332 (5-eq pure-fluid emission)
+// HLL : src/simulation/m_riemann_solver_hll.fpp:128-576
+// averages: src/simulation/include/inline_riemann.fpp:1-30
+// F[0..N) fluxes; Fs[0] face-normal velocity (u-interface modes) or Fs[0..NF) interface alphas (HLL method 1)
+// -------------------------------------------------------------------------------------------------
+template <int NF, int ND, int DIR, int RS>
+__device__ __forceinline__ void riemann_face(const DevP& P, double* qL, double* qR, double* F, double* Fs) {
+    constexpr int IM = NF, IE = NF + ND, IA = NF + ND + 1;
+    const int rs = (RS < 0) ? P.rs : RS;
+    double vel_L_rms = 0.0, vel_R_rms = 0.0;
+#pragma unroll
+    for (int a = 0; a < ND; a++) {
+        vel_L_rms = vel_L_rms + qL[IM + a] * qL[IM + a];
+        vel_R_rms = vel_R_rms + qR[IM + a] * qR[IM + a];
+    }
+    const double pres_L = qL[IE], pres_R = qR[IE];
+    double arho_L[NF], arho_R[NF], alf_L[NF], alf_R[NF];
+    if (rs == 2) {
+        if (P.mpp) {  // in-place limiter on the face states, hllc.fpp:938-958
+            double sL = 0.0, sR = 0.0;
+#pragma unroll
+            for (int f = 0; f < NF; f++) {
+                qL[f] = fmax(0.0, qL[f]);
+                qL[IA + f] = fmin(fmax(0.0, qL[IA + f]), 1.0);
+                qR[f] = fmax(0.0, qR[f]);
+                qR[IA + f] = fmin(fmax(0.0, qR[IA + f]), 1.0);
+                sL = sL + qL[IA + f];
+                sR = sR + qR[IA + f];
+            }
+#pragma unroll
+            for (int f = 0; f < NF; f++) {
+                qL[IA + f] = qL[IA + f] / fmax(sL, MFC5_SGM_EPS);
+                qR[IA + f] = qR[IA + f] / fmax(sR, MFC5_SGM_EPS);
+            }
+        }
+#pragma unroll
+        for (int f = 0; f < NF; f++) {
+            arho_L[f] = qL[f]; arho_R[f] = qR[f];
+            alf_L[f] = qL[IA + f]; alf_R[f] = qR[IA + f];
+        }
+    } else {
+#pragma unroll
+        for (int f = 0; f < NF; f++) {
+            arho_L[f] = qL[f]; arho_R[f] = qR[f];
+            alf_L[f] = qL[IA + f]; alf_R[f] = qR[IA + f];
+        }
+        if (P.mpp) {  // HLL limits local copies only, hll.fpp:187-200
+            double sL = 0.0, sR = 0.0;
+#pragma unroll
+            for (int f = 0; f < NF; f++) {
+                arho_L[f] = fmax(0.0, arho_L[f]);
+                alf_L[f] = fmin(fmax(0.0, alf_L[f]), 1.0);
+                sL = sL + alf_L[f];
+                arho_R[f] = fmax(0.0, arho_R[f]);
+                alf_R[f] = fmin(fmax(0.0, alf_R[f]), 1.0);
+                sR = sR + alf_R[f];
+            }
+#pragma unroll
+            for (int f = 0; f < NF; f++) {
+                alf_L[f] = alf_L[f] / fmax(sL, MFC5_SGM_EPS);
+                alf_R[f] = alf_R[f] / fmax(sR, MFC5_SGM_EPS);
+            }
+        }
+    }
+    // s_accumulate_mixture_properties, m_riemann_state.fpp:1036-1058
+    double rho_L = 0, gamma_L = 0, pi_inf_L = 0, qv_L = 0, rho_R = 0, gamma_R = 0, pi_inf_R = 0, qv_R = 0;
+#pragma unroll
+    for (int f = 0; f < NF; f++) {
+        rho_L = rho_L + arho_L[f];
+        gamma_L = gamma_L + alf_L[f] * P.gam[f];
+        pi_inf_L = pi_inf_L + alf_L[f] * P.pinf[f];
+        qv_L = qv_L + arho_L[f] * P.qv[f];
+    }
+#pragma unroll
+    for (int f = 0; f < NF; f++) {
+        rho_R = rho_R + arho_R[f];
+        gamma_R = gamma_R + alf_R[f] * P.gam[f];
+        pi_inf_R = pi_inf_R + alf_R[f] * P.pinf[f];
+        qv_R = qv_R + arho_R[f] * P.qv[f];
+    }
+    const double E_L = gamma_L * pres_L + pi_inf_L + 5.e-1 * rho_L * vel_L_rms + qv_L;
+    const double E_R = gamma_R * pres_R + pi_inf_R + 5.e-1 * rho_R * vel_R_rms + qv_R;
+    const double H_L = (E_L + pres_L) / rho_L;
+    const double H_R = (E_R + pres_R) / rho_R;
+    const double c_L = sound_speed(P, rho_L, gamma_L, H_L, vel_L_rms, qv_L);
+    const double c_R = sound_speed(P, rho_R, gamma_R, H_R, vel_R_rms, qv_R);
+    const double uL = qL[IM + DIR], uR = qR[IM + DIR];
+    double s_L, s_R, s_S;
+    if (P.ws == 1) {
+        s_L = fmin(uL - c_L, uR - c_R);
+        s_R = fmax(uR + c_R, uL + c_L);
+        s_S = (pres_R - pres_L + rho_L * uL * (s_L - uL) - rho_R * uR * (s_R - uR)) / (rho_L * (s_L - uL) - rho_R * (s_R - uR));
+    } else {
+        double rho_avg, vel_avg_rms, H_avg, gamma_avg, qv_avg;
+        if (P.avg == 1) {  // Roe
+            const double sl = sqrt(rho_L), sr = sqrt(rho_R);
+            rho_avg = sqrt(rho_L * rho_R);
+            H_avg = (sl * H_L + sr * H_R) / (sl + sr);
+            gamma_avg = (sl * gamma_L + sr * gamma_R) / (sl + sr);
+            vel_avg_rms = sq(sl * qL[IM] + sr * qR[IM]) / sq(sl + sr);  // component 1 only, inline_riemann.fpp:28
+            qv_avg = (sl * qv_L + sr * qv_R) / (sl + sr);
+        } else {
+            rho_avg = 5.e-1 * (rho_L + rho_R);
+            vel_avg_rms = 0.0;
+#pragma unroll
+            for (int a = 0; a < ND; a++) vel_avg_rms = vel_avg_rms + sq(5.e-1 * (qL[IM + a] + qR[IM + a]));
+            H_avg = 5.e-1 * (H_L + H_R);
+            gamma_avg = 5.e-1 * (gamma_L + gamma_R);
+            qv_avg = 5.e-1 * (qv_L + qv_R);
+        }
+        const double c_avg = sound_speed(P, rho_avg, gamma_avg, H_avg, vel_avg_rms, qv_avg);
+        const double pres_SL = 5.e-1 * (pres_L + pres_R + rho_avg * c_avg * (uL - uR));
+        const double pres_SR = pres_SL;
+        const double Ms_L = fmax(1.0, sqrt(1.0 + ((5.e-1 + gamma_L) / (1.0 + gamma_L)) * (pres_SL / pres_L - 1.0) * pres_L /
+                                                     ((pres_L + pi_inf_L / (1.0 + gamma_L)))));
+        const double Ms_R = fmax(1.0, sqrt(1.0 + ((5.e-1 + gamma_R) / (1.0 + gamma_R)) * (pres_SR / pres_R - 1.0) * pres_R /
+                                                     ((pres_R + pi_inf_R / (1.0 + gamma_R)))));
+        s_L = uL - c_L * Ms_L;
+        s_R = uR + c_R * Ms_R;
+        s_S = 5.e-1 * ((uL + uR) + (pres_L - pres_R) / (rho_avg * c_avg));
+    }
+    const double s_M = fmin(0.0, s_L), s_P = fmax(0.0, s_R);
+    if (rs == 2) {
+        const double xi_L = (s_L - uL) / fmin(s_L - s_S, -MFC5_SGM_EPS);
+        const double xi_R = (s_R - uR) / fmax(s_R - s_S, MFC5_SGM_EPS);
+        const double xi_L_m1 = (s_S - uL) / fmin(s_L - s_S, -MFC5_SGM_EPS);
+        const double xi_R_m1 = (s_S - uR) / fmax(s_R - s_S, MFC5_SGM_EPS);
+        const double xi_M = (5.e-1 + fsign(5.e-1, s_S));
+        const double xi_P = (5.e-1 - fsign(5.e-1, s_S));
+#pragma unroll
+        for (int f = 0; f < NF; f++) F[f] = xi_M * qL[f] * (uL + s_M * xi_L_m1) + xi_P * qR[f] * (uR + s_P * xi_R_m1);
+#pragma unroll
+        for (int a = 0; a < ND; a++) {
+            if (a == DIR)
+                F[IM + a] = xi_M * (rho_L * (uL * qL[IM + a] + s_M * (s_L)*xi_L_m1) + (pres_L)) +
+                            xi_P * (rho_R * (uR * qR[IM + a] + s_P * (s_R)*xi_R_m1) + (pres_R));
+            else
+                F[IM + a] = xi_M * (rho_L * (uL * qL[IM + a] + s_M * (qL[IM + a]) * xi_L_m1)) +
+                            xi_P * (rho_R * (uR * qR[IM + a] + s_P * (qR[IM + a]) * xi_R_m1));
+        }
+        F[IE] = xi_M * (uL * (E_L + pres_L) + s_M * (E_L * xi_L_m1 + xi_L * (s_S - uL) * (rho_L * s_S + pres_L / (s_L - uL)))) +
+                xi_P * (uR * (E_R + pres_R) + s_P * (E_R * xi_R_m1 + xi_R * (s_S - uR) * (rho_R * s_S + pres_R / (s_R - uR))));
+#pragma unroll
+        for (int f = 0; f < NF; f++)
+            F[IA + f] = xi_M * qL[IA + f] * (uL + s_M * xi_L_m1) + xi_P * qR[IA + f] * (uR + s_P * xi_R_m1);
+        Fs[0] = xi_M * (uL + s_M * xi_L_m1) + xi_P * (uR + s_P * xi_R_m1);
+    } else {
+#pragma unroll
+        for (int f = 0; f < NF; f++)
+            F[f] = (s_M * arho_R[f] * uR - s_P * arho_L[f] * uL + s_M * s_P * (arho_L[f] - arho_R[f])) / (s_M - s_P);
+#pragma unroll
+        for (int a = 0; a < ND; a++) {
+            const double flg = (a == DIR) ? 1.0 : 0.0;
+            F[IM + a] = (s_M * (rho_R * uR * qR[IM + a] + flg * pres_R) - s_P * (rho_L * uL * qL[IM + a] + flg * pres_L) +
+                         s_M * s_P * (rho_L * qL[IM + a] - rho_R * qR[IM + a])) / (s_M - s_P);
+        }
+        F[IE] = (s_M * uR * (E_R + pres_R) - s_P * uL * (E_L + pres_L) + s_M * s_P * (E_L - E_R)) / (s_M - s_P);
+        if (!P.hll_u) {
+#pragma unroll
+            for (int f = 0; f < NF; f++) {
+                F[IA + f] = (qL[IA + f] - qR[IA + f]) * s_M * s_P / (s_M - s_P);
+                Fs[f] = (s_M * qR[IA + f] - s_P * qL[IA + f]) / (s_M - s_P);
+            }
+        } else {
+#pragma unroll
+            for (int f = 0; f < NF; f++) {
+                const double aL = qL[IA + f], aR = qR[IA + f];
+                if (0.0 <= s_L) F[IA + f] = aL * uL;
+                else if (s_R <= 0.0) F[IA + f] = aR * uR;
+                else F[IA + f] = (s_R * aL * uL - s_L * aR * uR + s_L * s_R * (aR - aL)) / (s_R - s_L);
+            }
+            if (0.0 <= s_L) Fs[0] = uL;
+            else if (s_R <= 0.0) Fs[0] = uR;
+            else Fs[0] = (s_R * uL - s_L * uR) / (s_R - s_L);
+        }
+    }
+}
+
+}  // namespace mfc5

@@ -1,0 +1,600 @@
+// mfc5_kernels.cuh -- the kernels of one RK stage (sm_100a, FP64):
+//   k_cons2prim   cons -> prim on the interior                         (reference K1+K2)
+//   k_bc_fill     ghost-cell fill of prims for one (direction, side)   (K3)
+//   k_cbc         characteristic-BC replacement fluxes of one boundary plane (K9)
+//   k_sweep_x     fused WENO + Riemann + flux difference + alpha source [+ RK] along x: one warp
+//                 owns 30 consecutive cells, neighbour exchange by warp shuffles       (K4..K8,K10,K11[,K12])
+//   k_sweep_yz    same along y / z: lanes along x (coalesced), each thread marches along the sweep
+//                 direction carrying the previous face flux and right-edge state in registers
+//   k_reduce      ICFL max / dt min / NaN count                         (K13)
+// Face states and face fluxes never touch HBM.
+#pragma once
+#include "mfc5_dev.cuh"
+
+namespace mfc5 {
+
+template <int NF, int ND>
+struct Shape {
+    static constexpr int N = 2 * NF + ND + 1;
+    static constexpr int IM = NF, IE = NF + ND, IA = NF + ND + 1;
+};
+
+// mixture rule: s_compute_species_fraction (m_variables_conversion.fpp:1140-1188) followed by
+// s_convert_species_to_mixture_variables_kernel (:198-270); `passes` = number of limiter passes.
+template <int NF>
+__device__ __forceinline__ void mixture(const DevP& P, double* arho, double* alf, int passes, double& rho, double& gam, double& pinf,
+                                        double& qv) {
+    if (P.mpp) {
+        for (int pass = 0; pass < passes; pass++) {
+            double sum = 0.0;
+#pragma unroll
+            for (int i = 0; i < NF; i++) {
+                arho[i] = fmax(0.0, arho[i]);
+                alf[i] = fmin(fmax(0.0, alf[i]), 1.0);
+                sum = sum + alf[i];
+            }
+#pragma unroll
+            for (int i = 0; i < NF; i++) alf[i] = alf[i] / fmax(sum, MFC5_SGM_EPS);
+        }
+    }
+    rho = 0; gam = 0; pinf = 0; qv = 0;
+#pragma unroll
+    for (int i = 0; i < NF; i++) {
+        rho = rho + arho[i];
+        gam = gam + alf[i] * P.gam[i];
+        pinf = pinf + alf[i] * P.pinf[i];
+        qv = qv + arho[i] * P.qv[i];
+    }
+}
+
+// -------------------------------------------------------------------------------------------------
+// cons -> prim, interior cells: s_convert_conservative_to_primitive_variables,
+// src/common/m_variables_conversion.fpp:459-717 (density floor on: m_start_up.fpp:823)
+// -------------------------------------------------------------------------------------------------
+template <int NF, int ND>
+__global__ void __launch_bounds__(256) k_cons2prim(const __grid_constant__ DevP P) {
+    using S = Shape<NF, ND>;
+    const int nx = P.s[0] + 1, ny = P.s[1] + 1, nz = P.s[2] + 1;
+    const long long tot = (long long)nx * ny * nz;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < tot; t += (long long)gridDim.x * blockDim.x) {
+        const int i = (int)(t % nx);
+        const long long r = t / nx;
+        const int j = (int)(r % ny), k = (int)(r / ny);
+        const long long c = P.base + i + j * P.sy + k * P.sz;
+        double q[S::N];
+#pragma unroll
+        for (int v = 0; v < S::N; v++) q[v] = P.q1[v * P.fs + c];
+        double arho[NF], alf[NF], rho, gam, pinf, qv;
+#pragma unroll
+        for (int f = 0; f < NF; f++) { arho[f] = q[f]; alf[f] = q[S::IA + f]; }
+        mixture<NF>(P, arho, alf, 2, rho, gam, pinf, qv);
+        rho = fmax(rho, MFC5_SGM_EPS);
+        double dyn = 0.0;
+#pragma unroll
+        for (int a = 0; a < ND; a++) {
+            const double u = q[S::IM + a] / rho;
+            dyn = dyn + 5.e-1 * q[S::IM + a] * u;
+            P.primw[(S::IM + a) * P.fs + c] = u;
+        }
+        P.primw[S::IE * P.fs + c] = (q[S::IE] - dyn - pinf - qv) / gam;
+#pragma unroll
+        for (int f = 0; f < NF; f++) {
+            P.primw[f * P.fs + c] = q[f];
+            P.primw[(S::IA + f) * P.fs + c] = q[S::IA + f];
+        }
+    }
+}
+
+// -------------------------------------------------------------------------------------------------
+// Ghost-cell fill for one (direction, side): s_populate_bc_direction m_boundary_common.fpp:120-187,
+// kernels of m_boundary_primitives.fpp (:27 extrapolation, :114 symmetry, :338 periodic, :552 slip,
+// :704 no-slip, :877 Dirichlet).  One thread per (transverse point, variable); loops the b layers.
+// -------------------------------------------------------------------------------------------------
+#ifdef MFC5_HOST_TU
+__global__ void __launch_bounds__(256) k_bc_fill(const __grid_constant__ DevP P, int d, int side) {
+    const int bc = P.bc[d][side];
+    int lo[3] = {0, 0, 0}, hi[3] = {P.s[0], P.s[1], P.s[2]};
+    for (int e = 0; e < d; e++) { lo[e] = -P.b; hi[e] = P.s[e] + P.b; }
+    const int t1 = d == 0 ? 1 : 0, t2 = d == 2 ? 1 : 2;
+    const int n1 = hi[t1] - lo[t1] + 1, n2 = hi[t2] - lo[t2] + 1;
+    const long long tot = (long long)n1 * n2 * P.N;
+    const long long strd[3] = {1, P.sy, P.sz};
+    const int s = P.s[d];
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < tot; t += (long long)gridDim.x * blockDim.x) {
+        const int a1 = (int)(t % n1) + lo[t1];
+        const long long r = t / n1;
+        const int a2 = (int)(r % n2) + lo[t2];
+        const int v = (int)(r / n2);
+        double* f = P.primw + v * P.fs + P.base + a1 * strd[t1] + a2 * strd[t2];
+        const int comp = v - P.nf;  // velocity component if in [0, nd)
+        const double wv_n = side == 0 ? P.vb[d][d] : P.ve[d][d];
+        for (int l = 1; l <= P.b; l++) {
+            const int g = side == 0 ? -l : s + l;
+            const int edge = side == 0 ? 0 : s;
+            const int mir = side == 0 ? l - 1 : s - (l - 1);
+            const int per = side == 0 ? s - (l - 1) : l - 1;
+            double val;
+            switch (bc) {
+            case MFC5_BC_PERIODIC: val = f[per * strd[d]]; break;
+            case MFC5_BC_REFLECTIVE: val = (comp == d) ? -f[mir * strd[d]] : f[mir * strd[d]]; break;
+            case MFC5_BC_SLIP_WALL: val = (comp == d) ? -f[mir * strd[d]] + 2.0 * wv_n : f[edge * strd[d]]; break;
+            case MFC5_BC_NO_SLIP_WALL:
+                if (comp >= 0 && comp < P.nd) val = -f[mir * strd[d]] + 2.0 * (side == 0 ? P.vb[d][comp] : P.ve[d][comp]);
+                else val = f[edge * strd[d]];
+                break;
+            case MFC5_BC_DIRICHLET:
+                if (P.dirich[d][side]) {
+                    const int m1 = P.s[t1] + 1, m2 = P.s[t2] + 1;
+                    if (a1 < 0 || a1 >= m1 || a2 < 0 || a2 >= m2) val = 0.0;
+                    else val = P.dirich[d][side][((long long)v * m2 + a2) * m1 + a1];
+                } else val = f[edge * strd[d]];
+                break;
+            default: val = f[edge * strd[d]]; break;
+            }
+            f[g * strd[d]] = val;
+        }
+    }
+}
+
+#endif  // MFC5_HOST_TU
+
+// -------------------------------------------------------------------------------------------------
+// Characteristic boundary conditions: s_cbc src/simulation/m_cbc.fpp:464-927 (+ s_initialize_cbc
+// :930-1182 sign conventions, s_finalize_cbc :1185-1345), cell-centre fluxes
+// m_variables_conversion.fpp:952-1135, wave amplitudes m_compute_cbc.fpp:136-365.
+// For WENO3/5 the rewritten faces depend on the primitive variables only, so this kernel runs BEFORE
+// the sweep of direction d and stores the replacement flux / flux_src of local faces -1..nface-1 in
+// cbcbuf; the sweep kernel substitutes them for its Riemann fluxes.  One thread per plane point.
+// -------------------------------------------------------------------------------------------------
+struct CbcCoef {
+    double fd[8];
+    double pi[2][3];
+    double ds0, Del;
+    double vel_in[3], vel_out[3], pres_in, pres_out, arho_in[MFC5_MAX_FLUIDS], alf_in[MFC5_MAX_FLUIDS];
+    int grcbc_in, grcbc_out, grcbc_vel_out;
+};
+
+template <int NF, int ND>
+__global__ void __launch_bounds__(128) k_cbc(const __grid_constant__ DevP P, const __grid_constant__ CbcCoef K, int d, int side) {
+    using S = Shape<NF, ND>;
+    constexpr int N = S::N;
+    const int t1 = d == 0 ? 1 : 0, t2 = d == 2 ? 1 : 2;
+    const int n1 = P.s[t1] + 1, n2 = P.s[t2] + 1;
+    const long long plane = (long long)n1 * n2;
+    const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (t >= plane) return;
+    const int a1 = (int)(t % n1), a2 = (int)(t / n1);
+    const long long strd[3] = {1, P.sy, P.sz};
+    const long long base = P.base + a1 * strd[t1] + a2 * strd[t2];
+    const long long sd = strd[d];
+    const int s = P.s[d], b = P.b, bc = P.bc[d][side];
+    const double sgn = side == 0 ? 1.0 : -1.0;
+    const bool hll1 = (P.rs == 1 && !P.hll_u);
+    const int nface = P.nface;
+    int didx[3];
+    didx[0] = d;
+    if (d == 0) { didx[1] = 1; didx[2] = 2; } else if (d == 1) { didx[1] = 0; didx[2] = 2; } else { didx[1] = 0; didx[2] = 1; }
+
+    double q[6][N], Fc[4][N], Fsc[4][NF];
+    for (int jl = 0; jl <= b; jl++) {
+        const long long c = base + sd * (side == 0 ? jl : s - jl);
+        for (int v = 0; v < N; v++) q[jl][v] = P.prim[v * P.fs + c];
+        q[jl][S::IM + d] = q[jl][S::IM + d] * sgn;
+    }
+    for (int jl = 0; jl <= 3 && jl <= b; jl++) {
+        double arho[NF], alf[NF], vel[3] = {0, 0, 0}, vsum = 0, rho, gam, pinf, qv;
+        for (int f = 0; f < NF; f++) { arho[f] = q[jl][f]; alf[f] = q[jl][S::IA + f]; }
+        for (int a = 0; a < ND; a++) vel[a] = q[jl][S::IM + a];
+        for (int a = 0; a < ND; a++) vsum = vsum + vel[a] * vel[a];
+        const double pres = q[jl][S::IE];
+        mixture<NF>(P, arho, alf, 1, rho, gam, pinf, qv);
+        const double E = gam * pres + pinf + 5.e-1 * rho * vsum + qv;
+        for (int f = 0; f < NF; f++) Fc[jl][f] = arho[f] * vel[d];
+        for (int a = 0; a < ND; a++) Fc[jl][S::IM + a] = rho * vel[d] * vel[a] + pres * (a == d ? 1.0 : 0.0);
+        Fc[jl][S::IE] = vel[d] * (E + pres);
+        if (hll1) {
+            for (int f = 0; f < NF; f++) { Fc[jl][S::IA + f] = 0.0; Fsc[jl][f] = alf[f]; }
+        } else {
+            for (int f = 0; f < NF; f++) { Fc[jl][S::IA + f] = vel[d] * alf[f]; Fsc[jl][f] = vel[d]; }
+        }
+    }
+    double fl[3][N], fsl[3][NF];  // local faces -1, 0, 1 -> index +1
+    if (nface == 1) {
+        for (int v = 0; v < N; v++) fl[1][v] = Fc[0][v] + K.pi[0][0] * (Fc[1][v] - Fc[0][v]);
+        for (int f = 0; f < NF; f++) fsl[1][f] = Fsc[0][f] + (Fsc[1][f] - Fsc[0][f]) * K.pi[0][0];
+    } else {
+        for (int jl = 0; jl <= 1; jl++) {
+            for (int v = 0; v < N; v++)
+                fl[jl + 1][v] = Fc[jl][v] + K.pi[jl][0] * (Fc[3][v] - Fc[2][v]) + K.pi[jl][1] * (Fc[2][v] - Fc[1][v]) +
+                                K.pi[jl][2] * (Fc[1][v] - Fc[0][v]);
+            for (int f = 0; f < NF; f++)
+                fsl[jl + 1][f] = Fsc[jl][f] + (Fsc[3][f] - Fsc[2][f]) * K.pi[jl][0] + (Fsc[2][f] - Fsc[1][f]) * K.pi[jl][1] +
+                                 (Fsc[1][f] - Fsc[0][f]) * K.pi[jl][2];
+        }
+    }
+    double arho[NF], adv[NF], vel[3] = {0, 0, 0}, vel_K_sum = 0, rho, gam, pinf, qv;
+    for (int f = 0; f < NF; f++) arho[f] = q[0][f];
+    for (int a = 0; a < ND; a++) vel[a] = q[0][S::IM + a];
+    for (int a = 0; a < ND; a++) vel_K_sum = vel_K_sum + vel[a] * vel[a];
+    const double pres = q[0][S::IE];
+    for (int f = 0; f < NF; f++) adv[f] = q[0][S::IA + f];
+    mixture<NF>(P, arho, adv, 1, rho, gam, pinf, qv);
+    double mf[NF];
+    for (int f = 0; f < NF; f++) mf[f] = arho[f] / rho;
+    const double E = gam * pres + pinf + 5.e-1 * rho * vel_K_sum;
+    const double H = (E + pres) / rho;
+    const double c = sound_speed(P, rho, gam, H, vel_K_sum, qv);
+    double darho_ds[NF], dvel_ds[3] = {0, 0, 0}, dpres_ds = 0, dadv_ds[NF];
+    for (int f = 0; f < NF; f++) { darho_ds[f] = 0; dadv_ds[f] = 0; }
+    for (int jl = 0; jl <= b; jl++) {
+        for (int f = 0; f < NF; f++) darho_ds[f] = q[jl][f] * K.fd[jl] + darho_ds[f];
+        for (int a = 0; a < ND; a++) dvel_ds[a] = q[jl][S::IM + a] * K.fd[jl] + dvel_ds[a];
+        dpres_ds = q[jl][S::IE] * K.fd[jl] + dpres_ds;
+        for (int f = 0; f < NF; f++) dadv_ds[f] = q[jl][S::IA + f] * K.fd[jl] + dadv_ds[f];
+    }
+    const double lam1 = vel[d] - c, lam2 = vel[d], lam3 = vel[d] + c;
+    const double Ma = vel[d] / c;
+    double L[N];
+    for (int v = 0; v < N; v++) L[v] = 0.0;
+    constexpr int last = N - 1;
+    const double L1base = lam1 * (dpres_ds - rho * c * dvel_ds[d]);
+    auto fill = [&](double fac, double l2) {
+        for (int f = 0; f < NF; f++) L[1 + f] = fac * l2 * (c * c * darho_ds[f] - mf[f] * dpres_ds);
+        for (int ii = 1; ii < ND; ii++) L[S::IM + ii] = fac * l2 * dvel_ds[didx[ii]];
+        for (int f = 0; f < NF; f++) L[S::IE + f] = fac * l2 * dadv_ds[f];
+    };
+    switch (bc) {
+    case MFC5_BC_CHAR_SLIP_WALL: L[0] = L1base; L[last] = L[0]; break;
+    case MFC5_BC_CHAR_NR_SUB_BUFFER: {
+        double lf = (5.e-1 - 5.e-1 * fsign(1.0, lam1));
+        L[0] = lf * lam1 * (dpres_ds - rho * c * dvel_ds[d]);
+        lf = (5.e-1 - 5.e-1 * fsign(1.0, lam2));
+        fill(lf, lam2);
+        lf = (5.e-1 - 5.e-1 * fsign(1.0, lam3));
+        L[last] = lf * lam3 * (dpres_ds + rho * c * dvel_ds[d]);
+    } break;
+    case MFC5_BC_CHAR_NR_SUB_INFLOW:
+        L[0] = L1base;
+        if (K.grcbc_in) {
+            for (int f = 0; f < NF; f++)
+                L[1 + f] = pow(c, 3.0) * Ma * (arho[f] - K.arho_in[f]) / K.Del - c * Ma * (pres - K.pres_in) / K.Del;
+            if (ND > 1) {
+                L[S::IM + 1] = c * Ma * (vel[didx[1]] - K.vel_in[didx[1]]) / K.Del;
+                if (ND > 2) L[S::IM + 2] = c * Ma * (vel[didx[2]] - K.vel_in[didx[2]]) / K.Del;
+            }
+            for (int f = 0; f < NF; f++) L[S::IE + f] = c * Ma * (adv[f] - K.alf_in[f]) / K.Del;
+            L[last] = rho * sq(c) * (1.0 + Ma) * (vel[d] + K.vel_in[d] * (side == 0 ? -1.0 : 1.0)) / K.Del +
+                      c * (1.0 + Ma) * (pres - K.pres_in) / K.Del;
+        }
+        break;
+    case MFC5_BC_CHAR_NR_SUB_OUTFLOW:
+        L[0] = L1base; fill(1.0, lam2); L[last] = 0.0;
+        if (K.grcbc_out) {
+            L[last] = c * (1.0 - Ma) * (pres - K.pres_out) / K.Del;
+            if (K.grcbc_vel_out)
+                L[last] = L[last] + rho * sq(c) * (1.0 - Ma) * (vel[d] + K.vel_out[d] * (side == 0 ? -1.0 : 1.0)) / K.Del;
+        }
+        break;
+    case MFC5_BC_CHAR_FF_SUB_OUTFLOW: L[0] = L1base; fill(1.0, lam2); L[last] = L[0] + 2.0 * rho * c * lam2 * dvel_ds[d]; break;
+    case MFC5_BC_CHAR_CP_SUB_OUTFLOW: L[0] = L1base; fill(1.0, lam2); L[last] = -L[0]; break;
+    case MFC5_BC_CHAR_SUP_INFLOW: break;
+    case MFC5_BC_CHAR_SUP_OUTFLOW: L[0] = L1base; fill(1.0, lam2); L[last] = lam3 * (dpres_ds + rho * c * dvel_ds[d]); break;
+    }
+    const double dpres_dt = -5.e-1 * (L[last] + L[0]);
+    double darho_dt[NF], dvel_dt[3] = {0, 0, 0}, dadv_dt[NF];
+    for (int f = 0; f < NF; f++) darho_dt[f] = -(L[1 + f] - mf[f] * dpres_dt) / (c * c);
+    for (int ii = 0; ii < ND; ii++) {
+        const int a = didx[ii];
+        const double flg = (a == d) ? 1.0 : 0.0;
+        dvel_dt[a] = flg * (L[0] - L[last]) / (2.0 * rho * c) + (flg - 1.0) * L[S::IM + ii];
+    }
+    double vel_dv_dt_sum = 0.0;
+    for (int a = 0; a < ND; a++) vel_dv_dt_sum = vel_dv_dt_sum + vel[a] * dvel_dt[a];
+    for (int f = 0; f < NF; f++) dadv_dt[f] = -L[S::IE + f];
+    double drho_dt = 0, dgamma_dt = 0, dpi_inf_dt = 0, dqv_dt = 0;
+    for (int f = 0; f < NF; f++) {
+        drho_dt = drho_dt + darho_dt[f];
+        dgamma_dt = dgamma_dt + dadv_dt[f] * P.gam[f];
+        dpi_inf_dt = dpi_inf_dt + dadv_dt[f] * P.pinf[f];
+        dqv_dt = dqv_dt + darho_dt[f] * P.qv[f];
+    }
+    const double ds0 = K.ds0;
+    for (int f = 0; f < NF; f++) fl[0][f] = fl[1][f] + ds0 * darho_dt[f];
+    for (int a = 0; a < ND; a++) fl[0][S::IM + a] = fl[1][S::IM + a] + ds0 * (vel[a] * drho_dt + rho * dvel_dt[a]);
+    fl[0][S::IE] = fl[1][S::IE] + ds0 * (pres * dgamma_dt + gam * dpres_dt + dpi_inf_dt + dqv_dt + rho * vel_dv_dt_sum +
+                                         5.e-1 * drho_dt * vel_K_sum);
+    if (hll1) {
+        for (int f = 0; f < NF; f++) fl[0][S::IA + f] = 0.0;
+        for (int f = 0; f < NF; f++)
+            fsl[0][f] = 1.0 / fmax(fabs(vel[d]), MFC5_SGM_EPS) * fsign(1.0, vel[d]) *
+                        (fl[1][S::IA + f] + vel[d] * fsl[1][f] + ds0 * dadv_dt[f]);
+    } else {
+        for (int f = 0; f < NF; f++) fl[0][S::IA + f] = fl[1][S::IA + f] + ds0 * dadv_dt[f];
+        for (int f = 0; f < NF; f++) fsl[0][f] = fsl[1][f];
+    }
+    // store with the sign conventions of s_finalize_cbc; slot jl+1, comp-major, plane-minor
+    double* out = P.cbcbuf[d][side];
+    const int ncomp = P.ncbc_comp;
+    for (int jl = -1; jl <= nface - 1; jl++) {
+        for (int v = 0; v < N; v++) out[((long long)(jl + 1) * ncomp + v) * plane + t] = fl[jl + 1][v] * (v == S::IM + d ? 1.0 : sgn);
+        if (hll1) for (int f = 0; f < NF; f++) out[((long long)(jl + 1) * ncomp + N + f) * plane + t] = fsl[jl + 1][f];
+        else out[((long long)(jl + 1) * ncomp + N) * plane + t] = fsl[jl + 1][0] * sgn;
+    }
+}
+
+// -------------------------------------------------------------------------------------------------
+// shared tail of both sweep kernels: given the fluxes of the two faces of cell `c`, apply the flux
+// difference (m_rhs.fpp:1107-1120 / :1183-1196 / :1345-1358), the alpha source (:1440-1488) and,
+// when this is the last direction of a time-stepping stage, the fused TVD-RK update
+// (m_time_steppers.fpp:486-507).
+// -------------------------------------------------------------------------------------------------
+template <int NF, int ND, int DIR>
+__device__ __forceinline__ void finish_cell(const DevP& P, long long c, double inv_ds, const double* Fp, const double* Fsp, const double* Fc,
+                                            const double* Fsc) {
+    using S = Shape<NF, ND>;
+    const bool alpha_iface = (P.rs == 1 && !P.hll_u);
+    double r[S::N];
+#pragma unroll
+    for (int v = 0; v < S::N; v++) {
+        if (DIR == 0) r[v] = inv_ds * (Fp[v] - Fc[v]);
+        else r[v] = P.rhs[v * P.fs + c] + inv_ds * (Fp[v] - Fc[v]);
+    }
+    if (alpha_iface) {
+        const double coeff = __ldg(P.prim + (S::IM + DIR) * P.fs + c);
+#pragma unroll
+        for (int f = 0; f < NF; f++) r[S::IA + f] = r[S::IA + f] + inv_ds * coeff * (Fsp[f] - Fsc[f]);
+    } else {
+#pragma unroll
+        for (int f = 0; f < NF; f++) {
+            const double coeff = __ldg(P.prim + (S::IA + f) * P.fs + c);  // q_cons(adv) == q_prim(adv)
+            r[S::IA + f] = r[S::IA + f] + inv_ds * coeff * (Fsc[0] - Fsp[0]);
+        }
+    }
+    if (DIR == ND - 1 && P.do_rk) {
+#pragma unroll
+        for (int v = 0; v < S::N; v++) {
+            const double q1 = P.q1[v * P.fs + c];
+            const double q2 = P.q2[v * P.fs + c];
+            P.qout[v * P.fs + c] = (P.rk0 * q1 + P.rk1 * q2 + P.rk2 * P.dt * r[v]) / P.rk3;
+        }
+    } else {
+#pragma unroll
+        for (int v = 0; v < S::N; v++) P.rhs[v * P.fs + c] = r[v];
+    }
+}
+
+// replacement of a Riemann flux by the characteristic-BC flux on the faces the reference rewrites
+template <int NF, int ND, int DIR>
+__device__ __forceinline__ void cbc_override(const DevP& P, int face, long long plane_idx, long long plane, double* F, double* Fs) {
+    using S = Shape<NF, ND>;
+    const int s = P.s[DIR];
+    const bool hll1 = (P.rs == 1 && !P.hll_u);
+    int slot = -1, side = 0;
+    if (face > s) return;
+    if (P.cbc_on[DIR][0] && face <= P.nface - 1) { slot = face + 1; side = 0; }
+    if (P.cbc_on[DIR][1] && face >= s - P.nface) { slot = (s - 1 - face) + 1; side = 1; }  // local jl = s-1-face
+    if (slot < 0) return;
+    const double* buf = P.cbcbuf[DIR][side];
+    const int ncomp = P.ncbc_comp;
+#pragma unroll
+    for (int v = 0; v < S::N; v++) F[v] = buf[((long long)slot * ncomp + v) * plane + plane_idx];
+    if (hll1) {
+#pragma unroll
+        for (int f = 0; f < NF; f++) Fs[f] = buf[((long long)slot * ncomp + S::N + f) * plane + plane_idx];
+    } else Fs[0] = buf[((long long)slot * ncomp + S::N) * plane + plane_idx];
+}
+
+// -------------------------------------------------------------------------------------------------
+// x-sweep.  A warp owns cells [i0-1, i0+30] of one x-row: lane l reconstructs cell i0-1+l, receives
+// the left-edge state of cell +1 by __shfl_down, solves the Riemann problem of its right face,
+// receives the flux of its left face by __shfl_up; lanes 1..30 finish their cell.
+// -------------------------------------------------------------------------------------------------
+#define MFC5_XW 30  // cells finished per warp
+
+template <int NF, int ND, int WO, int WV, int RS>
+__global__ void __launch_bounds__(128) k_sweep_x(const __grid_constant__ DevP P) {
+    using S = Shape<NF, ND>;
+    constexpr int N = S::N;
+    const int lane = threadIdx.x & 31;
+    const long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+    const int nx = P.s[0] + 1;
+    const int segs = (nx + MFC5_XW - 1) / MFC5_XW;
+    const long long rows = (long long)(P.s[1] + 1) * (P.s[2] + 1);
+    if (warp >= rows * segs) return;  // warp-uniform
+    const int seg = (int)(warp % segs);
+    const long long row = warp / segs;
+    const int j = (int)(row % (P.s[1] + 1)), k = (int)(row / (P.s[1] + 1));
+    const int i0 = seg * MFC5_XW;
+    int i = i0 - 1 + lane;                    // my cell
+    const int ic = min(i, P.s[0] + 1);        // clamp loads (cells beyond m+1 are never used)
+    const long long rowbase = P.base + j * P.sy + k * P.sz;
+    const long long c = rowbase + ic;
+    const DirTables& T = P.T[0];
+    const int slot = ic + P.b;
+
+    double eL[N], eR[N];
+#pragma unroll
+    for (int v = 0; v < N; v++) {
+        const double* f = P.prim + v * P.fs + c;
+        const int wo = (WO < 0) ? P.wo : WO;
+        double f0 = 0, f1 = 0, f2 = __ldg(f), f3 = 0, f4 = 0;
+        if (wo >= 3) { f1 = __ldg(f - 1); f3 = __ldg(f + 1); }
+        if (wo >= 5) { f0 = __ldg(f - 2); f4 = __ldg(f + 2); }
+        weno_edges<WO, WV>(P, T, slot, f0, f1, f2, f3, f4, eL[v], eR[v]);
+    }
+    // right state of my right face = left edge of cell i+1
+    double qR[N];
+#pragma unroll
+    for (int v = 0; v < N; v++) qR[v] = __shfl_down_sync(0xffffffffu, eL[v], 1);
+    // BC -4 (Riemann extrapolation), m_riemann_state.fpp:149-206
+    if (P.bc[0][0] == MFC5_BC_RIEMANN_EXTRAP && i == -1) {
+#pragma unroll
+        for (int v = 0; v < N; v++) eR[v] = qR[v];
+    }
+    if (P.bc[0][1] == MFC5_BC_RIEMANN_EXTRAP && i == P.s[0]) {
+#pragma unroll
+        for (int v = 0; v < N; v++) qR[v] = eR[v];
+    }
+    double F[N], Fs[NF];
+#pragma unroll
+    for (int f = 0; f < NF; f++) Fs[f] = 0.0;
+    riemann_face<NF, ND, 0, RS>(P, eR, qR, F, Fs);
+    if (P.cbc_on[0][0] | P.cbc_on[0][1]) cbc_override<NF, ND, 0>(P, i, row, rows, F, Fs);
+    double Fp[N], Fsp[NF];
+#pragma unroll
+    for (int v = 0; v < N; v++) Fp[v] = __shfl_up_sync(0xffffffffu, F[v], 1);
+#pragma unroll
+    for (int f = 0; f < NF; f++) Fsp[f] = __shfl_up_sync(0xffffffffu, Fs[f], 1);
+    if (lane >= 1 && lane <= MFC5_XW && i <= P.s[0]) {
+        const double inv_ds = 1.0 / __ldg(T.ds + i + P.b);
+        finish_cell<NF, ND, 0>(P, rowbase + i, inv_ds, Fp, Fsp, F, Fs);
+    }
+}
+
+// -------------------------------------------------------------------------------------------------
+// y / z sweep.  Lanes run along x over the flattened transverse plane (coalesced loads/stores); each
+// thread marches a chunk of cells along DIR.  Iteration cc reconstructs cell cc, solves face cc-1
+// with the carried right-edge state of cell cc-1, finishes cell cc-1 with the carried flux of face
+// cc-2.  One WENO + one Riemann per cell plus a short prologue per chunk.
+// -------------------------------------------------------------------------------------------------
+template <int NF, int ND, int DIR, int WO, int WV, int RS>
+__global__ void __launch_bounds__(128) k_sweep_yz(const __grid_constant__ DevP P) {
+    using S = Shape<NF, ND>;
+    constexpr int N = S::N;
+    const int nx = P.s[0] + 1;
+    const int no = (DIR == 1) ? (P.s[2] + 1) : (P.s[1] + 1);  // the other transverse extent
+    const long long plane = (long long)nx * no;
+    const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (t >= plane) return;
+    const int i = (int)(t % nx), o = (int)(t / nx);
+    const long long sd = (DIR == 1) ? P.sy : P.sz;
+    const long long so = (DIR == 1) ? P.sz : P.sy;
+    const long long colbase = P.base + i + o * so;
+    const int s = P.s[DIR];
+    const int c0 = blockIdx.y * P.chunk;
+    const int c1 = min(c0 + P.chunk - 1, s);
+    const DirTables& T = P.T[DIR];
+    const int wo = (WO < 0) ? P.wo : WO;
+
+    double eRp[N];          // right-edge state of the previous cell
+    double Fp[N], Fsp[NF];  // flux of the previous face
+#pragma unroll
+    for (int v = 0; v < N; v++) { eRp[v] = 0.0; Fp[v] = 0.0; }
+#pragma unroll
+    for (int f = 0; f < NF; f++) Fsp[f] = 0.0;
+
+    for (int cc = c0 - 1; cc <= c1 + 1; cc++) {
+        const long long c = colbase + cc * sd;
+        double eL[N], eR[N];
+#pragma unroll
+        for (int v = 0; v < N; v++) {
+            const double* f = P.prim + v * P.fs + c;
+            double f0 = 0, f1 = 0, f2 = __ldg(f), f3 = 0, f4 = 0;
+            if (wo >= 3) { f1 = __ldg(f - sd); f3 = __ldg(f + sd); }
+            if (wo >= 5) { f0 = __ldg(f - 2 * sd); f4 = __ldg(f + 2 * sd); }
+            weno_edges<WO, WV>(P, T, cc + P.b, f0, f1, f2, f3, f4, eL[v], eR[v]);
+        }
+        if (cc >= c0) {
+            const int face = cc - 1;
+            double F[N], Fs[NF];
+#pragma unroll
+            for (int f = 0; f < NF; f++) Fs[f] = 0.0;
+            if (P.bc[DIR][0] == MFC5_BC_RIEMANN_EXTRAP && face == -1) {
+#pragma unroll
+                for (int v = 0; v < N; v++) eRp[v] = eL[v];
+            }
+            if (P.bc[DIR][1] == MFC5_BC_RIEMANN_EXTRAP && face == s) {
+#pragma unroll
+                for (int v = 0; v < N; v++) eL[v] = eRp[v];
+            }
+            riemann_face<NF, ND, DIR, RS>(P, eRp, eL, F, Fs);
+            if (P.cbc_on[DIR][0] | P.cbc_on[DIR][1]) cbc_override<NF, ND, DIR>(P, face, t, plane, F, Fs);
+            if (cc >= c0 + 1) {
+                const double inv_ds = 1.0 / __ldg(T.ds + (cc - 1) + P.b);
+                finish_cell<NF, ND, DIR>(P, c - sd, inv_ds, Fp, Fsp, F, Fs);
+            }
+#pragma unroll
+            for (int v = 0; v < N; v++) Fp[v] = F[v];
+#pragma unroll
+            for (int f = 0; f < NF; f++) Fsp[f] = Fs[f];
+        }
+#pragma unroll
+        for (int v = 0; v < N; v++) eRp[v] = eR[v];
+    }
+}
+
+// -------------------------------------------------------------------------------------------------
+// Reductions: ICFL max (m_data_output.fpp:159-224, m_sim_helpers.fpp:45-130), dt min
+// (m_sim_helpers.fpp:182-249) and NaN count.  Warp shuffle reduction + one atomic per warp.
+// out[0] = max icfl (as ordered-uint bits), out[1] = min dt_local bits, out[2] = nan count.
+// -------------------------------------------------------------------------------------------------
+template <int NF, int ND>
+__global__ void __launch_bounds__(256) k_reduce(const __grid_constant__ DevP P, double dt, unsigned long long* out) {
+    using S = Shape<NF, ND>;
+    const int nx = P.s[0] + 1, ny = P.s[1] + 1, nz = P.s[2] + 1;
+    const long long tot = (long long)nx * ny * nz;
+    double icfl_max = 0.0, dtl_min = 1.0e300;
+    unsigned long long nans = 0;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < tot; t += (long long)gridDim.x * blockDim.x) {
+        const int i = (int)(t % nx);
+        const long long r = t / nx;
+        const int j = (int)(r % ny), k = (int)(r / ny);
+        const long long c = P.base + i + j * P.sy + k * P.sz;
+        double arho[NF], alf[NF], rho, gam, pinf, qv, vel[3] = {0, 0, 0}, vs = 0;
+#pragma unroll
+        for (int f = 0; f < NF; f++) { arho[f] = P.prim[f * P.fs + c]; alf[f] = P.prim[(S::IA + f) * P.fs + c]; }
+        mixture<NF>(P, arho, alf, 2, rho, gam, pinf, qv);
+#pragma unroll
+        for (int a = 0; a < ND; a++) { vel[a] = P.prim[(S::IM + a) * P.fs + c]; vs = vs + vel[a] * vel[a]; }
+        const double pres = P.prim[S::IE * P.fs + c];
+        const double E = gam * pres + pinf + 5.e-1 * rho * vs + qv;
+        const double H = (E + pres) / rho;
+        const double cs = sound_speed(P, rho, gam, H, vs, qv);
+        double dtl = P.T[0].ds[i + P.b] / (fabs(vel[0]) + cs);
+        if (ND > 1) dtl = fmin(dtl, P.T[1].ds[j + P.b] / (fabs(vel[1]) + cs));
+        if (ND > 2) dtl = fmin(dtl, P.T[2].ds[k + P.b] / (fabs(vel[2]) + cs));
+        double icfl;
+        if (ND == 1) icfl = (dt / P.T[0].ds[i + P.b]) * (fabs(vel[0]) + cs);
+        else icfl = dt / dtl;
+        if (icfl != icfl) nans++;
+        icfl_max = fmax(icfl_max, icfl);
+        dtl_min = fmin(dtl_min, dtl);
+#pragma unroll
+        for (int v = 0; v < S::N; v++) { const double x = P.q1[v * P.fs + c]; if (x != x) nans++; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        icfl_max = fmax(icfl_max, __shfl_xor_sync(0xffffffffu, icfl_max, o));
+        dtl_min = fmin(dtl_min, __shfl_xor_sync(0xffffffffu, dtl_min, o));
+        nans += __shfl_xor_sync(0xffffffffu, nans, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        // positive doubles order like their bit patterns
+        atomicMax(out + 0, (unsigned long long)__double_as_longlong(icfl_max));
+        atomicMin(out + 1, (unsigned long long)__double_as_longlong(dtl_min));
+        if (nans) atomicAdd(out + 2, nans);
+    }
+}
+
+// packed halo faces for processor boundaries (replaces the pack/unpack loops of
+// s_mpi_sendrecv_variables_buffers, src/common/m_mpi_common.fpp:620-804,839-1065)
+#ifdef MFC5_HOST_TU
+__global__ void __launch_bounds__(256) k_halo_copy(const __grid_constant__ DevP P, int d, int first, double* buf, int pack) {
+    int lo[3] = {0, 0, 0}, hi[3] = {P.s[0], P.s[1], P.s[2]};
+    for (int e = 0; e < d; e++) { lo[e] = -P.b; hi[e] = P.s[e] + P.b; }
+    lo[d] = first; hi[d] = first + P.b - 1;
+    const int n0 = hi[0] - lo[0] + 1, n1 = hi[1] - lo[1] + 1, n2 = hi[2] - lo[2] + 1;
+    const long long per = (long long)n0 * n1 * n2, tot = per * P.N;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < tot; t += (long long)gridDim.x * blockDim.x) {
+        const int v = (int)(t / per);
+        long long r = t % per;
+        const int i = (int)(r % n0) + lo[0]; r /= n0;
+        const int j = (int)(r % n1) + lo[1];
+        const int k = (int)(r / n1) + lo[2];
+        double* f = P.primw + v * P.fs + P.base + i + j * P.sy + k * P.sz;
+        if (pack) buf[t] = *f; else *f = buf[t];
+    }
+}
+#endif  // MFC5_HOST_TU
+
+}  // namespace mfc5

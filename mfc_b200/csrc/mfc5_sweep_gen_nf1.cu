@@ -1,0 +1,5 @@
+// generic (run-time scheme) fused sweep kernels, num_fluids = 1
+#include "mfc5_host.cuh"
+namespace mfc5 {
+bool launch_sweep_generic_nf1(const DevP& P, int dir, cudaStream_t st) { return launch_sweep_generic<1>(P, dir, st); }
+}  // namespace mfc5
