@@ -1,0 +1,393 @@
+#!/usr/bin/env python
+"""bench.py -- grind time of the 5-equation RHS hot path on N B200s (driver contract).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path (libmfc5.so)
+    python bench.py --impl reference --gpus N ...            # the CPU arm: the reference algorithm
+                                                              # (oracle restatement, OpenMP, all host cores)
+
+Workload (``config.workload``): ``examples/3D_performance_test`` -- the case the reference's published
+figure of merit is quoted on (docs/documentation/expectedPerformance.md:92-118): 201^3 cells per GPU,
+two fluids (8 equations), stretched grid, WENO5-M + HLLC + mpp_lim, TVD-RK3, BC -2/-6, FP64.  A "step" is
+one s_tvd_rk call = 3 RK stages, each = cons->prim + ghost fill (+ halo exchange) + 3 fused sweeps + RK
+update.  N > 1: weak scaling, 201^3 cells per GPU, block decomposition as the reference, halo faces over NCCL.
+
+Metric: MFC's grind time, ns per grid point per equation per RHS evaluation,
+``t_stage * 1e9 / (sys_size * m_glb * n_glb * p_glb)`` (m_start_up.fpp:674-677), with t_stage = the average
+stage time over the K timed steps (the reference prints the minimum; that is reported as ``grind_min_stage``).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+PUBLISHED_H100 = 0.38  # ns/gp/eq/rhs, H100 SXM5, BASELINE.md section 2 (other hardware; nothing published for B200)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--case", default="3D_performance_test", choices=["3D_performance_test", "5eq_rk3_weno3_hllc", "3D_shockdroplet"])
+    ap.add_argument("--m", type=int, default=200, help="cells-1 per direction per GPU (3D_performance_test)")
+    ap.add_argument("--riemann", default="hllc", choices=["hllc", "hll"])
+    ap.add_argument("--gbpp", type=int, default=16, help="5eq_rk3_weno3_hllc: the reference's --gbpp")
+    ap.add_argument("--weno5z", action="store_true", help="3D_shockdroplet: the north star's WENO5-Z override")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--cpu-steps", type=int, default=2)
+    return ap.parse_args()
+
+
+def most_cubic(n):
+    return {1: (1, 1, 1), 2: (2, 1, 1), 4: (2, 2, 1), 8: (2, 2, 2)}.get(n) or (n, 1, 1)
+
+
+def build_case(args, nranks):
+    """Global case dictionary + processor grid."""
+    from mfc_b200 import cases, decomp
+    if args.case == "3D_performance_test":
+        case = cases.perf_test_3d(m=args.m, riemann=args.riemann)
+        name = f"examples/3D_performance_test {args.m + 1}^3 cells/GPU, WENO5-M, {args.riemann.upper()}, mpp_lim, RK3"
+    elif args.case == "5eq_rk3_weno3_hllc":
+        case = cases.bench_5eq_weno3_hllc(gbpp=args.gbpp, riemann=args.riemann)
+        name = f"benchmarks/5eq_rk3_weno3_{args.riemann} --gbpp {args.gbpp}: {case['m'] + 1}x{case['n'] + 1}x{case['p'] + 1} cells/GPU, WENO3-M"
+    else:
+        case = cases.shockdroplet_3d(**(dict(weno_order=5, mapped_weno="F", wenoz="T") if args.weno5z else {}))
+        name = "examples/3D_shockdroplet 201x101x101 " + ("WENO5-Z override" if args.weno5z else "WENO3-M as shipped") + ", HLLC"
+    dims = (1, 1, 1)
+    if nranks > 1:
+        if args.scaling == "weak":
+            dims = most_cubic(nranks)
+            for d, x in enumerate(("m", "n", "p")):
+                case[x] = (case[x] + 1) * dims[d] - 1
+            assert decomp.factorize(nranks, case["m"], case["n"], case["p"], case["weno_order"]) == dims, "processor grid differs from the reference's rule"
+        else:
+            dims = decomp.factorize(nranks, case["m"], case["n"], case["p"], case["weno_order"])
+    return case, dims, name
+
+
+def setup_rank(case, rank, nranks, dims):
+    """Local parameters, grid and initial condition of one rank."""
+    from mfc_b200 import decomp, pre_process
+    from mfc_b200.params import params_from_case
+    blk = decomp.Block(case, rank, nranks, dims)
+    lcase = blk.local_case(case)
+    lcase["parallel_io"] = "T"  # local grid = slice of the global grid
+    P = params_from_case(lcase)
+    cbs, ccs, gws = blk.grid(dict(case, parallel_io="T"), P.buff_size)
+    _, cons = pre_process.initial_condition(lcase, ccs, ds_min=pre_process.grid_minima(case))
+    return blk, lcase, P, cbs, gws, cons
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, pw, reasons = [], None, [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for t, line in self.rows:
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                mx = float(f[1])
+                if t0 - 0.05 <= t <= t1 + 0.05:
+                    sm.append(float(f[0]))
+                    pw.append(float(f[2]))
+                    for nm, v in zip(names, f[3:7]):
+                        if v.lower().startswith("active"):
+                            reasons.add(nm)
+            except ValueError:
+                continue
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "power_w_max": max(pw) if pw else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def cpu_arm(case, P, cbs, cons, nsteps, warm):
+    """Time the oracle (reference algorithm restated in C, OpenMP) on this box's host cores."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from oracle_lib import Oracle
+    o = Oracle(P, cbs, omp=True)
+    o.set_cons(cons)
+    dt = float(case["dt"])
+    for _ in range(warm):
+        o.step(dt)
+    ts = []
+    for _ in range(nsteps):
+        t = time.perf_counter()
+        o.step(dt)
+        ts.append(time.perf_counter() - t)
+    return ts, o.L.orc_num_threads(), o
+
+
+def grind(t_stage_s, P_glb_mnp, sys_size):
+    m, n, p = P_glb_mnp
+    return t_stage_s * 1e9 / (sys_size * float(m) * float(max(n, 1)) * float(max(p, 1)))
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    # the CPU arm runs the single-GPU workload (per-cell cost is size independent)
+    case, dims, name = build_case(args, 1)
+    full_m = case["m"]
+    sample = "one RK3 step of the full single-GPU workload per timed step"
+    blk, lcase, P, cbs, gws, cons = setup_rank(case, 0, 1, (1, 1, 1))
+    t = time.perf_counter()
+    ts, threads, o = cpu_arm(lcase, P, cbs, cons, 1, 0)
+    est = ts[0] * (args.steps + args.warmup)
+    if est > 240.0 and args.case == "3D_performance_test":
+        # bounded sample: a smaller cube of the same case (same scheme, same per-cell arithmetic)
+        del o
+        msmall = 99
+        sargs = argparse.Namespace(**vars(args))
+        sargs.m = msmall
+        case, dims, _ = build_case(sargs, 1)
+        blk, lcase, P, cbs, gws, cons = setup_rank(case, 0, 1, (1, 1, 1))
+        sample = f"one RK3 step of a {msmall + 1}^3 sub-sample of the workload per timed step (full size projected at {est:.0f} s)"
+    else:
+        del o
+    ts, threads, _ = cpu_arm(lcase, P, cbs, cons, args.steps, args.warmup)
+    t_step = float(np.mean(ts))
+    ns = P.time_stepper
+    g = grind(t_step / ns, (case["m"], case["n"], case["p"]), P.sys_size)
+    ncell = (case["m"] + 1) * (case["n"] + 1) * (case["p"] + 1)
+    out = {
+        "impl": "reference", "metric": "grind_time", "value": g, "unit": "ns/gp/eq/rhs", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": t_step * 1e3, "higher_is_better": False, "scaling": args.scaling, "vs_baseline": g / PUBLISHED_H100,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": name, "cells_timed": ncell, "sys_size": P.sys_size,
+                   "note": "reference algorithm as the CPU oracle restatement (gfortran/MPI/fypp absent: MFC itself cannot be built here)"},
+        "cells_steps_per_s": ncell / t_step,
+        "cpu_baseline": {"value": g, "unit": "ns/gp/eq/rhs", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": g, "unit": "ns/gp/eq/rhs", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(out), flush=True)
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (there is no CPU fallback for the native arm)")
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    if args.gpus > 1 and world == 1:
+        raise SystemExit("launch N > 1 with torch.distributed.run (one rank per GPU)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    from mfc_b200 import lib
+    from mfc_b200.lib import Mfc5
+
+    case, dims, name = build_case(args, world)
+    blk, lcase, P, cbs, gws, cons = setup_rank(case, rank, world, dims)
+    P.device = local_rank
+    g = Mfc5(P, cbs, ghost_widths=gws)
+    if world > 1:
+        uid = [lib.nccl_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        g.comm_init(uid[0], rank, world)
+    N, ns = g.N, P.time_stepper
+    dt = float(case["dt"])
+    ncell_loc = (P.m + 1) * (P.n + 1) * (P.p + 1)
+    ncell_glb = (case["m"] + 1) * (case["n"] + 1) * (case["p"] + 1)
+
+    # pinned host state (the caller's q_cons_vf arrays)
+    host = torch.empty(g.shape, dtype=torch.float64, pin_memory=True)
+    hq = host.numpy()
+    hq[...] = cons
+    g.set_cons(hq)
+    stream = torch.cuda.ExternalStream(g.compute_stream, device=torch.device("cuda", local_rank))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        g.sync()
+
+    # ---- device-resident throughput: W warm-up steps, K timed steps, CUDA events on the compute stream
+    g.steps(dt, args.warmup)
+    barrier()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    time.sleep(0.25 if rank == 0 else 0.0)
+    barrier()
+    l0 = g.kernel_launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.time()
+    e0.record(stream)
+    g.steps(dt, args.steps)
+    e1.record(stream)
+    barrier()
+    t1 = time.time()
+    launches = g.kernel_launches - l0
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop(t0, t1) if sampler else None
+    if world > 1:
+        tt = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms = float(tt.item())
+    ms_step = ms / args.steps
+    nan_count = g.reduce(2)
+
+    # ---- per-kernel-class device times (CUDA events inside the library), 3 profiled steps
+    prof = {}
+    nprof = 3
+    g.stage_time_min = 0.0
+    for _ in range(nprof):
+        g.step(dt)
+        for k, (kms, nl) in g.last_kernel_ms().items():
+            a = prof.setdefault(k, [0.0, 0])
+            a[0] += kms
+            a[1] += nl
+    stage_min_s = g.stage_time_min
+    if world > 1:
+        tt = torch.tensor([stage_min_s], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        stage_min_s = float(tt.item())
+
+    # ---- end to end through the C ABI with host buffers: upload q_cons, one s_tvd_rk, download q_cons
+    e2e = None
+    if not args.no_e2e:
+        ne = max(3, min(args.steps, 5))
+        for _ in range(2):
+            g.set_cons(hq); g.steps(dt, 1); g.L.mfc5_download_cons(g.h, g._field_ptrs(hq), 0)
+        barrier()
+        t = time.perf_counter()
+        for _ in range(ne):
+            g.set_cons(hq)
+            g.steps(dt, 1)
+            rc = g.L.mfc5_download_cons(g.h, g._field_ptrs(hq), 0)
+            assert rc == 0
+        barrier()
+        te = (time.perf_counter() - t) / ne
+        if world > 1:
+            tt = torch.tensor([te], device="cuda", dtype=torch.float64)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            te = float(tt.item())
+        nbytes = int(hq.nbytes)
+        e2e = {"value": grind(te / ns, (case["m"], case["n"], case["p"]), N), "unit": "ns/gp/eq/rhs", "h2d_bytes_per_step": nbytes,
+               "d2h_bytes_per_step": nbytes, "ms_per_step": te * 1e3, "timer": "host wall clock around upload + s_tvd_rk + download, synchronised both sides",
+               "note": "worst case: the whole conservative state crosses PCIe both ways every step; the reference (and this library) keep it resident between saves"}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (algorithmic bytes: SURVEY.md 8d / DESIGN.md)
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peaks = json.load(f)
+    except OSError:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "MEASURED_PEAKS.json hbm_gbs (measured)" if "hbm_gbs" in peaks else "B200_PROFILING.md fallback 6650 GB/s"
+    nd = P.num_dims
+    last = ["sweep_x", "sweep_y", "sweep_z"][nd - 1]
+    alg = {"cons2prim": 2 * N * 8, "sweep_x": 2 * N * 8, "sweep_y": 3 * N * 8, "sweep_z": 3 * N * 8}
+    alg[last] = (5 if nd > 1 else 4) * N * 8  # prim + rhs + q1 + q2 read, q written (1-D: no rhs read)
+    kern = {}
+    for k, (kms, nl) in prof.items():
+        if nl == 0:
+            continue
+        per = kms / nl
+        kern[k] = {"ms_per_launch": per, "launches_per_step": nl / nprof, "ms_per_step": kms / nprof}
+        if k in alg:
+            kern[k]["achieved_gbs"] = alg[k] * ncell_loc / (per * 1e-3) / 1e9
+    dom = max((k for k in kern if k in alg), key=lambda k: kern[k]["ms_per_step"])
+    roof = {"bound": "hbm", "kernel": dom, "achieved": kern[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s",
+            "frac": kern[dom]["achieved_gbs"] / peak, "traffic": None, "peak_source": peak_src,
+            "algorithmic_bytes_per_cell": alg[dom], "share_of_step": kern[dom]["ms_per_step"] / sum(v["ms_per_step"] for v in kern.values())}
+    stage_bytes = (12 if nd == 3 else 9 if nd == 2 else 6) * N * 8
+    t_stage = ms_step * 1e-3 / ns
+    roof_stage = {"achieved": stage_bytes * ncell_loc / t_stage / 1e9, "peak": peak, "unit": "GB/s",
+                  "frac": stage_bytes * ncell_loc / t_stage / 1e9 / peak, "algorithmic_bytes_per_cell_per_stage": stage_bytes}
+    prof_file = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(prof_file):
+        try:
+            with open(prof_file) as f:
+                roof["traffic"] = json.load(f).get(dom)
+        except (OSError, ValueError):
+            pass
+
+    value = grind(t_stage, (case["m"], case["n"], case["p"]), N)
+    out = {
+        "metric": "grind_time", "value": value, "unit": "ns/gp/eq/rhs", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_step, "higher_is_better": False, "scaling": args.scaling, "vs_baseline": value / PUBLISHED_H100,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": name, "cells_per_gpu": ncell_loc, "cells_global": ncell_glb, "sys_size": N, "proc_grid": list(dims),
+                   "l2": "inputs larger than L2 (state 4 x %.0f MB per GPU)" % (N * ncell_loc * 8 / 1e6),
+                   "vs_baseline_ref": "0.38 ns/gp/eq/rhs published for H100 SXM5 (BASELINE.md); nothing published for B200",
+                   "parallelism": "block domain decomposition %dx%dx%d, NCCL halo" % dims if world > 1 else "single GPU"},
+        "cells_steps_per_s": ncell_glb / (ms_step * 1e-3),
+        "grind_min_stage": grind(stage_min_s, (case["m"], case["n"], case["p"]), N),
+        "clocks": clocks, "gpu_launches": int(launches), "nan_count": nan_count,
+        "roofline": roof, "roofline_stage": roof_stage, "kernels": kern,
+    }
+    if e2e is not None:
+        out["e2e"] = e2e
+    # ---- CPU baseline on this box's host cores (bounded sample), N = 1 only
+    if world == 1 and not args.no_cpu_baseline:
+        g.close()
+        del g
+        bm = 200 if (args.case == "3D_performance_test" and ncell_loc > 12_000_000) else None
+        if bm is not None:
+            sargs = argparse.Namespace(**vars(args))
+            sargs.m = bm
+            bcase, _, _ = build_case(sargs, 1)
+            _, blcase, bP, bcbs, _, bcons = setup_rank(bcase, 0, 1, (1, 1, 1))
+            sample = f"{args.cpu_steps} RK3 steps (after 1 warm-up) of a {bm + 1}^3-cell cube of the same case"
+        else:
+            bcase, blcase, bP, bcbs, bcons = case, lcase, P, cbs, cons
+            sample = f"{args.cpu_steps} RK3 steps (after 1 warm-up) of the full workload"
+        ts, threads, _ = cpu_arm(blcase, bP, bcbs, bcons, args.cpu_steps, 1)
+        gcpu = grind(float(np.mean(ts)) / ns, (bcase["m"], bcase["n"], bcase["p"]), N)
+        out["cpu_baseline"] = {"value": gcpu, "unit": "ns/gp/eq/rhs", "cores": threads, "kind": "port", "sample": sample}
+    print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -91,9 +91,20 @@ int mfc5_comm_init(mfc5_handle* h, const char nccl_unique_id[128], int rank, int
 int mfc5_sys_size(const mfc5_handle* h);
 int mfc5_buff_size(const mfc5_handle* h);
 long long mfc5_kernel_launches(const mfc5_handle* h);   /* library kernels launched so far */
-/* device time (ms) of the sweep kernels (x,y,z) of the last mfc5_tvd_rk call, CUDA events on the
- * library's compute stream; dir in 0..2, returns < 0 if unavailable */
-double mfc5_last_sweep_ms(const mfc5_handle* h, int dir);
+/* device time (ms, CUDA events on the library's compute stream) and launch count of one kernel class,
+ * summed over the stages of the last mfc5_tvd_rk call; returns < 0 for a bad argument.  The classes
+ * are the analogue of the reference's NVTX ranges (m_rhs.fpp:594,640,644,912,1030,1041). */
+enum {
+    MFC5_K_CONS2PRIM = 0, /* RHS-CONVERT */
+    MFC5_K_BC_FILL = 1,   /* RHS-COMMUNICATION, physical boundaries */
+    MFC5_K_HALO = 2,      /* RHS-COMMUNICATION, pack + ncclSend/Recv + unpack */
+    MFC5_K_CBC = 3,       /* characteristic-BC planes */
+    MFC5_K_SWEEP_X = 4,   /* RHS-RECONSTRUCTION + RIEMANN-SOLVER + ADVECTION-SRC, fused, per direction */
+    MFC5_K_SWEEP_Y = 5,
+    MFC5_K_SWEEP_Z = 6,   /* the last direction of a stage also carries the RK update */
+    MFC5_NUM_KCLASS = 7
+};
+double mfc5_last_kernel_ms(const mfc5_handle* h, int kclass, long long* launches);
 void* mfc5_compute_stream(const mfc5_handle* h);        /* cudaStream_t */
 const char* mfc5_last_error(void);
 const char* mfc5_version(void);

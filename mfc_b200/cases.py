@@ -1,0 +1,165 @@
+"""The five BASELINE.json configurations as self-contained case dictionaries.
+
+The reference ships them as ``case.py`` scripts that print a JSON dictionary; ``/root/reference`` does
+not exist on the GPU box, so ``bench.py`` and the tests build the same dictionaries here (the keys are
+the reference's namelist names, consumed by ``params.params_from_case`` / ``pre_process``).  Each
+builder names the file it restates; ``tests/test_cases.py`` checks the three that have goldens
+against the parameter dictionaries the reference's own test generator expands
+(``tests/golden/cases.json``).
+"""
+import math
+
+
+def _fluids(case, fluids):
+    """fluids: [(gamma_phys, pi_inf_phys)] -> the reference's 1/(g-1), g*pi/(g-1) form."""
+    for k, (g, pinf) in enumerate(fluids, 1):
+        case[f"fluid_pp({k})%gamma"] = 1.0 / (g - 1.0)
+        case[f"fluid_pp({k})%pi_inf"] = g * pinf / (g - 1.0)
+    return case
+
+
+def _patch(case, i, geometry, alpha_rho, alpha, vel, pres, **geom):
+    pre = f"patch_icpp({i})%"
+    case[pre + "geometry"] = geometry
+    for k, v in geom.items():
+        case[pre + k] = v
+    for a, u in enumerate(vel, 1):
+        case[pre + f"vel({a})"] = u
+    case[pre + "pres"] = pres
+    for k, (ar, al) in enumerate(zip(alpha_rho, alpha), 1):
+        case[pre + f"alpha_rho({k})"] = ar
+        case[pre + f"alpha({k})"] = al
+
+
+def _scheme(case, weno_order, mapped="T", wenoz="F", riemann="hllc", mpp="T", mixerr="T"):
+    case.update({
+        "model_eqns": "5eq", "alt_soundspeed": "F", "mpp_lim": mpp, "mixture_err": mixerr, "time_stepper": "rk3",
+        "weno_order": weno_order, "weno_eps": 1.0e-16, "mapped_weno": mapped, "wenoz": wenoz, "null_weights": "F",
+        "mp_weno": "F", "riemann_solver": riemann, "wave_speeds": "direct", "avg_state": "arithmetic",
+    })
+
+
+def sod_1d(m=399):
+    """C1: examples/1D_sodshocktube/case.py (1 fluid, WENO5-M, HLLC, RK3, BC -3, 1000 steps)."""
+    nt = 1000
+    case = {"run_time_info": "T", "x_domain%beg": 0.0, "x_domain%end": 1.0, "m": m, "n": 0, "p": 0, "dt": 0.1 / (1.0 * nt),
+            "t_step_start": 0, "t_step_stop": nt, "t_step_save": int(math.ceil(nt / 10.0)), "num_patches": 2, "num_fluids": 1,
+            "bc_x%beg": -3, "bc_x%end": -3}
+    _scheme(case, 5, mpp="F", mixerr="F")
+    _patch(case, 1, 1, [1.0], [1.0], [0.0], 1.0, x_centroid=0.25, length_x=0.5)
+    _patch(case, 2, 1, [0.125], [1.0], [0.0], 0.1, x_centroid=0.75, length_x=0.5)
+    return _fluids(case, [(1.4, 0.0)])
+
+
+def shockbubble_2d(ny=100):
+    """C2: examples/2D_shockbubble/case.py (air/helium, WENO5-M, HLLC, mpp_lim, BC -6 on all sides)."""
+    ps, vel, leng = 248758.567, 230.0, 1.0
+    nx = ny * 3
+    c_l = math.sqrt(1.4 * ps / 1.0)
+    dt = 0.1 * (leng / float(nx)) / c_l
+    case = {"run_time_info": "T", "x_domain%beg": -leng / 2.0, "x_domain%end": leng / 2 + 2 * leng,
+            "y_domain%beg": -leng / 2.0, "y_domain%end": leng / 2.0, "m": int(nx), "n": int(ny), "p": 0, "dt": dt,
+            "t_step_start": 0, "t_step_stop": 1000, "t_step_save": 10, "num_patches": 3, "num_fluids": 2}
+    for x in "xy":
+        case[f"bc_{x}%beg"] = case[f"bc_{x}%end"] = -6
+    _scheme(case, 5)
+    _patch(case, 1, 3, [1.29, 0.0], [1.0, 0.0], [vel, 0.0], 101325.0, x_centroid=0.0, y_centroid=0.0, length_x=10 * leng,
+           length_y=leng)
+    _patch(case, 2, 3, [2.4, 0.0], [1.0, 0.0], [vel, 0.0], ps, x_centroid=-3 * leng / 8.0, y_centroid=0.0,
+           length_x=leng / 4.0, length_y=leng, **{"alter_patch(1)": "T"})
+    _patch(case, 3, 2, [0.0, 0.167], [0.0, 1.0], [0.0, 0.0], 101325.0, x_centroid=0.0, y_centroid=0.0, radius=leng / 5.0,
+           **{"alter_patch(1)": "T"})
+    return _fluids(case, [(1.4, 0.0), (1.6666, 0.0)])
+
+
+def _shock_droplet(nx, ny, nz, cfl):
+    """Mach-2.4 air shock about to hit a 1 mm water droplet: the set-up shared by
+    examples/3D_shockdroplet/case.py:4-160 and benchmarks/5eq_rk3_weno3_hllc/case.py:29-168."""
+    patm, d0 = 101325, 1.0e-3
+    isd = 5.0 / 8 * d0
+    p0a, rho0a, gama, pia = patm, 1.204, 1.40, 0
+    c_a = math.sqrt(gama * (p0a + pia) / rho0a)
+    p0w, rho0w, gamw, piw = p0a - (-0.0 * 4 / d0), 1000, 6.12, 3.43e08
+    mach = 2.4
+    ps_ratio = (mach ** 2 - 1) * 2 * gama / (gama + 1) + 1
+    rho_ratio = (1 + (gama + 1) / (gama - 1) * ps_ratio) / ((gama + 1) / (gama - 1) + ps_ratio)
+    ms = math.sqrt((gama + 1.0) / (2.0 * gama) * (ps_ratio - 1.0) * (p0a / (p0a + pia)) + 1.0)
+    ss = ms * c_a
+    ps, rhos = ps_ratio * p0a, rho_ratio * rho0a
+    vel = c_a / gama * (ps_ratio - 1.0) * p0a / (p0a + pia) / ms
+    xb, xe, yb, ye, zb, ze = -8.4707 * d0, 9.6226 * d0, 0 * d0, 10 * d0, 0 * d0, 10 * d0
+    stf = 4.0
+    dx = (xe - xb) / nx
+    case = {"x_domain%beg": xb, "x_domain%end": xe, "y_domain%beg": yb, "y_domain%end": ye, "z_domain%beg": zb,
+            "z_domain%end": ze, "m": nx, "n": ny, "p": nz, "dt": None, "t_step_start": 0, "num_patches": 3, "num_fluids": 2,
+            "bc_x%beg": -6, "bc_x%end": -6, "bc_y%beg": -2, "bc_y%end": -3, "bc_z%beg": -2, "bc_z%end": -3}
+    box = dict(y_centroid=(yb + ye) / 2 * stf, length_x=(xe - xb) * stf, length_y=(ye - yb) * stf, length_z=(ze - zb) * stf)
+    _patch(case, 1, 9, [0.0, rho0a], [0.0, 1.0], [0.0, 0.0, 0.0], p0a, x_centroid=(xb + xe) / 2 * stf,
+           z_centroid=(yb + ye) / 2 * stf, **box)
+    _patch(case, 2, 9, [0.0, rhos], [0.0, 1.0], [vel, 0.0, 0.0], ps, x_centroid=-isd - (xe - xb) / 2 * stf,
+           z_centroid=(zb + ze) / 2 * stf, **{"alter_patch(1)": "T"}, **box)
+    _patch(case, 3, 8, [rho0w, 0.0], [1.0, 0.0], [0.0, 0.0, 0.0], p0w, x_centroid=0.0, y_centroid=0.0, z_centroid=0.0,
+           radius=d0 / 2, **{"alter_patch(1)": "T"})
+    _fluids(case, [(gamw, piw), (gama, pia)])
+    return case, dict(dx=dx, ss=ss, cfl=cfl, d0=d0)
+
+
+def shockdroplet_3d(ny=100, weno_order=3, mapped_weno="T", wenoz="F", steps=None):
+    """C4: examples/3D_shockdroplet/case.py (200x100x100 stretched; WENO3-M as shipped; the north star's
+    WENO5-Z variant is ``weno_order=5, mapped_weno='F', wenoz='T'``)."""
+    nx, nz = ny * 2, ny
+    case, aux = _shock_droplet(nx, ny, nz, 0.05)
+    d0 = aux["d0"]
+    case["dt"] = aux["cfl"] * aux["dx"] / aux["ss"]
+    case.update({"run_time_info": "T", "t_step_stop": 50000 if steps is None else steps, "t_step_save": 100,
+                 "stretch_x": "T", "a_x": 20, "x_a": -1.2 * d0, "x_b": 1.2 * d0,
+                 "stretch_y": "T", "a_y": 20, "y_a": -0.0 * d0, "y_b": 1.2 * d0,
+                 "stretch_z": "T", "a_z": 20, "z_a": -0.0 * d0, "z_b": 1.2 * d0})
+    _scheme(case, weno_order, mapped=mapped_weno, wenoz=wenoz)
+    return case
+
+
+def bench_5eq_weno3_hllc(gbpp=16, ranks=1, s=None, steps=20, riemann="hllc"):
+    """C3: benchmarks/5eq_rk3_weno3_hllc/case.py (and ..._hll): 3-D ``2s x s x s``, WENO3-M, BC x -6, y/z -2/-3.
+    ``s = floor((5e5 * ranks * gbpp / 2)^(1/3))`` is the reference's memory rule (case.py:24-28); ``s``
+    overrides it.  Note the reference sets m, n, p = 2s, s, s (i.e. 2s+1 cells)."""
+    if s is None:
+        ncells = math.floor(8000000 / 16.0 * ranks * gbpp)
+        s = math.floor((ncells / 2.0) ** (1 / 3))
+    case, aux = _shock_droplet(2 * s, s, s, 0.1)
+    case["dt"] = aux["dx"] * aux["cfl"] / aux["ss"]
+    case.update({"run_time_info": "F", "t_step_stop": steps, "t_step_save": steps})
+    _scheme(case, 3, riemann=riemann)
+    return case
+
+
+def perf_test_3d(m=200, riemann="hllc", steps=30):
+    """C5: examples/3D_performance_test/case.py -- the reference's figure-of-merit case
+    (docs/documentation/expectedPerformance.md:92-97): (m+1)^3 cells, stretched grid, 90/10 water/air
+    with a smoothed air bubble, WENO5-M, HLLC (``riemann='hll'`` for the HLL variant), BC -2 / -6."""
+    case = {"run_time_info": "F", "m": m, "n": m, "p": m, "dt": 0.2e-09 / 1.0e-03, "t_step_start": 0, "t_step_stop": steps,
+            "t_step_save": steps, "num_patches": 2, "num_fluids": 2}
+    for x in "xyz":
+        case.update({f"{x}_domain%beg": 0.0, f"{x}_domain%end": 4.0e-03 / 1.0e-03, f"stretch_{x}": "T", f"a_{x}": 4.0,
+                     f"{x}_a": -1.5e-03 / 1.0e-03, f"{x}_b": 1.5e-03 / 1.0e-03, f"bc_{x}%beg": -2, f"bc_{x}%end": -6})
+    _scheme(case, 5, riemann=riemann)
+    c = 80.0e-03 / 1.0e-03
+    ln = 160.0e-03 / 1.0e-03
+    _patch(case, 1, 9, [1000.0, 0.1], [0.9, 0.1], [0.0, 0.0, 0.0], 1.0e05, x_centroid=c, y_centroid=c, z_centroid=c,
+           length_x=ln, length_y=ln, length_z=ln)
+    _patch(case, 2, 8, [100.0, 0.9], [0.1, 0.9], [0.0, 0.0, 0.0], 1.0e03, x_centroid=0.0, y_centroid=0.0, z_centroid=0.0,
+           radius=1.0e-03 / 1.0e-03, smoothen="T", smooth_patch_id=1, smooth_coeff=0.5, **{"alter_patch(1)": "T"})
+    case["fluid_pp(1)%gamma"] = 1.0 / (4.4 - 1.0)
+    case["fluid_pp(1)%pi_inf"] = 4.4 * 6.0e08 / (4.4 - 1.0)
+    case["fluid_pp(2)%gamma"] = 1.0 / (1.4 - 1.0)
+    case["fluid_pp(2)%pi_inf"] = 0.0
+    return case
+
+
+CONFIGS = {
+    "1D_sodshocktube": sod_1d,
+    "2D_shockbubble": shockbubble_2d,
+    "5eq_rk3_weno3_hllc": bench_5eq_weno3_hllc,
+    "3D_shockdroplet": shockdroplet_3d,
+    "3D_performance_test": perf_test_3d,
+}

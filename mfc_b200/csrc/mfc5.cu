@@ -93,10 +93,15 @@ struct mfc5_handle {
     double* d_dirich[3][2] = {};
     long long plane[3];
     cudaStream_t st = nullptr, st_comm = nullptr;
-    cudaEvent_t ev_stage[4] = {}, ev_sw[3][2] = {}, ev_comm = nullptr, ev_comp = nullptr;
+    cudaEvent_t ev_stage[4] = {}, ev_comm = nullptr, ev_comp = nullptr;
+    // per-kernel-class device timing of the last mfc5_tvd_rk call (events on the compute stream)
+    std::vector<cudaEvent_t> ev_pool;
+    std::vector<int> seg_cls;  // class of segment i = events (2i, 2i+1)
+    double cls_ms[MFC5_NUM_KCLASS] = {};
+    long long cls_launches[MFC5_NUM_KCLASS] = {};
+    bool timing = false;
     unsigned long long* d_red = nullptr;
     long long launches = 0;
-    float sweep_ms[3] = {-1, -1, -1};
     DevP D;
     // multi-GPU
     ncclComm_t comm = nullptr;
@@ -115,7 +120,11 @@ extern "C" const char* mfc5_version(void) { return "mfc5-b200 0.1 (sm_100a, fp64
 extern "C" int mfc5_sys_size(const mfc5_handle* h) { return h->N; }
 extern "C" int mfc5_buff_size(const mfc5_handle* h) { return h->b; }
 extern "C" long long mfc5_kernel_launches(const mfc5_handle* h) { return h->launches; }
-extern "C" double mfc5_last_sweep_ms(const mfc5_handle* h, int dir) { return (dir >= 0 && dir < 3) ? h->sweep_ms[dir] : -1.0; }
+extern "C" double mfc5_last_kernel_ms(const mfc5_handle* h, int kclass, long long* launches) {
+    if (!h || kclass < 0 || kclass >= MFC5_NUM_KCLASS) return -1.0;
+    if (launches) *launches = h->cls_launches[kclass];
+    return h->cls_ms[kclass];
+}
 extern "C" void* mfc5_compute_stream(const mfc5_handle* h) { return (void*)h->st; }
 
 extern "C" int mfc5_create(const mfc5_params* p, mfc5_handle** out) {
@@ -166,7 +175,6 @@ extern "C" int mfc5_create(const mfc5_params* p, mfc5_handle** out) {
     CK(cudaStreamCreateWithPriority(&h->st, cudaStreamNonBlocking, lo));
     CK(cudaStreamCreateWithPriority(&h->st_comm, cudaStreamNonBlocking, hi));
     for (auto& ev : h->ev_stage) CK(cudaEventCreate(&ev));
-    for (int d = 0; d < 3; d++) for (int k = 0; k < 2; k++) CK(cudaEventCreate(&h->ev_sw[d][k]));
     CK(cudaEventCreateWithFlags(&h->ev_comm, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&h->ev_comp, cudaEventDisableTiming));
     *out = h;
@@ -182,9 +190,9 @@ extern "C" int mfc5_destroy(mfc5_handle* h) {
     for (int d = 0; d < 3; d++) {
         for (int k = 0; k < 6; k++) cudaFree(h->d_tab[d][k]);
         for (int k = 0; k < 2; k++) { cudaFree(h->d_cbcbuf[d][k]); cudaFree(h->d_dirich[d][k]); cudaFree(h->d_send[d][k]); cudaFree(h->d_recv[d][k]); }
-        for (int k = 0; k < 2; k++) cudaEventDestroy(h->ev_sw[d][k]);
     }
     for (auto& ev : h->ev_stage) cudaEventDestroy(ev);
+    for (auto& ev : h->ev_pool) cudaEventDestroy(ev);
     cudaEventDestroy(h->ev_comm); cudaEventDestroy(h->ev_comp);
     if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
     cudaStreamDestroy(h->st); cudaStreamDestroy(h->st_comm);
@@ -455,8 +463,11 @@ static int copy_fields(mfc5_handle* h, double* dev, const double* const* hostc, 
         p.extent = make_cudaExtent(wx * sizeof(double), wy, wz);
         if (to_dev) { p.srcPtr = hptr; p.srcPos = hpos; p.dstPtr = dptr; p.dstPos = dpos; p.kind = cudaMemcpyHostToDevice; }
         else { p.srcPtr = dptr; p.srcPos = dpos; p.dstPtr = hptr; p.dstPos = hpos; p.kind = cudaMemcpyDeviceToHost; }
-        CK(cudaMemcpy3D(&p));
+        CK(cudaMemcpy3DAsync(&p, h->st));
     }
+    // stream-ordered on the compute stream (truly asynchronous for pinned host arrays); the call
+    // returns when the data has arrived, like the reference's GPU_UPDATE
+    CK(cudaStreamSynchronize(h->st));
     return 0;
 }
 
@@ -496,6 +507,28 @@ static int by_shape(const mfc5_handle* h, F&& f) {
 
 static unsigned grid_for(long long n, int block) { return (unsigned)std::min<long long>((n + block - 1) / block, 148LL * 16); }
 
+// timing segments: when h->timing, every kernel class is bracketed by a pair of events
+static int seg_begin(mfc5_handle* h, int cls) {
+    if (!h->timing) return 0;
+    const size_t i = h->seg_cls.size();
+    while (h->ev_pool.size() < 2 * (i + 1)) {
+        cudaEvent_t e;
+        CK(cudaEventCreate(&e));
+        h->ev_pool.push_back(e);
+    }
+    h->seg_cls.push_back(cls);
+    CK(cudaEventRecord(h->ev_pool[2 * i], h->st));
+    return 0;
+}
+static int seg_end(mfc5_handle* h, int nlaunch) {
+    h->launches += nlaunch;
+    if (!h->timing) return 0;
+    const size_t i = h->seg_cls.size() - 1;
+    h->cls_launches[h->seg_cls[i]] += nlaunch;
+    CK(cudaEventRecord(h->ev_pool[2 * i + 1], h->st));
+    return 0;
+}
+
 static int halo_count(const mfc5_handle* h, int d) {
     long long n = (long long)h->N * h->b;
     for (int e = 0; e < 3; e++) {
@@ -514,15 +547,20 @@ static int fill_direction(mfc5_handle* h, const DevP& D, int d) {
     if (t2 < d && t2 < h->nd) n2 += 2 * h->b;
     const long long tot = n1 * n2 * h->N;
     bool any_nb = false;
+    int nl = 0;
+    if (seg_begin(h, MFC5_K_BC_FILL)) return -1;
     for (int sd = 0; sd < 2; sd++) {
         if (h->P.bc[d][sd] < 0) {
             k_bc_fill<<<grid_for(tot, 256), 256, 0, h->st>>>(D, d, sd);
-            h->launches++;
+            nl++;
         } else any_nb = true;
     }
+    if (seg_end(h, nl)) return -1;
     if (any_nb) {
         if (!h->comm) return fail("processor boundary (bc >= 0) but mfc5_comm_init was not called");
         const int cnt = halo_count(h, d);
+        nl = 0;
+        if (seg_begin(h, MFC5_K_HALO)) return -1;
         for (int sd = 0; sd < 2; sd++) {
             if (h->P.bc[d][sd] < 0) continue;
             if (!h->d_send[d][sd]) {
@@ -530,7 +568,7 @@ static int fill_direction(mfc5_handle* h, const DevP& D, int d) {
                 CK(cudaMalloc(&h->d_recv[d][sd], (size_t)cnt * sizeof(double)));
             }
             k_halo_copy<<<grid_for(cnt, 256), 256, 0, h->st>>>(D, d, sd == 0 ? 0 : h->s[d] - h->b + 1, h->d_send[d][sd], 1);
-            h->launches++;
+            nl++;
         }
         NK(g_nccl.GroupStart());
         // sends low face then high face; receives in the opposite order so that the pairing is also
@@ -543,46 +581,51 @@ static int fill_direction(mfc5_handle* h, const DevP& D, int d) {
         for (int sd = 0; sd < 2; sd++) {
             if (h->P.bc[d][sd] < 0) continue;
             k_halo_copy<<<grid_for(cnt, 256), 256, 0, h->st>>>(D, d, sd == 0 ? -h->b : h->s[d] + 1, h->d_recv[d][sd], 0);
-            h->launches++;
+            nl++;
         }
+        if (seg_end(h, nl)) return -1;
     }
     return 0;
 }
 
 static int launch_sweep(mfc5_handle* h, const DevP& D, int dir) {
     bool ok = false;
+    if (seg_begin(h, MFC5_K_SWEEP_X + dir)) return -1;
     if (!getenv("MFC5_NO_OPT")) ok = launch_sweep_opt(D, dir, h->st);
     if (!ok) ok = launch_sweep_generic_nf1(D, dir, h->st) || launch_sweep_generic_nf2(D, dir, h->st) || launch_sweep_generic_nf3(D, dir, h->st);
     if (!ok) return fail("no sweep kernel for this configuration");
-    h->launches++;
-    return 0;
+    return seg_end(h, 1);
 }
 
 // one RHS evaluation (+ fused RK update when do_rk): q1 = state read, q2 = stage-1 copy, qout = target
-static int run_stage(mfc5_handle* h, const double* q1, const double* q2, double* qout, int do_rk, const double rk[4], double dt, bool timed) {
+static int run_stage(mfc5_handle* h, const double* q1, const double* q2, double* qout, int do_rk, const double rk[4], double dt) {
     DevP D = h->D;
     D.prim = h->d_prim; D.primw = h->d_prim; D.q1 = q1; D.q2 = q2; D.qout = qout; D.rhs = h->d_rhs;
     D.rk0 = rk[0]; D.rk1 = rk[1]; D.rk2 = rk[2]; D.rk3 = rk[3]; D.dt = dt; D.do_rk = do_rk;
     const long long ncell = (long long)(h->s[0] + 1) * (h->s[1] + 1) * (h->s[2] + 1);
+    if (seg_begin(h, MFC5_K_CONS2PRIM)) return -1;
     int rc = by_shape(h, [&](auto nf, auto nd) {
         k_cons2prim<decltype(nf)::value, decltype(nd)::value><<<grid_for(ncell, 256), 256, 0, h->st>>>(D);
     });
     if (rc) return rc;
-    h->launches++;
+    if (seg_end(h, 1)) return -1;
     for (int d = 0; d < h->nd; d++)
         if (fill_direction(h, D, d)) return -1;
     for (int d = 0; d < h->nd; d++) {
-        for (int sd = 0; sd < 2; sd++) {
-            if (!D.cbc_on[d][sd]) continue;
-            const CbcCoef K = h->cbc[d][sd];
-            by_shape(h, [&](auto nf, auto nd) {
-                k_cbc<decltype(nf)::value, decltype(nd)::value><<<(unsigned)((h->plane[d] + 127) / 128), 128, 0, h->st>>>(D, K, d, sd);
-            });
-            h->launches++;
+        if (D.cbc_on[d][0] || D.cbc_on[d][1]) {
+            int nl = 0;
+            if (seg_begin(h, MFC5_K_CBC)) return -1;
+            for (int sd = 0; sd < 2; sd++) {
+                if (!D.cbc_on[d][sd]) continue;
+                const CbcCoef K = h->cbc[d][sd];
+                by_shape(h, [&](auto nf, auto nd) {
+                    k_cbc<decltype(nf)::value, decltype(nd)::value><<<(unsigned)((h->plane[d] + 127) / 128), 128, 0, h->st>>>(D, K, d, sd);
+                });
+                nl++;
+            }
+            if (seg_end(h, nl)) return -1;
         }
-        if (timed) CK(cudaEventRecord(h->ev_sw[d][0], h->st));
         if (launch_sweep(h, D, d)) return -1;
-        if (timed) CK(cudaEventRecord(h->ev_sw[d][1], h->st));
     }
     CK(cudaGetLastError());
     return 0;
@@ -598,13 +641,19 @@ static int enqueue_step(mfc5_handle* h, double dt, bool timed) {
     const int ns = h->P.time_stepper;
     double* A = h->d_q[h->cur];
     double* B = ns > 1 ? h->d_q[h->cur ^ 1] : A;
+    h->timing = timed;
+    if (timed) {
+        h->seg_cls.clear();
+        for (int k = 0; k < MFC5_NUM_KCLASS; k++) { h->cls_ms[k] = 0.0; h->cls_launches[k] = 0; }
+    }
     for (int st = 1; st <= ns; st++) {
         const double* rk = ns == 3 ? RK3[st - 1] : ns == 2 ? RK2[st - 1] : RK1[0];
         const double* q1 = st == 1 ? A : B;
         if (timed) CK(cudaEventRecord(h->ev_stage[st - 1], h->st));
-        if (run_stage(h, q1, A, B, 1, rk, dt, timed && st == ns)) return -1;
+        if (run_stage(h, q1, A, B, 1, rk, dt)) { h->timing = false; return -1; }
     }
     if (timed) CK(cudaEventRecord(h->ev_stage[ns], h->st));
+    h->timing = false;
     if (ns > 1) h->cur ^= 1;
     return 0;
 }
@@ -613,7 +662,7 @@ extern "C" int mfc5_compute_rhs(mfc5_handle* h) {
     if (!h || !h->setup) return fail("mfc5_compute_rhs: handle not set up");
     CK(cudaSetDevice(h->P.device));
     const double rk[4] = {1, 0, 1, 1};
-    if (run_stage(h, h->d_q[h->cur], h->d_q[h->cur], h->d_q[h->cur], 0, rk, 0.0, false)) return -1;
+    if (run_stage(h, h->d_q[h->cur], h->d_q[h->cur], h->d_q[h->cur], 0, rk, 0.0)) return -1;
     CK(cudaStreamSynchronize(h->st));
     return 0;
 }
@@ -632,7 +681,11 @@ extern "C" int mfc5_tvd_rk(mfc5_handle* h, double dt, double* stage_time_min) {
             *stage_time_min = (*stage_time_min <= 0.0) ? t : std::min(*stage_time_min, t);
         }
     }
-    for (int d = 0; d < h->nd; d++) CK(cudaEventElapsedTime(&h->sweep_ms[d], h->ev_sw[d][0], h->ev_sw[d][1]));
+    for (size_t i = 0; i < h->seg_cls.size(); i++) {
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, h->ev_pool[2 * i], h->ev_pool[2 * i + 1]));
+        h->cls_ms[h->seg_cls[i]] += ms;
+    }
     return 0;
 }
 

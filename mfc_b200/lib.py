@@ -50,8 +50,8 @@ def load(strict=False):
     L.mfc5_buff_size.argtypes = [vp]
     L.mfc5_kernel_launches.argtypes = [vp]
     L.mfc5_kernel_launches.restype = C.c_longlong
-    L.mfc5_last_sweep_ms.argtypes = [vp, C.c_int]
-    L.mfc5_last_sweep_ms.restype = C.c_double
+    L.mfc5_last_kernel_ms.argtypes = [vp, C.c_int, C.POINTER(C.c_longlong)]
+    L.mfc5_last_kernel_ms.restype = C.c_double
     L.mfc5_compute_stream.argtypes = [vp]
     L.mfc5_compute_stream.restype = vp
     L.mfc5_last_error.restype = C.c_char_p
@@ -64,8 +64,11 @@ EXPORTED_SYMBOLS = [
     "mfc5_create", "mfc5_destroy", "mfc5_set_grid", "mfc5_finalize_setup", "mfc5_set_dirichlet", "mfc5_upload_cons",
     "mfc5_download_cons", "mfc5_download_prim", "mfc5_download_rhs", "mfc5_compute_rhs", "mfc5_tvd_rk", "mfc5_tvd_rk_n",
     "mfc5_sync", "mfc5_reduce", "mfc5_nccl_unique_id", "mfc5_comm_init", "mfc5_sys_size", "mfc5_buff_size",
-    "mfc5_kernel_launches", "mfc5_last_sweep_ms", "mfc5_compute_stream", "mfc5_last_error", "mfc5_version",
+    "mfc5_kernel_launches", "mfc5_last_kernel_ms", "mfc5_compute_stream", "mfc5_last_error", "mfc5_version",
 ]
+
+
+KERNEL_CLASSES = ["cons2prim", "bc_fill", "halo", "cbc", "sweep_x", "sweep_y", "sweep_z"]
 
 
 def _ptr(a):
@@ -165,8 +168,18 @@ class Mfc5:
     def kernel_launches(self):
         return int(self.L.mfc5_kernel_launches(self.h))
 
-    def last_sweep_ms(self):
-        return [self.L.mfc5_last_sweep_ms(self.h, d) for d in range(self.P.num_dims)]
+    def last_kernel_ms(self):
+        """{kernel class: (device ms, launches)} of the last ``step`` (CUDA events, compute stream)."""
+        out = {}
+        for k, name in enumerate(KERNEL_CLASSES):
+            n = C.c_longlong()
+            ms = self.L.mfc5_last_kernel_ms(self.h, k, C.byref(n))
+            out[name] = (ms, n.value)
+        return out
+
+    @property
+    def compute_stream(self):
+        return self.L.mfc5_compute_stream(self.h)
 
     def comm_init(self, unique_id, rank, nranks):
         self._ck(self.L.mfc5_comm_init(self.h, unique_id, rank, nranks))

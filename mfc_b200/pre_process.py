@@ -85,12 +85,31 @@ def generate_grid(case, local=None):
     return cbs, ccs
 
 
+def grid_minima(case):
+    """(dx_min, dy_min, dz_min) of the global grid: m_grid.f90:41,67 (x), :87,114 (y), :122,148 (z)."""
+    out = []
+    for x, s in zip("xyz", (int(case["m"]), int(case.get("n", 0)), int(case.get("p", 0)))):
+        if x != "x" and s == 0:
+            out.append(np.inf)
+            continue
+        cb = generate_grid_1d(case, x, s)
+        if _logical(case.get(f"stretch_{x}", "F")):
+            out.append(float(np.min(cb[1:] - cb[:-1])))
+        else:
+            beg, end = _domain(case, x)
+            out.append((end - beg) / float(s + 1))
+    return out
+
+
 def _patch(case, i, key, default=None):
     return case.get(f"patch_icpp({i})%{key}", default)
 
 
-def initial_condition(case, ccs):
-    """Primitive then conservative variables, arrays [N][nz][ny][nx] -> returned as (N, nz, ny, nx)."""
+def initial_condition(case, ccs, ds_min=None):
+    """Primitive then conservative variables, arrays [N][nz][ny][nx] -> returned as (N, nz, ny, nx).
+
+    ``ds_min`` = (dx_min, dy_min, dz_min) of the GLOBAL grid (m_grid.f90:41,67-69), needed only by
+    smoothed patches; ``grid_minima`` computes it."""
     nf = int(case["num_fluids"])
     nx, ny, nz = len(ccs[0]), len(ccs[1]), len(ccs[2])
     nd = 1 + (ny > 1) + (nz > 1)
@@ -103,8 +122,9 @@ def initial_condition(case, ccs):
     Z = ccs[2][:, None, None]
     for ip in range(1, int(case["num_patches"]) + 1):
         geom = int(_patch(case, ip, "geometry"))
-        if _logical(_patch(case, ip, "smoothen", "F")):
-            raise NotImplementedError("patch smoothing")
+        smooth = _logical(_patch(case, ip, "smoothen", "F"))
+        if smooth and geom != 8:
+            raise NotImplementedError("patch smoothing is implemented for the sphere only")
         if _patch(case, ip, "hcid") is not None:
             raise NotImplementedError("hard-coded patches")
         xc = float(_patch(case, ip, "x_centroid", 0.0))
@@ -128,6 +148,11 @@ def initial_condition(case, ccs):
         elif geom == 8:
             r = float(_patch(case, ip, "radius"))
             inside = (X - xc) ** 2 + (Y - yc) ** 2 + (Z - zc) ** 2 <= r ** 2
+            if smooth:  # m_icpp_patches.fpp:978-982
+                coeff = float(_patch(case, ip, "smooth_coeff"))
+                if ds_min is None:
+                    ds_min = grid_minima(case)
+                eta = np.tanh(coeff / min(ds_min[:nd]) * (np.sqrt((X - xc) ** 2 + (Y - yc) ** 2 + (Z - zc) ** 2) - r)) * (-0.5) + 0.5
         else:
             raise NotImplementedError(f"patch geometry {geom}")
         inside = np.broadcast_to(inside, pid.shape)
@@ -140,6 +165,24 @@ def initial_condition(case, ccs):
         if ip > 1:
             pass
         mask = inside & allowed[pid]
+        if smooth:
+            # s_assign_patch_species_primitive_variables with eta < 1 (m_assign_variables.fpp:350-405):
+            # blend with the cell's previous content; the cell changes owner only where 1 - eta < 1e-16
+            mask = mask | (pid == int(_patch(case, ip, "smooth_patch_id")))
+            eta = np.broadcast_to(eta, pid.shape)[mask]
+
+            def blend(v, arr):
+                arr[mask] = eta * v + (1.0 - eta) * arr[mask]
+            for f in range(nf):
+                blend(float(_patch(case, ip, f"alpha_rho({f + 1})")), prim[f])
+                blend(float(_patch(case, ip, f"alpha({f + 1})")), prim[iE + 1 + f])
+            for a in range(nd):
+                blend(float(_patch(case, ip, f"vel({a + 1})", 0.0)), prim[nf + a])
+            blend(float(_patch(case, ip, "pres")), prim[iE])
+            own = np.zeros(pid.shape, dtype=bool)
+            own[mask] = (1.0 - eta) < 1e-16
+            pid[own] = ip
+            continue
         for f in range(nf):
             prim[f][mask] = float(_patch(case, ip, f"alpha_rho({f + 1})"))
             prim[iE + 1 + f][mask] = float(_patch(case, ip, f"alpha({f + 1})"))
