@@ -386,7 +386,11 @@ extern "C" int mfc5_finalize_setup(mfc5_handle* h) {
     D.nd = h->nd; D.nf = h->nf; D.N = h->N; D.b = h->b; D.pn = h->pn; D.ns = h->ns;
     D.wo = h->P.weno_order; D.wv = h->P.mapped_weno ? 1 : (h->P.wenoz ? 2 : 0); D.rs = h->P.riemann_solver;
     D.hll_u = h->P.hll_u_interface; D.avg = h->P.avg_state; D.ws = h->P.wave_speeds; D.mpp = h->P.mpp_lim;
-    D.mixerr = h->P.mixture_err; D.fast = h->P.fast_math;
+    D.mixerr = h->P.mixture_err;
+    // division-light arithmetic only where its assumptions hold: direct wave speeds, no weight nulling,
+    // weno_eps large enough that products of four smoothness indicators cannot underflow
+    D.fast = h->P.fast_math && h->P.wave_speeds == 1 && !h->P.null_weights && h->P.weno_eps >= 1e-40;
+    if (getenv("MFC5_NO_FAST")) D.fast = 0;
     D.sy = h->px; D.sz = h->px * h->ey; D.fs = h->fs;
     D.base = h->ox + h->oy * D.sy + h->oz * D.sz;
     D.eps = h->P.weno_eps;
@@ -601,7 +605,7 @@ static int launch_sweep(mfc5_handle* h, const DevP& D, int dir) {
 static int run_stage(mfc5_handle* h, const double* q1, const double* q2, double* qout, int do_rk, const double rk[4], double dt) {
     DevP D = h->D;
     D.prim = h->d_prim; D.primw = h->d_prim; D.q1 = q1; D.q2 = q2; D.qout = qout; D.rhs = h->d_rhs;
-    D.rk0 = rk[0]; D.rk1 = rk[1]; D.rk2 = rk[2]; D.rk3 = rk[3]; D.dt = dt; D.do_rk = do_rk;
+    D.rk0 = rk[0]; D.rk1 = rk[1]; D.rk2 = rk[2]; D.rk3 = rk[3]; D.irk3 = 1.0 / rk[3]; D.dt = dt; D.do_rk = do_rk;
     const long long ncell = (long long)(h->s[0] + 1) * (h->s[1] + 1) * (h->s[2] + 1);
     if (seg_begin(h, MFC5_K_CONS2PRIM)) return -1;
     int rc = by_shape(h, [&](auto nf, auto nd) {

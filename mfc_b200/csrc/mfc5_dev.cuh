@@ -50,7 +50,7 @@ struct DevP {
     const double* q2;   // stage-1 copy (q_cons_ts(2))
     double* qout;       // where the fused RK update writes
     double* rhs;
-    double rk0, rk1, rk2, rk3, dt;
+    double rk0, rk1, rk2, rk3, irk3, dt;
     int do_rk;
     int chunk;          // marching chunk length of the y/z sweeps
 };
@@ -59,17 +59,152 @@ __device__ __forceinline__ double sq(double x) { return x * x; }
 __device__ __forceinline__ double fsign(double a, double b) { return copysign(fabs(a), b); }
 
 // -------------------------------------------------------------------------------------------------
+// Division-light formulations (product build).  Same algebra as the reference, different rounding:
+// the nonlinear weights are only ever used normalised, omega_q = a_q / sum(a), so every a_q may be
+// multiplied by a common positive factor.  Multiplying by the product of the denominators removes
+// all per-stencil divisions; one reciprocal per side remains (two with the WENO-M map, whose argument
+// must be a normalised weight).  The reference does 24 divisions per variable per cell for WENO5-M.
+// -------------------------------------------------------------------------------------------------
+// 1/x to double precision without the IEEE slow path: MUFU.RCP64H seed + two Newton steps.
+// Valid for normal, finite x (sums of weights, densities, wave-speed differences).
+__device__ __forceinline__ double rcp_nr(double x) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    double e = fma(-x, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-x, r, 1.0);
+    r = fma(r, e, r);
+    return r;
+}
+
+// WENO-M map of a normalised weight w with ideal weight d (m_weno.fpp:1150-1156), as numerator and
+// denominator:  g(w) = w (d + d^2 - 3 d w + w^2) / (d^2 + w (1 - 2 d))
+__device__ __forceinline__ void map_nd(double d, double w, double& num, double& den) {
+    num = w * fma(w, fma(-3.0, d, w), fma(d, d, d));
+    den = fma(w, fma(-2.0, d, 1.0), d * d);
+}
+
+template <int WV>
+__device__ __forceinline__ void weno5_fast(const DevP& P, const DirTables& T, int slot, const double f0, const double f1,
+                                           const double f2, const double f3, const double f4, double& eL, double& eR) {
+    const double eps = P.eps;
+    const double* cl = T.cL + slot * 6;
+    const double* cr = T.cR + slot * 6;
+    const double* dl = T.dL + slot * 3;
+    const double* dr = T.dR + slot * 3;
+    const double* bt = T.bt + slot * 9;
+    const double d1 = f4 - f3, d0 = f3 - f2, dm1 = f2 - f1, dm2 = f1 - f0;
+    double b0, b1, b2;
+    if (T.uniform) {
+        b0 = 13.0 / 12.0 * sq(d1 - d0) + 0.25 * sq(d1 - 3.0 * d0) + eps;
+        b1 = 13.0 / 12.0 * sq(d0 - dm1) + 0.25 * sq(d0 + dm1) + eps;
+        b2 = 13.0 / 12.0 * sq(dm1 - dm2) + 0.25 * sq(3.0 * dm1 - dm2) + eps;
+    } else {
+        b0 = __ldg(bt + 0) * d1 * d1 + __ldg(bt + 1) * d1 * d0 + __ldg(bt + 2) * d0 * d0 + eps;
+        b1 = __ldg(bt + 3) * d0 * d0 + __ldg(bt + 4) * d0 * dm1 + __ldg(bt + 5) * dm1 * dm1 + eps;
+        b2 = __ldg(bt + 6) * dm1 * dm1 + __ldg(bt + 7) * dm1 * dm2 + __ldg(bt + 8) * dm2 * dm2 + eps;
+    }
+    // common-denominator factors shared by both sides
+    double g0, g1, g2;
+    if (WV == 2) {  // Z: a_q = d_q (1 + tau/b_q)  ~  d_q (b_q + tau) b_r b_s
+        const double tau = fabs(b2 - b0);
+        g0 = (b0 + tau) * (b1 * b2);
+        g1 = (b1 + tau) * (b0 * b2);
+        g2 = (b2 + tau) * (b0 * b1);
+    } else {        // JS (and first stage of M): a_q = d_q / b_q^2  ~  d_q (b_r b_s)^2
+        const double p12 = b1 * b2, p02 = b0 * b2, p01 = b0 * b1;
+        g0 = p12 * p12; g1 = p02 * p02; g2 = p01 * p01;
+    }
+#pragma unroll
+    for (int side = 0; side < 2; side++) {
+        const double* dd = side == 0 ? dl : dr;
+        const double* cc = side == 0 ? cl : cr;
+        const double dd0 = __ldg(dd + 0), dd1 = __ldg(dd + 1), dd2 = __ldg(dd + 2);
+        const double p0 = f2 + __ldg(cc + 0) * d1 + __ldg(cc + 1) * d0;
+        const double p1 = f2 + __ldg(cc + 2) * d0 + __ldg(cc + 3) * dm1;
+        const double p2 = f2 + __ldg(cc + 4) * dm1 + __ldg(cc + 5) * dm2;
+        double a0 = dd0 * g0, a1 = dd1 * g1, a2 = dd2 * g2;
+        if (WV == 1) {
+            const double r = rcp_nr(a0 + a1 + a2);
+            double n0, n1, n2, e0, e1, e2;
+            map_nd(dd0, a0 * r, n0, e0);
+            map_nd(dd1, a1 * r, n1, e1);
+            map_nd(dd2, a2 * r, n2, e2);
+            a0 = n0 * (e1 * e2);
+            a1 = n1 * (e0 * e2);
+            a2 = n2 * (e0 * e1);
+        }
+        const double val = (a0 * p0 + a1 * p1 + a2 * p2) * rcp_nr(a0 + a1 + a2);
+        if (side == 0) eL = val; else eR = val;
+    }
+}
+
+template <int WV>
+__device__ __forceinline__ void weno3_fast(const DevP& P, const DirTables& T, int slot, const double f1, const double f2,
+                                           const double f3, double& eL, double& eR) {
+    const double eps = P.eps;
+    const double* cl = T.cL + slot * 2;
+    const double* cr = T.cR + slot * 2;
+    const double* dl = T.dL + slot * 2;
+    const double* dr = T.dR + slot * 2;
+    const double* bt = T.bt + slot * 6;
+    const double d0 = f3 - f2, dm1 = f2 - f1;
+    const double b0 = __ldg(bt + 0) * d0 * d0 + eps;
+    const double b1 = __ldg(bt + 3) * dm1 * dm1 + eps;
+    double g0, g1;
+    if (WV == 2) {
+        const double tau = fabs(b1 - b0);
+        g0 = (b0 + tau) * b1;
+        g1 = (b1 + tau) * b0;
+    } else {
+        g0 = b1 * b1;
+        g1 = b0 * b0;
+    }
+#pragma unroll
+    for (int side = 0; side < 2; side++) {
+        const double* dd = side == 0 ? dl : dr;
+        const double* cc = side == 0 ? cl : cr;
+        const double dd0 = __ldg(dd + 0), dd1 = __ldg(dd + 1);
+        const double p0 = f2 + __ldg(cc + 0) * d0;
+        const double p1 = f2 + __ldg(cc + 1) * dm1;
+        double a0 = dd0 * g0, a1 = dd1 * g1;
+        if (WV == 1) {
+            const double r = rcp_nr(a0 + a1);
+            double n0, n1, e0, e1;
+            map_nd(dd0, a0 * r, n0, e0);
+            map_nd(dd1, a1 * r, n1, e1);
+            a0 = n0 * e1;
+            a1 = n1 * e0;
+        }
+        const double val = (a0 * p0 + a1 * p1) * rcp_nr(a0 + a1);
+        if (side == 0) eL = val; else eR = val;
+    }
+}
+
+// -------------------------------------------------------------------------------------------------
 // WENO reconstruction of one variable in one cell: left- and right-boundary values.
 // reference: s_weno, src/simulation/m_weno.fpp:1007-1085 (WENO3), :1098-1239 (WENO5), :952-993 (1).
 // f[0..4] = v(j-2..j+2).  WO / WV < 0: read from P (generic kernels).
 // -------------------------------------------------------------------------------------------------
-template <int WO, int WV>
+template <int WO, int WV, int FAST>
 __device__ __forceinline__ void weno_edges(const DevP& P, const DirTables& T, int slot, const double f0, const double f1,
                                            const double f2, const double f3, const double f4, double& eL, double& eR) {
     const int wo = (WO < 0) ? P.wo : WO;
     const int wv = (WV < 0) ? P.wv : WV;
     const double eps = P.eps;
     if (wo == 1) { eL = f2; eR = f2; return; }
+    if (FAST) {
+        if (wo == 3) {
+            if (wv == 1) weno3_fast<1>(P, T, slot, f1, f2, f3, eL, eR);
+            else if (wv == 2) weno3_fast<2>(P, T, slot, f1, f2, f3, eL, eR);
+            else weno3_fast<0>(P, T, slot, f1, f2, f3, eL, eR);
+        } else {
+            if (wv == 1) weno5_fast<1>(P, T, slot, f0, f1, f2, f3, f4, eL, eR);
+            else if (wv == 2) weno5_fast<2>(P, T, slot, f0, f1, f2, f3, f4, eL, eR);
+            else weno5_fast<0>(P, T, slot, f0, f1, f2, f3, f4, eL, eR);
+        }
+        return;
+    }
     if (wo == 3) {
         const double* cl = T.cL + slot * 2;
         const double* cr = T.cR + slot * 2;
@@ -172,6 +307,128 @@ __device__ __forceinline__ double sound_speed(const DevP& P, double rho, double 
     const double c = (H - 5.e-1 * vel_sum - qv / rho) / gam;
     if (P.mixerr && c < 0.0) return 100.0 * MFC5_SGM_EPS;
     return sqrt(c);
+}
+
+// -------------------------------------------------------------------------------------------------
+// Division-light Riemann solve (product build, wave_speeds = 1 only; the host dispatch guarantees it).
+// Same formulas as riemann_face below; differences: reciprocals instead of divisions, and for HLLC only
+// the star state on the upwind side of the contact is evaluated (the reference evaluates both and
+// multiplies one by xi_M / xi_P = 0; identical unless the discarded side is non-finite).
+// -------------------------------------------------------------------------------------------------
+template <int NF, int ND, int DIR, int RS>
+__device__ __forceinline__ void riemann_face_fast(const DevP& P, double* qL, double* qR, double* F, double* Fs) {
+    constexpr int IM = NF, IE = NF + ND, IA = NF + ND + 1;
+    const int rs = (RS < 0) ? P.rs : RS;
+    double vel_L_rms = 0.0, vel_R_rms = 0.0;
+#pragma unroll
+    for (int a = 0; a < ND; a++) {
+        vel_L_rms = fma(qL[IM + a], qL[IM + a], vel_L_rms);
+        vel_R_rms = fma(qR[IM + a], qR[IM + a], vel_R_rms);
+    }
+    const double pres_L = qL[IE], pres_R = qR[IE];
+    double arho_L[NF], arho_R[NF], alf_L[NF], alf_R[NF];
+#pragma unroll
+    for (int f = 0; f < NF; f++) {
+        arho_L[f] = qL[f]; arho_R[f] = qR[f];
+        alf_L[f] = qL[IA + f]; alf_R[f] = qR[IA + f];
+    }
+    if (P.mpp) {
+        double sL = 0.0, sR = 0.0;
+#pragma unroll
+        for (int f = 0; f < NF; f++) {
+            arho_L[f] = fmax(0.0, arho_L[f]);
+            alf_L[f] = fmin(fmax(0.0, alf_L[f]), 1.0);
+            sL = sL + alf_L[f];
+            arho_R[f] = fmax(0.0, arho_R[f]);
+            alf_R[f] = fmin(fmax(0.0, alf_R[f]), 1.0);
+            sR = sR + alf_R[f];
+        }
+        const double iL = rcp_nr(fmax(sL, MFC5_SGM_EPS)), iR = rcp_nr(fmax(sR, MFC5_SGM_EPS));
+#pragma unroll
+        for (int f = 0; f < NF; f++) { alf_L[f] = alf_L[f] * iL; alf_R[f] = alf_R[f] * iR; }
+        if (rs == 2) {  // HLLC limits the face states in place (hllc.fpp:938-958); HLL only local copies
+#pragma unroll
+            for (int f = 0; f < NF; f++) { qL[f] = arho_L[f]; qR[f] = arho_R[f]; qL[IA + f] = alf_L[f]; qR[IA + f] = alf_R[f]; }
+        }
+    }
+    double rho_L = 0, gamma_L = 0, pi_inf_L = 0, qv_L = 0, rho_R = 0, gamma_R = 0, pi_inf_R = 0, qv_R = 0;
+#pragma unroll
+    for (int f = 0; f < NF; f++) {
+        rho_L = rho_L + arho_L[f];
+        gamma_L = fma(alf_L[f], P.gam[f], gamma_L);
+        pi_inf_L = fma(alf_L[f], P.pinf[f], pi_inf_L);
+        qv_L = fma(arho_L[f], P.qv[f], qv_L);
+        rho_R = rho_R + arho_R[f];
+        gamma_R = fma(alf_R[f], P.gam[f], gamma_R);
+        pi_inf_R = fma(alf_R[f], P.pinf[f], pi_inf_R);
+        qv_R = fma(arho_R[f], P.qv[f], qv_R);
+    }
+    const double E_L = gamma_L * pres_L + pi_inf_L + 5.e-1 * rho_L * vel_L_rms + qv_L;
+    const double E_R = gamma_R * pres_R + pi_inf_R + 5.e-1 * rho_R * vel_R_rms + qv_R;
+    const double irho_L = rcp_nr(rho_L), irho_R = rcp_nr(rho_R);
+    const double H_L = (E_L + pres_L) * irho_L;
+    const double H_R = (E_R + pres_R) * irho_R;
+    double c_L = (H_L - 5.e-1 * vel_L_rms - qv_L * irho_L) * rcp_nr(gamma_L);
+    double c_R = (H_R - 5.e-1 * vel_R_rms - qv_R * irho_R) * rcp_nr(gamma_R);
+    c_L = (P.mixerr && c_L < 0.0) ? 100.0 * MFC5_SGM_EPS : sqrt(c_L);
+    c_R = (P.mixerr && c_R < 0.0) ? 100.0 * MFC5_SGM_EPS : sqrt(c_R);
+    const double uL = qL[IM + DIR], uR = qR[IM + DIR];
+    const double s_L = fmin(uL - c_L, uR - c_R);
+    const double s_R = fmax(uR + c_R, uL + c_L);
+    const double s_M = fmin(0.0, s_L), s_P = fmax(0.0, s_R);
+    if (rs == 2) {
+        const double mL = rho_L * (s_L - uL), mR = rho_R * (s_R - uR);
+        const double s_S = (pres_R - pres_L + mL * uL - mR * uR) * rcp_nr(mL - mR);
+        const bool left = !signbit(s_S);  // xi_M = 1, xi_P = 0  (Fortran sign(0.5, s_S))
+        const double* qK = left ? qL : qR;
+        const double rho_K = left ? rho_L : rho_R, u_K = left ? uL : uR, p_K = left ? pres_L : pres_R, E_K = left ? E_L : E_R;
+        const double s_K = left ? s_L : s_R, s_MP = left ? s_M : s_P;
+        const double den = left ? fmin(s_L - s_S, -MFC5_SGM_EPS) : fmax(s_R - s_S, MFC5_SGM_EPS);
+        const double iden = rcp_nr(den);
+        const double xi_K = (s_K - u_K) * iden;
+        const double xi_K_m1 = (s_S - u_K) * iden;
+        const double adv = fma(s_MP, xi_K_m1, u_K);  // u_K + s_MP (xi_K - 1)
+#pragma unroll
+        for (int f = 0; f < NF; f++) { F[f] = qK[f] * adv; F[IA + f] = qK[IA + f] * adv; }
+#pragma unroll
+        for (int a = 0; a < ND; a++) {
+            if (a == DIR) F[IM + a] = rho_K * (u_K * u_K + s_MP * s_K * xi_K_m1) + p_K;
+            else F[IM + a] = rho_K * (qK[IM + a] * adv);
+        }
+        F[IE] = u_K * (E_K + p_K) + s_MP * (E_K * xi_K_m1 + xi_K * (s_S - u_K) * (rho_K * s_S + p_K * rcp_nr(s_K - u_K)));
+        Fs[0] = adv;
+    } else {
+        const double inv = rcp_nr(s_M - s_P);
+        const double smp = s_M * s_P;
+#pragma unroll
+        for (int f = 0; f < NF; f++) F[f] = (s_M * arho_R[f] * uR - s_P * arho_L[f] * uL + smp * (arho_L[f] - arho_R[f])) * inv;
+#pragma unroll
+        for (int a = 0; a < ND; a++) {
+            const double flg = (a == DIR) ? 1.0 : 0.0;
+            F[IM + a] = (s_M * (rho_R * uR * qR[IM + a] + flg * pres_R) - s_P * (rho_L * uL * qL[IM + a] + flg * pres_L) +
+                         smp * (rho_L * qL[IM + a] - rho_R * qR[IM + a])) * inv;
+        }
+        F[IE] = (s_M * uR * (E_R + pres_R) - s_P * uL * (E_L + pres_L) + smp * (E_L - E_R)) * inv;
+        if (!P.hll_u) {
+#pragma unroll
+            for (int f = 0; f < NF; f++) {
+                F[IA + f] = (qL[IA + f] - qR[IA + f]) * smp * inv;
+                Fs[f] = (s_M * qR[IA + f] - s_P * qL[IA + f]) * inv;
+            }
+        } else {
+            const double iw = rcp_nr(s_R - s_L);
+#pragma unroll
+            for (int f = 0; f < NF; f++) {
+                const double aL = qL[IA + f], aR = qR[IA + f];
+                if (0.0 <= s_L) F[IA + f] = aL * uL;
+                else if (s_R <= 0.0) F[IA + f] = aR * uR;
+                else F[IA + f] = (s_R * aL * uL - s_L * aR * uR + s_L * s_R * (aR - aL)) * iw;
+            }
+            if (0.0 <= s_L) Fs[0] = uL;
+            else if (s_R <= 0.0) Fs[0] = uR;
+            else Fs[0] = (s_R * uL - s_L * uR) * iw;
+        }
+    }
 }
 
 // -------------------------------------------------------------------------------------------------

@@ -26,36 +26,47 @@ inline void sweep_grid(const DevP& P, int dir, dim3& grid, dim3& block) {
     }
 }
 
-template <int NF, int ND, int WO, int WV, int RS>
+template <int NF, int ND, int WO, int WV, int RS, int FAST>
 inline bool launch_sweep_t(const DevP& P, int dir, cudaStream_t st) {
     dim3 grid, block;
     sweep_grid(P, dir, grid, block);
     if (dir == 0) {
-        k_sweep_x<NF, ND, WO, WV, RS><<<grid, block, 0, st>>>(P);
+        k_sweep_x<NF, ND, WO, WV, RS, FAST><<<grid, block, 0, st>>>(P);
         return true;
     }
     if constexpr (ND >= 2) {
         if (dir == 1) {
-            k_sweep_yz<NF, ND, 1, WO, WV, RS><<<grid, block, 0, st>>>(P);
+            k_sweep_yz<NF, ND, 1, WO, WV, RS, FAST><<<grid, block, 0, st>>>(P);
             return true;
         }
     }
     if constexpr (ND >= 3) {
         if (dir == 2) {
-            k_sweep_yz<NF, ND, 2, WO, WV, RS><<<grid, block, 0, st>>>(P);
+            k_sweep_yz<NF, ND, 2, WO, WV, RS, FAST><<<grid, block, 0, st>>>(P);
             return true;
         }
     }
     return false;
 }
 
+// P.fast selects the division-light arithmetic (product default) or the reference operation order
+// (bitwise comparable with the CPU oracle when built with -fmad=false).
 template <int NF>
 inline bool launch_sweep_generic(const DevP& P, int dir, cudaStream_t st) {
     if (P.nf != NF) return false;
+#ifndef MFC5_STRICT
+    if (P.fast) {
+        switch (P.nd) {
+        case 1: return launch_sweep_t<NF, 1, -1, -1, -1, 1>(P, dir, st);
+        case 2: return launch_sweep_t<NF, 2, -1, -1, -1, 1>(P, dir, st);
+        case 3: return launch_sweep_t<NF, 3, -1, -1, -1, 1>(P, dir, st);
+        }
+    }
+#endif
     switch (P.nd) {
-    case 1: return launch_sweep_t<NF, 1, -1, -1, -1>(P, dir, st);
-    case 2: return launch_sweep_t<NF, 2, -1, -1, -1>(P, dir, st);
-    case 3: return launch_sweep_t<NF, 3, -1, -1, -1>(P, dir, st);
+    case 1: return launch_sweep_t<NF, 1, -1, -1, -1, 0>(P, dir, st);
+    case 2: return launch_sweep_t<NF, 2, -1, -1, -1, 0>(P, dir, st);
+    case 3: return launch_sweep_t<NF, 3, -1, -1, -1, 0>(P, dir, st);
     }
     return false;
 }

@@ -328,9 +328,10 @@ __global__ void __launch_bounds__(128) k_cbc(const __grid_constant__ DevP P, con
 // when this is the last direction of a time-stepping stage, the fused TVD-RK update
 // (m_time_steppers.fpp:486-507).
 // -------------------------------------------------------------------------------------------------
-template <int NF, int ND, int DIR>
-__device__ __forceinline__ void finish_cell(const DevP& P, long long c, double inv_ds, const double* Fp, const double* Fsp, const double* Fc,
+template <int NF, int ND, int DIR, int FAST>
+__device__ __forceinline__ void finish_cell(const DevP& P, long long c, double ds, const double* Fp, const double* Fsp, const double* Fc,
                                             const double* Fsc) {
+    const double inv_ds = FAST ? rcp_nr(ds) : 1.0 / ds;
     using S = Shape<NF, ND>;
     const bool alpha_iface = (P.rs == 1 && !P.hll_u);
     double r[S::N];
@@ -355,7 +356,8 @@ __device__ __forceinline__ void finish_cell(const DevP& P, long long c, double i
         for (int v = 0; v < S::N; v++) {
             const double q1 = P.q1[v * P.fs + c];
             const double q2 = P.q2[v * P.fs + c];
-            P.qout[v * P.fs + c] = (P.rk0 * q1 + P.rk1 * q2 + P.rk2 * P.dt * r[v]) / P.rk3;
+            if (FAST) P.qout[v * P.fs + c] = (P.rk0 * q1 + P.rk1 * q2 + P.rk2 * P.dt * r[v]) * P.irk3;
+            else P.qout[v * P.fs + c] = (P.rk0 * q1 + P.rk1 * q2 + P.rk2 * P.dt * r[v]) / P.rk3;
         }
     } else {
 #pragma unroll
@@ -391,7 +393,7 @@ __device__ __forceinline__ void cbc_override(const DevP& P, int face, long long 
 // -------------------------------------------------------------------------------------------------
 #define MFC5_XW 30  // cells finished per warp
 
-template <int NF, int ND, int WO, int WV, int RS>
+template <int NF, int ND, int WO, int WV, int RS, int FAST>
 __global__ void __launch_bounds__(128) k_sweep_x(const __grid_constant__ DevP P) {
     using S = Shape<NF, ND>;
     constexpr int N = S::N;
@@ -420,7 +422,7 @@ __global__ void __launch_bounds__(128) k_sweep_x(const __grid_constant__ DevP P)
         double f0 = 0, f1 = 0, f2 = __ldg(f), f3 = 0, f4 = 0;
         if (wo >= 3) { f1 = __ldg(f - 1); f3 = __ldg(f + 1); }
         if (wo >= 5) { f0 = __ldg(f - 2); f4 = __ldg(f + 2); }
-        weno_edges<WO, WV>(P, T, slot, f0, f1, f2, f3, f4, eL[v], eR[v]);
+        weno_edges<WO, WV, FAST>(P, T, slot, f0, f1, f2, f3, f4, eL[v], eR[v]);
     }
     // right state of my right face = left edge of cell i+1
     double qR[N];
@@ -438,7 +440,8 @@ __global__ void __launch_bounds__(128) k_sweep_x(const __grid_constant__ DevP P)
     double F[N], Fs[NF];
 #pragma unroll
     for (int f = 0; f < NF; f++) Fs[f] = 0.0;
-    riemann_face<NF, ND, 0, RS>(P, eR, qR, F, Fs);
+    if (FAST) riemann_face_fast<NF, ND, 0, RS>(P, eR, qR, F, Fs);
+    else riemann_face<NF, ND, 0, RS>(P, eR, qR, F, Fs);
     if (P.cbc_on[0][0] | P.cbc_on[0][1]) cbc_override<NF, ND, 0>(P, i, row, rows, F, Fs);
     double Fp[N], Fsp[NF];
 #pragma unroll
@@ -446,8 +449,7 @@ __global__ void __launch_bounds__(128) k_sweep_x(const __grid_constant__ DevP P)
 #pragma unroll
     for (int f = 0; f < NF; f++) Fsp[f] = __shfl_up_sync(0xffffffffu, Fs[f], 1);
     if (lane >= 1 && lane <= MFC5_XW && i <= P.s[0]) {
-        const double inv_ds = 1.0 / __ldg(T.ds + i + P.b);
-        finish_cell<NF, ND, 0>(P, rowbase + i, inv_ds, Fp, Fsp, F, Fs);
+        finish_cell<NF, ND, 0, FAST>(P, rowbase + i, __ldg(T.ds + i + P.b), Fp, Fsp, F, Fs);
     }
 }
 
@@ -457,7 +459,7 @@ __global__ void __launch_bounds__(128) k_sweep_x(const __grid_constant__ DevP P)
 // with the carried right-edge state of cell cc-1, finishes cell cc-1 with the carried flux of face
 // cc-2.  One WENO + one Riemann per cell plus a short prologue per chunk.
 // -------------------------------------------------------------------------------------------------
-template <int NF, int ND, int DIR, int WO, int WV, int RS>
+template <int NF, int ND, int DIR, int WO, int WV, int RS, int FAST>
 __global__ void __launch_bounds__(128) k_sweep_yz(const __grid_constant__ DevP P) {
     using S = Shape<NF, ND>;
     constexpr int N = S::N;
@@ -492,7 +494,7 @@ __global__ void __launch_bounds__(128) k_sweep_yz(const __grid_constant__ DevP P
             double f0 = 0, f1 = 0, f2 = __ldg(f), f3 = 0, f4 = 0;
             if (wo >= 3) { f1 = __ldg(f - sd); f3 = __ldg(f + sd); }
             if (wo >= 5) { f0 = __ldg(f - 2 * sd); f4 = __ldg(f + 2 * sd); }
-            weno_edges<WO, WV>(P, T, cc + P.b, f0, f1, f2, f3, f4, eL[v], eR[v]);
+            weno_edges<WO, WV, FAST>(P, T, cc + P.b, f0, f1, f2, f3, f4, eL[v], eR[v]);
         }
         if (cc >= c0) {
             const int face = cc - 1;
@@ -507,11 +509,11 @@ __global__ void __launch_bounds__(128) k_sweep_yz(const __grid_constant__ DevP P
 #pragma unroll
                 for (int v = 0; v < N; v++) eL[v] = eRp[v];
             }
-            riemann_face<NF, ND, DIR, RS>(P, eRp, eL, F, Fs);
+            if (FAST) riemann_face_fast<NF, ND, DIR, RS>(P, eRp, eL, F, Fs);
+            else riemann_face<NF, ND, DIR, RS>(P, eRp, eL, F, Fs);
             if (P.cbc_on[DIR][0] | P.cbc_on[DIR][1]) cbc_override<NF, ND, DIR>(P, face, t, plane, F, Fs);
             if (cc >= c0 + 1) {
-                const double inv_ds = 1.0 / __ldg(T.ds + (cc - 1) + P.b);
-                finish_cell<NF, ND, DIR>(P, c - sd, inv_ds, Fp, Fsp, F, Fs);
+                finish_cell<NF, ND, DIR, FAST>(P, c - sd, __ldg(T.ds + (cc - 1) + P.b), Fp, Fsp, F, Fs);
             }
 #pragma unroll
             for (int v = 0; v < N; v++) Fp[v] = F[v];

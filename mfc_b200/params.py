@@ -84,8 +84,11 @@ class UnsupportedCase(ValueError):
     """Raised (like the reference's ``@:PROHIBIT`` / ``s_mpi_abort``) for cases outside the envelope."""
 
 
-def params_from_case(case, device=0, fast_math=0):
-    """Translate a case dictionary (what a reference ``case.py`` prints) into ``Mfc5Params``."""
+def params_from_case(case, device=0, fast_math=1):
+    """Translate a case dictionary (what a reference ``case.py`` prints) into ``Mfc5Params``.
+
+    ``fast_math`` (product-side knob, ignored by the oracle): 1 = division-light arithmetic (default),
+    0 = the reference's operation order."""
     for k in _UNSUPPORTED_TRUE:
         if _logical(case.get(k, "F")):
             raise UnsupportedCase(f"{k}=T is outside the 5-equation inviscid hot path")
