@@ -422,13 +422,9 @@ extern "C" int mfc5_finalize_setup(mfc5_handle* h) {
         }
         for (int a = 0; a < 3; a++) { D.vb[d][a] = h->P.bc_vb[d][a]; D.ve[d][a] = h->P.bc_ve[d][a]; }
     }
-    D.chunk = 32;
-    if (const char* e = getenv("MFC5_CHUNK")) D.chunk = std::max(1, atoi(e));
-    // small grids: shorten the marching chunks so the grid still fills the machine
-    if (h->nd > 1) {
-        const long long plane = (long long)(h->s[0] + 1) * (h->nd > 2 ? (long long)(h->s[1] + 1) : 1);
-        while (D.chunk > 8 && plane * ((h->s[h->nd - 1] + D.chunk) / D.chunk) < 148LL * 1024) D.chunk /= 2;
-    }
+    D.chunk = 0;
+    if (const char* e = getenv("MFC5_CHUNK")) D.chunk = std::max(0, atoi(e));
+    D.force_x_shuffle = getenv("MFC5_X_SHUFFLE") ? 1 : 0;
     h->setup = true;
     for (int i = 0; i < 2; i++) if (h->gexec[i]) { cudaGraphExecDestroy(h->gexec[i]); h->gexec[i] = nullptr; }
     return 0;

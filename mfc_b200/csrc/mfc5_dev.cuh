@@ -52,7 +52,8 @@ struct DevP {
     double* rhs;
     double rk0, rk1, rk2, rk3, irk3, dt;
     int do_rk;
-    int chunk;          // marching chunk length of the y/z sweeps
+    int chunk;          // marching chunk length (<= 0: chosen per launch)
+    int force_x_shuffle;  // use the warp-shuffle x kernel even when the marching kernel applies
 };
 
 __device__ __forceinline__ double sq(double x) { return x * x; }

@@ -1,5 +1,6 @@
 // mfc5_host.cuh -- internal interface between the C-ABI host code and the sweep translation units.
 #pragma once
+#include <cmath>
 #include "mfc5_kernels.cuh"
 
 namespace mfc5 {
@@ -13,38 +14,71 @@ bool launch_sweep_generic_nf1(const DevP& P, int dir, cudaStream_t st);
 bool launch_sweep_generic_nf2(const DevP& P, int dir, cudaStream_t st);
 bool launch_sweep_generic_nf3(const DevP& P, int dir, cudaStream_t st);
 
-inline void sweep_grid(const DevP& P, int dir, dim3& grid, dim3& block) {
+// x-sweep, warp-shuffle kernel: used when there are too few pencils for the marching kernel (1-D, thin 2-D)
+inline void sweep_grid_x(const DevP& P, dim3& grid, dim3& block) {
     block = dim3(128, 1, 1);
-    if (dir == 0) {
-        const long long segs = (P.s[0] + 1 + MFC5_XW - 1) / MFC5_XW;
-        const long long warps = segs * (long long)(P.s[1] + 1) * (P.s[2] + 1);
-        grid = dim3((unsigned)((warps * 32 + 127) / 128), 1, 1);
-    } else {
-        const long long plane = (long long)(P.s[0] + 1) * ((dir == 1 ? P.s[2] : P.s[1]) + 1);
-        const int chunks = (P.s[dir] + 1 + P.chunk - 1) / P.chunk;
-        grid = dim3((unsigned)((plane + 127) / 128), (unsigned)chunks, 1);
+    const long long segs = (P.s[0] + 1 + MFC5_XW - 1) / MFC5_XW;
+    const long long warps = segs * (long long)(P.s[1] + 1) * (P.s[2] + 1);
+    grid = dim3((unsigned)((warps * 32 + 127) / 128), 1, 1);
+}
+
+inline long long march_pencils(const DevP& P, int dir) {
+    return dir == 0 ? (long long)(P.s[1] + 1) * (P.s[2] + 1) : (long long)(P.s[0] + 1) * ((dir == 1 ? P.s[2] : P.s[1]) + 1);
+}
+
+// chunk length along the marching direction: the number of blocks should be close to a whole number of
+// waves of the resident-block capacity (148 SMs x blocks/SM), chunks as long as possible (each chunk
+// re-does 2 cells of reconstruction and a (2*PN)-plane prologue).
+inline int march_chunk(const DevP& P, int dir, int blocks_per_sm) {
+    const long long lanes_blocks = (march_pencils(P, dir) + MFC5_MARCH_THREADS - 1) / MFC5_MARCH_THREADS;
+    const int n = P.s[dir] + 1;
+    const double slots = 148.0 * blocks_per_sm;
+    int best = n;
+    double best_cost = 1e300;
+    for (int nch = 1; nch <= n; nch++) {
+        const int chunk = (n + nch - 1) / nch;
+        if (chunk < 4 && nch > 1) break;
+        const int real = (n + chunk - 1) / chunk;
+        const double waves = std::ceil(lanes_blocks * real / slots);
+        const double cost = waves * (chunk + 2 + 1.0);  // per-block time ~ cells reconstructed + prologue
+        if (cost < best_cost) { best_cost = cost; best = chunk; }
     }
+    return best;
+}
+
+template <int NF, int ND, int DIR, int WO, int WV, int RS, int FAST>
+inline bool launch_march(const DevP& P0, cudaStream_t st) {
+    constexpr size_t smem = march_smem_bytes<NF, ND, WO>();
+    auto kern = k_sweep_march<NF, ND, DIR, WO, WV, RS, FAST>;
+    static bool attr_done = false;
+    if (!attr_done) {
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return false;
+        attr_done = true;
+    }
+    DevP P = P0;
+    if (P.chunk <= 0) P.chunk = march_chunk(P, DIR, (2 * NF + ND + 1 <= 8) ? 3 : 2);
+    const long long lanes_blocks = (march_pencils(P, DIR) + MFC5_MARCH_THREADS - 1) / MFC5_MARCH_THREADS;
+    const int chunks = (P.s[DIR] + 1 + P.chunk - 1) / P.chunk;
+    kern<<<dim3((unsigned)lanes_blocks, (unsigned)chunks, 1), MFC5_MARCH_THREADS, smem, st>>>(P);
+    return true;
 }
 
 template <int NF, int ND, int WO, int WV, int RS, int FAST>
 inline bool launch_sweep_t(const DevP& P, int dir, cudaStream_t st) {
-    dim3 grid, block;
-    sweep_grid(P, dir, grid, block);
     if (dir == 0) {
-        k_sweep_x<NF, ND, WO, WV, RS, FAST><<<grid, block, 0, st>>>(P);
-        return true;
+        if (march_pencils(P, 0) < 4096 || P.force_x_shuffle) {
+            dim3 grid, block;
+            sweep_grid_x(P, grid, block);
+            k_sweep_x<NF, ND, WO, WV, RS, FAST><<<grid, block, 0, st>>>(P);
+            return true;
+        }
+        if constexpr (ND >= 2) return launch_march<NF, ND, 0, WO, WV, RS, FAST>(P, st);
     }
     if constexpr (ND >= 2) {
-        if (dir == 1) {
-            k_sweep_yz<NF, ND, 1, WO, WV, RS, FAST><<<grid, block, 0, st>>>(P);
-            return true;
-        }
+        if (dir == 1) return launch_march<NF, ND, 1, WO, WV, RS, FAST>(P, st);
     }
     if constexpr (ND >= 3) {
-        if (dir == 2) {
-            k_sweep_yz<NF, ND, 2, WO, WV, RS, FAST><<<grid, block, 0, st>>>(P);
-            return true;
-        }
+        if (dir == 2) return launch_march<NF, ND, 2, WO, WV, RS, FAST>(P, st);
     }
     return false;
 }

@@ -4,8 +4,8 @@
 //   k_cbc         characteristic-BC replacement fluxes of one boundary plane (K9)
 //   k_sweep_x     fused WENO + Riemann + flux difference + alpha source [+ RK] along x: one warp
 //                 owns 30 consecutive cells, neighbour exchange by warp shuffles       (K4..K8,K10,K11[,K12])
-//   k_sweep_yz    same along y / z: lanes along x (coalesced), each thread marches along the sweep
-//                 direction carrying the previous face flux and right-edge state in registers
+//   k_sweep_march same along any direction: each thread marches a pencil; the stencil window of the
+//                 primitive variables is staged in a shared-memory ring, next plane prefetched
 //   k_reduce      ICFL max / dt min / NaN count                         (K13)
 // Face states and face fluxes never touch HBM.
 #pragma once
@@ -454,74 +454,174 @@ __global__ void __launch_bounds__(128) k_sweep_x(const __grid_constant__ DevP P)
 }
 
 // -------------------------------------------------------------------------------------------------
-// y / z sweep.  Lanes run along x over the flattened transverse plane (coalesced loads/stores); each
-// thread marches a chunk of cells along DIR.  Iteration cc reconstructs cell cc, solves face cc-1
-// with the carried right-edge state of cell cc-1, finishes cell cc-1 with the carried flux of face
-// cc-2.  One WENO + one Riemann per cell plus a short prologue per chunk.
+// Marching sweep (all three directions).  Each thread owns one pencil of cells along DIR and marches a
+// chunk [c0, c1] of it; the 128 threads of a block are 128 neighbouring pencils:
+//     DIR = 1, 2 : lanes run along x (coalesced loads / stores),
+//     DIR = 0    : lanes run along y; a lane's 8-byte accesses to consecutive x fill 32-byte sectors
+//                  over 4 successive iterations out of L1 / L2.
+// Data staging: the (2*PN+1)-plane WENO stencil window of the primitive variables lives in a
+// per-thread ring in SHARED MEMORY (layout [slot][var][lane], conflict free, no block barrier needed:
+// a lane only ever touches its own column).  The plane entering the window is fetched one iteration
+// ahead into registers, so the global-load latency is covered by a whole iteration of arithmetic.
+// Right-edge states cross iterations through shared memory as well; face states and face fluxes never
+// touch HBM.  Iteration cc reconstructs cell cc, solves face cc-1 with the stored right edge of cell
+// cc-1, finishes cell cc-1 with the carried flux of face cc-2 (flux difference, alpha source, fused RK).
+// The WENO tables are indexed by the marching position, i.e. uniform over the block.
 // -------------------------------------------------------------------------------------------------
+#define MFC5_MARCH_THREADS 128
+
+template <int WO>
+struct MarchCfg {
+    static constexpr int PN = WO < 0 ? 2 : (WO - 1) / 2;  // generic kernels reserve the WENO5 window
+    static constexpr int R = 2 * PN + 1;
+};
+
+template <int NF, int ND, int WO>
+constexpr size_t march_smem_bytes() {
+    return (size_t)(MarchCfg<WO>::R + 2) * (2 * NF + ND + 1) * MFC5_MARCH_THREADS * sizeof(double);
+}
+
 template <int NF, int ND, int DIR, int WO, int WV, int RS, int FAST>
-__global__ void __launch_bounds__(128) k_sweep_yz(const __grid_constant__ DevP P) {
+__global__ void __launch_bounds__(MFC5_MARCH_THREADS, (2 * NF + ND + 1 <= 8) ? 3 : 2) k_sweep_march(const __grid_constant__ DevP P) {
     using S = Shape<NF, ND>;
     constexpr int N = S::N;
-    const int nx = P.s[0] + 1;
-    const int no = (DIR == 1) ? (P.s[2] + 1) : (P.s[1] + 1);  // the other transverse extent
-    const long long plane = (long long)nx * no;
-    const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    constexpr int PN = MarchCfg<WO>::PN, R = MarchCfg<WO>::R;
+    constexpr int NT = MFC5_MARCH_THREADS;
+    extern __shared__ double smem[];
+    double* ring = smem;              // [R][N][NT]
+    double* sER = smem + R * N * NT;  // [2][N][NT]  right-edge states, ping-pong over iterations
+    const int tid = threadIdx.x;
+
+    const int n_a = (DIR == 0) ? P.s[1] + 1 : P.s[0] + 1;
+    const int n_b = (DIR == 2) ? P.s[1] + 1 : P.s[2] + 1;
+    const long long plane = (long long)n_a * n_b;
+    const long long t = blockIdx.x * (long long)NT + tid;
     if (t >= plane) return;
-    const int i = (int)(t % nx), o = (int)(t / nx);
-    const long long sd = (DIR == 1) ? P.sy : P.sz;
-    const long long so = (DIR == 1) ? P.sz : P.sy;
-    const long long colbase = P.base + i + o * so;
+    const int a = (int)(t % n_a), bb = (int)(t / n_a);
+    const long long sa = (DIR == 0) ? P.sy : 1;
+    const long long sb = (DIR == 2) ? P.sy : P.sz;
+    const long long sd = (DIR == 0) ? 1 : (DIR == 1 ? P.sy : P.sz);
+    const long long colbase = P.base + a * sa + bb * sb;
     const int s = P.s[DIR];
     const int c0 = blockIdx.y * P.chunk;
     const int c1 = min(c0 + P.chunk - 1, s);
     const DirTables& T = P.T[DIR];
-    const int wo = (WO < 0) ? P.wo : WO;
+    const int lo = -P.b, hi = s + P.b;  // planes outside the ghost region are never used; clamp the loads
 
-    double eRp[N];          // right-edge state of the previous cell
+    // prologue: planes c0-1-PN .. c0-1+PN-1 -> slots 0 .. R-2 ; plane c0-1+PN prefetched into registers
+#pragma unroll
+    for (int k = 0; k < R - 1; k++) {
+        const int pl = min(max(c0 - 1 - PN + k, lo), hi);
+#pragma unroll
+        for (int v = 0; v < N; v++) ring[(k * N + v) * NT + tid] = __ldg(P.prim + v * P.fs + colbase + pl * sd);
+    }
+    double nw[N];
+    {
+        const int pl = min(max(c0 - 1 + PN, lo), hi);
+#pragma unroll
+        for (int v = 0; v < N; v++) nw[v] = __ldg(P.prim + v * P.fs + colbase + pl * sd);
+    }
+    int head = R - 1;  // slot that receives the newest plane (cc + PN)
+
     double Fp[N], Fsp[NF];  // flux of the previous face
 #pragma unroll
-    for (int v = 0; v < N; v++) { eRp[v] = 0.0; Fp[v] = 0.0; }
+    for (int v = 0; v < N; v++) Fp[v] = 0.0;
 #pragma unroll
     for (int f = 0; f < NF; f++) Fsp[f] = 0.0;
 
     for (int cc = c0 - 1; cc <= c1 + 1; cc++) {
-        const long long c = colbase + cc * sd;
-        double eL[N], eR[N];
+#pragma unroll
+        for (int v = 0; v < N; v++) ring[(head * N + v) * NT + tid] = nw[v];
+        if (cc <= c1) {
+            const int pl = min(max(cc + 1 + PN, lo), hi);
+#pragma unroll
+            for (int v = 0; v < N; v++) nw[v] = __ldg(P.prim + v * P.fs + colbase + pl * sd);
+        }
+        // tap k (plane cc-PN+k) sits in slot (head+1+k) mod R
+        int off[R];
+#pragma unroll
+        for (int k = 0; k < R; k++) {
+            int sl = head + 1 + k;
+            if (sl >= R) sl -= R;
+            off[k] = sl * N * NT + tid;
+        }
+        double* sERc = sER + ((cc & 1) ? N * NT : 0) + tid;
+        const double* sERp = sER + ((cc & 1) ? 0 : N * NT) + tid;
+        double eL[N];
 #pragma unroll
         for (int v = 0; v < N; v++) {
-            const double* f = P.prim + v * P.fs + c;
-            double f0 = 0, f1 = 0, f2 = __ldg(f), f3 = 0, f4 = 0;
-            if (wo >= 3) { f1 = __ldg(f - sd); f3 = __ldg(f + sd); }
-            if (wo >= 5) { f0 = __ldg(f - 2 * sd); f4 = __ldg(f + 2 * sd); }
-            weno_edges<WO, WV, FAST>(P, T, cc + P.b, f0, f1, f2, f3, f4, eL[v], eR[v]);
+            double f0 = 0, f1 = 0, f3 = 0, f4 = 0, eR;
+            const double f2 = ring[off[PN] + v * NT];
+            if (PN >= 1) { f1 = ring[off[PN - 1] + v * NT]; f3 = ring[off[PN + (PN >= 1 ? 1 : 0)] + v * NT]; }
+            if (PN >= 2) { f0 = ring[off[0] + v * NT]; f4 = ring[off[R - 1] + v * NT]; }
+            weno_edges<WO, WV, FAST>(P, T, cc + P.b, f0, f1, f2, f3, f4, eL[v], eR);
+            sERc[v * NT] = eR;
         }
         if (cc >= c0) {
             const int face = cc - 1;
-            double F[N], Fs[NF];
+            const long long c = colbase + (long long)(cc - 1) * sd;  // the cell finished in this iteration
+            const bool fin = cc >= c0 + 1;
+            // inputs of the finishing step, requested before the Riemann solve so that their latency is covered
+            double rin[N], q1in[N], q2in[N], acoef[NF];
+            const bool rk = (DIR == ND - 1) && P.do_rk;
+            const bool alpha_iface = (P.rs == 1 && !P.hll_u);
+            if (fin) {
+#pragma unroll
+                for (int v = 0; v < N; v++) {
+                    rin[v] = (DIR == 0) ? 0.0 : P.rhs[v * P.fs + c];
+                    if (rk) { q1in[v] = __ldg(P.q1 + v * P.fs + c); q2in[v] = __ldg(P.q2 + v * P.fs + c); }
+                }
+#pragma unroll
+                for (int f = 0; f < NF; f++) acoef[f] = __ldg(P.prim + (alpha_iface ? (S::IM + DIR) : (S::IA + f)) * P.fs + c);
+            }
+            double qL[N], F[N], Fs[NF];
+#pragma unroll
+            for (int v = 0; v < N; v++) qL[v] = sERp[v * NT];
 #pragma unroll
             for (int f = 0; f < NF; f++) Fs[f] = 0.0;
-            if (P.bc[DIR][0] == MFC5_BC_RIEMANN_EXTRAP && face == -1) {
+            if (P.bc[DIR][0] == MFC5_BC_RIEMANN_EXTRAP && face == -1) {  // m_riemann_state.fpp:149-206
 #pragma unroll
-                for (int v = 0; v < N; v++) eRp[v] = eL[v];
+                for (int v = 0; v < N; v++) qL[v] = eL[v];
             }
             if (P.bc[DIR][1] == MFC5_BC_RIEMANN_EXTRAP && face == s) {
 #pragma unroll
-                for (int v = 0; v < N; v++) eL[v] = eRp[v];
+                for (int v = 0; v < N; v++) eL[v] = qL[v];
             }
-            if (FAST) riemann_face_fast<NF, ND, DIR, RS>(P, eRp, eL, F, Fs);
-            else riemann_face<NF, ND, DIR, RS>(P, eRp, eL, F, Fs);
+            if (FAST) riemann_face_fast<NF, ND, DIR, RS>(P, qL, eL, F, Fs);
+            else riemann_face<NF, ND, DIR, RS>(P, qL, eL, F, Fs);
             if (P.cbc_on[DIR][0] | P.cbc_on[DIR][1]) cbc_override<NF, ND, DIR>(P, face, t, plane, F, Fs);
-            if (cc >= c0 + 1) {
-                finish_cell<NF, ND, DIR, FAST>(P, c - sd, __ldg(T.ds + (cc - 1) + P.b), Fp, Fsp, F, Fs);
+            if (fin) {
+                const double ds = __ldg(T.ds + (cc - 1) + P.b);
+                const double inv_ds = FAST ? rcp_nr(ds) : 1.0 / ds;
+                double r[N];
+#pragma unroll
+                for (int v = 0; v < N; v++) {
+                    if (DIR == 0) r[v] = inv_ds * (Fp[v] - F[v]);
+                    else r[v] = rin[v] + inv_ds * (Fp[v] - F[v]);
+                }
+#pragma unroll
+                for (int f = 0; f < NF; f++) {
+                    if (alpha_iface) r[S::IA + f] = r[S::IA + f] + inv_ds * acoef[f] * (Fsp[f] - Fs[f]);
+                    else r[S::IA + f] = r[S::IA + f] + inv_ds * acoef[f] * (Fs[0] - Fsp[0]);
+                }
+                if (rk) {
+#pragma unroll
+                    for (int v = 0; v < N; v++) {
+                        if (FAST) P.qout[v * P.fs + c] = (P.rk0 * q1in[v] + P.rk1 * q2in[v] + P.rk2 * P.dt * r[v]) * P.irk3;
+                        else P.qout[v * P.fs + c] = (P.rk0 * q1in[v] + P.rk1 * q2in[v] + P.rk2 * P.dt * r[v]) / P.rk3;
+                    }
+                } else {
+#pragma unroll
+                    for (int v = 0; v < N; v++) P.rhs[v * P.fs + c] = r[v];
+                }
             }
 #pragma unroll
             for (int v = 0; v < N; v++) Fp[v] = F[v];
 #pragma unroll
             for (int f = 0; f < NF; f++) Fsp[f] = Fs[f];
         }
-#pragma unroll
-        for (int v = 0; v < N; v++) eRp[v] = eR[v];
+        head = head + 1;
+        if (head >= R) head = 0;
     }
 }
 

@@ -1,0 +1,47 @@
+"""The BASELINE configurations (mfc_b200/cases.py) against the parameter dictionaries the reference's own
+test generator expands for its example-based goldens (tests/golden/cases.json, made by make_fixtures.py)."""
+import numpy as np
+import pytest
+
+from golden_util import CASES
+from mfc_b200 import cases, pre_process
+from mfc_b200.params import _NAMED, params_from_case
+
+
+def _norm(k, v):
+    return _NAMED[k][v] if isinstance(v, str) and k in _NAMED else v
+
+
+@pytest.mark.parametrize("builder,uuid,skip", [
+    (cases.sod_1d, "BCA926AC", ("t_step_stop", "t_step_save")),
+    (cases.shockbubble_2d, "24FD489A", ("t_step_stop", "t_step_save", "m", "n")),
+    (cases.shockdroplet_3d, "B5F0C655", ("t_step_stop", "t_step_save", "m", "n", "p")),
+])
+def test_builder_matches_reference_expansion(builder, uuid, skip):
+    mine, ref = builder(), CASES[uuid]["params"]
+    for k, v in mine.items():
+        if k in skip or (k not in ref and v == "F"):
+            continue
+        assert k in ref, k
+        assert _norm(k, v) == _norm(k, ref[k]), (k, v, ref[k])
+
+
+def test_benchmark_size_rule():
+    # benchmarks/5eq_rk3_weno3_hllc/case.py:24-28: --gbpp 16 on one rank -> s = floor((8e6/2)^(1/3)) = 158
+    c = cases.bench_5eq_weno3_hllc(gbpp=16)
+    assert (c["m"], c["n"], c["p"]) == (316, 158, 158)
+    c = cases.bench_5eq_weno3_hllc(gbpp=180)
+    assert (c["m"], c["n"], c["p"]) == (710, 355, 355)
+
+
+def test_perf_test_initial_condition_is_smoothed_and_bounded():
+    case = cases.perf_test_3d(m=31)
+    P = params_from_case(case)
+    assert (P.weno_order, P.mapped_weno, P.riemann_solver, P.mpp_lim, P.sys_size) == (5, 1, 2, 1, 8)
+    cbs, ccs = pre_process.generate_grid(case)
+    prim, cons = pre_process.initial_condition(case, ccs)
+    a1 = prim[6]
+    assert 0.1 - 1e-12 <= a1.min() and a1.max() <= 0.9 + 1e-12
+    assert len(np.unique(np.round(a1, 6))) > 10  # tanh profile, not a step
+    np.testing.assert_allclose(prim[6] + prim[7], 1.0, atol=1e-14)
+    assert np.all(np.diff(cbs[0]) > 0) and abs(np.diff(cbs[0]).max() / np.diff(cbs[0]).min()) > 1.5  # stretched

@@ -96,3 +96,50 @@ def test_icfl_reduction_matches_oracle():
     dt = float(case["dt"])
     assert abs(g.icfl_max(dt) - o.icfl_max(dt)) <= 1e-14 * o.icfl_max(dt)
     assert g.reduce(2) == 0.0
+
+
+# ---- the BASELINE.json configurations themselves (case-optimised kernels), reduced grids ----------------
+def _baseline_cases():
+    from mfc_b200 import cases
+    return {
+        "C5_perf_hllc_weno5m": cases.perf_test_3d(m=39, steps=10),
+        "C5_perf_hll_weno5m": cases.perf_test_3d(m=39, riemann="hll", steps=10),
+        "C4_droplet_weno3m": dict(cases.shockdroplet_3d(ny=30, steps=10)),
+        "C4_droplet_weno5z": dict(cases.shockdroplet_3d(ny=30, weno_order=5, mapped_weno="F", wenoz="T", steps=10)),
+        "C3_bench_weno3m": cases.bench_5eq_weno3_hllc(s=30, steps=10),
+        "C2_shockbubble": dict(cases.shockbubble_2d(ny=40), t_step_stop=20),
+        "C1_sod": dict(cases.sod_1d(), t_step_stop=100),
+    }
+
+
+@pytest.mark.parametrize("name", ["C5_perf_hllc_weno5m", "C5_perf_hll_weno5m", "C4_droplet_weno3m", "C4_droplet_weno5z",
+                                  "C3_bench_weno3m", "C2_shockbubble", "C1_sod"])
+@pytest.mark.parametrize("mode", ["strict", "fast", "ref_order"])
+def test_baseline_config_vs_oracle(name, mode):
+    """BASELINE configs (reduced grids, first steps) through the C ABI against the oracle:
+    strict build bit-exact; product build (fast and reference-order arithmetic) within 1e-10 max relative
+    error of max|q| per variable (north-star bar)."""
+    from mfc_b200 import pre_process
+    from mfc_b200.lib import Mfc5
+    from mfc_b200.params import params_from_case
+    from oracle_lib import Oracle
+    case = _baseline_cases()[name]
+    P = params_from_case(case, fast_math=1 if mode == "fast" else 0)
+    cbs, ccs = pre_process.generate_grid(case)
+    _, cons = pre_process.initial_condition(case, ccs)
+    g = Mfc5(P, cbs, strict=(mode == "strict"))
+    o = Oracle(P, cbs, omp=True)
+    g.set_cons(cons)
+    o.set_cons(cons)
+    driver.run(g, case)
+    driver.run(o, case)
+    a, b = g.get_cons(), o.get_cons()
+    assert not np.isnan(a).any()
+    if mode == "strict":
+        np.testing.assert_array_equal(a, b)
+    else:
+        for v in range(a.shape[0]):
+            scale = np.max(np.abs(b[v])) + 1e-300
+            err = np.max(np.abs(a[v] - b[v])) / scale
+            assert err <= 1e-10, f"{name} var {v + 1}: {err:.3e}"
+    g.close()
