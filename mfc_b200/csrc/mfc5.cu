@@ -424,7 +424,7 @@ extern "C" int mfc5_finalize_setup(mfc5_handle* h) {
     }
     D.chunk = 0;
     if (const char* e = getenv("MFC5_CHUNK")) D.chunk = std::max(0, atoi(e));
-    D.force_x_shuffle = getenv("MFC5_X_SHUFFLE") ? 1 : 0;
+    D.x_march = getenv("MFC5_X_MARCH") ? 1 : 0;
     h->setup = true;
     for (int i = 0; i < 2; i++) if (h->gexec[i]) { cudaGraphExecDestroy(h->gexec[i]); h->gexec[i] = nullptr; }
     return 0;
@@ -594,6 +594,13 @@ static int launch_sweep(mfc5_handle* h, const DevP& D, int dir) {
     if (!getenv("MFC5_NO_OPT")) ok = launch_sweep_opt(D, dir, h->st);
     if (!ok) ok = launch_sweep_generic_nf1(D, dir, h->st) || launch_sweep_generic_nf2(D, dir, h->st) || launch_sweep_generic_nf3(D, dir, h->st);
     if (!ok) return fail("no sweep kernel for this configuration");
+    {
+        cudaError_t e_ = cudaPeekAtLastError();
+        if (e_ != cudaSuccess) {
+            cudaGetLastError();
+            return fail(std::string("sweep launch failed, direction ") + std::to_string(dir) + ": " + cudaGetErrorString(e_));
+        }
+    }
     return seg_end(h, 1);
 }
 

@@ -53,7 +53,7 @@ struct DevP {
     double rk0, rk1, rk2, rk3, irk3, dt;
     int do_rk;
     int chunk;          // marching chunk length (<= 0: chosen per launch)
-    int force_x_shuffle;  // use the warp-shuffle x kernel even when the marching kernel applies
+    int x_march;        // x sweep with the marching kernel (lanes along y) instead of the warp-shuffle kernel
 };
 
 __device__ __forceinline__ double sq(double x) { return x * x; }

@@ -52,7 +52,10 @@ inline bool launch_march(const DevP& P0, cudaStream_t st) {
     auto kern = k_sweep_march<NF, ND, DIR, WO, WV, RS, FAST>;
     static bool attr_done = false;
     if (!attr_done) {
-        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return false;
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+            cudaGetLastError();
+            return false;
+        }
         attr_done = true;
     }
     DevP P = P0;
@@ -66,7 +69,7 @@ inline bool launch_march(const DevP& P0, cudaStream_t st) {
 template <int NF, int ND, int WO, int WV, int RS, int FAST>
 inline bool launch_sweep_t(const DevP& P, int dir, cudaStream_t st) {
     if (dir == 0) {
-        if (march_pencils(P, 0) < 4096 || P.force_x_shuffle) {
+        if (march_pencils(P, 0) < 4096 || !P.x_march) {
             dim3 grid, block;
             sweep_grid_x(P, grid, block);
             k_sweep_x<NF, ND, WO, WV, RS, FAST><<<grid, block, 0, st>>>(P);

@@ -461,8 +461,9 @@ __global__ void __launch_bounds__(128) k_sweep_x(const __grid_constant__ DevP P)
 //                  over 4 successive iterations out of L1 / L2.
 // Data staging: the (2*PN+1)-plane WENO stencil window of the primitive variables lives in a
 // per-thread ring in SHARED MEMORY (layout [slot][var][lane], conflict free, no block barrier needed:
-// a lane only ever touches its own column).  The plane entering the window is fetched one iteration
-// ahead into registers, so the global-load latency is covered by a whole iteration of arithmetic.
+// a lane only ever touches its own column).  The plane entering the window is requested one iteration
+// ahead with cp.async (LDGSTS, global -> shared without register staging), so the HBM latency is
+// covered by a whole iteration of arithmetic; the inputs of the finishing step are pulled into L2.
 // Right-edge states cross iterations through shared memory as well; face states and face fluxes never
 // touch HBM.  Iteration cc reconstructs cell cc, solves face cc-1 with the stored right edge of cell
 // cc-1, finishes cell cc-1 with the carried flux of face cc-2 (flux difference, alpha source, fused RK).
@@ -470,26 +471,36 @@ __global__ void __launch_bounds__(128) k_sweep_x(const __grid_constant__ DevP P)
 // -------------------------------------------------------------------------------------------------
 #define MFC5_MARCH_THREADS 128
 
+// 8-byte asynchronous global -> shared copy (LDGSTS): no register staging, completion by group
+__device__ __forceinline__ void cp_async8(double* sdst, const double* gsrc) {
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(sdst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sa), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void prefetch_l2(const double* g) { asm volatile("prefetch.global.L2 [%0];" ::"l"(g)); }
+
 template <int WO>
 struct MarchCfg {
     static constexpr int PN = WO < 0 ? 2 : (WO - 1) / 2;  // generic kernels reserve the WENO5 window
-    static constexpr int R = 2 * PN + 1;
+    static constexpr int R = 2 * PN + 1;   // stencil window
+    static constexpr int NSLOT = R + 1;    // ring slots: window + the plane in flight
 };
 
 template <int NF, int ND, int WO>
 constexpr size_t march_smem_bytes() {
-    return (size_t)(MarchCfg<WO>::R + 2) * (2 * NF + ND + 1) * MFC5_MARCH_THREADS * sizeof(double);
+    return (size_t)(MarchCfg<WO>::NSLOT + 2) * (2 * NF + ND + 1) * MFC5_MARCH_THREADS * sizeof(double);
 }
 
 template <int NF, int ND, int DIR, int WO, int WV, int RS, int FAST>
 __global__ void __launch_bounds__(MFC5_MARCH_THREADS, (2 * NF + ND + 1 <= 8) ? 3 : 2) k_sweep_march(const __grid_constant__ DevP P) {
     using S = Shape<NF, ND>;
     constexpr int N = S::N;
-    constexpr int PN = MarchCfg<WO>::PN, R = MarchCfg<WO>::R;
+    constexpr int PN = MarchCfg<WO>::PN, R = MarchCfg<WO>::R, NSLOT = MarchCfg<WO>::NSLOT;
     constexpr int NT = MFC5_MARCH_THREADS;
     extern __shared__ double smem[];
-    double* ring = smem;              // [R][N][NT]
-    double* sER = smem + R * N * NT;  // [2][N][NT]  right-edge states, ping-pong over iterations
+    double* ring = smem;                  // [NSLOT][N][NT]
+    double* sER = smem + NSLOT * N * NT;  // [2][N][NT]  right-edge states, ping-pong over iterations
     const int tid = threadIdx.x;
 
     const int n_a = (DIR == 0) ? P.s[1] + 1 : P.s[0] + 1;
@@ -508,20 +519,15 @@ __global__ void __launch_bounds__(MFC5_MARCH_THREADS, (2 * NF + ND + 1 <= 8) ? 3
     const DirTables& T = P.T[DIR];
     const int lo = -P.b, hi = s + P.b;  // planes outside the ghost region are never used; clamp the loads
 
-    // prologue: planes c0-1-PN .. c0-1+PN-1 -> slots 0 .. R-2 ; plane c0-1+PN prefetched into registers
+    // prologue: the window of cell c0-1, planes c0-1-PN .. c0-1+PN -> slots 0 .. R-1
 #pragma unroll
-    for (int k = 0; k < R - 1; k++) {
+    for (int k = 0; k < R; k++) {
         const int pl = min(max(c0 - 1 - PN + k, lo), hi);
 #pragma unroll
-        for (int v = 0; v < N; v++) ring[(k * N + v) * NT + tid] = __ldg(P.prim + v * P.fs + colbase + pl * sd);
+        for (int v = 0; v < N; v++) cp_async8(ring + (k * N + v) * NT + tid, P.prim + v * P.fs + colbase + pl * sd);
     }
-    double nw[N];
-    {
-        const int pl = min(max(c0 - 1 + PN, lo), hi);
-#pragma unroll
-        for (int v = 0; v < N; v++) nw[v] = __ldg(P.prim + v * P.fs + colbase + pl * sd);
-    }
-    int head = R - 1;  // slot that receives the newest plane (cc + PN)
+    cp_async_commit();
+    int tail = 0;  // slot of the oldest plane of the window (cc - PN)
 
     double Fp[N], Fsp[NF];  // flux of the previous face
 #pragma unroll
@@ -530,19 +536,32 @@ __global__ void __launch_bounds__(MFC5_MARCH_THREADS, (2 * NF + ND + 1 <= 8) ? 3
     for (int f = 0; f < NF; f++) Fsp[f] = 0.0;
 
     for (int cc = c0 - 1; cc <= c1 + 1; cc++) {
-#pragma unroll
-        for (int v = 0; v < N; v++) ring[(head * N + v) * NT + tid] = nw[v];
-        if (cc <= c1) {
+        cp_async_wait_all();  // the window of cell cc is complete (requested one iteration ago)
+        if (cc <= c1) {       // request plane cc+1+PN into the free slot; it lands while this cell is computed
+            int sl = tail + R;
+            if (sl >= NSLOT) sl -= NSLOT;
             const int pl = min(max(cc + 1 + PN, lo), hi);
 #pragma unroll
-            for (int v = 0; v < N; v++) nw[v] = __ldg(P.prim + v * P.fs + colbase + pl * sd);
+            for (int v = 0; v < N; v++) cp_async8(ring + (sl * N + v) * NT + tid, P.prim + v * P.fs + colbase + pl * sd);
+            cp_async_commit();
         }
-        // tap k (plane cc-PN+k) sits in slot (head+1+k) mod R
+        if (cc >= c0 + 1) {   // inputs of the finishing step of cell cc-1: pull them into L2 now
+            const long long c = colbase + (long long)(cc - 1) * sd;
+            if (DIR != 0) {
+#pragma unroll
+                for (int v = 0; v < N; v++) prefetch_l2(P.rhs + v * P.fs + c);
+            }
+            if ((DIR == ND - 1) && P.do_rk) {
+#pragma unroll
+                for (int v = 0; v < N; v++) { prefetch_l2(P.q1 + v * P.fs + c); prefetch_l2(P.q2 + v * P.fs + c); }
+            }
+        }
+        // tap k (plane cc-PN+k) sits in slot (tail+k) mod NSLOT
         int off[R];
 #pragma unroll
         for (int k = 0; k < R; k++) {
-            int sl = head + 1 + k;
-            if (sl >= R) sl -= R;
+            int sl = tail + k;
+            if (sl >= NSLOT) sl -= NSLOT;
             off[k] = sl * N * NT + tid;
         }
         double* sERc = sER + ((cc & 1) ? N * NT : 0) + tid;
@@ -620,8 +639,8 @@ __global__ void __launch_bounds__(MFC5_MARCH_THREADS, (2 * NF + ND + 1 <= 8) ? 3
 #pragma unroll
             for (int f = 0; f < NF; f++) Fsp[f] = Fs[f];
         }
-        head = head + 1;
-        if (head >= R) head = 0;
+        tail = tail + 1;
+        if (tail >= NSLOT) tail = 0;
     }
 }
 
