@@ -19,6 +19,13 @@
 #define MFC5_H
 #include "mfc5_params.h"
 
+/* the library is built with -fvisibility=hidden; only the C ABI below is exported */
+#if defined(__GNUC__)
+#define MFC5_API __attribute__((visibility("default")))
+#else
+#define MFC5_API
+#endif
+
 #ifdef __cplusplus
 extern "C" {
 #endif
@@ -28,10 +35,10 @@ typedef struct mfc5_handle mfc5_handle;
 /* replaces s_initialize_{weno,riemann_solvers,cbc,rhs,time_steppers}_module
  * (reference src/simulation/m_start_up.fpp:840-946): validates parameters (m_checker.fpp:52-69),
  * allocates device state. */
-int mfc5_create(const mfc5_params* p, mfc5_handle** out);
+MFC5_API int mfc5_create(const mfc5_params* p, mfc5_handle** out);
 
 /* replaces s_finalize_*_module (m_start_up.fpp:1106-1141) */
-int mfc5_destroy(mfc5_handle* h);
+MFC5_API int mfc5_destroy(mfc5_handle* h);
 
 /* Grid of one direction (0,1,2).  s_cb: interior cell boundaries x_cb(-1:m) (m_start_up.fpp:179-191).
  * Ghost metrics are rebuilt as s_populate_grid_variables_buffers does (m_boundary_common.fpp:384-468);
@@ -39,38 +46,38 @@ int mfc5_destroy(mfc5_handle* h);
  * s_mpi_sendrecv_grid_variable_buffer would deliver (m_mpi_common.fpp:1745-1796), else NULL.
  * Call once per direction, then mfc5_finalize_setup (builds WENO / CBC tables:
  * s_compute_weno_coefficients m_weno.fpp:170-893, s_compute_cbc_coefficients m_cbc.fpp:327-408). */
-int mfc5_set_grid(mfc5_handle* h, int dir, const double* s_cb, const double* ghost_ds_beg, const double* ghost_ds_end);
-int mfc5_finalize_setup(mfc5_handle* h);
+MFC5_API int mfc5_set_grid(mfc5_handle* h, int dir, const double* s_cb, const double* ghost_ds_beg, const double* ghost_ds_end);
+MFC5_API int mfc5_finalize_setup(mfc5_handle* h);
 
 /* Dirichlet (-17) face values = the reference's bc_buffers(dir,loc)%sf read by
  * s_read_serial_boundary_condition_files (src/common/m_boundary_io.fpp:160-205).
  * Layout [sys_size][t2][t1] over the transverse interior. */
-int mfc5_set_dirichlet(mfc5_handle* h, int dir, int side, const double* values);
+MFC5_API int mfc5_set_dirichlet(mfc5_handle* h, int dir, int side, const double* values);
 
 /* replaces the GPU_UPDATE(device=...) of q_cons_ts(1) in s_initialize_gpu_vars (m_start_up.fpp:1034-1042) */
-int mfc5_upload_cons(mfc5_handle* h, const double* const* q_cons_vf, int ghosted);
+MFC5_API int mfc5_upload_cons(mfc5_handle* h, const double* const* q_cons_vf, int ghosted);
 /* replaces GPU_UPDATE(host=...) in s_save_data (m_start_up.fpp:739) */
-int mfc5_download_cons(mfc5_handle* h, double* const* q_cons_vf, int ghosted);
+MFC5_API int mfc5_download_cons(mfc5_handle* h, double* const* q_cons_vf, int ghosted);
 /* q_prim_vf of the last RHS evaluation, ghost cells filled (m_rhs.fpp:884-898); ghosted layout fills
  * the buffer cells too */
-int mfc5_download_prim(mfc5_handle* h, double* const* q_prim_vf, int ghosted);
+MFC5_API int mfc5_download_prim(mfc5_handle* h, double* const* q_prim_vf, int ghosted);
 /* rhs_vf(1:sys_size)%sf(0:m,0:n,0:p) of the last mfc5_compute_rhs */
-int mfc5_download_rhs(mfc5_handle* h, double* const* rhs_vf, int ghosted);
+MFC5_API int mfc5_download_rhs(mfc5_handle* h, double* const* rhs_vf, int ghosted);
 
 /* replaces s_compute_rhs(q_cons_vf, ..., rhs_vf, ..., t_step, stage) (m_rhs.fpp:574): evaluates
  * the RHS of the current conservative state into the device rhs buffer (no state update). */
-int mfc5_compute_rhs(mfc5_handle* h);
+MFC5_API int mfc5_compute_rhs(mfc5_handle* h);
 
 /* replaces s_tvd_rk(t_step, time_avg, nstage) (m_time_steppers.fpp:438-611): one full TVD-RK step
  * of size dt (time_stepper stages, each = RHS + halo + fused RK update).  stage_time_min, if not
  * NULL, is updated with the reference's grind timer rule (minimum stage wall time in seconds,
  * m_time_steppers.fpp:559-577): pass the running value (<= 0 to start). */
-int mfc5_tvd_rk(mfc5_handle* h, double dt, double* stage_time_min);
+MFC5_API int mfc5_tvd_rk(mfc5_handle* h, double dt, double* stage_time_min);
 
 /* Enqueue `nsteps` steps of size dt without host synchronisation between them (CUDA-graph replay of
  * the captured step); returns after enqueue.  mfc5_sync waits. */
-int mfc5_tvd_rk_n(mfc5_handle* h, double dt, int nsteps);
-int mfc5_sync(mfc5_handle* h);
+MFC5_API int mfc5_tvd_rk_n(mfc5_handle* h, double dt, int nsteps);
+MFC5_API int mfc5_sync(mfc5_handle* h);
 
 /* reductions over the interior, using the primitive variables of the current state:
  * what = 0: ICFL max  = max dt/min_d(ds_d/(|u_d|+c))  (m_sim_helpers.fpp:108-130, m_data_output.fpp:159-224)
@@ -78,19 +85,19 @@ int mfc5_sync(mfc5_handle* h);
  * what = 2: NaN count of the conservative state (the reference's save-time NaN scan, m_start_up.fpp:741-751)
  * In a multi-rank run the result is reduced over ranks (ncclAllReduce), replacing
  * s_mpi_allreduce_min / s_mpi_reduce_stability_criteria_extrema (m_mpi_common.fpp:330-342,439). */
-int mfc5_reduce(mfc5_handle* h, int what, double dt, double* out);
+MFC5_API int mfc5_reduce(mfc5_handle* h, int what, double dt, double* out);
 
 /* Multi-GPU: replaces MPI_CART / s_mpi_sendrecv_variables_buffers (m_mpi_common.fpp:549-1070) with
  * packed halo faces exchanged by ncclSend/ncclRecv on a communication stream.  nccl_unique_id is the
  * 128-byte ncclUniqueId created by rank 0 (mfc5_nccl_unique_id) and broadcast by the host
  * (torch.distributed / MPI_Bcast).  Neighbour ranks are the non-negative bc[][] entries. */
-int mfc5_nccl_unique_id(char id_out[128]);
-int mfc5_comm_init(mfc5_handle* h, const char nccl_unique_id[128], int rank, int nranks);
+MFC5_API int mfc5_nccl_unique_id(char id_out[128]);
+MFC5_API int mfc5_comm_init(mfc5_handle* h, const char nccl_unique_id[128], int rank, int nranks);
 
 /* introspection used by tests and bench.py */
-int mfc5_sys_size(const mfc5_handle* h);
-int mfc5_buff_size(const mfc5_handle* h);
-long long mfc5_kernel_launches(const mfc5_handle* h);   /* library kernels launched so far */
+MFC5_API int mfc5_sys_size(const mfc5_handle* h);
+MFC5_API int mfc5_buff_size(const mfc5_handle* h);
+MFC5_API long long mfc5_kernel_launches(const mfc5_handle* h);   /* library kernels launched so far */
 /* device time (ms, CUDA events on the library's compute stream) and launch count of one kernel class,
  * summed over the stages of the last mfc5_tvd_rk call; returns < 0 for a bad argument.  The classes
  * are the analogue of the reference's NVTX ranges (m_rhs.fpp:594,640,644,912,1030,1041). */
@@ -104,10 +111,10 @@ enum {
     MFC5_K_SWEEP_Z = 6,   /* the last direction of a stage also carries the RK update */
     MFC5_NUM_KCLASS = 7
 };
-double mfc5_last_kernel_ms(const mfc5_handle* h, int kclass, long long* launches);
-void* mfc5_compute_stream(const mfc5_handle* h);        /* cudaStream_t */
-const char* mfc5_last_error(void);
-const char* mfc5_version(void);
+MFC5_API double mfc5_last_kernel_ms(const mfc5_handle* h, int kclass, long long* launches);
+MFC5_API void* mfc5_compute_stream(const mfc5_handle* h);        /* cudaStream_t */
+MFC5_API const char* mfc5_last_error(void);
+MFC5_API const char* mfc5_version(void);
 
 #ifdef __cplusplus
 }

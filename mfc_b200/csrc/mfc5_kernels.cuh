@@ -19,6 +19,15 @@ struct Shape {
     static constexpr int IM = NF, IE = NF + ND, IA = NF + ND + 1;
 };
 
+// 8-byte asynchronous global -> shared copy (LDGSTS): no register staging, completion by group
+__device__ __forceinline__ void cp_async8(double* sdst, const double* gsrc) {
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(sdst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sa), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void prefetch_l2(const double* g) { asm volatile("prefetch.global.L2 [%0];" ::"l"(g)); }
+
 // mixture rule: s_compute_species_fraction (m_variables_conversion.fpp:1140-1188) followed by
 // s_convert_species_to_mixture_variables_kernel (:198-270); `passes` = number of limiter passes.
 template <int NF>
@@ -414,15 +423,27 @@ __global__ void __launch_bounds__(128) k_sweep_x(const __grid_constant__ DevP P)
     const DirTables& T = P.T[0];
     const int slot = ic + P.b;
 
+    // stage the warp's 36-cell window of every variable in shared memory with cp.async (one batched
+    // wait instead of one exposed load latency per variable); lane l then reads cells l .. l+4
+    constexpr int XT = 40;
+    __shared__ double sx[4][N][XT];
+    double(*my)[XT] = sx[(threadIdx.x >> 5) & 3];
+    {
+        const int hi = P.s[0] + P.b;
+        const int ca = min(i0 - 3 + lane, hi), cb = min(i0 - 3 + 32 + lane, hi);
+#pragma unroll
+        for (int v = 0; v < N; v++) {
+            cp_async8(&my[v][lane], P.prim + v * P.fs + rowbase + ca);
+            if (lane < 4) cp_async8(&my[v][32 + lane], P.prim + v * P.fs + rowbase + cb);
+        }
+        cp_async_commit();
+        cp_async_wait_all();
+        __syncwarp();
+    }
     double eL[N], eR[N];
 #pragma unroll
     for (int v = 0; v < N; v++) {
-        const double* f = P.prim + v * P.fs + c;
-        const int wo = (WO < 0) ? P.wo : WO;
-        double f0 = 0, f1 = 0, f2 = __ldg(f), f3 = 0, f4 = 0;
-        if (wo >= 3) { f1 = __ldg(f - 1); f3 = __ldg(f + 1); }
-        if (wo >= 5) { f0 = __ldg(f - 2); f4 = __ldg(f + 2); }
-        weno_edges<WO, WV, FAST>(P, T, slot, f0, f1, f2, f3, f4, eL[v], eR[v]);
+        weno_edges<WO, WV, FAST>(P, T, slot, my[v][lane], my[v][lane + 1], my[v][lane + 2], my[v][lane + 3], my[v][lane + 4], eL[v], eR[v]);
     }
     // right state of my right face = left edge of cell i+1
     double qR[N];
@@ -470,15 +491,6 @@ __global__ void __launch_bounds__(128) k_sweep_x(const __grid_constant__ DevP P)
 // The WENO tables are indexed by the marching position, i.e. uniform over the block.
 // -------------------------------------------------------------------------------------------------
 #define MFC5_MARCH_THREADS 128
-
-// 8-byte asynchronous global -> shared copy (LDGSTS): no register staging, completion by group
-__device__ __forceinline__ void cp_async8(double* sdst, const double* gsrc) {
-    const unsigned sa = (unsigned)__cvta_generic_to_shared(sdst);
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sa), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
-__device__ __forceinline__ void prefetch_l2(const double* g) { asm volatile("prefetch.global.L2 [%0];" ::"l"(g)); }
 
 template <int WO>
 struct MarchCfg {
