@@ -86,7 +86,7 @@ struct mfc5_handle {
     std::vector<double> scb[3], ds[3];
     bool grid_set[3] = {false, false, false};
     bool setup = false;
-    double* d_tab[3][6] = {};  // cL cR dL dR bt ds
+    double* d_tab[3][7] = {};  // cL cR dL dR bt ds + combined rows
     int uniform[3] = {1, 1, 1};
     CbcCoef cbc[3][2];
     double* d_cbcbuf[3][2] = {};
@@ -188,7 +188,7 @@ extern "C" int mfc5_destroy(mfc5_handle* h) {
     for (int i = 0; i < 2; i++) { cudaFree(h->d_q[i]); if (h->gexec[i]) cudaGraphExecDestroy(h->gexec[i]); }
     cudaFree(h->d_prim); cudaFree(h->d_rhs); cudaFree(h->d_red);
     for (int d = 0; d < 3; d++) {
-        for (int k = 0; k < 6; k++) cudaFree(h->d_tab[d][k]);
+        for (int k = 0; k < 7; k++) cudaFree(h->d_tab[d][k]);
         for (int k = 0; k < 2; k++) { cudaFree(h->d_cbcbuf[d][k]); cudaFree(h->d_dirich[d][k]); cudaFree(h->d_send[d][k]); cudaFree(h->d_recv[d][k]); }
     }
     for (auto& ev : h->ev_stage) cudaEventDestroy(ev);
@@ -407,6 +407,29 @@ extern "C" int mfc5_finalize_setup(mfc5_handle* h) {
         if (upload(&h->d_tab[d][5], h->ds[d])) return -1;
         D.T[d].cL = h->d_tab[d][0]; D.T[d].cR = h->d_tab[d][1]; D.T[d].dL = h->d_tab[d][2]; D.T[d].dR = h->d_tab[d][3];
         D.T[d].bt = h->d_tab[d][4]; D.T[d].ds = h->d_tab[d][5]; D.T[d].uniform = uni;
+        {   // combined rows for the division-light kernels (layout: DirTables::tab)
+            const int nslot = h->s[d] + 1 + 2 * h->b, ns = h->ns, pr = h->pn > 0 ? h->pn : 1;
+            std::vector<double> rows((size_t)nslot * MFC5_TAB, 0.0);
+            for (int sl = 0; sl < nslot; sl++) {
+                double* r = rows.data() + (size_t)sl * MFC5_TAB;
+                for (int q = 0; q < ns; q++) {
+                    for (int k = 0; k < pr && h->pn > 0; k++) {
+                        r[0 + q * pr + k] = tab[0][((size_t)sl * ns + q) * pr + k];
+                        r[6 + q * pr + k] = tab[1][((size_t)sl * ns + q) * pr + k];
+                    }
+                    const double dl = tab[2][(size_t)sl * ns + q], dr = tab[3][(size_t)sl * ns + q];
+                    r[12 + q] = dl; r[15 + q] = dr;
+                    r[27 + q] = dl + dl * dl; r[30 + q] = dr + dr * dr;
+                    r[33 + q] = 1.0 - 2.0 * dl; r[36 + q] = 1.0 - 2.0 * dr;
+                    r[39 + q] = dl * dl; r[42 + q] = dr * dr;
+                    for (int k = 0; k < 3; k++) r[18 + q * 3 + k] = tab[4][((size_t)sl * ns + q) * 3 + k];
+                }
+                r[45] = h->ds[d][sl];
+                r[46] = 1.0 / h->ds[d][sl];
+            }
+            if (upload(&h->d_tab[d][6], rows)) return -1;
+            D.T[d].tab = h->d_tab[d][6];
+        }
         const int t1 = d == 0 ? 1 : 0, t2 = d == 2 ? 1 : 2;
         h->plane[d] = (long long)(h->s[t1] + 1) * (h->s[t2] + 1);
         for (int sd = 0; sd < 2; sd++) {

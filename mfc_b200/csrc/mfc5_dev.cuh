@@ -23,8 +23,14 @@ struct DirTables {
     const double* dR;  // [slot][q]     d_cbR
     const double* bt;  // [slot][q][3]  beta_coef
     const double* ds;  // cell widths, index i in [-b, s+b] -> slot (i + b)
+    // the same numbers as one row of MFC5_TAB doubles per slot (one base pointer, immediate offsets),
+    // plus the ideal-weight terms of the WENO-M map; used by the division-light kernels:
+    //   [0,6) cL  [6,12) cR  [12,15) dL  [15,18) dR  [18,27) beta
+    //   [27,30) dL+dL^2  [30,33) dR+dR^2  [33,36) 1-2dL  [36,39) 1-2dR  [39,42) dL^2  [42,45) dR^2  [45] ds  [46] 1/ds
+    const double* tab;
     int uniform;       // uniform_grid(dir), m_weno.fpp:869-879
 };
+#define MFC5_TAB 48
 
 // Everything a kernel needs, passed by value (__grid_constant__).
 struct DevP {
@@ -79,31 +85,26 @@ __device__ __forceinline__ double rcp_nr(double x) {
 }
 
 // WENO-M map of a normalised weight w with ideal weight d (m_weno.fpp:1150-1156), as numerator and
-// denominator:  g(w) = w (d + d^2 - 3 d w + w^2) / (d^2 + w (1 - 2 d))
-__device__ __forceinline__ void map_nd(double d, double w, double& num, double& den) {
-    num = w * fma(w, fma(-3.0, d, w), fma(d, d, d));
-    den = fma(w, fma(-2.0, d, 1.0), d * d);
+// denominator:  g(w) = w (d + d^2 - 3 d w + w^2) / (d^2 + w (1 - 2 d));  c1 = d + d^2, c2 = 1 - 2d, dsq = d^2
+__device__ __forceinline__ void map_nd(double d, double c1, double c2, double dsq, double w, double& num, double& den) {
+    num = w * fma(w, fma(-3.0, d, w), c1);
+    den = fma(w, c2, dsq);
 }
 
 template <int WV>
-__device__ __forceinline__ void weno5_fast(const DevP& P, const DirTables& T, int slot, const double f0, const double f1,
-                                           const double f2, const double f3, const double f4, double& eL, double& eR) {
+__device__ __forceinline__ void weno5_fast(const DevP& P, const DirTables& T, const double* __restrict__ row, const double f0,
+                                           const double f1, const double f2, const double f3, const double f4, double& eL, double& eR) {
     const double eps = P.eps;
-    const double* cl = T.cL + slot * 6;
-    const double* cr = T.cR + slot * 6;
-    const double* dl = T.dL + slot * 3;
-    const double* dr = T.dR + slot * 3;
-    const double* bt = T.bt + slot * 9;
     const double d1 = f4 - f3, d0 = f3 - f2, dm1 = f2 - f1, dm2 = f1 - f0;
     double b0, b1, b2;
     if (T.uniform) {
         b0 = 13.0 / 12.0 * sq(d1 - d0) + 0.25 * sq(d1 - 3.0 * d0) + eps;
         b1 = 13.0 / 12.0 * sq(d0 - dm1) + 0.25 * sq(d0 + dm1) + eps;
         b2 = 13.0 / 12.0 * sq(dm1 - dm2) + 0.25 * sq(3.0 * dm1 - dm2) + eps;
-    } else {
-        b0 = __ldg(bt + 0) * d1 * d1 + __ldg(bt + 1) * d1 * d0 + __ldg(bt + 2) * d0 * d0 + eps;
-        b1 = __ldg(bt + 3) * d0 * d0 + __ldg(bt + 4) * d0 * dm1 + __ldg(bt + 5) * dm1 * dm1 + eps;
-        b2 = __ldg(bt + 6) * dm1 * dm1 + __ldg(bt + 7) * dm1 * dm2 + __ldg(bt + 8) * dm2 * dm2 + eps;
+    } else {  // B0 x^2 + B1 x y + B2 y^2 + eps  =  x (B0 x + B1 y) + (B2 y) y + eps : 5 operations
+        b0 = fma(d1, fma(row[18], d1, row[19] * d0), fma(row[20] * d0, d0, eps));
+        b1 = fma(d0, fma(row[21], d0, row[22] * dm1), fma(row[23] * dm1, dm1, eps));
+        b2 = fma(dm1, fma(row[24], dm1, row[25] * dm2), fma(row[26] * dm2, dm2, eps));
     }
     // common-denominator factors shared by both sides
     double g0, g1, g2;
@@ -118,40 +119,38 @@ __device__ __forceinline__ void weno5_fast(const DevP& P, const DirTables& T, in
     }
 #pragma unroll
     for (int side = 0; side < 2; side++) {
-        const double* dd = side == 0 ? dl : dr;
-        const double* cc = side == 0 ? cl : cr;
-        const double dd0 = __ldg(dd + 0), dd1 = __ldg(dd + 1), dd2 = __ldg(dd + 2);
-        const double p0 = f2 + __ldg(cc + 0) * d1 + __ldg(cc + 1) * d0;
-        const double p1 = f2 + __ldg(cc + 2) * d0 + __ldg(cc + 3) * dm1;
-        const double p2 = f2 + __ldg(cc + 4) * dm1 + __ldg(cc + 5) * dm2;
+        const double* cc = row + side * 6;
+        const double* dd = row + 12 + side * 3;
+        const double dd0 = dd[0], dd1 = dd[1], dd2 = dd[2];
+        const double p0 = fma(cc[1], d0, fma(cc[0], d1, f2));
+        const double p1 = fma(cc[3], dm1, fma(cc[2], d0, f2));
+        const double p2 = fma(cc[5], dm2, fma(cc[4], dm1, f2));
         double a0 = dd0 * g0, a1 = dd1 * g1, a2 = dd2 * g2;
         if (WV == 1) {
             const double r = rcp_nr(a0 + a1 + a2);
+            const double* c1 = row + 27 + side * 3;
+            const double* c2 = row + 33 + side * 3;
+            const double* dq = row + 39 + side * 3;
             double n0, n1, n2, e0, e1, e2;
-            map_nd(dd0, a0 * r, n0, e0);
-            map_nd(dd1, a1 * r, n1, e1);
-            map_nd(dd2, a2 * r, n2, e2);
+            map_nd(dd0, c1[0], c2[0], dq[0], a0 * r, n0, e0);
+            map_nd(dd1, c1[1], c2[1], dq[1], a1 * r, n1, e1);
+            map_nd(dd2, c1[2], c2[2], dq[2], a2 * r, n2, e2);
             a0 = n0 * (e1 * e2);
             a1 = n1 * (e0 * e2);
             a2 = n2 * (e0 * e1);
         }
-        const double val = (a0 * p0 + a1 * p1 + a2 * p2) * rcp_nr(a0 + a1 + a2);
+        const double val = fma(a2, p2, fma(a1, p1, a0 * p0)) * rcp_nr(a0 + a1 + a2);
         if (side == 0) eL = val; else eR = val;
     }
 }
 
 template <int WV>
-__device__ __forceinline__ void weno3_fast(const DevP& P, const DirTables& T, int slot, const double f1, const double f2,
-                                           const double f3, double& eL, double& eR) {
+__device__ __forceinline__ void weno3_fast(const DevP& P, const DirTables& T, const double* __restrict__ row, const double f1,
+                                           const double f2, const double f3, double& eL, double& eR) {
     const double eps = P.eps;
-    const double* cl = T.cL + slot * 2;
-    const double* cr = T.cR + slot * 2;
-    const double* dl = T.dL + slot * 2;
-    const double* dr = T.dR + slot * 2;
-    const double* bt = T.bt + slot * 6;
     const double d0 = f3 - f2, dm1 = f2 - f1;
-    const double b0 = __ldg(bt + 0) * d0 * d0 + eps;
-    const double b1 = __ldg(bt + 3) * dm1 * dm1 + eps;
+    const double b0 = fma(row[18] * d0, d0, eps);
+    const double b1 = fma(row[21] * dm1, dm1, eps);
     double g0, g1;
     if (WV == 2) {
         const double tau = fabs(b1 - b0);
@@ -163,21 +162,21 @@ __device__ __forceinline__ void weno3_fast(const DevP& P, const DirTables& T, in
     }
 #pragma unroll
     for (int side = 0; side < 2; side++) {
-        const double* dd = side == 0 ? dl : dr;
-        const double* cc = side == 0 ? cl : cr;
-        const double dd0 = __ldg(dd + 0), dd1 = __ldg(dd + 1);
-        const double p0 = f2 + __ldg(cc + 0) * d0;
-        const double p1 = f2 + __ldg(cc + 1) * dm1;
+        const double* cc = row + side * 6;
+        const double* dd = row + 12 + side * 3;
+        const double dd0 = dd[0], dd1 = dd[1];
+        const double p0 = fma(cc[0], d0, f2);
+        const double p1 = fma(cc[1], dm1, f2);
         double a0 = dd0 * g0, a1 = dd1 * g1;
         if (WV == 1) {
             const double r = rcp_nr(a0 + a1);
             double n0, n1, e0, e1;
-            map_nd(dd0, a0 * r, n0, e0);
-            map_nd(dd1, a1 * r, n1, e1);
+            map_nd(dd0, row[27 + side * 3], row[33 + side * 3], row[39 + side * 3], a0 * r, n0, e0);
+            map_nd(dd1, row[28 + side * 3], row[34 + side * 3], row[40 + side * 3], a1 * r, n1, e1);
             a0 = n0 * e1;
             a1 = n1 * e0;
         }
-        const double val = (a0 * p0 + a1 * p1) * rcp_nr(a0 + a1);
+        const double val = fma(a1, p1, a0 * p0) * rcp_nr(a0 + a1);
         if (side == 0) eL = val; else eR = val;
     }
 }
@@ -187,22 +186,23 @@ __device__ __forceinline__ void weno3_fast(const DevP& P, const DirTables& T, in
 // reference: s_weno, src/simulation/m_weno.fpp:1007-1085 (WENO3), :1098-1239 (WENO5), :952-993 (1).
 // f[0..4] = v(j-2..j+2).  WO / WV < 0: read from P (generic kernels).
 // -------------------------------------------------------------------------------------------------
+// `row`: this cell's row of DirTables::tab (global or staged in shared memory), used when FAST
 template <int WO, int WV, int FAST>
-__device__ __forceinline__ void weno_edges(const DevP& P, const DirTables& T, int slot, const double f0, const double f1,
-                                           const double f2, const double f3, const double f4, double& eL, double& eR) {
+__device__ __forceinline__ void weno_edges(const DevP& P, const DirTables& T, int slot, const double* __restrict__ row, const double f0,
+                                           const double f1, const double f2, const double f3, const double f4, double& eL, double& eR) {
     const int wo = (WO < 0) ? P.wo : WO;
     const int wv = (WV < 0) ? P.wv : WV;
     const double eps = P.eps;
     if (wo == 1) { eL = f2; eR = f2; return; }
     if (FAST) {
         if (wo == 3) {
-            if (wv == 1) weno3_fast<1>(P, T, slot, f1, f2, f3, eL, eR);
-            else if (wv == 2) weno3_fast<2>(P, T, slot, f1, f2, f3, eL, eR);
-            else weno3_fast<0>(P, T, slot, f1, f2, f3, eL, eR);
+            if (wv == 1) weno3_fast<1>(P, T, row, f1, f2, f3, eL, eR);
+            else if (wv == 2) weno3_fast<2>(P, T, row, f1, f2, f3, eL, eR);
+            else weno3_fast<0>(P, T, row, f1, f2, f3, eL, eR);
         } else {
-            if (wv == 1) weno5_fast<1>(P, T, slot, f0, f1, f2, f3, f4, eL, eR);
-            else if (wv == 2) weno5_fast<2>(P, T, slot, f0, f1, f2, f3, f4, eL, eR);
-            else weno5_fast<0>(P, T, slot, f0, f1, f2, f3, f4, eL, eR);
+            if (wv == 1) weno5_fast<1>(P, T, row, f0, f1, f2, f3, f4, eL, eR);
+            else if (wv == 2) weno5_fast<2>(P, T, row, f0, f1, f2, f3, f4, eL, eR);
+            else weno5_fast<0>(P, T, row, f0, f1, f2, f3, f4, eL, eR);
         }
         return;
     }
@@ -222,9 +222,9 @@ __device__ __forceinline__ void weno_edges(const DevP& P, const DirTables& T, in
         for (int side = 0; side < 2; side++) {
             const double* dd = side == 0 ? dl : dr;
             const double* cc = side == 0 ? cl : cr;
-            const double dd0 = __ldg(dd + 0), dd1 = __ldg(dd + 1);
-            const double p0 = vp0 + __ldg(cc + 0) * d0;
-            const double p1 = vp0 + __ldg(cc + 1) * dm1;
+            const double dd0 = dd[0], dd1 = dd[1];
+            const double p0 = vp0 + cc[0] * d0;
+            const double p1 = vp0 + cc[1] * dm1;
             double a0, a1;
             if (wv == 1) {
                 a0 = dd0 / (b0 * b0);
@@ -272,10 +272,10 @@ __device__ __forceinline__ void weno_edges(const DevP& P, const DirTables& T, in
         for (int side = 0; side < 2; side++) {
             const double* dd = side == 0 ? dl : dr;
             const double* cc = side == 0 ? cl : cr;
-            const double dd0 = __ldg(dd + 0), dd1 = __ldg(dd + 1), dd2 = __ldg(dd + 2);
-            const double p0 = vp0 + __ldg(cc + 0) * d1 + __ldg(cc + 1) * d0;
-            const double p1 = vp0 + __ldg(cc + 2) * d0 + __ldg(cc + 3) * dm1;
-            const double p2 = vp0 + __ldg(cc + 4) * dm1 + __ldg(cc + 5) * dm2;
+            const double dd0 = dd[0], dd1 = dd[1], dd2 = dd[2];
+            const double p0 = vp0 + cc[0] * d1 + cc[1] * d0;
+            const double p1 = vp0 + cc[2] * d0 + cc[3] * dm1;
+            const double p2 = vp0 + cc[4] * dm1 + cc[5] * dm2;
             double a0, a1, a2;
             if (wv == 1) {
                 a0 = dd0 / (b0 * b0);

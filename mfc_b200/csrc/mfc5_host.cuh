@@ -1,5 +1,6 @@
 // mfc5_host.cuh -- internal interface between the C-ABI host code and the sweep translation units.
 #pragma once
+#include <algorithm>
 #include <cmath>
 #include "mfc5_kernels.cuh"
 
@@ -29,7 +30,7 @@ inline long long march_pencils(const DevP& P, int dir) {
 // chunk length along the marching direction: the number of blocks should be close to a whole number of
 // waves of the resident-block capacity (148 SMs x blocks/SM), chunks as long as possible (each chunk
 // re-does 2 cells of reconstruction and a (2*PN)-plane prologue).
-inline int march_chunk(const DevP& P, int dir, int blocks_per_sm) {
+inline int march_chunk(const DevP& P, int dir, int blocks_per_sm, int max_chunk) {
     const long long lanes_blocks = (march_pencils(P, dir) + MFC5_MARCH_THREADS - 1) / MFC5_MARCH_THREADS;
     const int n = P.s[dir] + 1;
     const double slots = 148.0 * blocks_per_sm;
@@ -37,6 +38,7 @@ inline int march_chunk(const DevP& P, int dir, int blocks_per_sm) {
     double best_cost = 1e300;
     for (int nch = 1; nch <= n; nch++) {
         const int chunk = (n + nch - 1) / nch;
+        if (chunk > max_chunk) continue;
         if (chunk < 4 && nch > 1) break;
         const int real = (n + chunk - 1) / chunk;
         const double waves = std::ceil(lanes_blocks * real / slots);
@@ -48,21 +50,25 @@ inline int march_chunk(const DevP& P, int dir, int blocks_per_sm) {
 
 template <int NF, int ND, int DIR, int WO, int WV, int RS, int FAST>
 inline bool launch_march(const DevP& P0, cudaStream_t st) {
-    constexpr size_t smem = march_smem_bytes<NF, ND, WO>();
+    constexpr int bps = (2 * NF + ND + 1 <= 8) ? 2 : 1;  // resident blocks per SM the kernel is built for
     auto kern = k_sweep_march<NF, ND, DIR, WO, WV, RS, FAST>;
     static bool attr_done = false;
     if (!attr_done) {
-        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024) != cudaSuccess) {
             cudaGetLastError();
             return false;
         }
         attr_done = true;
     }
     DevP P = P0;
-    if (P.chunk <= 0) P.chunk = march_chunk(P, DIR, (2 * NF + ND + 1 <= 8) ? 3 : 2);
+    // longest chunk whose table rows still let `bps` blocks share the 227 KB of an SM
+    const long long budget = (227LL * 1024 - bps * 1024) / bps - (long long)march_smem_bytes<NF, ND, WO>(-2);
+    const int max_chunk = (int)std::max<long long>(4, budget / (MFC5_TAB * (long long)sizeof(double)) - 2);
+    if (P.chunk <= 0) P.chunk = march_chunk(P, DIR, bps, max_chunk);
+    P.chunk = std::min(P.chunk, max_chunk);
     const long long lanes_blocks = (march_pencils(P, DIR) + MFC5_MARCH_THREADS - 1) / MFC5_MARCH_THREADS;
     const int chunks = (P.s[DIR] + 1 + P.chunk - 1) / P.chunk;
-    kern<<<dim3((unsigned)lanes_blocks, (unsigned)chunks, 1), MFC5_MARCH_THREADS, smem, st>>>(P);
+    kern<<<dim3((unsigned)lanes_blocks, (unsigned)chunks, 1), MFC5_MARCH_THREADS, march_smem_bytes<NF, ND, WO>(P.chunk), st>>>(P);
     return true;
 }
 

@@ -440,10 +440,11 @@ __global__ void __launch_bounds__(128) k_sweep_x(const __grid_constant__ DevP P)
         cp_async_wait_all();
         __syncwarp();
     }
+    const double* __restrict__ xrow = T.tab + (long long)slot * MFC5_TAB;
     double eL[N], eR[N];
 #pragma unroll
     for (int v = 0; v < N; v++) {
-        weno_edges<WO, WV, FAST>(P, T, slot, my[v][lane], my[v][lane + 1], my[v][lane + 2], my[v][lane + 3], my[v][lane + 4], eL[v], eR[v]);
+        weno_edges<WO, WV, FAST>(P, T, slot, xrow, my[v][lane], my[v][lane + 1], my[v][lane + 2], my[v][lane + 3], my[v][lane + 4], eL[v], eR[v]);
     }
     // right state of my right face = left edge of cell i+1
     double qR[N];
@@ -490,7 +491,7 @@ __global__ void __launch_bounds__(128) k_sweep_x(const __grid_constant__ DevP P)
 // cc-1, finishes cell cc-1 with the carried flux of face cc-2 (flux difference, alpha source, fused RK).
 // The WENO tables are indexed by the marching position, i.e. uniform over the block.
 // -------------------------------------------------------------------------------------------------
-#define MFC5_MARCH_THREADS 128
+#define MFC5_MARCH_THREADS 192
 
 template <int WO>
 struct MarchCfg {
@@ -499,13 +500,15 @@ struct MarchCfg {
     static constexpr int NSLOT = R + 1;    // ring slots: window + the plane in flight
 };
 
+// dynamic shared memory of a block marching a chunk of `chunk` cells: stencil ring + right-edge ping-pong
+// + the chunk's rows of the WENO table
 template <int NF, int ND, int WO>
-constexpr size_t march_smem_bytes() {
-    return (size_t)(MarchCfg<WO>::NSLOT + 2) * (2 * NF + ND + 1) * MFC5_MARCH_THREADS * sizeof(double);
+inline size_t march_smem_bytes(int chunk) {
+    return ((size_t)(MarchCfg<WO>::NSLOT + 2) * (2 * NF + ND + 1) * MFC5_MARCH_THREADS + (size_t)(chunk + 2) * MFC5_TAB) * sizeof(double);
 }
 
 template <int NF, int ND, int DIR, int WO, int WV, int RS, int FAST>
-__global__ void __launch_bounds__(MFC5_MARCH_THREADS, (2 * NF + ND + 1 <= 8) ? 3 : 2) k_sweep_march(const __grid_constant__ DevP P) {
+__global__ void __launch_bounds__(MFC5_MARCH_THREADS, (2 * NF + ND + 1 <= 8) ? 2 : 1) k_sweep_march(const __grid_constant__ DevP P) {
     using S = Shape<NF, ND>;
     constexpr int N = S::N;
     constexpr int PN = MarchCfg<WO>::PN, R = MarchCfg<WO>::R, NSLOT = MarchCfg<WO>::NSLOT;
@@ -513,7 +516,16 @@ __global__ void __launch_bounds__(MFC5_MARCH_THREADS, (2 * NF + ND + 1 <= 8) ? 3
     extern __shared__ double smem[];
     double* ring = smem;                  // [NSLOT][N][NT]
     double* sER = smem + NSLOT * N * NT;  // [2][N][NT]  right-edge states, ping-pong over iterations
+    double* srow = sER + 2 * N * NT;      // [chunk+2][MFC5_TAB]  WENO table rows of cells c0-1 .. c1+1
     const int tid = threadIdx.x;
+    if (FAST) {  // cooperative, coalesced copy; every thread of the block takes part before any returns
+        const int s_ = P.s[DIR];
+        const int c0_ = blockIdx.y * P.chunk, c1_ = min(c0_ + P.chunk - 1, s_);
+        const double* src = P.T[DIR].tab + (long long)(c0_ - 1 + P.b) * MFC5_TAB;
+        const int nrow = (c1_ - c0_ + 3) * MFC5_TAB;
+        for (int k = tid; k < nrow; k += NT) srow[k] = __ldg(src + k);
+        __syncthreads();
+    }
 
     const int n_a = (DIR == 0) ? P.s[1] + 1 : P.s[0] + 1;
     const int n_b = (DIR == 2) ? P.s[1] + 1 : P.s[2] + 1;
@@ -585,7 +597,7 @@ __global__ void __launch_bounds__(MFC5_MARCH_THREADS, (2 * NF + ND + 1 <= 8) ? 3
             const double f2 = ring[off[PN] + v * NT];
             if (PN >= 1) { f1 = ring[off[PN - 1] + v * NT]; f3 = ring[off[PN + (PN >= 1 ? 1 : 0)] + v * NT]; }
             if (PN >= 2) { f0 = ring[off[0] + v * NT]; f4 = ring[off[R - 1] + v * NT]; }
-            weno_edges<WO, WV, FAST>(P, T, cc + P.b, f0, f1, f2, f3, f4, eL[v], eR);
+            weno_edges<WO, WV, FAST>(P, T, cc + P.b, srow + (cc - (c0 - 1)) * MFC5_TAB, f0, f1, f2, f3, f4, eL[v], eR);
             sERc[v * NT] = eR;
         }
         if (cc >= c0) {
@@ -622,8 +634,7 @@ __global__ void __launch_bounds__(MFC5_MARCH_THREADS, (2 * NF + ND + 1 <= 8) ? 3
             else riemann_face<NF, ND, DIR, RS>(P, qL, eL, F, Fs);
             if (P.cbc_on[DIR][0] | P.cbc_on[DIR][1]) cbc_override<NF, ND, DIR>(P, face, t, plane, F, Fs);
             if (fin) {
-                const double ds = __ldg(T.ds + (cc - 1) + P.b);
-                const double inv_ds = FAST ? rcp_nr(ds) : 1.0 / ds;
+                const double inv_ds = FAST ? srow[(cc - 1 - (c0 - 1)) * MFC5_TAB + 46] : 1.0 / __ldg(T.ds + (cc - 1) + P.b);
                 double r[N];
 #pragma unroll
                 for (int v = 0; v < N; v++) {

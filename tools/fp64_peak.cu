@@ -64,6 +64,34 @@ double run(const char* name, int nsm, double ops_per_elem, int clock_khz) {
     return rate;
 }
 
+// dependent-issue latency: one warp, one chain
+template <int OP>
+__global__ void lat(double* out, long long* cyc, double seed) {
+    double a = seed, b = 1.0000001, c = 1e-9;
+    long long t0 = clock64();
+#pragma unroll 1
+    for (int it = 0; it < 256; it++) {
+#pragma unroll
+        for (int u = 0; u < 16; u++) {
+            if (OP == 0) a = fma(a, b, c);
+            else if (OP == 1) { double r; asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(a)); a = r + 1.5; }
+            else if (OP == 2) a = a * b;
+        }
+    }
+    long long t1 = clock64();
+    if (threadIdx.x == 0) { out[0] = a; cyc[0] = t1 - t0; }
+}
+template <int OP>
+void runlat(const char* name, int chain_ops) {
+    double* d; long long* c; long long h;
+    cudaMalloc(&d, 8); cudaMalloc(&c, 8);
+    lat<OP><<<1, 32>>>(d, c, 1.0);
+    lat<OP><<<1, 32>>>(d, c, 1.0);
+    cudaMemcpy(&h, c, 8, cudaMemcpyDeviceToHost);
+    printf("latency %-14s %.2f cycles per dependent step (%d FP64 ops per step)\n", name, (double)h / (256.0 * 16.0), chain_ops);
+    cudaFree(d); cudaFree(c);
+}
+
 int main() {
     cudaDeviceProp p;
     cudaGetDeviceProperties(&p, 0);
@@ -77,5 +105,8 @@ int main() {
     run<3>("rcp_nr+add", nsm, 1, khz);
     run<4>("1/x+add", nsm, 1, khz);
     run<5>("sqrt+add", nsm, 1, khz);
+    runlat<0>("DFMA", 1);
+    runlat<2>("DMUL", 1);
+    runlat<1>("MUFU.RCP64H+DADD", 1);
     return 0;
 }
