@@ -86,7 +86,7 @@ struct mfc5_handle {
     std::vector<double> scb[3], ds[3];
     bool grid_set[3] = {false, false, false};
     bool setup = false;
-    double* d_tab[3][7] = {};  // cL cR dL dR bt ds + combined rows
+    double* d_tab[3][8] = {};  // cL cR dL dR bt ds + combined rows + their transpose
     int uniform[3] = {1, 1, 1};
     CbcCoef cbc[3][2];
     double* d_cbcbuf[3][2] = {};
@@ -188,7 +188,7 @@ extern "C" int mfc5_destroy(mfc5_handle* h) {
     for (int i = 0; i < 2; i++) { cudaFree(h->d_q[i]); if (h->gexec[i]) cudaGraphExecDestroy(h->gexec[i]); }
     cudaFree(h->d_prim); cudaFree(h->d_rhs); cudaFree(h->d_red);
     for (int d = 0; d < 3; d++) {
-        for (int k = 0; k < 7; k++) cudaFree(h->d_tab[d][k]);
+        for (int k = 0; k < 8; k++) cudaFree(h->d_tab[d][k]);
         for (int k = 0; k < 2; k++) { cudaFree(h->d_cbcbuf[d][k]); cudaFree(h->d_dirich[d][k]); cudaFree(h->d_send[d][k]); cudaFree(h->d_recv[d][k]); }
     }
     for (auto& ev : h->ev_stage) cudaEventDestroy(ev);
@@ -429,6 +429,12 @@ extern "C" int mfc5_finalize_setup(mfc5_handle* h) {
             }
             if (upload(&h->d_tab[d][6], rows)) return -1;
             D.T[d].tab = h->d_tab[d][6];
+            std::vector<double> rowsT((size_t)nslot * MFC5_TAB);
+            for (int sl = 0; sl < nslot; sl++)
+                for (int k = 0; k < MFC5_TAB; k++) rowsT[(size_t)k * nslot + sl] = rows[(size_t)sl * MFC5_TAB + k];
+            if (upload(&h->d_tab[d][7], rowsT)) return -1;
+            D.T[d].tabT = h->d_tab[d][7];
+            D.T[d].nslot = nslot;
         }
         const int t1 = d == 0 ? 1 : 0, t2 = d == 2 ? 1 : 2;
         h->plane[d] = (long long)(h->s[t1] + 1) * (h->s[t2] + 1);

@@ -28,6 +28,8 @@ struct DirTables {
     //   [0,6) cL  [6,12) cR  [12,15) dL  [15,18) dR  [18,27) beta
     //   [27,30) dL+dL^2  [30,33) dR+dR^2  [33,36) 1-2dL  [36,39) 1-2dR  [39,42) dL^2  [42,45) dR^2  [45] ds  [46] 1/ds
     const double* tab;
+    const double* tabT;  // the same, transposed: [MFC5_TAB][nslot]
+    int nslot;
     int uniform;       // uniform_grid(dir), m_weno.fpp:869-879
 };
 #define MFC5_TAB 48
@@ -84,6 +86,19 @@ __device__ __forceinline__ double rcp_nr(double x) {
     return r;
 }
 
+// One cell's row of DirTables::tab.  RowAoS: MFC5_TAB consecutive doubles (marching kernels: staged in
+// shared memory, block-uniform).  RowSoA: element k at p[k * stride] (x kernel: lanes own consecutive
+// cells, so consecutive lanes read consecutive addresses of the transposed table).
+struct RowAoS {
+    const double* __restrict__ p;
+    __device__ __forceinline__ double operator[](int k) const { return p[k]; }
+};
+struct RowSoA {
+    const double* __restrict__ p;
+    long long stride;
+    __device__ __forceinline__ double operator[](int k) const { return __ldg(p + k * stride); }
+};
+
 // WENO-M map of a normalised weight w with ideal weight d (m_weno.fpp:1150-1156), as numerator and
 // denominator:  g(w) = w (d + d^2 - 3 d w + w^2) / (d^2 + w (1 - 2 d));  c1 = d + d^2, c2 = 1 - 2d, dsq = d^2
 __device__ __forceinline__ void map_nd(double d, double c1, double c2, double dsq, double w, double& num, double& den) {
@@ -91,8 +106,8 @@ __device__ __forceinline__ void map_nd(double d, double c1, double c2, double ds
     den = fma(w, c2, dsq);
 }
 
-template <int WV>
-__device__ __forceinline__ void weno5_fast(const DevP& P, const DirTables& T, const double* __restrict__ row, const double f0,
+template <int WV, class ROW>
+__device__ __forceinline__ void weno5_fast(const DevP& P, const DirTables& T, const ROW row, const double f0,
                                            const double f1, const double f2, const double f3, const double f4, double& eL, double& eR) {
     const double eps = P.eps;
     const double d1 = f4 - f3, d0 = f3 - f2, dm1 = f2 - f1, dm2 = f1 - f0;
@@ -119,22 +134,19 @@ __device__ __forceinline__ void weno5_fast(const DevP& P, const DirTables& T, co
     }
 #pragma unroll
     for (int side = 0; side < 2; side++) {
-        const double* cc = row + side * 6;
-        const double* dd = row + 12 + side * 3;
-        const double dd0 = dd[0], dd1 = dd[1], dd2 = dd[2];
-        const double p0 = fma(cc[1], d0, fma(cc[0], d1, f2));
-        const double p1 = fma(cc[3], dm1, fma(cc[2], d0, f2));
-        const double p2 = fma(cc[5], dm2, fma(cc[4], dm1, f2));
+        const int cc = side * 6, dd = 12 + side * 3;
+        const double dd0 = row[dd + 0], dd1 = row[dd + 1], dd2 = row[dd + 2];
+        const double p0 = fma(row[cc + 1], d0, fma(row[cc + 0], d1, f2));
+        const double p1 = fma(row[cc + 3], dm1, fma(row[cc + 2], d0, f2));
+        const double p2 = fma(row[cc + 5], dm2, fma(row[cc + 4], dm1, f2));
         double a0 = dd0 * g0, a1 = dd1 * g1, a2 = dd2 * g2;
         if (WV == 1) {
             const double r = rcp_nr(a0 + a1 + a2);
-            const double* c1 = row + 27 + side * 3;
-            const double* c2 = row + 33 + side * 3;
-            const double* dq = row + 39 + side * 3;
+            const int c1 = 27 + side * 3, c2 = 33 + side * 3, dq = 39 + side * 3;
             double n0, n1, n2, e0, e1, e2;
-            map_nd(dd0, c1[0], c2[0], dq[0], a0 * r, n0, e0);
-            map_nd(dd1, c1[1], c2[1], dq[1], a1 * r, n1, e1);
-            map_nd(dd2, c1[2], c2[2], dq[2], a2 * r, n2, e2);
+            map_nd(dd0, row[c1 + 0], row[c2 + 0], row[dq + 0], a0 * r, n0, e0);
+            map_nd(dd1, row[c1 + 1], row[c2 + 1], row[dq + 1], a1 * r, n1, e1);
+            map_nd(dd2, row[c1 + 2], row[c2 + 2], row[dq + 2], a2 * r, n2, e2);
             a0 = n0 * (e1 * e2);
             a1 = n1 * (e0 * e2);
             a2 = n2 * (e0 * e1);
@@ -144,8 +156,8 @@ __device__ __forceinline__ void weno5_fast(const DevP& P, const DirTables& T, co
     }
 }
 
-template <int WV>
-__device__ __forceinline__ void weno3_fast(const DevP& P, const DirTables& T, const double* __restrict__ row, const double f1,
+template <int WV, class ROW>
+__device__ __forceinline__ void weno3_fast(const DevP& P, const DirTables& T, const ROW row, const double f1,
                                            const double f2, const double f3, double& eL, double& eR) {
     const double eps = P.eps;
     const double d0 = f3 - f2, dm1 = f2 - f1;
@@ -162,11 +174,10 @@ __device__ __forceinline__ void weno3_fast(const DevP& P, const DirTables& T, co
     }
 #pragma unroll
     for (int side = 0; side < 2; side++) {
-        const double* cc = row + side * 6;
-        const double* dd = row + 12 + side * 3;
-        const double dd0 = dd[0], dd1 = dd[1];
-        const double p0 = fma(cc[0], d0, f2);
-        const double p1 = fma(cc[1], dm1, f2);
+        const int cc = side * 6, dd = 12 + side * 3;
+        const double dd0 = row[dd + 0], dd1 = row[dd + 1];
+        const double p0 = fma(row[cc + 0], d0, f2);
+        const double p1 = fma(row[cc + 1], dm1, f2);
         double a0 = dd0 * g0, a1 = dd1 * g1;
         if (WV == 1) {
             const double r = rcp_nr(a0 + a1);
@@ -186,9 +197,9 @@ __device__ __forceinline__ void weno3_fast(const DevP& P, const DirTables& T, co
 // reference: s_weno, src/simulation/m_weno.fpp:1007-1085 (WENO3), :1098-1239 (WENO5), :952-993 (1).
 // f[0..4] = v(j-2..j+2).  WO / WV < 0: read from P (generic kernels).
 // -------------------------------------------------------------------------------------------------
-// `row`: this cell's row of DirTables::tab (global or staged in shared memory), used when FAST
-template <int WO, int WV, int FAST>
-__device__ __forceinline__ void weno_edges(const DevP& P, const DirTables& T, int slot, const double* __restrict__ row, const double f0,
+// `row`: this cell's row of DirTables::tab (RowAoS / RowSoA), used when FAST
+template <int WO, int WV, int FAST, class ROW>
+__device__ __forceinline__ void weno_edges(const DevP& P, const DirTables& T, int slot, const ROW row, const double f0,
                                            const double f1, const double f2, const double f3, const double f4, double& eL, double& eR) {
     const int wo = (WO < 0) ? P.wo : WO;
     const int wv = (WV < 0) ? P.wv : WV;

@@ -50,7 +50,7 @@ inline int march_chunk(const DevP& P, int dir, int blocks_per_sm, int max_chunk)
 
 template <int NF, int ND, int DIR, int WO, int WV, int RS, int FAST>
 inline bool launch_march(const DevP& P0, cudaStream_t st) {
-    constexpr int bps = (2 * NF + ND + 1 <= 8) ? 2 : 1;  // resident blocks per SM the kernel is built for
+    constexpr int bps = (2 * NF + ND + 1 <= 8) ? MFC5_MARCH_MINB : 1;  // resident blocks per SM the kernel is built for
     auto kern = k_sweep_march<NF, ND, DIR, WO, WV, RS, FAST>;
     static bool attr_done = false;
     if (!attr_done) {

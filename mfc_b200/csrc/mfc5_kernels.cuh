@@ -402,8 +402,11 @@ __device__ __forceinline__ void cbc_override(const DevP& P, int face, long long 
 // -------------------------------------------------------------------------------------------------
 #define MFC5_XW 30  // cells finished per warp
 
+#ifndef MFC5_X_MINB
+#define MFC5_X_MINB 1
+#endif
 template <int NF, int ND, int WO, int WV, int RS, int FAST>
-__global__ void __launch_bounds__(128) k_sweep_x(const __grid_constant__ DevP P) {
+__global__ void __launch_bounds__(128, MFC5_X_MINB) k_sweep_x(const __grid_constant__ DevP P) {
     using S = Shape<NF, ND>;
     constexpr int N = S::N;
     const int lane = threadIdx.x & 31;
@@ -440,7 +443,7 @@ __global__ void __launch_bounds__(128) k_sweep_x(const __grid_constant__ DevP P)
         cp_async_wait_all();
         __syncwarp();
     }
-    const double* __restrict__ xrow = T.tab + (long long)slot * MFC5_TAB;
+    const RowSoA xrow{T.tabT + slot, (long long)T.nslot};
     double eL[N], eR[N];
 #pragma unroll
     for (int v = 0; v < N; v++) {
@@ -491,7 +494,12 @@ __global__ void __launch_bounds__(128) k_sweep_x(const __grid_constant__ DevP P)
 // cc-1, finishes cell cc-1 with the carried flux of face cc-2 (flux difference, alpha source, fused RK).
 // The WENO tables are indexed by the marching position, i.e. uniform over the block.
 // -------------------------------------------------------------------------------------------------
+#ifndef MFC5_MARCH_THREADS
 #define MFC5_MARCH_THREADS 192
+#endif
+#ifndef MFC5_MARCH_MINB
+#define MFC5_MARCH_MINB 2   // resident blocks per SM the marching kernel is built for (N <= 8)
+#endif
 
 template <int WO>
 struct MarchCfg {
@@ -508,7 +516,7 @@ inline size_t march_smem_bytes(int chunk) {
 }
 
 template <int NF, int ND, int DIR, int WO, int WV, int RS, int FAST>
-__global__ void __launch_bounds__(MFC5_MARCH_THREADS, (2 * NF + ND + 1 <= 8) ? 2 : 1) k_sweep_march(const __grid_constant__ DevP P) {
+__global__ void __launch_bounds__(MFC5_MARCH_THREADS, (2 * NF + ND + 1 <= 8) ? MFC5_MARCH_MINB : 1) k_sweep_march(const __grid_constant__ DevP P) {
     using S = Shape<NF, ND>;
     constexpr int N = S::N;
     constexpr int PN = MarchCfg<WO>::PN, R = MarchCfg<WO>::R, NSLOT = MarchCfg<WO>::NSLOT;
@@ -597,7 +605,7 @@ __global__ void __launch_bounds__(MFC5_MARCH_THREADS, (2 * NF + ND + 1 <= 8) ? 2
             const double f2 = ring[off[PN] + v * NT];
             if (PN >= 1) { f1 = ring[off[PN - 1] + v * NT]; f3 = ring[off[PN + (PN >= 1 ? 1 : 0)] + v * NT]; }
             if (PN >= 2) { f0 = ring[off[0] + v * NT]; f4 = ring[off[R - 1] + v * NT]; }
-            weno_edges<WO, WV, FAST>(P, T, cc + P.b, srow + (cc - (c0 - 1)) * MFC5_TAB, f0, f1, f2, f3, f4, eL[v], eR);
+            weno_edges<WO, WV, FAST>(P, T, cc + P.b, RowAoS{srow + (cc - (c0 - 1)) * MFC5_TAB}, f0, f1, f2, f3, f4, eL[v], eR);
             sERc[v * NT] = eR;
         }
         if (cc >= c0) {

@@ -27,6 +27,8 @@ def load(strict=False):
     if name in _libs:
         return _libs[name]
     path = os.path.join(_HERE, name)
+    if not strict and os.environ.get("MFC5_LIB"):  # kernel-variant experiments (tools/sweep_bench.py)
+        path = os.environ["MFC5_LIB"]
     if not os.path.exists(path):
         raise Mfc5Error(f"{path} is missing: build it with `make -C mfc_b200/csrc` (or __graft_entry__.build()); "
                         "there is no CPU fallback")
