@@ -136,6 +136,8 @@ class ClockSampler:
 
 def cpu_arm(case, P, cbs, cons, nsteps, warm):
     """Time the oracle (reference algorithm restated in C, OpenMP) on this box's host cores."""
+    # all host cores, also under torchrun (which exports OMP_NUM_THREADS=1); must be set before libgomp starts
+    os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     from oracle_lib import Oracle
     o = Oracle(P, cbs, omp=True)
