@@ -90,10 +90,12 @@ __device__ __forceinline__ double rcp_nr(double x) {
 // shared memory, block-uniform).  RowSoA: element k at p[k * stride] (x kernel: lanes own consecutive
 // cells, so consecutive lanes read consecutive addresses of the transposed table).
 struct RowAoS {
+    static constexpr bool kHasMapTerms = true;   // read d + d^2, 1 - 2d, d^2 from the row
     const double* __restrict__ p;
     __device__ __forceinline__ double operator[](int k) const { return p[k]; }
 };
 struct RowSoA {
+    static constexpr bool kHasMapTerms = false;  // per-lane loads are dearer than 3 flops: recompute them
     const double* __restrict__ p;
     long long stride;
     __device__ __forceinline__ double operator[](int k) const { return __ldg(p + k * stride); }
@@ -144,9 +146,15 @@ __device__ __forceinline__ void weno5_fast(const DevP& P, const DirTables& T, co
             const double r = rcp_nr(a0 + a1 + a2);
             const int c1 = 27 + side * 3, c2 = 33 + side * 3, dq = 39 + side * 3;
             double n0, n1, n2, e0, e1, e2;
-            map_nd(dd0, row[c1 + 0], row[c2 + 0], row[dq + 0], a0 * r, n0, e0);
-            map_nd(dd1, row[c1 + 1], row[c2 + 1], row[dq + 1], a1 * r, n1, e1);
-            map_nd(dd2, row[c1 + 2], row[c2 + 2], row[dq + 2], a2 * r, n2, e2);
+            if (ROW::kHasMapTerms) {
+                map_nd(dd0, row[c1 + 0], row[c2 + 0], row[dq + 0], a0 * r, n0, e0);
+                map_nd(dd1, row[c1 + 1], row[c2 + 1], row[dq + 1], a1 * r, n1, e1);
+                map_nd(dd2, row[c1 + 2], row[c2 + 2], row[dq + 2], a2 * r, n2, e2);
+            } else {
+                map_nd(dd0, fma(dd0, dd0, dd0), fma(-2.0, dd0, 1.0), dd0 * dd0, a0 * r, n0, e0);
+                map_nd(dd1, fma(dd1, dd1, dd1), fma(-2.0, dd1, 1.0), dd1 * dd1, a1 * r, n1, e1);
+                map_nd(dd2, fma(dd2, dd2, dd2), fma(-2.0, dd2, 1.0), dd2 * dd2, a2 * r, n2, e2);
+            }
             a0 = n0 * (e1 * e2);
             a1 = n1 * (e0 * e2);
             a2 = n2 * (e0 * e1);
@@ -182,8 +190,13 @@ __device__ __forceinline__ void weno3_fast(const DevP& P, const DirTables& T, co
         if (WV == 1) {
             const double r = rcp_nr(a0 + a1);
             double n0, n1, e0, e1;
-            map_nd(dd0, row[27 + side * 3], row[33 + side * 3], row[39 + side * 3], a0 * r, n0, e0);
-            map_nd(dd1, row[28 + side * 3], row[34 + side * 3], row[40 + side * 3], a1 * r, n1, e1);
+            if (ROW::kHasMapTerms) {
+                map_nd(dd0, row[27 + side * 3], row[33 + side * 3], row[39 + side * 3], a0 * r, n0, e0);
+                map_nd(dd1, row[28 + side * 3], row[34 + side * 3], row[40 + side * 3], a1 * r, n1, e1);
+            } else {
+                map_nd(dd0, fma(dd0, dd0, dd0), fma(-2.0, dd0, 1.0), dd0 * dd0, a0 * r, n0, e0);
+                map_nd(dd1, fma(dd1, dd1, dd1), fma(-2.0, dd1, 1.0), dd1 * dd1, a1 * r, n1, e1);
+            }
             a0 = n0 * e1;
             a1 = n1 * e0;
         }

@@ -30,9 +30,7 @@ inline long long march_pencils(const DevP& P, int dir) {
 // chunk length along the marching direction: the number of blocks should be close to a whole number of
 // waves of the resident-block capacity (148 SMs x blocks/SM), chunks as long as possible (each chunk
 // re-does 2 cells of reconstruction and a (2*PN)-plane prologue).
-inline int march_chunk(const DevP& P, int dir, int blocks_per_sm, int max_chunk) {
-    const long long lanes_blocks = (march_pencils(P, dir) + MFC5_MARCH_THREADS - 1) / MFC5_MARCH_THREADS;
-    const int n = P.s[dir] + 1;
+inline int march_chunk_n(int n, long long lanes_blocks, int blocks_per_sm, int max_chunk, int extra) {
     const double slots = 148.0 * blocks_per_sm;
     int best = n;
     double best_cost = 1e300;
@@ -42,10 +40,13 @@ inline int march_chunk(const DevP& P, int dir, int blocks_per_sm, int max_chunk)
         if (chunk < 4 && nch > 1) break;
         const int real = (n + chunk - 1) / chunk;
         const double waves = std::ceil(lanes_blocks * real / slots);
-        const double cost = waves * (chunk + 2 + 1.0);  // per-block time ~ cells reconstructed + prologue
+        const double cost = waves * (chunk + extra + 1.0);  // per-block time ~ iterations + prologue
         if (cost < best_cost) { best_cost = cost; best = chunk; }
     }
     return best;
+}
+inline int march_chunk(const DevP& P, int dir, int blocks_per_sm, int max_chunk) {
+    return march_chunk_n(P.s[dir] + 1, (march_pencils(P, dir) + MFC5_MARCH_THREADS - 1) / MFC5_MARCH_THREADS, blocks_per_sm, max_chunk, 2);
 }
 
 template <int NF, int ND, int DIR, int WO, int WV, int RS, int FAST>

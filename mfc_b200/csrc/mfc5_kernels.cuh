@@ -403,7 +403,7 @@ __device__ __forceinline__ void cbc_override(const DevP& P, int face, long long 
 #define MFC5_XW 30  // cells finished per warp
 
 #ifndef MFC5_X_MINB
-#define MFC5_X_MINB 1
+#define MFC5_X_MINB 4   // 128 registers: 16 warps per SM (measured best of 3, 4, 5 blocks)
 #endif
 template <int NF, int ND, int WO, int WV, int RS, int FAST>
 __global__ void __launch_bounds__(128, MFC5_X_MINB) k_sweep_x(const __grid_constant__ DevP P) {
