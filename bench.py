@@ -98,7 +98,7 @@ class ClockSampler:
     def __init__(self, index):
         self.rows, self.proc = [], None
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -109,11 +109,21 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append((time.time(), line.strip()))
 
-    def stop(self, t0, t1):
+    def stop(self, t0, t1, busy0=None):
+        """Clocks over the timed region [t0, t1]; if nvidia-smi delivered fewer than 3 samples there, over
+        the whole GPU-busy window since `busy0` (warm-up + timed steps), and the window is named."""
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
         self.proc.terminate()
+        out = self._window(t0, t1)
+        out["window"] = "timed region"
+        if out["samples"] < 3 and busy0 is not None:
+            out = self._window(busy0, t1)
+            out["window"] = "warm-up + timed region (timed region shorter than 3 nvidia-smi samples)"
+        return out
+
+    def _window(self, t0, t1):
         sm, mx, pw, reasons = [], None, [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for t, line in self.rows:
@@ -248,10 +258,11 @@ def main():
         g.sync()
 
     # ---- device-resident throughput: W warm-up steps, K timed steps, CUDA events on the compute stream
-    g.steps(dt, args.warmup)
-    barrier()
     sampler = ClockSampler(local_rank) if rank == 0 else None
-    time.sleep(0.25 if rank == 0 else 0.0)
+    time.sleep(0.3 if rank == 0 else 0.0)
+    barrier()
+    busy0 = time.time()
+    g.steps(dt, args.warmup)
     barrier()
     l0 = g.kernel_launches
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -263,7 +274,7 @@ def main():
     t1 = time.time()
     launches = g.kernel_launches - l0
     ms = e0.elapsed_time(e1)
-    clocks = sampler.stop(t0, t1) if sampler else None
+    clocks = sampler.stop(t0, t1, busy0) if sampler else None
     if world > 1:
         tt = torch.tensor([ms], device="cuda", dtype=torch.float64)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)

@@ -108,6 +108,9 @@ struct mfc5_handle {
     int rank = 0, nranks = 1;
     double* d_send[3][2] = {};
     double* d_recv[3][2] = {};
+    bool any_phys = false, any_nb = false, any_cbc = false;
+    CbcCoef* d_cbccoef = nullptr;  // [6], index 2*dir + side
+    cudaEvent_t ev_prim = nullptr, ev_halo = nullptr;
     // graph replay of a whole step, keyed by (cur, dt)
     cudaGraphExec_t gexec[2] = {nullptr, nullptr};
     double gdt[2] = {0, 0};
@@ -177,6 +180,9 @@ extern "C" int mfc5_create(const mfc5_params* p, mfc5_handle** out) {
     for (auto& ev : h->ev_stage) CK(cudaEventCreate(&ev));
     CK(cudaEventCreateWithFlags(&h->ev_comm, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&h->ev_comp, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&h->ev_prim, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&h->ev_halo, cudaEventDisableTiming));
+    CK(cudaMalloc(&h->d_cbccoef, 6 * sizeof(CbcCoef)));
     *out = h;
     return 0;
 }
@@ -194,6 +200,8 @@ extern "C" int mfc5_destroy(mfc5_handle* h) {
     for (auto& ev : h->ev_stage) cudaEventDestroy(ev);
     for (auto& ev : h->ev_pool) cudaEventDestroy(ev);
     cudaEventDestroy(h->ev_comm); cudaEventDestroy(h->ev_comp);
+    cudaEventDestroy(h->ev_prim); cudaEventDestroy(h->ev_halo);
+    cudaFree(h->d_cbccoef);
     if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
     cudaStreamDestroy(h->st); cudaStreamDestroy(h->st_comm);
     delete h;
@@ -451,6 +459,17 @@ extern "C" int mfc5_finalize_setup(mfc5_handle* h) {
         }
         for (int a = 0; a < 3; a++) { D.vb[d][a] = h->P.bc_vb[d][a]; D.ve[d][a] = h->P.bc_ve[d][a]; }
     }
+    h->any_phys = h->any_nb = h->any_cbc = false;
+    {
+        CbcCoef all[6];
+        std::memset(all, 0, sizeof(all));
+        for (int d = 0; d < h->nd; d++)
+            for (int sd = 0; sd < 2; sd++) {
+                if (h->P.bc[d][sd] < 0) h->any_phys = true; else h->any_nb = true;
+                if (D.cbc_on[d][sd]) { h->any_cbc = true; all[2 * d + sd] = h->cbc[d][sd]; }
+            }
+        CK(cudaMemcpy(h->d_cbccoef, all, sizeof(all), cudaMemcpyHostToDevice));
+    }
     D.chunk = 0;
     if (const char* e = getenv("MFC5_CHUNK")) D.chunk = std::max(0, atoi(e));
     D.x_march = getenv("MFC5_X_MARCH") ? 1 : 0;
@@ -470,6 +489,8 @@ extern "C" int mfc5_set_dirichlet(mfc5_handle* h, int d, int side, const double*
     h->D.dirich[d][side] = h->d_dirich[d][side];
     return 0;
 }
+
+static int fill_full(mfc5_handle* h, const DevP& D);
 
 // ---- host <-> device field copies ------------------------------------------------------------------
 static int copy_fields(mfc5_handle* h, double* dev, const double* const* hostc, double* const* hostm, int ghosted, bool to_dev) {
@@ -510,6 +531,12 @@ extern "C" int mfc5_download_cons(mfc5_handle* h, double* const* q, int ghosted)
 }
 extern "C" int mfc5_download_prim(mfc5_handle* h, double* const* q, int ghosted) {
     if (!h || !q) return fail("mfc5_download_prim: null argument");
+    if (ghosted && h->setup) {  // edges and corners as the reference fills them (the sweeps do not need them)
+        CK(cudaSetDevice(h->P.device));
+        DevP D = h->D;
+        D.prim = h->d_prim; D.primw = h->d_prim;
+        if (fill_full(h, D)) return -1;
+    }
     return copy_fields(h, h->d_prim, nullptr, q, ghosted, false);
 }
 extern "C" int mfc5_download_rhs(mfc5_handle* h, double* const* q, int ghosted) {
@@ -537,8 +564,9 @@ static int by_shape(const mfc5_handle* h, F&& f) {
 static unsigned grid_for(long long n, int block) { return (unsigned)std::min<long long>((n + block - 1) / block, 148LL * 16); }
 
 // timing segments: when h->timing, every kernel class is bracketed by a pair of events
-static int seg_begin(mfc5_handle* h, int cls) {
+static int seg_begin(mfc5_handle* h, int cls, cudaStream_t st = nullptr) {
     if (!h->timing) return 0;
+    if (!st) st = h->st;
     const size_t i = h->seg_cls.size();
     while (h->ev_pool.size() < 2 * (i + 1)) {
         cudaEvent_t e;
@@ -546,91 +574,150 @@ static int seg_begin(mfc5_handle* h, int cls) {
         h->ev_pool.push_back(e);
     }
     h->seg_cls.push_back(cls);
-    CK(cudaEventRecord(h->ev_pool[2 * i], h->st));
+    CK(cudaEventRecord(h->ev_pool[2 * i], st));
     return 0;
 }
-static int seg_end(mfc5_handle* h, int nlaunch) {
+static int seg_end(mfc5_handle* h, int nlaunch, cudaStream_t st = nullptr) {
     h->launches += nlaunch;
     if (!h->timing) return 0;
+    if (!st) st = h->st;
     const size_t i = h->seg_cls.size() - 1;
     h->cls_launches[h->seg_cls[i]] += nlaunch;
-    CK(cudaEventRecord(h->ev_pool[2 * i + 1], h->st));
+    CK(cudaEventRecord(h->ev_pool[2 * i + 1], st));
     return 0;
 }
 
-static int halo_count(const mfc5_handle* h, int d) {
+// doubles in one packed halo face of direction d: b layers x transverse interior x N variables
+static long long halo_count(const mfc5_handle* h, int d) {
     long long n = (long long)h->N * h->b;
-    for (int e = 0; e < 3; e++) {
-        if (e == d) continue;
-        n *= (e < d) ? (h->s[e] + 1 + 2 * (e < h->nd ? h->b : 0)) : (h->s[e] + 1);
-    }
-    return (int)n;
+    for (int e = 0; e < 3; e++)
+        if (e != d) n *= (h->s[e] + 1);
+    return n;
 }
 
-// ghost fill of one direction: physical BCs locally, processor boundaries by NCCL send/recv of packed
-// faces (replaces s_mpi_sendrecv_variables_buffers, m_mpi_common.fpp:549-1070)
-static int fill_direction(mfc5_handle* h, const DevP& D, int d) {
-    const int t1 = d == 0 ? 1 : 0, t2 = d == 2 ? 1 : 2;
-    long long n1 = h->s[t1] + 1, n2 = h->s[t2] + 1;
-    if (t1 < d) n1 += 2 * h->b;
-    if (t2 < d && t2 < h->nd) n2 += 2 * h->b;
-    const long long tot = n1 * n2 * h->N;
-    bool any_nb = false;
-    int nl = 0;
-    if (seg_begin(h, MFC5_K_BC_FILL)) return -1;
-    for (int sd = 0; sd < 2; sd++) {
-        if (h->P.bc[d][sd] < 0) {
-            k_bc_fill<<<grid_for(tot, 256), 256, 0, h->st>>>(D, d, sd);
-            nl++;
-        } else any_nb = true;
+static unsigned faces_grid_x(const mfc5_handle* h, long long per_thread_items) {
+    long long mx = 1;
+    for (int d = 0; d < h->nd; d++) {
+        long long n = per_thread_items;
+        for (int e = 0; e < 3; e++)
+            if (e != d) n *= (h->s[e] + 1);
+        mx = std::max(mx, n);
     }
-    if (seg_end(h, nl)) return -1;
-    if (any_nb) {
-        if (!h->comm) return fail("processor boundary (bc >= 0) but mfc5_comm_init was not called");
-        const int cnt = halo_count(h, d);
-        nl = 0;
-        if (seg_begin(h, MFC5_K_HALO)) return -1;
-        for (int sd = 0; sd < 2; sd++) {
-            if (h->P.bc[d][sd] < 0) continue;
-            if (!h->d_send[d][sd]) {
-                CK(cudaMalloc(&h->d_send[d][sd], (size_t)cnt * sizeof(double)));
-                CK(cudaMalloc(&h->d_recv[d][sd], (size_t)cnt * sizeof(double)));
-            }
-            k_halo_copy<<<grid_for(cnt, 256), 256, 0, h->st>>>(D, d, sd == 0 ? 0 : h->s[d] - h->b + 1, h->d_send[d][sd], 1);
-            nl++;
-        }
-        NK(g_nccl.GroupStart());
-        // sends low face then high face; receives in the opposite order so that the pairing is also
-        // right when both neighbours are the same rank (periodic direction split over 2 ranks)
+    return grid_for(mx, 256);
+}
+
+// reference-order ghost fill (edges and corners included) of the physical faces, for callers that ask for
+// the ghosted q_prim_vf (m_rhs.fpp:884-898); processor-face ghosts hold the transverse interior only
+static int fill_full(mfc5_handle* h, const DevP& D) {
+    for (int d = 0; d < h->nd; d++) {
+        const int t1 = d == 0 ? 1 : 0, t2 = d == 2 ? 1 : 2;
+        long long n1 = h->s[t1] + 1, n2 = h->s[t2] + 1;
+        if (t1 < d) n1 += 2 * h->b;
+        if (t2 < d && t2 < h->nd) n2 += 2 * h->b;
         for (int sd = 0; sd < 2; sd++)
-            if (h->P.bc[d][sd] >= 0) NK(g_nccl.Send(h->d_send[d][sd], cnt, NCCL_FLOAT64, h->P.bc[d][sd], h->comm, h->st));
-        for (int sd = 1; sd >= 0; sd--)
-            if (h->P.bc[d][sd] >= 0) NK(g_nccl.Recv(h->d_recv[d][sd], cnt, NCCL_FLOAT64, h->P.bc[d][sd], h->comm, h->st));
-        NK(g_nccl.GroupEnd());
-        for (int sd = 0; sd < 2; sd++) {
-            if (h->P.bc[d][sd] < 0) continue;
-            k_halo_copy<<<grid_for(cnt, 256), 256, 0, h->st>>>(D, d, sd == 0 ? -h->b : h->s[d] + 1, h->d_recv[d][sd], 0);
-            nl++;
-        }
-        if (seg_end(h, nl)) return -1;
+            if (h->P.bc[d][sd] < 0) {
+                k_bc_fill<<<grid_for(n1 * n2 * h->N, 256), 256, 0, h->st>>>(D, d, sd, 1);
+                h->launches++;
+            }
     }
+    CK(cudaGetLastError());
     return 0;
 }
 
-static int launch_sweep(mfc5_handle* h, const DevP& D, int dir) {
+// halo exchange of every processor face on the communication stream: one pack launch, one NCCL group,
+// one unpack launch (replaces s_mpi_sendrecv_variables_buffers, m_mpi_common.fpp:549-1070).  The faces of
+// the three directions are independent because only the transverse interior travels.
+static int exchange_halos(mfc5_handle* h, const DevP& D) {
+    if (!h->comm) return fail("processor boundary (bc >= 0) but mfc5_comm_init was not called");
+    cudaStream_t sc = h->st_comm;
+    HaloBufs snd, rcv;
+    for (int d = 0; d < 3; d++)
+        for (int sd = 0; sd < 2; sd++) {
+            snd.buf[2 * d + sd] = rcv.buf[2 * d + sd] = nullptr;
+            if (d >= h->nd || h->P.bc[d][sd] < 0) continue;
+            if (!h->d_send[d][sd]) {
+                const size_t nb = (size_t)halo_count(h, d) * sizeof(double);
+                CK(cudaMalloc(&h->d_send[d][sd], nb));
+                CK(cudaMalloc(&h->d_recv[d][sd], nb));
+            }
+            snd.buf[2 * d + sd] = h->d_send[d][sd];
+            rcv.buf[2 * d + sd] = h->d_recv[d][sd];
+        }
+    const dim3 grid(faces_grid_x(h, (long long)h->N * h->b), 6, 1);
+    CK(cudaStreamWaitEvent(sc, h->ev_prim, 0));
+    if (seg_begin(h, MFC5_K_HALO, sc)) return -1;
+    k_halo_faces<<<grid, 256, 0, sc>>>(D, snd, 1);
+    NK(g_nccl.GroupStart());
+    // per direction: send low face then high face, receive high then low, so that the pairing is also
+    // right when both neighbours are the same rank (periodic direction split over 2 ranks)
+    for (int d = 0; d < h->nd; d++) {
+        const size_t cnt = (size_t)halo_count(h, d);
+        for (int sd = 0; sd < 2; sd++)
+            if (h->P.bc[d][sd] >= 0) NK(g_nccl.Send(h->d_send[d][sd], cnt, NCCL_FLOAT64, h->P.bc[d][sd], h->comm, sc));
+        for (int sd = 1; sd >= 0; sd--)
+            if (h->P.bc[d][sd] >= 0) NK(g_nccl.Recv(h->d_recv[d][sd], cnt, NCCL_FLOAT64, h->P.bc[d][sd], h->comm, sc));
+    }
+    NK(g_nccl.GroupEnd());
+    k_halo_faces<<<grid, 256, 0, sc>>>(D, rcv, 0);
+    if (seg_end(h, 2, sc)) return -1;
+    CK(cudaEventRecord(h->ev_halo, sc));
+    return 0;
+}
+
+static int launch_sweep_raw(mfc5_handle* h, const DevP& D, int dir) {
     bool ok = false;
-    if (seg_begin(h, MFC5_K_SWEEP_X + dir)) return -1;
     if (!getenv("MFC5_NO_OPT")) ok = launch_sweep_opt(D, dir, h->st);
     if (!ok) ok = launch_sweep_generic_nf1(D, dir, h->st) || launch_sweep_generic_nf2(D, dir, h->st) || launch_sweep_generic_nf3(D, dir, h->st);
     if (!ok) return fail("no sweep kernel for this configuration");
-    {
-        cudaError_t e_ = cudaPeekAtLastError();
-        if (e_ != cudaSuccess) {
-            cudaGetLastError();
-            return fail(std::string("sweep launch failed, direction ") + std::to_string(dir) + ": " + cudaGetErrorString(e_));
-        }
+    cudaError_t e_ = cudaPeekAtLastError();
+    if (e_ != cudaSuccess) {
+        cudaGetLastError();
+        return fail(std::string("sweep launch failed, direction ") + std::to_string(dir) + ": " + cudaGetErrorString(e_));
     }
-    return seg_end(h, 1);
+    return 0;
+}
+
+// the sweep of one direction.  With processor boundaries the x sweep (first of the stage) is split: the
+// segments that touch no ghost cell start at once and overlap the halo exchange running on the
+// communication stream; the edge segments and the later sweeps wait for it.
+static int launch_sweep(mfc5_handle* h, const DevP& D0, int dir, bool* halo_pending) {
+    DevP D = D0;
+    int nl = 0;
+    if (seg_begin(h, MFC5_K_SWEEP_X + dir)) return -1;
+    const bool x_shuffle = dir == 0 && !(D.x_march && (long long)(h->s[1] + 1) * (h->s[2] + 1) >= 4096 && h->nd >= 2);
+    if (*halo_pending && x_shuffle) {
+        const int nx = h->s[0] + 1, segs = (nx + MFC5_XW - 1) / MFC5_XW;
+        // segment g reads cells [30 g - 3, min(30 g + 32, m + 3)]: interior iff that range is within [0, m]
+        int lo = 0, hi = segs;  // interior segments [lo, hi)
+        while (lo < segs && MFC5_XW * lo - 3 < 0) lo++;
+        while (hi > lo && std::min(MFC5_XW * (hi - 1) + 32, h->s[0] + 3) > h->s[0]) hi--;
+        if (hi > lo) {
+            D.xseg_lo = lo; D.xseg_n = hi - lo;
+            if (launch_sweep_raw(h, D, 0)) return -1;
+            nl++;
+        }
+        CK(cudaStreamWaitEvent(h->st, h->ev_halo, 0));
+        *halo_pending = false;
+        if (lo > 0) {
+            D.xseg_lo = 0; D.xseg_n = lo;
+            if (launch_sweep_raw(h, D, 0)) return -1;
+            nl++;
+        }
+        if (hi < segs) {
+            D.xseg_lo = hi; D.xseg_n = segs - hi;
+            if (launch_sweep_raw(h, D, 0)) return -1;
+            nl++;
+        }
+    } else {
+        if (*halo_pending) {
+            CK(cudaStreamWaitEvent(h->st, h->ev_halo, 0));
+            *halo_pending = false;
+        }
+        D.xseg_lo = 0; D.xseg_n = 0;
+        if (launch_sweep_raw(h, D, dir)) return -1;
+        nl++;
+    }
+    return seg_end(h, nl);
 }
 
 // one RHS evaluation (+ fused RK update when do_rk): q1 = state read, q2 = stage-1 copy, qout = target
@@ -645,24 +732,32 @@ static int run_stage(mfc5_handle* h, const double* q1, const double* q2, double*
     });
     if (rc) return rc;
     if (seg_end(h, 1)) return -1;
-    for (int d = 0; d < h->nd; d++)
-        if (fill_direction(h, D, d)) return -1;
-    for (int d = 0; d < h->nd; d++) {
-        if (D.cbc_on[d][0] || D.cbc_on[d][1]) {
-            int nl = 0;
-            if (seg_begin(h, MFC5_K_CBC)) return -1;
-            for (int sd = 0; sd < 2; sd++) {
-                if (!D.cbc_on[d][sd]) continue;
-                const CbcCoef K = h->cbc[d][sd];
-                by_shape(h, [&](auto nf, auto nd) {
-                    k_cbc<decltype(nf)::value, decltype(nd)::value><<<(unsigned)((h->plane[d] + 127) / 128), 128, 0, h->st>>>(D, K, d, sd);
-                });
-                nl++;
-            }
-            if (seg_end(h, nl)) return -1;
-        }
-        if (launch_sweep(h, D, d)) return -1;
+    bool halo_pending = false;
+    if (h->any_nb) {
+        CK(cudaEventRecord(h->ev_prim, h->st));
+        if (exchange_halos(h, D)) return -1;
+        halo_pending = true;
     }
+    if (h->any_phys) {
+        if (seg_begin(h, MFC5_K_BC_FILL)) return -1;
+        k_bc_faces<<<dim3(faces_grid_x(h, h->N), 6, 1), 256, 0, h->st>>>(D);
+        if (seg_end(h, 1)) return -1;
+    }
+    if (h->any_cbc) {
+        if (seg_begin(h, MFC5_K_CBC)) return -1;
+        long long mx = 1;
+        for (int d = 0; d < h->nd; d++) mx = std::max(mx, h->plane[d]);
+        const CbcCoef* K = h->d_cbccoef;
+        by_shape(h, [&](auto nf, auto nd) {
+            k_cbc<decltype(nf)::value, decltype(nd)::value><<<dim3((unsigned)((mx + 127) / 128), 6, 1), 128, 0, h->st>>>(D, K);
+        });
+        if (seg_end(h, 1)) return -1;
+    }
+    for (int d = 0; d < h->nd; d++)
+        if (launch_sweep(h, D, d, &halo_pending)) return -1;
+    // the next stage's cons2prim overwrites prim: the communication stream must be done reading it (it is:
+    // every sweep waited for ev_halo), and the next pack must not start before this stage's sweeps finished
+    // reading the ghosts it will overwrite -- ev_prim of the next stage is recorded after them on h->st.
     CK(cudaGetLastError());
     return 0;
 }

@@ -18,7 +18,7 @@ bool launch_sweep_generic_nf3(const DevP& P, int dir, cudaStream_t st);
 // x-sweep, warp-shuffle kernel: used when there are too few pencils for the marching kernel (1-D, thin 2-D)
 inline void sweep_grid_x(const DevP& P, dim3& grid, dim3& block) {
     block = dim3(128, 1, 1);
-    const long long segs = (P.s[0] + 1 + MFC5_XW - 1) / MFC5_XW;
+    const long long segs = P.xseg_n > 0 ? P.xseg_n : (P.s[0] + 1 + MFC5_XW - 1) / MFC5_XW;
     const long long warps = segs * (long long)(P.s[1] + 1) * (P.s[2] + 1);
     grid = dim3((unsigned)((warps * 32 + 127) / 128), 1, 1);
 }

@@ -100,16 +100,20 @@ __global__ void __launch_bounds__(256) k_cons2prim(const __grid_constant__ DevP 
 // :704 no-slip, :877 Dirichlet).  One thread per (transverse point, variable); loops the b layers.
 // -------------------------------------------------------------------------------------------------
 #ifdef MFC5_HOST_TU
-__global__ void __launch_bounds__(256) k_bc_fill(const __grid_constant__ DevP P, int d, int side) {
+// `full` = 1: the reference's sequential semantics (direction d spans the ghosts of directions < d, so
+// edges and corners get filled; needed only when a caller asks for the ghosted q_prim_vf);
+// `full` = 0: transverse interior only -- all the inviscid sweeps, CBC and the reductions ever read
+// (faces use the transverse interior, m_rhs.fpp:1020-1027), which makes the six faces independent.
+__device__ __forceinline__ void bc_fill_face(const DevP& P, int d, int side, int full, long long t0, long long nthreads) {
     const int bc = P.bc[d][side];
     int lo[3] = {0, 0, 0}, hi[3] = {P.s[0], P.s[1], P.s[2]};
-    for (int e = 0; e < d; e++) { lo[e] = -P.b; hi[e] = P.s[e] + P.b; }
+    if (full) for (int e = 0; e < d; e++) { lo[e] = -P.b; hi[e] = P.s[e] + P.b; }
     const int t1 = d == 0 ? 1 : 0, t2 = d == 2 ? 1 : 2;
     const int n1 = hi[t1] - lo[t1] + 1, n2 = hi[t2] - lo[t2] + 1;
     const long long tot = (long long)n1 * n2 * P.N;
     const long long strd[3] = {1, P.sy, P.sz};
     const int s = P.s[d];
-    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < tot; t += (long long)gridDim.x * blockDim.x) {
+    for (long long t = t0; t < tot; t += nthreads) {
         const int a1 = (int)(t % n1) + lo[t1];
         const long long r = t / n1;
         const int a2 = (int)(r % n2) + lo[t2];
@@ -145,6 +149,18 @@ __global__ void __launch_bounds__(256) k_bc_fill(const __grid_constant__ DevP P,
     }
 }
 
+// one (direction, side), reference order (used for the ghosted q_prim_vf download)
+__global__ void __launch_bounds__(256) k_bc_fill(const __grid_constant__ DevP P, int d, int side, int full) {
+    bc_fill_face(P, d, side, full, blockIdx.x * (long long)blockDim.x + threadIdx.x, (long long)gridDim.x * blockDim.x);
+}
+
+// every physical face of the block in ONE launch: blockIdx.y = 2 * direction + side
+__global__ void __launch_bounds__(256) k_bc_faces(const __grid_constant__ DevP P) {
+    const int d = blockIdx.y >> 1, side = blockIdx.y & 1;
+    if (d >= P.nd || P.bc[d][side] >= 0) return;
+    bc_fill_face(P, d, side, 0, blockIdx.x * (long long)blockDim.x + threadIdx.x, (long long)gridDim.x * blockDim.x);
+}
+
 #endif  // MFC5_HOST_TU
 
 // -------------------------------------------------------------------------------------------------
@@ -163,10 +179,14 @@ struct CbcCoef {
     int grcbc_in, grcbc_out, grcbc_vel_out;
 };
 
+// every characteristic-BC face of the block in ONE launch (blockIdx.y = 2 * direction + side); Kall[6] in HBM
 template <int NF, int ND>
-__global__ void __launch_bounds__(128) k_cbc(const __grid_constant__ DevP P, const __grid_constant__ CbcCoef K, int d, int side) {
+__global__ void __launch_bounds__(128) k_cbc(const __grid_constant__ DevP P, const CbcCoef* __restrict__ Kall) {
     using S = Shape<NF, ND>;
     constexpr int N = S::N;
+    const int d = blockIdx.y >> 1, side = blockIdx.y & 1;
+    if (d >= ND || !P.cbc_on[d][side]) return;
+    const CbcCoef& K = Kall[blockIdx.y];
     const int t1 = d == 0 ? 1 : 0, t2 = d == 2 ? 1 : 2;
     const int n1 = P.s[t1] + 1, n2 = P.s[t2] + 1;
     const long long plane = (long long)n1 * n2;
@@ -412,10 +432,10 @@ __global__ void __launch_bounds__(128, MFC5_X_MINB) k_sweep_x(const __grid_const
     const int lane = threadIdx.x & 31;
     const long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
     const int nx = P.s[0] + 1;
-    const int segs = (nx + MFC5_XW - 1) / MFC5_XW;
+    const int segs = P.xseg_n > 0 ? P.xseg_n : (nx + MFC5_XW - 1) / MFC5_XW;  // segments of this launch
     const long long rows = (long long)(P.s[1] + 1) * (P.s[2] + 1);
     if (warp >= rows * segs) return;  // warp-uniform
-    const int seg = (int)(warp % segs);
+    const int seg = P.xseg_lo + (int)(warp % segs);
     const long long row = warp / segs;
     const int j = (int)(row % (P.s[1] + 1)), k = (int)(row / (P.s[1] + 1));
     const int i0 = seg * MFC5_XW;
@@ -729,14 +749,23 @@ __global__ void __launch_bounds__(256) k_reduce(const __grid_constant__ DevP P, 
 }
 
 // packed halo faces for processor boundaries (replaces the pack/unpack loops of
-// s_mpi_sendrecv_variables_buffers, src/common/m_mpi_common.fpp:620-804,839-1065)
+// s_mpi_sendrecv_variables_buffers, src/common/m_mpi_common.fpp:620-804,839-1065), every processor face
+// of the block in ONE launch (blockIdx.y = 2 * direction + side).  Only the transverse interior travels
+// (the reference also ships the edge/corner ghosts, which the inviscid path never reads).
+struct HaloBufs {
+    double* buf[6];
+};
 #ifdef MFC5_HOST_TU
-__global__ void __launch_bounds__(256) k_halo_copy(const __grid_constant__ DevP P, int d, int first, double* buf, int pack) {
+__global__ void __launch_bounds__(256) k_halo_faces(const __grid_constant__ DevP P, const __grid_constant__ HaloBufs B, int pack) {
+    const int d = blockIdx.y >> 1, side = blockIdx.y & 1;
+    if (d >= P.nd || P.bc[d][side] < 0) return;
     int lo[3] = {0, 0, 0}, hi[3] = {P.s[0], P.s[1], P.s[2]};
-    for (int e = 0; e < d; e++) { lo[e] = -P.b; hi[e] = P.s[e] + P.b; }
+    // pack: the b interior layers next to the face; unpack: the b ghost layers beyond it
+    const int first = pack ? (side == 0 ? 0 : P.s[d] - P.b + 1) : (side == 0 ? -P.b : P.s[d] + 1);
     lo[d] = first; hi[d] = first + P.b - 1;
     const int n0 = hi[0] - lo[0] + 1, n1 = hi[1] - lo[1] + 1, n2 = hi[2] - lo[2] + 1;
     const long long per = (long long)n0 * n1 * n2, tot = per * P.N;
+    double* buf = B.buf[blockIdx.y];
     for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < tot; t += (long long)gridDim.x * blockDim.x) {
         const int v = (int)(t / per);
         long long r = t % per;
