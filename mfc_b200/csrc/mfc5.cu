@@ -114,6 +114,9 @@ struct mfc5_handle {
     // graph replay of a whole step, keyed by (cur, dt)
     cudaGraphExec_t gexec[2] = {nullptr, nullptr};
     double gdt[2] = {0, 0};
+    long long glaunches[2] = {0, 0};  // kernel launches inside each captured step
+    bool warmed = false;              // one step has run uncaptured (lazy allocations, function attributes)
+    int use_graph = 1;
 };
 
 static bool is_cbc(int bc) { return bc <= MFC5_BC_CHAR_SLIP_WALL && bc >= MFC5_BC_CHAR_SUP_OUTFLOW; }
@@ -473,6 +476,8 @@ extern "C" int mfc5_finalize_setup(mfc5_handle* h) {
     D.chunk = 0;
     if (const char* e = getenv("MFC5_CHUNK")) D.chunk = std::max(0, atoi(e));
     D.x_march = getenv("MFC5_X_MARCH") ? 1 : 0;
+    h->use_graph = getenv("MFC5_NO_GRAPH") ? 0 : 1;
+    h->warmed = false;
     h->setup = true;
     for (int i = 0; i < 2; i++) if (h->gexec[i]) { cudaGraphExecDestroy(h->gexec[i]); h->gexec[i] = nullptr; }
     return 0;
@@ -820,11 +825,51 @@ extern "C" int mfc5_tvd_rk(mfc5_handle* h, double dt, double* stage_time_min) {
     return 0;
 }
 
+// Enqueue `nsteps` steps without host synchronisation.  After one uncaptured step the whole step (every
+// kernel of the 3 stages, the communication-stream fork/join and the NCCL group) is captured once per
+// ping-pong parity into a CUDA graph and replayed: a step costs one graph launch instead of ~15-50 kernel
+// launches, which is what matters on the small configurations (C1, C2, C4 strong scaling).
 extern "C" int mfc5_tvd_rk_n(mfc5_handle* h, double dt, int nsteps) {
     if (!h || !h->setup) return fail("mfc5_tvd_rk_n: handle not set up");
     CK(cudaSetDevice(h->P.device));
-    for (int i = 0; i < nsteps; i++)
-        if (enqueue_step(h, dt, false)) return -1;
+    for (int i = 0; i < nsteps; i++) {
+        if (!h->use_graph || !h->warmed) {
+            if (enqueue_step(h, dt, false)) return -1;
+            h->warmed = true;
+            continue;
+        }
+        const int par = h->cur;
+        if (!h->gexec[par] || h->gdt[par] != dt) {
+            if (h->gexec[par]) { cudaGraphExecDestroy(h->gexec[par]); h->gexec[par] = nullptr; }
+            const long long l0 = h->launches;
+            cudaGraph_t graph = nullptr;
+            cudaError_t e = cudaStreamBeginCapture(h->st, cudaStreamCaptureModeRelaxed);
+            int rc = 0;
+            if (e == cudaSuccess) {
+                rc = enqueue_step(h, dt, false);
+                e = cudaStreamEndCapture(h->st, &graph);
+            }
+            if (e == cudaSuccess && rc == 0 && graph) e = cudaGraphInstantiate(&h->gexec[par], graph, 0);
+            if (graph) cudaGraphDestroy(graph);
+            if (e != cudaSuccess || rc != 0 || !h->gexec[par]) {
+                // capture not possible here (e.g. an NCCL build without graph support): run eagerly from now on
+                cudaGetLastError();
+                h->gexec[par] = nullptr;
+                h->use_graph = 0;
+                h->launches = l0;
+                if (rc == 0 && h->cur != par) h->cur = par;  // the captured enqueue flipped the parity without running
+                if (enqueue_step(h, dt, false)) return -1;
+                continue;
+            }
+            h->glaunches[par] = h->launches - l0;
+            h->gdt[par] = dt;
+            h->launches = l0;
+            h->cur = par;  // enqueue_step flipped it while capturing; the replay below flips it for real
+        }
+        CK(cudaGraphLaunch(h->gexec[par], h->st));
+        h->launches += h->glaunches[par];
+        if (h->P.time_stepper > 1) h->cur ^= 1;
+    }
     return 0;
 }
 

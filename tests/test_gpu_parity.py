@@ -143,3 +143,18 @@ def test_baseline_config_vs_oracle(name, mode):
             err = np.max(np.abs(a[v] - b[v])) / scale
             assert err <= 1e-10, f"{name} var {v + 1}: {err:.3e}"
     g.close()
+
+
+@pytest.mark.parametrize("uuid", ["2AB32975", "4129A23A", "B5F0C655"])
+def test_graph_replay_is_bitwise_eager(uuid):
+    """mfc5_tvd_rk_n (CUDA-graph replay of the captured step) == the same number of mfc5_tvd_rk calls."""
+    case, P, cbs, cons, dbuf, g1 = _gpu(uuid, strict=False)
+    _, _, _, _, _, g2 = _gpu(uuid, strict=False)
+    dt = float(case["dt"])
+    for _ in range(7):
+        g1.step(dt)
+    l0 = g2.kernel_launches
+    g2.steps(dt, 7)
+    g2.sync()
+    assert g2.kernel_launches - l0 == g1.kernel_launches
+    np.testing.assert_array_equal(g1.get_cons(), g2.get_cons())
