@@ -86,7 +86,7 @@ struct mfc5_handle {
     std::vector<double> scb[3], ds[3];
     bool grid_set[3] = {false, false, false};
     bool setup = false;
-    double* d_tab[3][8] = {};  // cL cR dL dR bt ds + combined rows + their transpose
+    double* d_tab[3][9] = {};  // cL cR dL dR bt ds + combined rows + their transpose + x-segment layout
     int uniform[3] = {1, 1, 1};
     CbcCoef cbc[3][2];
     double* d_cbcbuf[3][2] = {};
@@ -197,7 +197,7 @@ extern "C" int mfc5_destroy(mfc5_handle* h) {
     for (int i = 0; i < 2; i++) { cudaFree(h->d_q[i]); if (h->gexec[i]) cudaGraphExecDestroy(h->gexec[i]); }
     cudaFree(h->d_prim); cudaFree(h->d_rhs); cudaFree(h->d_red);
     for (int d = 0; d < 3; d++) {
-        for (int k = 0; k < 8; k++) cudaFree(h->d_tab[d][k]);
+        for (int k = 0; k < 9; k++) cudaFree(h->d_tab[d][k]);
         for (int k = 0; k < 2; k++) { cudaFree(h->d_cbcbuf[d][k]); cudaFree(h->d_dirich[d][k]); cudaFree(h->d_send[d][k]); cudaFree(h->d_recv[d][k]); }
     }
     for (auto& ev : h->ev_stage) cudaEventDestroy(ev);
@@ -446,6 +446,17 @@ extern "C" int mfc5_finalize_setup(mfc5_handle* h) {
             if (upload(&h->d_tab[d][7], rowsT)) return -1;
             D.T[d].tabT = h->d_tab[d][7];
             D.T[d].nslot = nslot;
+            if (d == 0) {  // x kernel: [segment][MFC5_TAB][lane], lane l of segment g = cell 30 g - 1 + l (clamped to s + 1)
+                const int nseg = (h->s[0] + 1 + MFC5_XW - 1) / MFC5_XW;
+                std::vector<double> rowsX((size_t)nseg * MFC5_TAB * 32);
+                for (int g = 0; g < nseg; g++)
+                    for (int l = 0; l < 32; l++) {
+                        const int sl = std::min(MFC5_XW * g - 1 + l, h->s[0] + 1) + h->b;
+                        for (int k = 0; k < MFC5_TAB; k++) rowsX[((size_t)g * MFC5_TAB + k) * 32 + l] = rows[(size_t)sl * MFC5_TAB + k];
+                    }
+                if (upload(&h->d_tab[d][8], rowsX)) return -1;
+                D.T[d].tabX = h->d_tab[d][8];
+            }
         }
         const int t1 = d == 0 ? 1 : 0, t2 = d == 2 ? 1 : 2;
         h->plane[d] = (long long)(h->s[t1] + 1) * (h->s[t2] + 1);
@@ -496,6 +507,7 @@ extern "C" int mfc5_set_dirichlet(mfc5_handle* h, int d, int side, const double*
 }
 
 static int fill_full(mfc5_handle* h, const DevP& D);
+static unsigned grid_for(long long n, int block) { return (unsigned)std::min<long long>((n + block - 1) / block, 148LL * 16); }
 
 // ---- host <-> device field copies ------------------------------------------------------------------
 static int copy_fields(mfc5_handle* h, double* dev, const double* const* hostc, double* const* hostm, int ghosted, bool to_dev) {
@@ -507,19 +519,40 @@ static int copy_fields(mfc5_handle* h, double* dev, const double* const* hostc, 
     // copy region: upload -> interior only; download -> everything the host array holds
     const int cgx = to_dev ? 0 : gx, cgy = to_dev ? 0 : gy, cgz = to_dev ? 0 : gz;
     const size_t wx = h->s[0] + 1 + 2 * cgx, wy = h->s[1] + 1 + 2 * cgy, wz = h->s[2] + 1 + 2 * cgz;
+    // Staging image = the other ping-pong state buffer: between calls it only holds the stale previous state
+    // (stage 1 of the next step rewrites its whole interior), and one field of the host shape fits in one
+    // device field (px >= m + 1 + 2b).  One contiguous DMA per field (one in total when the caller's fields
+    // are adjacent in memory) + one repack kernel at HBM rate.
+    double* stage = h->d_q[h->cur ^ 1];
+    if (dev == stage) return fail("copy_fields: source aliases the staging buffer");
+    const size_t hfs = hx * hy * hz;
+    if ((long long)hfs > h->fs) return fail("copy_fields: staging image does not fit");
+    RepackGeom G;
+    G.N = h->N; G.wx = (int)wx; G.wy = (int)wy; G.wz = (int)wz;
+    G.dev_off = (h->ox - cgx) + (long long)(h->oy - cgy) * h->px + (long long)(h->oz - cgz) * h->px * h->ey;
+    G.sy = h->px; G.sz = h->px * h->ey; G.fs = h->fs;
+    G.st_off = (gx - cgx) + (long long)(gy - cgy) * hx + (long long)(gz - cgz) * hx * hy;
+    G.hx = hx; G.hxy = hx * hy; G.hfs = hfs;
+    bool adjacent = true;
     for (int v = 0; v < h->N; v++) {
-        cudaMemcpy3DParms p = {};
-        double* hp = to_dev ? const_cast<double*>(hostc[v]) : hostm[v];
+        const double* hp = to_dev ? hostc[v] : hostm[v];
         if (!hp) return fail("null field pointer");
-        cudaPitchedPtr hptr = make_cudaPitchedPtr(hp, hx * sizeof(double), hx, hy);
-        cudaPitchedPtr dptr = make_cudaPitchedPtr(dev + (size_t)v * h->fs, h->px * sizeof(double), h->px, h->ey);
-        cudaPos hpos = make_cudaPos((gx - cgx) * sizeof(double), gy - cgy, gz - cgz);
-        cudaPos dpos = make_cudaPos((h->ox - cgx) * sizeof(double), h->oy - cgy, h->oz - cgz);
-        p.extent = make_cudaExtent(wx * sizeof(double), wy, wz);
-        if (to_dev) { p.srcPtr = hptr; p.srcPos = hpos; p.dstPtr = dptr; p.dstPos = dpos; p.kind = cudaMemcpyHostToDevice; }
-        else { p.srcPtr = dptr; p.srcPos = dpos; p.dstPtr = hptr; p.dstPos = hpos; p.kind = cudaMemcpyDeviceToHost; }
-        CK(cudaMemcpy3DAsync(&p, h->st));
+        const double* h0 = to_dev ? hostc[0] : hostm[0];
+        if (hp != h0 + (size_t)v * hfs) adjacent = false;
     }
+    const unsigned grid = grid_for((long long)wx * wy * wz * h->N, 256);
+    if (!to_dev) { k_repack<<<grid, 256, 0, h->st>>>(dev, stage, G, 0); h->launches++; }
+    if (adjacent) {
+        if (to_dev) CK(cudaMemcpyAsync(stage, hostc[0], hfs * h->N * sizeof(double), cudaMemcpyHostToDevice, h->st));
+        else CK(cudaMemcpyAsync(hostm[0], stage, hfs * h->N * sizeof(double), cudaMemcpyDeviceToHost, h->st));
+    } else {
+        for (int v = 0; v < h->N; v++) {
+            if (to_dev) CK(cudaMemcpyAsync(stage + (size_t)v * hfs, hostc[v], hfs * sizeof(double), cudaMemcpyHostToDevice, h->st));
+            else CK(cudaMemcpyAsync(hostm[v], stage + (size_t)v * hfs, hfs * sizeof(double), cudaMemcpyDeviceToHost, h->st));
+        }
+    }
+    if (to_dev) { k_repack<<<grid, 256, 0, h->st>>>(dev, stage, G, 1); h->launches++; }
+    CK(cudaGetLastError());
     // stream-ordered on the compute stream (truly asynchronous for pinned host arrays); the call
     // returns when the data has arrived, like the reference's GPU_UPDATE
     CK(cudaStreamSynchronize(h->st));
@@ -566,7 +599,6 @@ static int by_shape(const mfc5_handle* h, F&& f) {
     return fail("unsupported (num_fluids, num_dims)");
 }
 
-static unsigned grid_for(long long n, int block) { return (unsigned)std::min<long long>((n + block - 1) / block, 148LL * 16); }
 
 // timing segments: when h->timing, every kernel class is bracketed by a pair of events
 static int seg_begin(mfc5_handle* h, int cls, cudaStream_t st = nullptr) {

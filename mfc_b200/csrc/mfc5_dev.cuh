@@ -29,6 +29,9 @@ struct DirTables {
     //   [27,30) dL+dL^2  [30,33) dR+dR^2  [33,36) 1-2dL  [36,39) 1-2dR  [39,42) dL^2  [42,45) dR^2  [45] ds  [46] 1/ds
     const double* tab;
     const double* tabT;  // the same, transposed: [MFC5_TAB][nslot]
+    // x kernel: per 30-cell warp segment, [segment][MFC5_TAB][32 lanes]; lane l holds the row of cell
+    // 30*segment - 1 + l (clamped to s+1): lane-contiguous loads at immediate offsets
+    const double* tabX;
     int nslot;
     int uniform;       // uniform_grid(dir), m_weno.fpp:869-879
 };
@@ -102,6 +105,12 @@ struct RowSoA {
     __device__ __forceinline__ double operator[](int k) const { return __ldg(p + k * stride); }
 };
 
+struct RowSeg {
+    static constexpr bool kHasMapTerms = true;
+    const double* __restrict__ p;                // tabX + segment * MFC5_TAB * 32 + lane
+    __device__ __forceinline__ double operator[](int k) const { return __ldg(p + k * 32); }
+};
+
 // WENO-M map of a normalised weight w with ideal weight d (m_weno.fpp:1150-1156), as numerator and
 // denominator:  g(w) = w (d + d^2 - 3 d w + w^2) / (d^2 + w (1 - 2 d));  c1 = d + d^2, c2 = 1 - 2d, dsq = d^2
 __device__ __forceinline__ void map_nd(double d, double c1, double c2, double dsq, double w, double& num, double& den) {
@@ -109,100 +118,139 @@ __device__ __forceinline__ void map_nd(double d, double c1, double c2, double ds
     den = fma(w, c2, dsq);
 }
 
-template <int WV, class ROW>
-__device__ __forceinline__ void weno5_fast(const DevP& P, const DirTables& T, const ROW row, const double f0,
-                                           const double f1, const double f2, const double f3, const double f4, double& eL, double& eR) {
+// NV variables of one cell at a time: every table value is loaded once and applied to all NV stencils
+// (f[u][0..4] = v(j-2..j+2) of variable u), which also gives the FP64 pipe NV independent chains.
+template <int WV, int NV, class ROW>
+__device__ __forceinline__ void weno5_fast(const DevP& P, const DirTables& T, const ROW row, const double (&f)[NV][5],
+                                           double (&eL)[NV], double (&eR)[NV]) {
     const double eps = P.eps;
-    const double d1 = f4 - f3, d0 = f3 - f2, dm1 = f2 - f1, dm2 = f1 - f0;
-    double b0, b1, b2;
-    if (T.uniform) {
-        b0 = 13.0 / 12.0 * sq(d1 - d0) + 0.25 * sq(d1 - 3.0 * d0) + eps;
-        b1 = 13.0 / 12.0 * sq(d0 - dm1) + 0.25 * sq(d0 + dm1) + eps;
-        b2 = 13.0 / 12.0 * sq(dm1 - dm2) + 0.25 * sq(3.0 * dm1 - dm2) + eps;
-    } else {  // B0 x^2 + B1 x y + B2 y^2 + eps  =  x (B0 x + B1 y) + (B2 y) y + eps : 5 operations
-        b0 = fma(d1, fma(row[18], d1, row[19] * d0), fma(row[20] * d0, d0, eps));
-        b1 = fma(d0, fma(row[21], d0, row[22] * dm1), fma(row[23] * dm1, dm1, eps));
-        b2 = fma(dm1, fma(row[24], dm1, row[25] * dm2), fma(row[26] * dm2, dm2, eps));
-    }
-    // common-denominator factors shared by both sides
-    double g0, g1, g2;
-    if (WV == 2) {  // Z: a_q = d_q (1 + tau/b_q)  ~  d_q (b_q + tau) b_r b_s
-        const double tau = fabs(b2 - b0);
-        g0 = (b0 + tau) * (b1 * b2);
-        g1 = (b1 + tau) * (b0 * b2);
-        g2 = (b2 + tau) * (b0 * b1);
-    } else {        // JS (and first stage of M): a_q = d_q / b_q^2  ~  d_q (b_r b_s)^2
-        const double p12 = b1 * b2, p02 = b0 * b2, p01 = b0 * b1;
-        g0 = p12 * p12; g1 = p02 * p02; g2 = p01 * p01;
+    double d1[NV], d0[NV], dm1[NV], dm2[NV], g0[NV], g1[NV], g2[NV];
+#pragma unroll
+    for (int u = 0; u < NV; u++) { d1[u] = f[u][4] - f[u][3]; d0[u] = f[u][3] - f[u][2]; dm1[u] = f[u][2] - f[u][1]; dm2[u] = f[u][1] - f[u][0]; }
+    {
+        double b0[NV], b1[NV], b2[NV];
+        if (T.uniform) {
+#pragma unroll
+            for (int u = 0; u < NV; u++) {
+                b0[u] = 13.0 / 12.0 * sq(d1[u] - d0[u]) + 0.25 * sq(d1[u] - 3.0 * d0[u]) + eps;
+                b1[u] = 13.0 / 12.0 * sq(d0[u] - dm1[u]) + 0.25 * sq(d0[u] + dm1[u]) + eps;
+                b2[u] = 13.0 / 12.0 * sq(dm1[u] - dm2[u]) + 0.25 * sq(3.0 * dm1[u] - dm2[u]) + eps;
+            }
+        } else {  // B0 x^2 + B1 x y + B2 y^2 + eps  =  x (B0 x + B1 y) + (B2 y) y + eps : 5 operations
+            const double r18 = row[18], r19 = row[19], r20 = row[20], r21 = row[21], r22 = row[22], r23 = row[23], r24 = row[24],
+                         r25 = row[25], r26 = row[26];
+#pragma unroll
+            for (int u = 0; u < NV; u++) {
+                b0[u] = fma(d1[u], fma(r18, d1[u], r19 * d0[u]), fma(r20 * d0[u], d0[u], eps));
+                b1[u] = fma(d0[u], fma(r21, d0[u], r22 * dm1[u]), fma(r23 * dm1[u], dm1[u], eps));
+                b2[u] = fma(dm1[u], fma(r24, dm1[u], r25 * dm2[u]), fma(r26 * dm2[u], dm2[u], eps));
+            }
+        }
+        // common-denominator factors shared by both sides
+#pragma unroll
+        for (int u = 0; u < NV; u++) {
+            if (WV == 2) {  // Z: a_q = d_q (1 + tau/b_q)  ~  d_q (b_q + tau) b_r b_s
+                const double tau = fabs(b2[u] - b0[u]);
+                g0[u] = (b0[u] + tau) * (b1[u] * b2[u]);
+                g1[u] = (b1[u] + tau) * (b0[u] * b2[u]);
+                g2[u] = (b2[u] + tau) * (b0[u] * b1[u]);
+            } else {        // JS (and first stage of M): a_q = d_q / b_q^2  ~  d_q (b_r b_s)^2
+                const double p12 = b1[u] * b2[u], p02 = b0[u] * b2[u], p01 = b0[u] * b1[u];
+                g0[u] = p12 * p12; g1[u] = p02 * p02; g2[u] = p01 * p01;
+            }
+        }
     }
 #pragma unroll
     for (int side = 0; side < 2; side++) {
         const int cc = side * 6, dd = 12 + side * 3;
         const double dd0 = row[dd + 0], dd1 = row[dd + 1], dd2 = row[dd + 2];
-        const double p0 = fma(row[cc + 1], d0, fma(row[cc + 0], d1, f2));
-        const double p1 = fma(row[cc + 3], dm1, fma(row[cc + 2], d0, f2));
-        const double p2 = fma(row[cc + 5], dm2, fma(row[cc + 4], dm1, f2));
-        double a0 = dd0 * g0, a1 = dd1 * g1, a2 = dd2 * g2;
+        const double c0 = row[cc + 0], c1 = row[cc + 1], c2 = row[cc + 2], c3 = row[cc + 3], c4 = row[cc + 4], c5 = row[cc + 5];
+        double m1[3], m2[3], m3[3];  // d + d^2, 1 - 2d, d^2
         if (WV == 1) {
-            const double r = rcp_nr(a0 + a1 + a2);
-            const int c1 = 27 + side * 3, c2 = 33 + side * 3, dq = 39 + side * 3;
-            double n0, n1, n2, e0, e1, e2;
             if (ROW::kHasMapTerms) {
-                map_nd(dd0, row[c1 + 0], row[c2 + 0], row[dq + 0], a0 * r, n0, e0);
-                map_nd(dd1, row[c1 + 1], row[c2 + 1], row[dq + 1], a1 * r, n1, e1);
-                map_nd(dd2, row[c1 + 2], row[c2 + 2], row[dq + 2], a2 * r, n2, e2);
+#pragma unroll
+                for (int q = 0; q < 3; q++) { m1[q] = row[27 + side * 3 + q]; m2[q] = row[33 + side * 3 + q]; m3[q] = row[39 + side * 3 + q]; }
             } else {
-                map_nd(dd0, fma(dd0, dd0, dd0), fma(-2.0, dd0, 1.0), dd0 * dd0, a0 * r, n0, e0);
-                map_nd(dd1, fma(dd1, dd1, dd1), fma(-2.0, dd1, 1.0), dd1 * dd1, a1 * r, n1, e1);
-                map_nd(dd2, fma(dd2, dd2, dd2), fma(-2.0, dd2, 1.0), dd2 * dd2, a2 * r, n2, e2);
+                m1[0] = fma(dd0, dd0, dd0); m2[0] = fma(-2.0, dd0, 1.0); m3[0] = dd0 * dd0;
+                m1[1] = fma(dd1, dd1, dd1); m2[1] = fma(-2.0, dd1, 1.0); m3[1] = dd1 * dd1;
+                m1[2] = fma(dd2, dd2, dd2); m2[2] = fma(-2.0, dd2, 1.0); m3[2] = dd2 * dd2;
             }
-            a0 = n0 * (e1 * e2);
-            a1 = n1 * (e0 * e2);
-            a2 = n2 * (e0 * e1);
         }
-        const double val = fma(a2, p2, fma(a1, p1, a0 * p0)) * rcp_nr(a0 + a1 + a2);
-        if (side == 0) eL = val; else eR = val;
+#pragma unroll
+        for (int u = 0; u < NV; u++) {
+            const double f2 = f[u][2];
+            const double p0 = fma(c1, d0[u], fma(c0, d1[u], f2));
+            const double p1 = fma(c3, dm1[u], fma(c2, d0[u], f2));
+            const double p2 = fma(c5, dm2[u], fma(c4, dm1[u], f2));
+            double a0 = dd0 * g0[u], a1 = dd1 * g1[u], a2 = dd2 * g2[u];
+            if (WV == 1) {
+                const double r = rcp_nr(a0 + a1 + a2);
+                double n0, n1, n2, e0, e1, e2;
+                map_nd(dd0, m1[0], m2[0], m3[0], a0 * r, n0, e0);
+                map_nd(dd1, m1[1], m2[1], m3[1], a1 * r, n1, e1);
+                map_nd(dd2, m1[2], m2[2], m3[2], a2 * r, n2, e2);
+                a0 = n0 * (e1 * e2);
+                a1 = n1 * (e0 * e2);
+                a2 = n2 * (e0 * e1);
+            }
+            const double val = fma(a2, p2, fma(a1, p1, a0 * p0)) * rcp_nr(a0 + a1 + a2);
+            if (side == 0) eL[u] = val; else eR[u] = val;
+        }
     }
 }
 
-template <int WV, class ROW>
-__device__ __forceinline__ void weno3_fast(const DevP& P, const DirTables& T, const ROW row, const double f1,
-                                           const double f2, const double f3, double& eL, double& eR) {
+template <int WV, int NV, class ROW>
+__device__ __forceinline__ void weno3_fast(const DevP& P, const DirTables& T, const ROW row, const double (&f)[NV][5],
+                                           double (&eL)[NV], double (&eR)[NV]) {
     const double eps = P.eps;
-    const double d0 = f3 - f2, dm1 = f2 - f1;
-    const double b0 = fma(row[18] * d0, d0, eps);
-    const double b1 = fma(row[21] * dm1, dm1, eps);
-    double g0, g1;
-    if (WV == 2) {
-        const double tau = fabs(b1 - b0);
-        g0 = (b0 + tau) * b1;
-        g1 = (b1 + tau) * b0;
-    } else {
-        g0 = b1 * b1;
-        g1 = b0 * b0;
+    double d0[NV], dm1[NV], g0[NV], g1[NV];
+    const double r18 = row[18], r21 = row[21];
+#pragma unroll
+    for (int u = 0; u < NV; u++) {
+        d0[u] = f[u][3] - f[u][2]; dm1[u] = f[u][2] - f[u][1];
+        const double b0 = fma(r18 * d0[u], d0[u], eps);
+        const double b1 = fma(r21 * dm1[u], dm1[u], eps);
+        if (WV == 2) {
+            const double tau = fabs(b1 - b0);
+            g0[u] = (b0 + tau) * b1;
+            g1[u] = (b1 + tau) * b0;
+        } else {
+            g0[u] = b1 * b1;
+            g1[u] = b0 * b0;
+        }
     }
 #pragma unroll
     for (int side = 0; side < 2; side++) {
         const int cc = side * 6, dd = 12 + side * 3;
         const double dd0 = row[dd + 0], dd1 = row[dd + 1];
-        const double p0 = fma(row[cc + 0], d0, f2);
-        const double p1 = fma(row[cc + 1], dm1, f2);
-        double a0 = dd0 * g0, a1 = dd1 * g1;
+        const double c0 = row[cc + 0], c1 = row[cc + 1];
+        double m1[2], m2[2], m3[2];
         if (WV == 1) {
-            const double r = rcp_nr(a0 + a1);
-            double n0, n1, e0, e1;
             if (ROW::kHasMapTerms) {
-                map_nd(dd0, row[27 + side * 3], row[33 + side * 3], row[39 + side * 3], a0 * r, n0, e0);
-                map_nd(dd1, row[28 + side * 3], row[34 + side * 3], row[40 + side * 3], a1 * r, n1, e1);
+#pragma unroll
+                for (int q = 0; q < 2; q++) { m1[q] = row[27 + side * 3 + q]; m2[q] = row[33 + side * 3 + q]; m3[q] = row[39 + side * 3 + q]; }
             } else {
-                map_nd(dd0, fma(dd0, dd0, dd0), fma(-2.0, dd0, 1.0), dd0 * dd0, a0 * r, n0, e0);
-                map_nd(dd1, fma(dd1, dd1, dd1), fma(-2.0, dd1, 1.0), dd1 * dd1, a1 * r, n1, e1);
+                m1[0] = fma(dd0, dd0, dd0); m2[0] = fma(-2.0, dd0, 1.0); m3[0] = dd0 * dd0;
+                m1[1] = fma(dd1, dd1, dd1); m2[1] = fma(-2.0, dd1, 1.0); m3[1] = dd1 * dd1;
             }
-            a0 = n0 * e1;
-            a1 = n1 * e0;
         }
-        const double val = fma(a1, p1, a0 * p0) * rcp_nr(a0 + a1);
-        if (side == 0) eL = val; else eR = val;
+#pragma unroll
+        for (int u = 0; u < NV; u++) {
+            const double f2 = f[u][2];
+            const double p0 = fma(c0, d0[u], f2);
+            const double p1 = fma(c1, dm1[u], f2);
+            double a0 = dd0 * g0[u], a1 = dd1 * g1[u];
+            if (WV == 1) {
+                const double r = rcp_nr(a0 + a1);
+                double n0, n1, e0, e1;
+                map_nd(dd0, m1[0], m2[0], m3[0], a0 * r, n0, e0);
+                map_nd(dd1, m1[1], m2[1], m3[1], a1 * r, n1, e1);
+                a0 = n0 * e1;
+                a1 = n1 * e0;
+            }
+            const double val = fma(a1, p1, a0 * p0) * rcp_nr(a0 + a1);
+            if (side == 0) eL[u] = val; else eR[u] = val;
+        }
     }
 }
 
@@ -220,15 +268,18 @@ __device__ __forceinline__ void weno_edges(const DevP& P, const DirTables& T, in
     const double eps = P.eps;
     if (wo == 1) { eL = f2; eR = f2; return; }
     if (FAST) {
+        const double f[1][5] = {{f0, f1, f2, f3, f4}};
+        double l[1], r[1];
         if (wo == 3) {
-            if (wv == 1) weno3_fast<1>(P, T, row, f1, f2, f3, eL, eR);
-            else if (wv == 2) weno3_fast<2>(P, T, row, f1, f2, f3, eL, eR);
-            else weno3_fast<0>(P, T, row, f1, f2, f3, eL, eR);
+            if (wv == 1) weno3_fast<1, 1>(P, T, row, f, l, r);
+            else if (wv == 2) weno3_fast<2, 1>(P, T, row, f, l, r);
+            else weno3_fast<0, 1>(P, T, row, f, l, r);
         } else {
-            if (wv == 1) weno5_fast<1>(P, T, row, f0, f1, f2, f3, f4, eL, eR);
-            else if (wv == 2) weno5_fast<2>(P, T, row, f0, f1, f2, f3, f4, eL, eR);
-            else weno5_fast<0>(P, T, row, f0, f1, f2, f3, f4, eL, eR);
+            if (wv == 1) weno5_fast<1, 1>(P, T, row, f, l, r);
+            else if (wv == 2) weno5_fast<2, 1>(P, T, row, f, l, r);
+            else weno5_fast<0, 1>(P, T, row, f, l, r);
         }
+        eL = l[0]; eR = r[0];
         return;
     }
     if (wo == 3) {
@@ -326,6 +377,29 @@ __device__ __forceinline__ void weno_edges(const DevP& P, const DirTables& T, in
             if (side == 0) eL = val; else eR = val;
         }
     }
+}
+
+// NV variables at once (the sweep kernels' rolled variable loop): FAST -> the shared-table versions above,
+// otherwise the reference-order routine per variable.
+template <int WO, int WV, int FAST, int NV, class ROW>
+__device__ __forceinline__ void weno_edges_nv(const DevP& P, const DirTables& T, int slot, const ROW row, const double (&f)[NV][5],
+                                              double (&eL)[NV], double (&eR)[NV]) {
+    const int wo = (WO < 0) ? P.wo : WO;
+    const int wv = (WV < 0) ? P.wv : WV;
+    if (FAST && wo == 5) {
+        if (wv == 1) weno5_fast<1, NV>(P, T, row, f, eL, eR);
+        else if (wv == 2) weno5_fast<2, NV>(P, T, row, f, eL, eR);
+        else weno5_fast<0, NV>(P, T, row, f, eL, eR);
+        return;
+    }
+    if (FAST && wo == 3) {
+        if (wv == 1) weno3_fast<1, NV>(P, T, row, f, eL, eR);
+        else if (wv == 2) weno3_fast<2, NV>(P, T, row, f, eL, eR);
+        else weno3_fast<0, NV>(P, T, row, f, eL, eR);
+        return;
+    }
+#pragma unroll
+    for (int u = 0; u < NV; u++) weno_edges<WO, WV, 0>(P, T, slot, row, f[u][0], f[u][1], f[u][2], f[u][3], f[u][4], eL[u], eR[u]);
 }
 
 // s_compute_speed_of_sound, 5-eq branch: src/common/m_variables_conversion.fpp:1248-1260

@@ -421,6 +421,9 @@ __device__ __forceinline__ void cbc_override(const DevP& P, int face, long long 
 // receives the flux of its left face by __shfl_up; lanes 1..30 finish their cell.
 // -------------------------------------------------------------------------------------------------
 #define MFC5_XW 30  // cells finished per warp
+#ifndef MFC5_WENO_NV
+#define MFC5_WENO_NV 2  // variables reconstructed per iteration of the rolled WENO loop
+#endif
 
 #ifndef MFC5_X_MINB
 #define MFC5_X_MINB 4   // 128 registers: 16 warps per SM (measured best of 3, 4, 5 blocks)
@@ -445,12 +448,15 @@ __global__ void __launch_bounds__(128, MFC5_X_MINB) k_sweep_x(const __grid_const
     const long long c = rowbase + ic;
     const DirTables& T = P.T[0];
     const int slot = ic + P.b;
-
     // stage the warp's 36-cell window of every variable in shared memory with cp.async (one batched
     // wait instead of one exposed load latency per variable); lane l then reads cells l .. l+4
     constexpr int XT = 40;
+    constexpr int NV = MFC5_WENO_NV;
     __shared__ double sx[4][N][XT];
+    __shared__ double sedge[4][2][N][32];  // per lane: right edge of my cell, left edge of cell +1 (spill space of the rolled loop)
     double(*my)[XT] = sx[(threadIdx.x >> 5) & 3];
+    double(*myR)[32] = sedge[(threadIdx.x >> 5) & 3][0];
+    double(*myQ)[32] = sedge[(threadIdx.x >> 5) & 3][1];
     {
         const int hi = P.s[0] + P.b;
         const int ca = min(i0 - 3 + lane, hi), cb = min(i0 - 3 + 32 + lane, hi);
@@ -463,16 +469,30 @@ __global__ void __launch_bounds__(128, MFC5_X_MINB) k_sweep_x(const __grid_const
         cp_async_wait_all();
         __syncwarp();
     }
-    const RowSoA xrow{T.tabT + slot, (long long)T.nslot};
-    double eL[N], eR[N];
+    // WENO of NV variables per iteration of a ROLLED loop (code size: the instruction cache, not the
+    // register file, is what the fully unrolled version ran out of); the left edge of cell i+1 arrives by
+    // warp shuffle; edge states wait in shared memory for the Riemann solve
+    const RowSeg xrow{T.tabX + (long long)seg * (MFC5_TAB * 32) + lane};
+#pragma unroll 1
+    for (int v0 = 0; v0 < N; v0 += NV) {
+        double f[NV][5], l[NV], r[NV];
+        int vv[NV];
 #pragma unroll
-    for (int v = 0; v < N; v++) {
-        weno_edges<WO, WV, FAST>(P, T, slot, xrow, my[v][lane], my[v][lane + 1], my[v][lane + 2], my[v][lane + 3], my[v][lane + 4], eL[v], eR[v]);
+        for (int u = 0; u < NV; u++) {
+            vv[u] = min(v0 + u, N - 1);
+#pragma unroll
+            for (int k = 0; k < 5; k++) f[u][k] = my[vv[u]][lane + k];
+        }
+        weno_edges_nv<WO, WV, FAST, NV>(P, T, slot, xrow, f, l, r);
+#pragma unroll
+        for (int u = 0; u < NV; u++) {
+            myR[vv[u]][lane] = r[u];
+            myQ[vv[u]][lane] = __shfl_down_sync(0xffffffffu, l[u], 1);
+        }
     }
-    // right state of my right face = left edge of cell i+1
-    double qR[N];
+    double eR[N], qR[N];
 #pragma unroll
-    for (int v = 0; v < N; v++) qR[v] = __shfl_down_sync(0xffffffffu, eL[v], 1);
+    for (int v = 0; v < N; v++) { eR[v] = myR[v][lane]; qR[v] = myQ[v][lane]; }
     // BC -4 (Riemann extrapolation), m_riemann_state.fpp:149-206
     if (P.bc[0][0] == MFC5_BC_RIEMANN_EXTRAP && i == -1) {
 #pragma unroll
@@ -525,14 +545,14 @@ template <int WO>
 struct MarchCfg {
     static constexpr int PN = WO < 0 ? 2 : (WO - 1) / 2;  // generic kernels reserve the WENO5 window
     static constexpr int R = 2 * PN + 1;   // stencil window
-    static constexpr int NSLOT = R + 1;    // ring slots: window + the plane in flight
+    static constexpr int NSLOT = R;        // ring slots: the window; the entering plane replaces the leaving one
 };
 
 // dynamic shared memory of a block marching a chunk of `chunk` cells: stencil ring + right-edge ping-pong
-// + the chunk's rows of the WENO table
+// + left edges + the chunk's rows of the WENO table
 template <int NF, int ND, int WO>
 inline size_t march_smem_bytes(int chunk) {
-    return ((size_t)(MarchCfg<WO>::NSLOT + 2) * (2 * NF + ND + 1) * MFC5_MARCH_THREADS + (size_t)(chunk + 2) * MFC5_TAB) * sizeof(double);
+    return ((size_t)(MarchCfg<WO>::NSLOT + 3) * (2 * NF + ND + 1) * MFC5_MARCH_THREADS + (size_t)(chunk + 2) * MFC5_TAB) * sizeof(double);
 }
 
 template <int NF, int ND, int DIR, int WO, int WV, int RS, int FAST>
@@ -544,7 +564,8 @@ __global__ void __launch_bounds__(MFC5_MARCH_THREADS, (2 * NF + ND + 1 <= 8) ? M
     extern __shared__ double smem[];
     double* ring = smem;                  // [NSLOT][N][NT]
     double* sER = smem + NSLOT * N * NT;  // [2][N][NT]  right-edge states, ping-pong over iterations
-    double* srow = sER + 2 * N * NT;      // [chunk+2][MFC5_TAB]  WENO table rows of cells c0-1 .. c1+1
+    double* sEL = sER + 2 * N * NT;       // [N][NT]     left-edge states of the cell reconstructed in this iteration
+    double* srow = sEL + N * NT;          // [chunk+2][MFC5_TAB]  WENO table rows of cells c0-1 .. c1+1
     const int tid = threadIdx.x;
     if (FAST) {  // cooperative, coalesced copy; every thread of the block takes part before any returns
         const int s_ = P.s[DIR];
@@ -587,15 +608,13 @@ __global__ void __launch_bounds__(MFC5_MARCH_THREADS, (2 * NF + ND + 1 <= 8) ? M
 #pragma unroll
     for (int f = 0; f < NF; f++) Fsp[f] = 0.0;
 
+    constexpr int NV = MFC5_WENO_NV;
     for (int cc = c0 - 1; cc <= c1 + 1; cc++) {
-        cp_async_wait_all();  // the window of cell cc is complete (requested one iteration ago)
-        if (cc <= c1) {       // request plane cc+1+PN into the free slot; it lands while this cell is computed
-            int sl = tail + R;
-            if (sl >= NSLOT) sl -= NSLOT;
-            const int pl = min(max(cc + 1 + PN, lo), hi);
+        cp_async_wait_all();  // the window of cell cc is complete
+        if (cc < c1) {        // the plane requested after the NEXT reconstruction: pull it into L2 now
+            const int pl = min(max(cc + 2 + PN, lo), hi);
 #pragma unroll
-            for (int v = 0; v < N; v++) cp_async8(ring + (sl * N + v) * NT + tid, P.prim + v * P.fs + colbase + pl * sd);
-            cp_async_commit();
+            for (int v = 0; v < N; v++) prefetch_l2(P.prim + v * P.fs + colbase + pl * sd);
         }
         if (cc >= c0 + 1) {   // inputs of the finishing step of cell cc-1: pull them into L2 now
             const long long c = colbase + (long long)(cc - 1) * sd;
@@ -618,15 +637,33 @@ __global__ void __launch_bounds__(MFC5_MARCH_THREADS, (2 * NF + ND + 1 <= 8) ? M
         }
         double* sERc = sER + ((cc & 1) ? N * NT : 0) + tid;
         const double* sERp = sER + ((cc & 1) ? 0 : N * NT) + tid;
-        double eL[N];
+        // WENO of NV variables per iteration of a ROLLED loop (code size; the table row is read once per NV
+        // variables); edge states go to this thread's column of shared memory
+        {
+            const RowAoS mrow{srow + (cc - (c0 - 1)) * MFC5_TAB};
+#pragma unroll 1
+            for (int v0 = 0; v0 < N; v0 += NV) {
+                double f[NV][5], l[NV], r[NV];
+                int vv[NV];
 #pragma unroll
-        for (int v = 0; v < N; v++) {
-            double f0 = 0, f1 = 0, f3 = 0, f4 = 0, eR;
-            const double f2 = ring[off[PN] + v * NT];
-            if (PN >= 1) { f1 = ring[off[PN - 1] + v * NT]; f3 = ring[off[PN + (PN >= 1 ? 1 : 0)] + v * NT]; }
-            if (PN >= 2) { f0 = ring[off[0] + v * NT]; f4 = ring[off[R - 1] + v * NT]; }
-            weno_edges<WO, WV, FAST>(P, T, cc + P.b, RowAoS{srow + (cc - (c0 - 1)) * MFC5_TAB}, f0, f1, f2, f3, f4, eL[v], eR);
-            sERc[v * NT] = eR;
+                for (int u = 0; u < NV; u++) {
+                    vv[u] = min(v0 + u, N - 1);
+#pragma unroll
+                    for (int k = 0; k < 5; k++) f[u][k] = 0.0;
+                    f[u][2] = ring[off[PN] + vv[u] * NT];
+                    if (PN >= 1) { f[u][1] = ring[off[PN - 1] + vv[u] * NT]; f[u][3] = ring[off[PN + (PN >= 1 ? 1 : 0)] + vv[u] * NT]; }
+                    if (PN >= 2) { f[u][0] = ring[off[0] + vv[u] * NT]; f[u][4] = ring[off[R - 1] + vv[u] * NT]; }
+                }
+                weno_edges_nv<WO, WV, FAST, NV>(P, T, cc + P.b, mrow, f, l, r);
+#pragma unroll
+                for (int u = 0; u < NV; u++) { sEL[vv[u] * NT + tid] = l[u]; sERc[vv[u] * NT] = r[u]; }
+            }
+        }
+        if (cc <= c1) {       // plane cc+1+PN enters the window in the slot of plane cc-PN; lands during the Riemann solve
+            const int pl = min(max(cc + 1 + PN, lo), hi);
+#pragma unroll
+            for (int v = 0; v < N; v++) cp_async8(ring + (tail * N + v) * NT + tid, P.prim + v * P.fs + colbase + pl * sd);
+            cp_async_commit();
         }
         if (cc >= c0) {
             const int face = cc - 1;
@@ -645,9 +682,9 @@ __global__ void __launch_bounds__(MFC5_MARCH_THREADS, (2 * NF + ND + 1 <= 8) ? M
 #pragma unroll
                 for (int f = 0; f < NF; f++) acoef[f] = __ldg(P.prim + (alpha_iface ? (S::IM + DIR) : (S::IA + f)) * P.fs + c);
             }
-            double qL[N], F[N], Fs[NF];
+            double qL[N], eL[N], F[N], Fs[NF];
 #pragma unroll
-            for (int v = 0; v < N; v++) qL[v] = sERp[v * NT];
+            for (int v = 0; v < N; v++) { qL[v] = sERp[v * NT]; eL[v] = sEL[v * NT + tid]; }
 #pragma unroll
             for (int f = 0; f < NF; f++) Fs[f] = 0.0;
             if (P.bc[DIR][0] == MFC5_BC_RIEMANN_EXTRAP && face == -1) {  // m_riemann_state.fpp:149-206
@@ -774,6 +811,28 @@ __global__ void __launch_bounds__(256) k_halo_faces(const __grid_constant__ DevP
         const int k = (int)(r / n1) + lo[2];
         double* f = P.primw + v * P.fs + P.base + i + j * P.sy + k * P.sz;
         if (pack) buf[t] = *f; else *f = buf[t];
+    }
+}
+
+// Host <-> device field copies go through a contiguous staging image (one large DMA per field at full PCIe
+// rate instead of a pitched 3-D copy of 1.6 kB rows); this kernel moves the copy region between the
+// staging image [N][hz][hy][hx] and the padded device layout.  to_dev = 1: staging -> device.
+struct RepackGeom {
+    int N, wx, wy, wz;          // copy region
+    long long dev_off, sy, sz, fs;      // device: offset of the region's first cell inside a field, strides, field size
+    long long st_off, hx, hxy, hfs;     // staging: the same for the host-shaped image
+};
+__global__ void __launch_bounds__(256) k_repack(double* __restrict__ dev, double* __restrict__ stage, const __grid_constant__ RepackGeom G, int to_dev) {
+    const long long per = (long long)G.wx * G.wy * G.wz, tot = per * G.N;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < tot; t += (long long)gridDim.x * blockDim.x) {
+        const int v = (int)(t / per);
+        long long r = t % per;
+        const int i = (int)(r % G.wx); r /= G.wx;
+        const int j = (int)(r % G.wy);
+        const int k = (int)(r / G.wy);
+        double* d = dev + v * G.fs + G.dev_off + i + j * G.sy + k * G.sz;
+        double* s = stage + v * G.hfs + G.st_off + i + j * G.hx + k * G.hxy;
+        if (to_dev) *d = *s; else *s = *d;
     }
 }
 #endif  // MFC5_HOST_TU
