@@ -400,7 +400,7 @@ extern "C" int mfc5_finalize_setup(mfc5_handle* h) {
     D.mixerr = h->P.mixture_err;
     // division-light arithmetic only where its assumptions hold: direct wave speeds, no weight nulling,
     // weno_eps large enough that products of four smoothness indicators cannot underflow
-    D.fast = h->P.fast_math && h->P.wave_speeds == 1 && !h->P.null_weights && h->P.weno_eps >= 1e-40;
+    D.fast = h->P.fast_math && h->P.wave_speeds == 1 && !h->P.null_weights && h->P.weno_eps >= 1e-30;
     if (getenv("MFC5_NO_FAST")) D.fast = 0;
     D.sy = h->px; D.sz = h->px * h->ey; D.fs = h->fs;
     D.base = h->ox + h->oy * D.sy + h->oz * D.sz;

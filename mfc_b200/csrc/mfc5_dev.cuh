@@ -36,6 +36,9 @@ struct DirTables {
     int uniform;       // uniform_grid(dir), m_weno.fpp:869-879
 };
 #define MFC5_TAB 48
+#ifndef MFC5_MERGE_RCP
+#define MFC5_MERGE_RCP 0  // 1: left/right reciprocals of the WENO normalisations from one reciprocal (measured slower: 0.970 vs 0.912 ms x sweep)
+#endif
 
 // Everything a kernel needs, passed by value (__grid_constant__).
 struct DevP {
@@ -83,11 +86,19 @@ __device__ __forceinline__ double fsign(double a, double b) { return copysign(fa
 __device__ __forceinline__ double rcp_nr(double x) {
     double r;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
-    double e = fma(-x, r, 1.0);
-    r = fma(r, e, r);
-    e = fma(-x, r, 1.0);
-    r = fma(r, e, r);
-    return r;
+    // e = 1 - x r;  r1 = r (1 + e) has residual exactly e^2, so the second Newton step is r1 (1 + e^2):
+    // e^2 and r1 are independent -> 3 dependent FP64 operations after the seed instead of 4
+    const double e = fma(-x, r, 1.0);
+    const double r1 = fma(r, e, r);
+    const double e2 = e * e;
+    return fma(r1, e2, r1);
+}
+// 1/a and 1/b from ONE reciprocal: r = 1/(a b), 1/a = r b, 1/b = r a  (8 FP64 operations instead of 10, one
+// MUFU instead of two).  Callers guarantee that a b neither overflows nor underflows.
+__device__ __forceinline__ void rcp_nr2(double a, double b, double& ia, double& ib) {
+    const double r = rcp_nr(a * b);
+    ia = r * b;
+    ib = r * a;
 }
 
 // One cell's row of DirTables::tab.  RowAoS: MFC5_TAB consecutive doubles (marching kernels: staged in
@@ -160,6 +171,66 @@ __device__ __forceinline__ void weno5_fast(const DevP& P, const DirTables& T, co
             }
         }
     }
+#if MFC5_MERGE_RCP
+    // both sides together: the left and right reciprocals of each normalisation come out of ONE reciprocal of
+    // the product of the two sums (rcp_nr2).  The sums are ~ beta^4, so the product stays far inside the
+    // FP64 range for weno_eps >= 1e-30 (the fast-path guard of mfc5_finalize_setup).
+    double dq[2][3], m1[2][3], m2[2][3], m3[2][3], cf[2][6];
+#pragma unroll
+    for (int side = 0; side < 2; side++) {
+#pragma unroll
+        for (int q = 0; q < 3; q++) dq[side][q] = row[12 + side * 3 + q];
+#pragma unroll
+        for (int k = 0; k < 6; k++) cf[side][k] = row[side * 6 + k];
+        if (WV == 1) {
+#pragma unroll
+            for (int q = 0; q < 3; q++) {
+                if (ROW::kHasMapTerms) {
+                    m1[side][q] = row[27 + side * 3 + q]; m2[side][q] = row[33 + side * 3 + q]; m3[side][q] = row[39 + side * 3 + q];
+                } else {
+                    const double d = dq[side][q];
+                    m1[side][q] = fma(d, d, d); m2[side][q] = fma(-2.0, d, 1.0); m3[side][q] = d * d;
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < NV; u++) {
+        const double f2 = f[u][2];
+        double a[2][3], num[2], sum[2];
+#pragma unroll
+        for (int side = 0; side < 2; side++) {
+            a[side][0] = dq[side][0] * g0[u]; a[side][1] = dq[side][1] * g1[u]; a[side][2] = dq[side][2] * g2[u];
+        }
+        if (WV == 1) {
+            double r[2];
+            rcp_nr2(a[0][0] + a[0][1] + a[0][2], a[1][0] + a[1][1] + a[1][2], r[0], r[1]);
+#pragma unroll
+            for (int side = 0; side < 2; side++) {
+                double n0, n1, n2, e0, e1, e2;
+                map_nd(dq[side][0], m1[side][0], m2[side][0], m3[side][0], a[side][0] * r[side], n0, e0);
+                map_nd(dq[side][1], m1[side][1], m2[side][1], m3[side][1], a[side][1] * r[side], n1, e1);
+                map_nd(dq[side][2], m1[side][2], m2[side][2], m3[side][2], a[side][2] * r[side], n2, e2);
+                a[side][0] = n0 * (e1 * e2);
+                a[side][1] = n1 * (e0 * e2);
+                a[side][2] = n2 * (e0 * e1);
+            }
+        }
+#pragma unroll
+        for (int side = 0; side < 2; side++) {
+            const double* c = cf[side];
+            const double p0 = fma(c[1], d0[u], fma(c[0], d1[u], f2));
+            const double p1 = fma(c[3], dm1[u], fma(c[2], d0[u], f2));
+            const double p2 = fma(c[5], dm2[u], fma(c[4], dm1[u], f2));
+            num[side] = fma(a[side][2], p2, fma(a[side][1], p1, a[side][0] * p0));
+            sum[side] = a[side][0] + a[side][1] + a[side][2];
+        }
+        double iL, iR;
+        rcp_nr2(sum[0], sum[1], iL, iR);
+        eL[u] = num[0] * iL;
+        eR[u] = num[1] * iR;
+    }
+#else
 #pragma unroll
     for (int side = 0; side < 2; side++) {
         const int cc = side * 6, dd = 12 + side * 3;
@@ -197,6 +268,7 @@ __device__ __forceinline__ void weno5_fast(const DevP& P, const DirTables& T, co
             if (side == 0) eL[u] = val; else eR[u] = val;
         }
     }
+#endif
 }
 
 template <int WV, int NV, class ROW>
@@ -443,7 +515,8 @@ __device__ __forceinline__ void riemann_face_fast(const DevP& P, double* qL, dou
             alf_R[f] = fmin(fmax(0.0, alf_R[f]), 1.0);
             sR = sR + alf_R[f];
         }
-        const double iL = rcp_nr(fmax(sL, MFC5_SGM_EPS)), iR = rcp_nr(fmax(sR, MFC5_SGM_EPS));
+        double iL, iR;
+        rcp_nr2(fmax(sL, MFC5_SGM_EPS), fmax(sR, MFC5_SGM_EPS), iL, iR);
 #pragma unroll
         for (int f = 0; f < NF; f++) { alf_L[f] = alf_L[f] * iL; alf_R[f] = alf_R[f] * iR; }
         if (rs == 2) {  // HLLC limits the face states in place (hllc.fpp:938-958); HLL only local copies
@@ -465,11 +538,13 @@ __device__ __forceinline__ void riemann_face_fast(const DevP& P, double* qL, dou
     }
     const double E_L = gamma_L * pres_L + pi_inf_L + 5.e-1 * rho_L * vel_L_rms + qv_L;
     const double E_R = gamma_R * pres_R + pi_inf_R + 5.e-1 * rho_R * vel_R_rms + qv_R;
-    const double irho_L = rcp_nr(rho_L), irho_R = rcp_nr(rho_R);
+    double irho_L, irho_R, igam_L, igam_R;
+    rcp_nr2(rho_L, rho_R, irho_L, irho_R);
+    rcp_nr2(gamma_L, gamma_R, igam_L, igam_R);
     const double H_L = (E_L + pres_L) * irho_L;
     const double H_R = (E_R + pres_R) * irho_R;
-    double c_L = (H_L - 5.e-1 * vel_L_rms - qv_L * irho_L) * rcp_nr(gamma_L);
-    double c_R = (H_R - 5.e-1 * vel_R_rms - qv_R * irho_R) * rcp_nr(gamma_R);
+    double c_L = (H_L - 5.e-1 * vel_L_rms - qv_L * irho_L) * igam_L;
+    double c_R = (H_R - 5.e-1 * vel_R_rms - qv_R * irho_R) * igam_R;
     c_L = (P.mixerr && c_L < 0.0) ? 100.0 * MFC5_SGM_EPS : sqrt(c_L);
     c_R = (P.mixerr && c_R < 0.0) ? 100.0 * MFC5_SGM_EPS : sqrt(c_R);
     const double uL = qL[IM + DIR], uR = qR[IM + DIR];
@@ -478,13 +553,20 @@ __device__ __forceinline__ void riemann_face_fast(const DevP& P, double* qL, dou
     const double s_M = fmin(0.0, s_L), s_P = fmax(0.0, s_R);
     if (rs == 2) {
         const double mL = rho_L * (s_L - uL), mR = rho_R * (s_R - uR);
-        const double s_S = (pres_R - pres_L + mL * uL - mR * uR) * rcp_nr(mL - mR);
-        const bool left = !signbit(s_S);  // xi_M = 1, xi_P = 0  (Fortran sign(0.5, s_S))
+        // s_S = A / B.  Its sign (which selects the upwind side) is known before the division, and
+        // 1 / (s_K - s_S) = B / (s_K B - A): both reciprocals come out of one (rcp_nr2), in parallel
+        // with the one of s_K - u_K, instead of two dependent ones.
+        const double A = pres_R - pres_L + mL * uL - mR * uR, B = mL - mR;
+        const bool left = signbit(A) == signbit(B);  // xi_M = 1, xi_P = 0  (Fortran sign(0.5, s_S))
         const double* qK = left ? qL : qR;
         const double rho_K = left ? rho_L : rho_R, u_K = left ? uL : uR, p_K = left ? pres_L : pres_R, E_K = left ? E_L : E_R;
         const double s_K = left ? s_L : s_R, s_MP = left ? s_M : s_P;
-        const double den = left ? fmin(s_L - s_S, -MFC5_SGM_EPS) : fmax(s_R - s_S, MFC5_SGM_EPS);
-        const double iden = rcp_nr(den);
+        double iB, iX;
+        rcp_nr2(B, fma(s_K, B, -A), iB, iX);
+        const double s_S = A * iB;
+        const double gap = s_K - s_S;  // the reference clamps it away from zero: min(., -eps) / max(., eps)
+        const bool clamped = left ? !(gap < -MFC5_SGM_EPS) : !(gap > MFC5_SGM_EPS);
+        const double iden = clamped ? (left ? -1.0 / MFC5_SGM_EPS : 1.0 / MFC5_SGM_EPS) : B * iX;
         const double xi_K = (s_K - u_K) * iden;
         const double xi_K_m1 = (s_S - u_K) * iden;
         const double adv = fma(s_MP, xi_K_m1, u_K);  // u_K + s_MP (xi_K - 1)

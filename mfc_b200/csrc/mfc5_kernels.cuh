@@ -26,7 +26,11 @@ __device__ __forceinline__ void cp_async8(double* sdst, const double* gsrc) {
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+#ifdef MFC5_NO_PREFETCH
+__device__ __forceinline__ void prefetch_l2(const double*) {}
+#else
 __device__ __forceinline__ void prefetch_l2(const double* g) { asm volatile("prefetch.global.L2 [%0];" ::"l"(g)); }
+#endif
 
 // mixture rule: s_compute_species_fraction (m_variables_conversion.fpp:1140-1188) followed by
 // s_convert_species_to_mixture_variables_kernel (:198-270); `passes` = number of limiter passes.
