@@ -79,7 +79,10 @@ typedef struct mfc5_params {
     /* product-side knobs (ignored by the oracle) */
     int device;          /* CUDA device ordinal */
     int fast_math;       /* 0: reference operation order; 1: division-light WENO weights */
-    int reserved[6];
+    /* Riemann-solver extras; they occupy former reserved words, so the struct size is unchanged */
+    int low_Mach;        /* 0 off; 1 pressure correction (HLL, HLLC); 2 velocity correction (HLLC): inline_riemann.fpp:71-93 */
+    int alt_soundspeed;  /* Wood sound speed + K div(u) term in the alpha equations (2 fluids; HLLC or HLL with hll_u_interface) */
+    int reserved[4];
 } mfc5_params;
 
 #ifdef __cplusplus

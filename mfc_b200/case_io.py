@@ -29,7 +29,11 @@ def load_case(path, args=(), mfc_args=None):
     if not os.path.exists(path):
         raise CaseError(f"Input file '{path}' does not exist. Please check the path is valid.")
     if path.endswith(".py"):
-        cmd = [sys.executable, os.path.abspath(path), "--mfc", json.dumps(mfc_args or {})] + list(args)
+        # the reference hands its run arguments over (toolchain/mfc/state.py ARGS()); the case files that look at them
+        # read "gpu" (benchmarks/*/case.py:22) -- this library always runs on the GPU
+        margs = {"gpu": "acc", "mpi": True, "targets": ["pre_process", "simulation"], "case_optimization": True}
+        margs.update(mfc_args or {})
+        cmd = [sys.executable, os.path.abspath(path), "--mfc", json.dumps(margs)] + list(args)
         r = subprocess.run(cmd, capture_output=True, text=True, cwd=os.path.dirname(os.path.abspath(path)) or ".")
         if r.returncode != 0:
             raise CaseError(f"Input file {path} terminated with a non-zero exit code. Please make sure running the file "

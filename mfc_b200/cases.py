@@ -39,6 +39,10 @@ def _scheme(case, weno_order, mapped="T", wenoz="F", riemann="hllc", mpp="T", mi
     })
 
 
+# database output block shared by the stock example case files (e.g. examples/1D_sodshocktube/case.py:49-52)
+OUTPUT = {"prim_vars_wrt": "T", "parallel_io": "T"}
+
+
 def sod_1d(m=399):
     """C1: examples/1D_sodshocktube/case.py (1 fluid, WENO5-M, HLLC, RK3, BC -3, 1000 steps)."""
     nt = 1000
@@ -48,6 +52,7 @@ def sod_1d(m=399):
     _scheme(case, 5, mpp="F", mixerr="F")
     _patch(case, 1, 1, [1.0], [1.0], [0.0], 1.0, x_centroid=0.25, length_x=0.5)
     _patch(case, 2, 1, [0.125], [1.0], [0.0], 0.1, x_centroid=0.75, length_x=0.5)
+    case.update(OUTPUT)
     return _fluids(case, [(1.4, 0.0)])
 
 
@@ -69,6 +74,7 @@ def shockbubble_2d(ny=100):
            length_x=leng / 4.0, length_y=leng, **{"alter_patch(1)": "T"})
     _patch(case, 3, 2, [0.0, 0.167], [0.0, 1.0], [0.0, 0.0], 101325.0, x_centroid=0.0, y_centroid=0.0, radius=leng / 5.0,
            **{"alter_patch(1)": "T"})
+    case.update(OUTPUT)
     return _fluids(case, [(1.4, 0.0), (1.6666, 0.0)])
 
 
@@ -116,6 +122,7 @@ def shockdroplet_3d(ny=100, weno_order=3, mapped_weno="T", wenoz="F", steps=None
                  "stretch_y": "T", "a_y": 20, "y_a": -0.0 * d0, "y_b": 1.2 * d0,
                  "stretch_z": "T", "a_z": 20, "z_a": -0.0 * d0, "z_b": 1.2 * d0})
     _scheme(case, weno_order, mapped=mapped_weno, wenoz=wenoz)
+    case.update(OUTPUT)
     return case
 
 
@@ -128,7 +135,7 @@ def bench_5eq_weno3_hllc(gbpp=16, ranks=1, s=None, steps=20, riemann="hllc"):
         s = math.floor((ncells / 2.0) ** (1 / 3))
     case, aux = _shock_droplet(2 * s, s, s, 0.1)
     case["dt"] = aux["dx"] * aux["cfl"] / aux["ss"]
-    case.update({"run_time_info": "F", "t_step_stop": steps, "t_step_save": steps})
+    case.update({"run_time_info": "F", "t_step_stop": steps, "t_step_save": steps, "prim_vars_wrt": "T", "parallel_io": "F"})
     _scheme(case, 3, riemann=riemann)
     return case
 
@@ -153,6 +160,7 @@ def perf_test_3d(m=200, riemann="hllc", steps=30):
     case["fluid_pp(1)%pi_inf"] = 4.4 * 6.0e08 / (4.4 - 1.0)
     case["fluid_pp(2)%gamma"] = 1.0 / (1.4 - 1.0)
     case["fluid_pp(2)%pi_inf"] = 0.0
+    case.update(OUTPUT)
     return case
 
 

@@ -144,6 +144,9 @@ extern "C" int mfc5_create(const mfc5_params* p, mfc5_handle** out) {
     if (p->weno_order != 1 && p->weno_order != 3 && p->weno_order != 5) return fail("weno_order must be 1, 3 or 5");
     if (p->riemann_solver != 1 && p->riemann_solver != 2) return fail("riemann_solver must be 1 (HLL) or 2 (HLLC)");
     if (p->mapped_weno && p->wenoz) return fail("mapped_weno and wenoz are mutually exclusive");
+    if (p->alt_soundspeed && (p->num_fluids != 2 || p->avg_state != 2 || (p->riemann_solver == 1 && !p->hll_u_interface)))
+        return fail("alt_soundspeed needs 2 fluids, avg_state = 2 and a u-interface solver (HLLC, or HLL with hll_u_interface)");
+    if (p->low_Mach < 0 || p->low_Mach > 2 || (p->low_Mach == 2 && p->riemann_solver != 2)) return fail("low_Mach must be 0, 1 or 2 (2: HLLC only)");
     if (p->time_stepper < 1 || p->time_stepper > 3) return fail("time_stepper must be 1..3");
     if (p->m < 0 || p->n < 0 || p->p < 0 || (p->n == 0 && p->p > 0)) return fail("invalid m, n, p");
     // m_checker.fpp:52-69: at least num_stcls_min*weno_order cells per direction
@@ -400,7 +403,10 @@ extern "C" int mfc5_finalize_setup(mfc5_handle* h) {
     D.mixerr = h->P.mixture_err;
     // division-light arithmetic only where its assumptions hold: direct wave speeds, no weight nulling,
     // weno_eps large enough that products of four smoothness indicators cannot underflow
-    D.fast = h->P.fast_math && h->P.wave_speeds == 1 && !h->P.null_weights && h->P.weno_eps >= 1e-30;
+    D.low_mach = h->P.low_Mach;
+    D.alt_ss = h->P.alt_soundspeed;
+    D.fast = h->P.fast_math && h->P.wave_speeds == 1 && !h->P.null_weights && h->P.weno_eps >= 1e-30 && h->P.low_Mach == 0 &&
+             !h->P.alt_soundspeed;
     if (getenv("MFC5_NO_FAST")) D.fast = 0;
     D.sy = h->px; D.sz = h->px * h->ey; D.fs = h->fs;
     D.base = h->ox + h->oy * D.sy + h->oz * D.sz;

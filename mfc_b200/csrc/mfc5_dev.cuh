@@ -46,6 +46,8 @@ struct DevP {
     int nd, nf, N, b, pn, ns;
     int wo, wv, rs;    // weno_order; variant 0 JS / 1 M / 2 Z; riemann_solver 1 HLL / 2 HLLC
     int hll_u, avg, ws, mpp, mixerr, fast;
+    int low_mach;      // 0 / 1 / 2, inline_riemann.fpp:71-93 (reference-order kernels only)
+    int alt_ss;        // alt_soundspeed: Wood sound speed + K div(u) term (reference-order kernels only)
     long long sy, sz, fs, base;  // strides (x stride = 1), field size, offset of cell (0,0,0)
     double eps;
     double gam[MFC5_MAX_FLUIDS], pinf[MFC5_MAX_FLUIDS], qv[MFC5_MAX_FLUIDS];
@@ -474,11 +476,27 @@ __device__ __forceinline__ void weno_edges_nv(const DevP& P, const DirTables& T,
     for (int u = 0; u < NV; u++) weno_edges<WO, WV, 0>(P, T, slot, row, f[u][0], f[u][1], f[u][2], f[u][3], f[u][4], eL[u], eR[u]);
 }
 
-// s_compute_speed_of_sound, 5-eq branch: src/common/m_variables_conversion.fpp:1248-1260
-__device__ __forceinline__ double sound_speed(const DevP& P, double rho, double gam, double H, double vel_sum, double qv) {
-    const double c = (H - 5.e-1 * vel_sum - qv / rho) / gam;
+// s_compute_speed_of_sound, 5-eq branch: src/common/m_variables_conversion.fpp:1233-1260
+// (alt_soundspeed: Wood's mixture sound speed from the two bulk moduli; adv = the two volume fractions)
+__device__ __forceinline__ double sound_speed(const DevP& P, double pres, double rho, double gam, double H, const double* adv,
+                                              double vel_sum, double qv) {
+    double c;
+    if (P.alt_ss) {
+        const double blkmod1 = ((P.gam[0] + 1.0) * pres + P.pinf[0]) / P.gam[0];
+        const double blkmod2 = ((P.gam[1] + 1.0) * pres + P.pinf[1]) / P.gam[1];
+        c = (1.0 / (rho * (adv[0] / blkmod1 + adv[1] / blkmod2)));
+    } else {
+        c = (H - 5.e-1 * vel_sum - qv / rho) / gam;
+    }
     if (P.mixerr && c < 0.0) return 100.0 * MFC5_SGM_EPS;
     return sqrt(c);
+}
+
+// Kapila K coefficient of a cell (m_rhs.fpp:1070-1095): pressure from q_prim, volume fractions from q_cons
+__device__ __forceinline__ double k_term(const DevP& P, double pres, double alpha1, double alpha2) {
+    const double blkmod1 = ((P.gam[0] + 1.0) * pres + P.pinf[0]) / P.gam[0] + (4.0 / 3.0) * 0.0;
+    const double blkmod2 = ((P.gam[1] + 1.0) * pres + P.pinf[1]) / P.gam[1] + (4.0 / 3.0) * 0.0;
+    return alpha1 * alpha2 * (blkmod2 - blkmod1) / (alpha1 * blkmod2 + alpha2 * blkmod1);
 }
 
 // -------------------------------------------------------------------------------------------------
@@ -633,6 +651,9 @@ __device__ __forceinline__ void riemann_face(const DevP& P, double* qL, double* 
     }
     const double pres_L = qL[IE], pres_R = qR[IE];
     double arho_L[NF], arho_R[NF], alf_L[NF], alf_R[NF];
+    double adv_L[NF], adv_R[NF];  // alpha_L/R handed to s_compute_speed_of_sound: hllc.fpp:889-892 loads them before the limiter
+#pragma unroll
+    for (int f = 0; f < NF; f++) { adv_L[f] = qL[IA + f]; adv_R[f] = qR[IA + f]; }
     if (rs == 2) {
         if (P.mpp) {  // in-place limiter on the face states, hllc.fpp:938-958
             double sL = 0.0, sR = 0.0;
@@ -680,6 +701,10 @@ __device__ __forceinline__ void riemann_face(const DevP& P, double* qL, double* 
             }
         }
     }
+    if (rs != 2) {  // hll.fpp:187-200 limits alpha_L/R themselves
+#pragma unroll
+        for (int f = 0; f < NF; f++) { adv_L[f] = alf_L[f]; adv_R[f] = alf_R[f]; }
+    }
     // s_accumulate_mixture_properties, m_riemann_state.fpp:1036-1058
     double rho_L = 0, gamma_L = 0, pi_inf_L = 0, qv_L = 0, rho_R = 0, gamma_R = 0, pi_inf_R = 0, qv_R = 0;
 #pragma unroll
@@ -700,8 +725,17 @@ __device__ __forceinline__ void riemann_face(const DevP& P, double* qL, double* 
     const double E_R = gamma_R * pres_R + pi_inf_R + 5.e-1 * rho_R * vel_R_rms + qv_R;
     const double H_L = (E_L + pres_L) / rho_L;
     const double H_R = (E_R + pres_R) / rho_R;
-    const double c_L = sound_speed(P, rho_L, gamma_L, H_L, vel_L_rms, qv_L);
-    const double c_R = sound_speed(P, rho_R, gamma_R, H_R, vel_R_rms, qv_R);
+    const double c_L = sound_speed(P, pres_L, rho_L, gamma_L, H_L, adv_L, vel_L_rms, qv_L);
+    const double c_R = sound_speed(P, pres_R, rho_R, gamma_R, H_R, adv_R, vel_R_rms, qv_R);
+    // low Mach corrections, inline_riemann.fpp:71-93 (hllc.fpp:1084-1086,1137-1141; hll.fpp:400-404)
+    double zcoef = 0.0;
+    if (P.low_mach != 0) zcoef = fmin(1.0, fmax(sqrt(vel_L_rms) / c_L, sqrt(vel_R_rms) / c_R));
+    if (rs == 2 && P.low_mach == 2) {  // the face-normal velocities of the local copies are replaced
+        const double vel_L_tmp = 5.e-1 * ((qL[IM + DIR] + qR[IM + DIR]) + zcoef * (qL[IM + DIR] - qR[IM + DIR]));
+        const double vel_R_tmp = 5.e-1 * ((qL[IM + DIR] + qR[IM + DIR]) + zcoef * (qR[IM + DIR] - qL[IM + DIR]));
+        qL[IM + DIR] = vel_L_tmp;
+        qR[IM + DIR] = vel_R_tmp;
+    }
     const double uL = qL[IM + DIR], uR = qR[IM + DIR];
     double s_L, s_R, s_S;
     if (P.ws == 1) {
@@ -726,7 +760,7 @@ __device__ __forceinline__ void riemann_face(const DevP& P, double* qL, double* 
             gamma_avg = 5.e-1 * (gamma_L + gamma_R);
             qv_avg = 5.e-1 * (qv_L + qv_R);
         }
-        const double c_avg = sound_speed(P, rho_avg, gamma_avg, H_avg, vel_avg_rms, qv_avg);
+        const double c_avg = sound_speed(P, pres_R, rho_avg, gamma_avg, H_avg, adv_R, vel_avg_rms, qv_avg);  // pres_R, alpha_R: placeholders, hllc.fpp:1063-1066
         const double pres_SL = 5.e-1 * (pres_L + pres_R + rho_avg * c_avg * (uL - uR));
         const double pres_SR = pres_SL;
         const double Ms_L = fmax(1.0, sqrt(1.0 + ((5.e-1 + gamma_L) / (1.0 + gamma_L)) * (pres_SL / pres_L - 1.0) * pres_L /
@@ -738,6 +772,11 @@ __device__ __forceinline__ void riemann_face(const DevP& P, double* qL, double* 
         s_S = 5.e-1 * ((uL + uR) + (pres_L - pres_R) / (rho_avg * c_avg));
     }
     const double s_M = fmin(0.0, s_L), s_P = fmax(0.0, s_R);
+    double pcorr = 0.0;
+    if (P.low_mach == 1) {
+        if (rs == 2) pcorr = rho_L * rho_R * (s_L - uL) * (s_R - uR) * (uR - uL) / (rho_R * (s_R - uR) - rho_L * (s_L - uL)) * (zcoef - 1.0);
+        else pcorr = -(s_P - s_M) * (rho_L + rho_R) / 8.0 * (zcoef - 1.0);
+    }
     if (rs == 2) {
         const double xi_L = (s_L - uL) / fmin(s_L - s_S, -MFC5_SGM_EPS);
         const double xi_R = (s_R - uR) / fmax(s_R - s_S, MFC5_SGM_EPS);
@@ -758,6 +797,10 @@ __device__ __forceinline__ void riemann_face(const DevP& P, double* qL, double* 
         }
         F[IE] = xi_M * (uL * (E_L + pres_L) + s_M * (E_L * xi_L_m1 + xi_L * (s_S - uL) * (rho_L * s_S + pres_L / (s_L - uL)))) +
                 xi_P * (uR * (E_R + pres_R) + s_P * (E_R * xi_R_m1 + xi_R * (s_S - uR) * (rho_R * s_S + pres_R / (s_R - uR))));
+        if (P.low_mach == 1) {
+            F[IM + DIR] = F[IM + DIR] + (s_M / s_L) * (s_P / s_R) * pcorr;
+            F[IE] = F[IE] + (s_M / s_L) * (s_P / s_R) * pcorr * s_S;
+        }
 #pragma unroll
         for (int f = 0; f < NF; f++)
             F[IA + f] = xi_M * qL[IA + f] * (uL + s_M * xi_L_m1) + xi_P * qR[IA + f] * (uR + s_P * xi_R_m1);
@@ -773,6 +816,11 @@ __device__ __forceinline__ void riemann_face(const DevP& P, double* qL, double* 
                          s_M * s_P * (rho_L * qL[IM + a] - rho_R * qR[IM + a])) / (s_M - s_P);
         }
         F[IE] = (s_M * uR * (E_R + pres_R) - s_P * uL * (E_L + pres_L) + s_M * s_P * (E_L - E_R)) / (s_M - s_P);
+        if (P.low_mach == 1) {
+#pragma unroll
+            for (int a = 0; a < ND; a++) F[IM + a] = F[IM + a] + (s_M / s_L) * (s_P / s_R) * pcorr * (qR[IM + a] - qL[IM + a]);
+            F[IE] = F[IE] + (s_M / s_L) * (s_P / s_R) * pcorr * (vel_R_rms - vel_L_rms) / 2.0;
+        }
         if (!P.hll_u) {
 #pragma unroll
             for (int f = 0; f < NF; f++) {

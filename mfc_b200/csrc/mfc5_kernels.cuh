@@ -256,7 +256,7 @@ __global__ void __launch_bounds__(128) k_cbc(const __grid_constant__ DevP P, con
     for (int f = 0; f < NF; f++) mf[f] = arho[f] / rho;
     const double E = gam * pres + pinf + 5.e-1 * rho * vel_K_sum;
     const double H = (E + pres) / rho;
-    const double c = sound_speed(P, rho, gam, H, vel_K_sum, qv);
+    const double c = sound_speed(P, pres, rho, gam, H, adv, vel_K_sum, qv);
     double darho_ds[NF], dvel_ds[3] = {0, 0, 0}, dpres_ds = 0, dadv_ds[NF];
     for (int f = 0; f < NF; f++) { darho_ds[f] = 0; dadv_ds[f] = 0; }
     for (int jl = 0; jl <= b; jl++) {
@@ -383,6 +383,11 @@ __device__ __forceinline__ void finish_cell(const DevP& P, long long c, double d
             const double coeff = __ldg(P.prim + (S::IA + f) * P.fs + c);  // q_cons(adv) == q_prim(adv)
             r[S::IA + f] = r[S::IA + f] + inv_ds * coeff * (Fsc[0] - Fsp[0]);
         }
+    }
+    if (!FAST && P.alt_ss) {  // K div(u) correction, u-interface form (m_rhs.fpp:1489-1503)
+        const double K = k_term(P, __ldg(P.prim + S::IE * P.fs + c), __ldg(P.prim + S::IA * P.fs + c), __ldg(P.prim + (S::IA + NF - 1) * P.fs + c));
+        r[S::IA] = r[S::IA] + K * inv_ds * (Fsc[0] - Fsp[0]);
+        r[S::IA + NF - 1] = r[S::IA + NF - 1] - K * inv_ds * (Fsc[0] - Fsp[0]);
     }
     if (DIR == ND - 1 && P.do_rk) {
 #pragma unroll
@@ -715,6 +720,11 @@ __global__ void __launch_bounds__(MFC5_MARCH_THREADS, (2 * NF + ND + 1 <= 8) ? M
                     if (alpha_iface) r[S::IA + f] = r[S::IA + f] + inv_ds * acoef[f] * (Fsp[f] - Fs[f]);
                     else r[S::IA + f] = r[S::IA + f] + inv_ds * acoef[f] * (Fs[0] - Fsp[0]);
                 }
+                if (!FAST && P.alt_ss) {  // K div(u) correction, u-interface form (m_rhs.fpp:1568-1582,1714-1728)
+                    const double K = k_term(P, __ldg(P.prim + S::IE * P.fs + c), __ldg(P.prim + S::IA * P.fs + c), __ldg(P.prim + (S::IA + NF - 1) * P.fs + c));
+                    r[S::IA] = r[S::IA] + K * inv_ds * (Fs[0] - Fsp[0]);
+                    r[S::IA + NF - 1] = r[S::IA + NF - 1] - K * inv_ds * (Fs[0] - Fsp[0]);
+                }
                 if (rk) {
 #pragma unroll
                     for (int v = 0; v < N; v++) {
@@ -762,7 +772,7 @@ __global__ void __launch_bounds__(256) k_reduce(const __grid_constant__ DevP P, 
         const double pres = P.prim[S::IE * P.fs + c];
         const double E = gam * pres + pinf + 5.e-1 * rho * vs + qv;
         const double H = (E + pres) / rho;
-        const double cs = sound_speed(P, rho, gam, H, vs, qv);
+        const double cs = sound_speed(P, pres, rho, gam, H, alf, vs, qv);
         double dtl = P.T[0].ds[i + P.b] / (fabs(vel[0]) + cs);
         if (ND > 1) dtl = fmin(dtl, P.T[1].ds[j + P.b] / (fabs(vel[1]) + cs));
         if (ND > 2) dtl = fmin(dtl, P.T[2].ds[k + P.b] / (fabs(vel[2]) + cs));

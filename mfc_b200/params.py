@@ -38,7 +38,7 @@ class Mfc5Params(C.Structure):
         ("alpha_rho_in", (C.c_double * MAX_FLUIDS) * 3), ("alpha_in", (C.c_double * MAX_FLUIDS) * 3),
         ("fluid_gamma", C.c_double * MAX_FLUIDS), ("fluid_pi_inf", C.c_double * MAX_FLUIDS),
         ("fluid_qv", C.c_double * MAX_FLUIDS),
-        ("device", C.c_int), ("fast_math", C.c_int), ("reserved", C.c_int * 6),
+        ("device", C.c_int), ("fast_math", C.c_int), ("low_Mach", C.c_int), ("alt_soundspeed", C.c_int), ("reserved", C.c_int * 4),
     ]
 
     @property
@@ -74,7 +74,7 @@ def _val(case, key, default=None):
 
 
 _UNSUPPORTED_TRUE = [
-    "alt_soundspeed", "viscous", "surface_tension", "bubbles_euler", "bubbles_lagrange", "qbmm", "hypoelasticity",
+    "viscous", "surface_tension", "bubbles_euler", "bubbles_lagrange", "qbmm", "hypoelasticity",
     "hyperelasticity", "mhd", "relativity", "chemistry", "igr", "ib", "cyl_coord", "acoustic_source", "relax",
     "mp_weno", "teno", "cfl_adap_dt", "cfl_const_dt", "cont_damage", "hyper_cleaning",
 ]
@@ -92,8 +92,6 @@ def params_from_case(case, device=0, fast_math=1):
     for k in _UNSUPPORTED_TRUE:
         if _logical(case.get(k, "F")):
             raise UnsupportedCase(f"{k}=T is outside the 5-equation inviscid hot path")
-    if int(_val(case, "low_Mach", 0) or 0) != 0:
-        raise UnsupportedCase("low_Mach != 0 is not supported")
     ic = case.get("int_comp", 0)
     if (_logical(ic) if isinstance(ic, str) else int(ic or 0) != 0):
         raise UnsupportedCase("interface compression is not supported")
@@ -122,6 +120,19 @@ def params_from_case(case, device=0, fast_math=1):
     P.wave_speeds = int(_val(case, "wave_speeds", 1))
     P.mpp_lim = _logical(case.get("mpp_lim", "F"))
     P.mixture_err = _logical(case.get("mixture_err", "F"))
+    P.alt_soundspeed = _logical(case.get("alt_soundspeed", "F"))
+    if P.alt_soundspeed:  # toolchain/mfc/case_validator.py:1394-1418
+        if P.num_fluids != 2:
+            raise UnsupportedCase("alt_soundspeed requires exactly 2 fluid components (the Kapila K coefficient is a two-fluid closure)")
+        if P.avg_state != 2:
+            raise UnsupportedCase("alt_soundspeed requires avg_state = 2")
+        if P.riemann_solver == 1 and not P.hll_u_interface:
+            raise UnsupportedCase("alt_soundspeed with HLL method 1 (interface alphas) is outside the hot path; use hll_u_interface = T or HLLC")
+    P.low_Mach = int(_val(case, "low_Mach", 0) or 0)
+    if P.low_Mach not in (0, 1, 2):
+        raise UnsupportedCase("low_Mach must be 0, 1 or 2")
+    if P.low_Mach == 2 and P.riemann_solver != 2:
+        raise UnsupportedCase("low_Mach = 2 requires riemann_solver = 2 (HLLC)")  # m_checker_common / case_validator
     P.time_stepper = int(_val(case, "time_stepper", 3))
     P.dt = float(case["dt"])
     nd = P.num_dims

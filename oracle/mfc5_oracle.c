@@ -343,9 +343,17 @@ static void mixture(const orc_state* S, double* arho, double* alf, int passes, d
     *rho = r; *gam = g; *pinf = pi; *qv = q;
 }
 
-/* s_compute_speed_of_sound, 5-eq non-bubble branch: m_variables_conversion.fpp:1248-1260 */
-static double sound_speed(const orc_state* S, double rho, double gam, double H, double vel_sum, double qv) {
-    double c = (H - 5.e-1 * vel_sum - qv / rho) / gam;
+/* s_compute_speed_of_sound, 5-eq non-bubble branch: m_variables_conversion.fpp:1233-1260
+ * (alt_soundspeed: Wood's mixture sound speed from the two bulk moduli, :1233-1236) */
+static double sound_speed(const orc_state* S, double pres, double rho, double gam, double H, const double* adv, double vel_sum, double qv) {
+    double c;
+    if (S->P.alt_soundspeed) {
+        double blkmod1 = ((S->P.fluid_gamma[0] + 1.0) * pres + S->P.fluid_pi_inf[0]) / S->P.fluid_gamma[0];
+        double blkmod2 = ((S->P.fluid_gamma[1] + 1.0) * pres + S->P.fluid_pi_inf[1]) / S->P.fluid_gamma[1];
+        c = (1.0 / (rho * (adv[0] / blkmod1 + adv[1] / blkmod2)));
+    } else {
+        c = (H - 5.e-1 * vel_sum - qv / rho) / gam;
+    }
     if (S->P.mixture_err && c < 0.0) return 100.0 * SGM_EPS;
     return sqrt(c);
 }
@@ -622,6 +630,8 @@ static void riemann_dir(orc_state* S, int d) {
                 }
                 double pres_L = qL[S->iE], pres_R = qR[S->iE];
                 double arho_L[MAXF], arho_R[MAXF], alf_L[MAXF], alf_R[MAXF];
+                double adv_L[MAXF], adv_R[MAXF]; /* alpha_L/R handed to s_compute_speed_of_sound: hllc.fpp:889-892 (pre-limiter loads) */
+                for (int f = 0; f < nf; f++) { adv_L[f] = qL[S->iadv + f]; adv_R[f] = qR[S->iadv + f]; }
                 if (hllc) {
                     /* in-place limiter on the face buffers: hllc.fpp:938-958 */
                     if (P->mpp_lim) {
@@ -665,6 +675,7 @@ static void riemann_dir(orc_state* S, int d) {
                         }
                     }
                 }
+                if (!hllc) for (int f = 0; f < nf; f++) { adv_L[f] = alf_L[f]; adv_R[f] = alf_R[f]; } /* hll.fpp:187-200: alpha_L itself is limited */
                 /* s_accumulate_mixture_properties: m_riemann_state.fpp:1036-1058 */
                 double rho_L = 0, gamma_L = 0, pi_inf_L = 0, qv_L = 0, rho_R = 0, gamma_R = 0, pi_inf_R = 0, qv_R = 0;
                 for (int f = 0; f < nf; f++) {
@@ -702,9 +713,19 @@ static void riemann_dir(orc_state* S, int d) {
                     gamma_avg = 5.e-1 * (gamma_L + gamma_R);
                     qv_avg = 5.e-1 * (qv_L + qv_R);
                 }
-                double c_L = sound_speed(S, rho_L, gamma_L, H_L, vel_L_rms, qv_L);
-                double c_R = sound_speed(S, rho_R, gamma_R, H_R, vel_R_rms, qv_R);
-                double c_avg = sound_speed(S, rho_avg, gamma_avg, H_avg, vel_avg_rms, qv_avg);
+                double c_L = sound_speed(S, pres_L, rho_L, gamma_L, H_L, adv_L, vel_L_rms, qv_L);
+                double c_R = sound_speed(S, pres_R, rho_R, gamma_R, H_R, adv_R, vel_R_rms, qv_R);
+                /* the average call passes pres_R and alpha_R as placeholders (hllc.fpp:1063-1066) */
+                double c_avg = sound_speed(S, pres_R, rho_avg, gamma_avg, H_avg, adv_R, vel_avg_rms, qv_avg);
+                /* low Mach corrections, inline_riemann.fpp:71-93 (call sites hllc.fpp:1084-1086,1137-1141; hll.fpp:400-404) */
+                double zcoef = 0.0;
+                if (P->low_Mach != 0) zcoef = dmin(1.0, dmax(sqrt(vel_L_rms) / c_L, sqrt(vel_R_rms) / c_R));
+                if (hllc && P->low_Mach == 2) {
+                    double vel_L_tmp = 5.e-1 * ((vel_L[d] + vel_R[d]) + zcoef * (vel_L[d] - vel_R[d]));
+                    double vel_R_tmp = 5.e-1 * ((vel_L[d] + vel_R[d]) + zcoef * (vel_R[d] - vel_L[d]));
+                    vel_L[d] = vel_L_tmp;
+                    vel_R[d] = vel_R_tmp;
+                }
                 double uL = vel_L[d], uR = vel_R[d];
                 double s_L, s_R, s_S;
                 if (P->wave_speeds == 1) {
@@ -723,7 +744,11 @@ static void riemann_dir(orc_state* S, int d) {
                     s_S = 5.e-1 * ((uL + uR) + (pres_L - pres_R) / (rho_avg * c_avg));
                 }
                 double s_M = dmin(0.0, s_L), s_P = dmax(0.0, s_R);
-                const double pcorr = 0.0; /* low_Mach = 0 */
+                double pcorr = 0.0;
+                if (P->low_Mach == 1) {
+                    if (hllc) pcorr = rho_L * rho_R * (s_L - uL) * (s_R - uR) * (uR - uL) / (rho_R * (s_R - uR) - rho_L * (s_L - uL)) * (zcoef - 1.0);
+                    else pcorr = -(s_P - s_M) * (rho_L + rho_R) / 8.0 * (zcoef - 1.0);
+                }
                 double F[MAXN], Fsrc[MAXF];
                 for (int f = 0; f < MAXF; f++) Fsrc[f] = 0.0;
                 if (hllc) {
@@ -875,7 +900,7 @@ static void cbc_dir_side(orc_state* S, int d, int side) {
                 for (int f = 0; f < nf; f++) mf[f] = arho[f] / rho;
                 double E = gam * pres + pinf + 5.e-1 * rho * vel_K_sum;
                 double H = (E + pres) / rho;
-                double c = sound_speed(S, rho, gam, H, vel_K_sum, qv);
+                double c = sound_speed(S, pres, rho, gam, H, adv, vel_K_sum, qv);
                 double darho_ds[MAXF], dvel_ds[3] = {0, 0, 0}, dpres_ds = 0, dadv_ds[MAXF];
                 for (int f = 0; f < nf; f++) { darho_ds[f] = 0; dadv_ds[f] = 0; }
                 for (int jl = 0; jl <= b; jl++) {
@@ -1001,6 +1026,14 @@ static void flux_difference(orc_state* S, int d) {
                     if (d == 0) S->rhs[v * S->fsz + c] = inv_ds * (f1 - f2);
                     else S->rhs[v * S->fsz + c] = S->rhs[v * S->fsz + c] + inv_ds * (f1 - f2);
                 }
+                double Kterm = 0.0;
+                if (S->P.alt_soundspeed) { /* m_rhs.fpp:1070-1095: cell-centre pressure (prim) and volume fractions (cons) */
+                    double pres = S->prim[S->iE * S->fsz + c];
+                    double blkmod1 = ((S->P.fluid_gamma[0] + 1.0) * pres + S->P.fluid_pi_inf[0]) / S->P.fluid_gamma[0] + (4.0 / 3.0) * 0.0;
+                    double blkmod2 = ((S->P.fluid_gamma[1] + 1.0) * pres + S->P.fluid_pi_inf[1]) / S->P.fluid_gamma[1] + (4.0 / 3.0) * 0.0;
+                    double alpha1 = S->q1[S->iadv * S->fsz + c], alpha2 = S->q1[(S->iadv + nf - 1) * S->fsz + c];
+                    Kterm = alpha1 * alpha2 * (blkmod2 - blkmod1) / (alpha1 * blkmod2 + alpha2 * blkmod1);
+                }
                 for (int f = 0; f < nf; f++) {
                     long v = (S->iadv + f) * S->fsz + c;
                     if (alpha_iface) {
@@ -1012,6 +1045,12 @@ static void flux_difference(orc_state* S, int d) {
                         double f1 = S->fsrc[c], f2 = S->fsrc[c - sd];
                         S->rhs[v] = S->rhs[v] + inv_ds * coeff * (f1 - f2);
                     }
+                }
+                if (S->P.alt_soundspeed) { /* K div(u) correction, u-interface form: m_rhs.fpp:1489-1503,1568-1582,1714-1728 */
+                    double f1 = S->fsrc[c], f2 = S->fsrc[c - sd];
+                    long v0 = S->iadv * S->fsz + c, v1 = (S->iadv + nf - 1) * S->fsz + c;
+                    S->rhs[v0] = S->rhs[v0] + Kterm * inv_ds * (f1 - f2);
+                    S->rhs[v1] = S->rhs[v1] - Kterm * inv_ds * (f1 - f2);
                 }
             }
 }
@@ -1075,7 +1114,7 @@ double orc_icfl_max(orc_state* S, double dt) {
                 double pres = S->prim[S->iE * S->fsz + c];
                 double E = gam * pres + pinf + 5.e-1 * rho * vs + qv;
                 double H = (E + pres) / rho;
-                double cs = sound_speed(S, rho, gam, H, vs, qv);
+                double cs = sound_speed(S, pres, rho, gam, H, alf, vs, qv);
                 double icfl;
                 if (nd == 3) icfl = dt / dmin(dmin(S->ds[0][i] / (fabs(vel[0]) + cs), S->ds[1][j] / (fabs(vel[1]) + cs)), S->ds[2][k] / (fabs(vel[2]) + cs));
                 else if (nd == 2) icfl = dt / dmin(S->ds[0][i] / (fabs(vel[0]) + cs), S->ds[1][j] / (fabs(vel[1]) + cs));

@@ -22,7 +22,8 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 REF = sys.argv[1] if len(sys.argv) > 1 else "/root/reference"
 
-# UUIDs inside the 5-eq / WENO{3,5}{JS,M,Z} / HLL|HLLC / RK3 envelope
+# UUIDs inside the 5-eq / WENO{3,5}{JS,M,Z} / HLL|HLLC / RK3 envelope;
+# last lines: the f-4 widening (low_Mach = 1 / 2, tolerance 1e-10 by the reference's own rule; alt_soundspeed)
 UUIDS = """
 D79C3E6F 8A59E8E6 2AB32975 70DAE9E8 3AE495F4 5EC236F2 48CCE072 AED93D34 C5B79059 727F72ED A60691E7 3FC6FC4A
 2FD933A2 ED728400 9D92767D 63CD6ADF
@@ -42,6 +43,8 @@ B8F5F1C8 A0B82851 C7B686C0
 0FCCE9F1 8C7AA13B CE232828
 05D092C5 59C3F366 B49877F3 1A379909 C3A4DBAE
 BCA926AC 24FD489A B5F0C655 82152069 BCB15E8E 02D1E522
+4D88A48D 07C1FECC 0853FBD1 F9E0BE95 F5F06EA3 C462AA3E
+7C8F1BA9 A26B7E00 E47F81A2
 """.split()
 
 
