@@ -105,6 +105,45 @@ def _patch(case, i, key, default=None):
     return case.get(f"patch_icpp({i})%{key}", default)
 
 
+# ---- analytic patch values --------------------------------------------------------------------------------
+# A case file may give alpha_rho / vel / pres / alpha of a patch as a Python-syntax expression of the cell-centre
+# coordinates (reference toolchain/mfc/case.py:152-255 generates Fortran from it; names and intrinsics as in
+# toolchain/mfc/analytic_expr.py:11-36).  Here the expression is evaluated with numpy over the patch's cells.
+_INTRINSICS = {"sin": np.sin, "cos": np.cos, "tan": np.tan, "asin": np.arcsin, "acos": np.arccos, "atan": np.arctan,
+               "atan2": np.arctan2, "sinh": np.sinh, "cosh": np.cosh, "tanh": np.tanh, "exp": np.exp, "log": np.log,
+               "log10": np.log10, "sqrt": np.sqrt, "abs": np.abs, "min": np.minimum, "max": np.maximum, "mod": np.fmod,
+               "sign": lambda a, b: np.copysign(np.abs(a), b)}
+
+
+def _is_analytic(v):
+    if not isinstance(v, str):
+        return False
+    try:
+        float(v)
+        return False
+    except ValueError:
+        return True
+
+
+def _eval_analytic(expr, names):
+    import ast
+    tree = ast.parse(expr, mode="eval")
+    for node in ast.walk(tree):
+        if isinstance(node, ast.Name) and node.id not in names and node.id not in _INTRINSICS:
+            raise ValueError(f"unknown name '{node.id}' in analytic expression {expr!r}")
+        if isinstance(node, (ast.Attribute, ast.Subscript, ast.Lambda, ast.Import, ast.ImportFrom)):
+            raise ValueError(f"unsupported syntax in analytic expression {expr!r}")
+    env = dict(_INTRINSICS)
+    env.update(names)
+    return eval(compile(tree, "<analytic>", "eval"), {"__builtins__": {}}, env)
+
+
+def _num(case, ip, key, default=None):
+    """Numeric value of a patch attribute; an analytic expression counts as 0 (the namelist gets ``0d0``, case.py:95-98)."""
+    v = _patch(case, ip, key, default)
+    return 0.0 if _is_analytic(v) else float(v)
+
+
 def initial_condition(case, ccs, ds_min=None):
     """Primitive then conservative variables, arrays [N][nz][ny][nx] -> returned as (N, nz, ny, nx).
 
@@ -125,8 +164,8 @@ def initial_condition(case, ccs, ds_min=None):
         smooth = _logical(_patch(case, ip, "smoothen", "F"))
         if smooth and geom != 8:
             raise NotImplementedError("patch smoothing is implemented for the sphere only")
-        if _patch(case, ip, "hcid") is not None:
-            raise NotImplementedError("hard-coded patches")
+        if _patch(case, ip, "hcid") is not None and smooth:
+            raise NotImplementedError("hard-coded profile on a smoothed patch")
         xc = float(_patch(case, ip, "x_centroid", 0.0))
         yc = float(_patch(case, ip, "y_centroid", 0.0))
         zc = float(_patch(case, ip, "z_centroid", 0.0))
@@ -184,13 +223,89 @@ def initial_condition(case, ccs, ds_min=None):
             pid[own] = ip
             continue
         for f in range(nf):
-            prim[f][mask] = float(_patch(case, ip, f"alpha_rho({f + 1})"))
-            prim[iE + 1 + f][mask] = float(_patch(case, ip, f"alpha({f + 1})"))
+            prim[f][mask] = _num(case, ip, f"alpha_rho({f + 1})")
+            prim[iE + 1 + f][mask] = _num(case, ip, f"alpha({f + 1})")
         for a in range(nd):
-            prim[nf + a][mask] = float(_patch(case, ip, f"vel({a + 1})", 0.0))
-        prim[iE][mask] = float(_patch(case, ip, "pres"))
+            prim[nf + a][mask] = _num(case, ip, f"vel({a + 1})", 0.0)
+        prim[iE][mask] = _num(case, ip, "pres")
         pid[mask] = ip
+        # analytic expressions and hard-coded profiles overwrite the constants in the cells the patch took
+        # (m_assign_variables.fpp: @:analytical() / @:Hardcoded1D() after the constant assignment)
+        names = {"x": np.broadcast_to(X, pid.shape), "y": np.broadcast_to(Y, pid.shape), "z": np.broadcast_to(Z, pid.shape),
+                 "xc": xc, "yc": yc, "zc": zc, "pi": math.pi}
+        for nm, key in (("lx", "length_x"), ("ly", "length_y"), ("lz", "length_z"), ("r", "radius"), ("eps", "epsilon"), ("beta", "beta")):
+            if _patch(case, ip, key) is not None:
+                names[nm] = float(_patch(case, ip, key))
+        targets = [(f, f"alpha_rho({f + 1})") for f in range(nf)] + [(iE + 1 + f, f"alpha({f + 1})") for f in range(nf)]
+        targets += [(nf + a, f"vel({a + 1})") for a in range(nd)] + [(iE, "pres")]
+        for v, key in targets:
+            val = _patch(case, ip, key)
+            if _is_analytic(val):
+                prim[v][mask] = np.broadcast_to(_eval_analytic(val, names), pid.shape)[mask]
+        hcid = _patch(case, ip, "hcid")
+        if hcid is not None:
+            xm = names["x"][mask]
+            if int(hcid) == 180:    # Shu-Osher, src/common/include/1dHardcodedIC.fpp:21-26 (second patch only)
+                if ip == 2:
+                    prim[0][mask] = 1 + float(np.float32(0.2)) * np.sin(5 * xm)  # `0.2` is a default-kind (single) literal there
+            elif int(hcid) == 181:  # Titarev-Toro, :27-30
+                prim[0][mask] = 1 + float(np.float32(0.1)) * np.sin(20 * xm * math.pi)
+            else:
+                raise NotImplementedError(f"hard-coded patch hcid = {hcid}")
+    if _logical(case.get("elliptic_smoothing", "F")):
+        prim = elliptic_smoothing(case, prim, nf, nd, int(case["elliptic_smoothing_iters"]))
     return prim, prim_to_cons(case, prim, nf, nd)
+
+
+def _ghost_layer(case, prim, nf, nd):
+    """One ghost layer of the primitive variables on a single rank (``s_populate_variables_buffers`` as pre_process
+    calls it, m_boundary_common.fpp:92-187): periodic, reflective, slip / no-slip walls, extrapolation for the rest."""
+    q = prim
+    for d, x in enumerate("xyz"[:nd]):
+        ax = 3 - d
+        n = q.shape[ax]
+        lo_bc, hi_bc = int(case[f"bc_{x}%beg"]), int(case[f"bc_{x}%end"])
+        if lo_bc >= 0 or hi_bc >= 0:
+            raise NotImplementedError("elliptic smoothing across processor boundaries")
+
+        def face(bc, edge, mirror, wrap, wall):
+            if bc == -1:
+                g = np.take(q, [wrap], axis=ax)
+            elif bc == -2:
+                g = np.take(q, [mirror], axis=ax).copy()
+                g[nf + d] = -g[nf + d]
+            elif bc in (-15, -16):
+                g = np.take(q, [edge], axis=ax).copy()
+                m = np.take(q, [mirror], axis=ax)
+                for a in range(nd):
+                    if bc == -16 or a == d:
+                        g[nf + a] = -m[nf + a] + 2.0 * float(case.get(f"bc_{x}%v{wall}{a + 1}", 0.0))
+            else:
+                g = np.take(q, [edge], axis=ax)
+            return g
+        glo = face(lo_bc, 0, 0, n - 1, "b")
+        ghi = face(hi_bc, n - 1, n - 1, 0, "e")
+        q = np.concatenate([glo, q, ghi], axis=ax)
+    return q
+
+
+def elliptic_smoothing(case, prim, nf, nd, iters):
+    """``s_elliptic_smoothing`` (reference src/pre_process/m_perturbation.fpp:88-144): ``iters`` Jacobi sweeps of the
+    (1, 2, 1)/4, 5-point/8 or 7-point/12 filter over every primitive variable, ghost layer from the boundary conditions."""
+    for _ in range(iters):
+        g = _ghost_layer(case, prim, nf, nd)
+        if nd == 1:
+            c = g[:, :, :, 1:-1]
+            prim = (1.0 / 4.0) * (g[:, :, :, 2:] + g[:, :, :, :-2] + 2.0 * c)
+        elif nd == 2:
+            c = g[:, :, 1:-1, 1:-1]
+            prim = (1.0 / 8.0) * (g[:, :, 1:-1, 2:] + g[:, :, 1:-1, :-2] + g[:, :, 2:, 1:-1] + g[:, :, :-2, 1:-1] + 4.0 * c)
+        else:
+            c = g[:, 1:-1, 1:-1, 1:-1]
+            prim = (1.0 / 12.0) * (g[:, 1:-1, 1:-1, 2:] + g[:, 1:-1, 1:-1, :-2] + g[:, 1:-1, 2:, 1:-1] + g[:, 1:-1, :-2, 1:-1]
+                                   + g[:, 2:, 1:-1, 1:-1] + g[:, :-2, 1:-1, 1:-1] + 6.0 * c)
+        prim = np.ascontiguousarray(prim)
+    return prim
 
 
 def prim_to_cons(case, prim, nf, nd):

@@ -46,3 +46,34 @@ def test_perf_test_initial_condition_is_smoothed_and_bounded():
     assert len(np.unique(np.round(a1, 6))) > 10  # tanh profile, not a step
     np.testing.assert_allclose(prim[6] + prim[7], 1.0, atol=1e-14)
     assert np.all(np.diff(cbs[0]) > 0) and abs(np.diff(cbs[0]).max() / np.diff(cbs[0]).min()) > 1.5  # stretched
+
+
+def test_analytic_patch_expression_and_hardcoded_profile():
+    """Analytic patch values (toolchain/mfc/case.py:152-255) evaluated over the patch's cells; hcid 180 is the same
+    Shu-Osher profile with the reference's single-precision 0.2 (src/common/include/1dHardcodedIC.fpp:21-26)."""
+    base = dict(CASES["B50DE910"]["params"])
+    cbs, ccs = pre_process.generate_grid(base)
+    prim_h, _ = pre_process.initial_condition(base, ccs)
+    ana = dict(base)
+    del ana["patch_icpp(2)%hcid"]
+    ana["patch_icpp(2)%alpha_rho(1)"] = "1 + 0.2*sin(5*x)"
+    prim_a, _ = pre_process.initial_condition(ana, ccs)
+    x = ccs[0]
+    inside = np.abs(x - float(base["patch_icpp(2)%x_centroid"])) <= 0.5 * float(base["patch_icpp(2)%length_x"])
+    np.testing.assert_array_equal(prim_a[0][0, 0, inside], 1 + 0.2 * np.sin(5 * x[inside]))
+    assert np.max(np.abs(prim_a[0] - prim_h[0])) < 4e-9 and np.max(np.abs(prim_a[0] - prim_h[0])) > 1e-10
+    np.testing.assert_array_equal(prim_a[0][0, 0, ~inside], prim_h[0][0, 0, ~inside])
+    with pytest.raises(ValueError):
+        pre_process.initial_condition(dict(ana, **{"patch_icpp(2)%alpha_rho(1)": "__import__('os').getcwd()"}), ccs)
+    with pytest.raises(ValueError):
+        pre_process.initial_condition(dict(ana, **{"patch_icpp(2)%alpha_rho(1)": "1 + q"}), ccs)
+
+
+def test_elliptic_smoothing_is_conservative_filter():
+    case = dict(CASES["8C1E22E4"]["params"])
+    cbs, ccs = pre_process.generate_grid(case)
+    prim_s, _ = pre_process.initial_condition(case, ccs)
+    prim_0, _ = pre_process.initial_condition(dict(case, elliptic_smoothing="F"), ccs)
+    assert prim_s.shape == prim_0.shape and not np.array_equal(prim_s, prim_0)
+    for v in range(prim_0.shape[0]):  # a convex filter cannot create new extrema
+        assert prim_s[v].min() >= prim_0[v].min() - 1e-14 and prim_s[v].max() <= prim_0[v].max() + 1e-14

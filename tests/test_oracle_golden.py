@@ -33,9 +33,12 @@ def test_golden(uuid):
     shape = q.shape[1:]
     nstep = int(case["t_step_stop"])
     tol = CASES[uuid]["tol"]
+    # EF3E3FF1 (Titarev-Toro, hcid 181): the golden's step-0 profile was generated with a single-precision pi
+    # (1.4e-14 from 1 + 0.1 sin(20 x pi_sp)); the current source (1dHardcodedIC.fpp:27-30) uses pi of kind wp, 8.4e-7 away
+    ic_tol = 1e-6 if uuid == "EF3E3FF1" else 1e-13
     for v in range(q.shape[0]):
         # the regenerated initial condition must reproduce the golden's own step-0 lines
-        ok0, a0, _ = compare(cons0[v], golden_field(g, "cons", v + 1, 0, 0, shape), 1e-13)
+        ok0, a0, _ = compare(cons0[v], golden_field(g, "cons", v + 1, 0, 0, shape), ic_tol)
         assert ok0, f"{uuid} IC var {v + 1}: max abs err {a0:.3e}"
         ok, a, w = compare(q[v], golden_field(g, "cons", v + 1, 0, nstep, shape), tol)
         assert ok, f"{uuid} ({CASES[uuid]['trace']}) var {v + 1}: worst min(abs,rel) err {w:.3e} > {tol}"
