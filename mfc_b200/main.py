@@ -82,6 +82,8 @@ def run_pre_process(case, case_dir, world=None, log=print):
     cbs, ccs, _ = blk.grid(case, P.buff_size)
     prim, cons = pre_process.initial_condition(lcase, ccs, ds_min=pre_process.grid_minima(case))
     t0 = int(case.get("t_step_start", 0))
+    if _logical(case.get("cfl_adap_dt", "F")) or _logical(case.get("cfl_const_dt", "F")):
+        t0 = int(case.get("n_start", 0))   # src/pre_process/m_data_output.fpp:185
     if par_io:
         if world.rank == 0:
             glb_cbs, _ = pre_process.generate_grid(case)
@@ -114,12 +116,20 @@ def run_simulation(case, case_dir, world=None, make_state=None, log=print):
     lcase = blk.local_case(case)
     P = params_from_case(lcase)
     par_io = _logical(case.get("parallel_io", "F"))
-    t0, t1 = int(case.get("t_step_start", 0)), int(case["t_step_stop"])
+    t0, t1 = int(case.get("t_step_start", 0)), int(case.get("t_step_stop", 0))
     t_save = int(case.get("t_step_save", max(t1 - t0, 1)))
     t_print = int(case.get("t_step_print", 1))
     run_time_info = _logical(case.get("run_time_info", "F"))
     prim_wrt = _logical(case.get("prim_vars_wrt", "F"))
     dt = float(case["dt"])
+    # CFL-based time stepping (cfl_adap_dt / cfl_const_dt): dt from s_compute_dt (m_time_steppers.fpp:639-710), the run is
+    # bounded by t_stop and saved every t_save of simulated time; the start data sit in directory n_start (p_main.fpp:48-50)
+    cfl_adap, cfl_const = _logical(case.get("cfl_adap_dt", "F")), _logical(case.get("cfl_const_dt", "F"))
+    cfl_dt = cfl_adap or cfl_const
+    if cfl_dt:
+        t_stop_time, t_save_time = float(case["t_stop"]), float(case["t_save"])
+        n_start, cfl_target = int(case.get("n_start", 0)), float(case["cfl_target"])
+        t0 = n_start
 
     # ---- start data (s_read_data_files): grid + q_cons of t_step_start
     if par_io:
@@ -166,7 +176,41 @@ def run_simulation(case, case_dir, world=None, make_state=None, log=print):
         io_time += time.perf_counter() - t
         n_saves += 1
 
-    while t_step != t1:
+    if cfl_dt:
+        t_step, mytime, dt_init = 0, t_save_time * n_start, 0.0
+        while mytime < t_stop_time:
+            if (cfl_const and t_step == 0) or cfl_adap:
+                dt = cfl_target * state.reduce(1)            # s_compute_dt: cfl_target * min over cells and ranks
+            if t_step == 0:
+                dt_init = dt
+            if cfl_adap and dt < 1.0e-3 * dt_init:           # m_start_up.fpp:579-582
+                raise FloatingPointError(f"Delta t = {dt}: Delta t has become too small")
+            if (mytime + dt) >= t_stop_time:
+                dt = t_stop_time - mytime
+            if world.rank == 0 and t_step % t_print == 0:
+                eta = wall_avg * (t_stop_time - mytime) / max(dt, sys.float_info.min)
+                log(" [%3d%%] Time %16.6E dt = %16.6E @ Time Step = %8d Time Avg = %16.6E Time/step = %12.6E ETA (HH:MM:SS) = %d:%02d:%02d"
+                    % (int(math.ceil(100.0 * (mytime / t_stop_time))), mytime, dt, t_step, wall_avg, wall, int(eta) // 3600,
+                       (int(eta) % 3600) // 60, int(eta) % 60))
+            if rti is not None or (run_time_info and world.size > 1):
+                icfl = state.icfl_max(dt)
+                if rti is not None:
+                    rti.write(t_step, dt, mytime, icfl)
+            ws = time.perf_counter()
+            state.step(dt)
+            wall = time.perf_counter() - ws
+            if timed_api:
+                if t_step < N_WARMUP:
+                    state.stage_time_min = 0.0
+                time_avg = state.stage_time_min
+            wall_avg = (wall + (t_step - 2) * wall_avg) / (t_step - 1) if t_step >= 2 else 0.0
+            mytime = mytime + dt
+            t_step += 1
+            if abs(math.fmod(mytime, t_save_time)) < dt or mytime >= t_stop_time:   # p_main.fpp:79-81
+                save(int(mytime / t_save_time))                                      # save_count, m_start_up.fpp:758-759
+        t1 = t_step
+
+    while not cfl_dt and t_step != t1:
         # how many steps until the next event (print / save / end); whole segments go to the device at once
         # when nothing has to be observed in between
         if (mytime + dt) >= finaltime:              # m_start_up.fpp:589-594

@@ -76,7 +76,7 @@ def _val(case, key, default=None):
 _UNSUPPORTED_TRUE = [
     "viscous", "surface_tension", "bubbles_euler", "bubbles_lagrange", "qbmm", "hypoelasticity",
     "hyperelasticity", "mhd", "relativity", "chemistry", "igr", "ib", "cyl_coord", "acoustic_source", "relax",
-    "mp_weno", "teno", "cfl_adap_dt", "cfl_const_dt", "cont_damage", "hyper_cleaning",
+    "mp_weno", "teno", "cont_damage", "hyper_cleaning",
 ]
 
 

@@ -188,3 +188,45 @@ def test_cli_parallel_io_round_trip(tmp_path):
     out, _ = run_case(case, str(tmp_path), targets=("simulation",))
     ref, _ = run_case(dict(case, parallel_io="F"), str(tmp_path / "serial"))
     assert np.array_equal(out["cons"], ref["cons"])
+
+
+class OracleCfl(OracleState):
+    """dt_min of the current state for the CFL-driven loop (the CUDA library: mfc5_reduce(what = 1)); numpy here."""
+
+    def reduce(self, what, dt=0.0):
+        self.cons2prim()                 # what == 2 (NaN count) is only used by the driver to refresh the primitives
+        if what != 1:
+            return 0.0
+        q = self.get_prim()
+        P = self.P
+        nf, nd = P.num_fluids, P.num_dims
+        assert nf == 1 and nd == 1
+        rho, u, p = q[0], q[1], q[2]
+        g, pinf = P.fluid_gamma[0], P.fluid_pi_inf[0]
+        E = g * p + pinf + 0.5 * rho * u * u
+        H = (E + p) / rho
+        c = np.sqrt((H - 0.5 * u * u) / g)
+        return float(np.min(self._dx / (np.abs(u) + c)))
+
+
+def test_cfl_driven_time_stepping(tmp_path):
+    """cfl_adap_dt: dt = cfl_target * min(dx / (|u| + c)) every step, run bounded by t_stop, saves every t_save
+    (s_compute_dt m_time_steppers.fpp:639-710, p_main.fpp:48-81)."""
+    case = dict(CASES["2AB32975"]["params"], cfl_adap_dt="T", cfl_target=0.4, t_stop=0.02, t_save=0.01, n_start=0, run_time_info="T")
+    lines = []
+    w = SerialWorld()
+    main.run_pre_process(case, str(tmp_path), w, log=lines.append)
+
+    def make(P, cbs, gws, dirichlet):
+        o = OracleCfl(P, cbs, ghost_widths=gws)
+        o._dx = np.diff(cbs[0])[None, None, :]
+        return o
+    out = main.run_simulation(case, str(tmp_path), w, make_state=make, log=lines.append)
+    rows = [l for l in open(tmp_path / "run_time.inf").read().split("\n") if l.strip() and l.split()[0].isdigit()]
+    dts = np.array([float(r.split()[1]) for r in rows])
+    icfl = np.array([float(r.split()[3]) for r in rows])
+    assert len(rows) == out["t_step"] and out["t_step"] > 10
+    assert np.all(np.abs(icfl[:-1] - 0.4) < 2e-6)                # ICFL == cfl_target by construction (the last step is clipped)
+    assert abs(dts.sum() - 0.02) < 1e-5
+    assert os.path.isdir(tmp_path / "p_all" / "p0" / "1") and os.path.isdir(tmp_path / "p_all" / "p0" / "2")
+    assert any(l.startswith(" [  0%] Time ") for l in lines)
