@@ -250,6 +250,8 @@ def initial_condition(case, ccs, ds_min=None):
                     prim[0][mask] = 1 + float(np.float32(0.2)) * np.sin(5 * xm)  # `0.2` is a default-kind (single) literal there
             elif int(hcid) == 181:  # Titarev-Toro, :27-30
                 prim[0][mask] = 1 + float(np.float32(0.1)) * np.sin(20 * xm * math.pi)
+            elif int(hcid) in (203, 207, 281, 282):
+                _hardcoded_2d(case, int(hcid), ip, prim, mask, names, nf, iE)
             else:
                 raise NotImplementedError(f"hard-coded patch hcid = {hcid}")
     if _logical(case.get("elliptic_smoothing", "F")):
@@ -306,6 +308,47 @@ def elliptic_smoothing(case, prim, nf, nd, iters):
                                    + g[:, 2:, 1:-1, 1:-1] + g[:, :-2, 1:-1, 1:-1] + 6.0 * c)
         prim = np.ascontiguousarray(prim)
     return prim
+
+
+def _hardcoded_2d(case, hcid, ip, prim, mask, names, nf, iE):
+    """The 2-D hard-coded profiles the in-scope examples use (reference src/common/include/2dHardcodedIC.fpp):
+    203 Gresho vortex with density correction (:70-92), 207 Kelvin-Helmholtz perturbation (:152-156), 281 acoustic pulse
+    (:477-485), 282 zero-circulation vortex (:486-498).  Literals without a kind suffix are single precision there."""
+    x, y = names["x"][mask], names["y"][mask]
+    f32 = np.float32
+    if hcid == 203:
+        r = ((x - 0.5) ** 2.0 + (y - 0.5) ** 2) ** 0.5
+        rmax = 0.2
+        gam = 1.0 + 1.0 / float(case["fluid_pp(1)%gamma"])
+        v2 = _num(case, ip, "vel(2)", 0.0)
+        umax = 2 * math.pi * rmax * v2
+        p0 = umax ** 2 * (1.0 / (gam * v2 ** 2) - 0.5)
+        inner, mid = r < rmax, (r >= rmax) & (r < 2 * rmax)
+        rs = np.where(r > 0, r, 1.0)
+        u = np.where(inner, -(y - 0.5) * umax / rmax, np.where(mid, -((y - 0.5) / rs) * umax * (2.0 - r / rmax), 0.0))
+        v = np.where(inner, (x - 0.5) * umax / rmax, np.where(mid, ((x - 0.5) / rs) * umax * (2.0 - r / rmax), 0.0))
+        with np.errstate(divide="ignore", invalid="ignore"):
+            pm = p0 + umax ** 2 * ((r / rmax) ** 2 / 2.0 + 4.0 * (1.0 - (r / rmax) + np.log(r / rmax)))
+        pr = np.where(inner, p0 + umax ** 2 * ((r / rmax) ** 2.0 / 2.0), np.where(mid, pm, p0 + umax ** 2.0 * (-2.0 + 4 * math.log(2.0))))
+        prim[nf][mask], prim[nf + 1][mask], prim[iE][mask] = u, v, pr
+        prim[0][mask] = pr ** (1.0 / gam)
+    elif hcid == 207:
+        sigma = 0.05 / math.sqrt(2.0)
+        gauss1 = np.exp(-(y - 0.75) ** 2 / (2.0 * sigma ** 2))
+        gauss2 = np.exp(-(y - 0.25) ** 2 / (2.0 * sigma ** 2))
+        prim[nf + 1][mask] = 0.1 * np.sin(4.0 * math.pi * x) * (gauss1 + gauss2)
+    elif ip == 2:  # 281 / 282 act on the second patch only
+        gm1 = f32(1.4) - f32(1)
+        mach2 = f32(0.4) ** 2 if hcid == 281 else (f32(0.1) / f32(0.3)) ** 2
+        coef = float(f32(0.5) * gm1 * mach2)
+        e = np.exp(0.5 * (1 - np.sqrt(x ** 2 + y ** 2)))
+        base = 1 - coef * e
+        prim[iE][mask] = 101325 * base ** float(f32(1.4) / gm1)
+        prim[0][mask] = 1 * base ** float(f32(1) / gm1)
+        if hcid == 282:
+            ratio = float(f32(0.1) / f32(0.3))
+            prim[nf][mask] = 112.99092883944267 * (1 - ratio) * y * e
+            prim[nf + 1][mask] = 112.99092883944267 * ratio * x * e
 
 
 def prim_to_cons(case, prim, nf, nd):

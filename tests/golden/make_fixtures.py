@@ -46,6 +46,7 @@ BCA926AC 24FD489A B5F0C655 82152069 BCB15E8E 02D1E522
 4D88A48D 07C1FECC 0853FBD1 F9E0BE95 F5F06EA3 C462AA3E
 7C8F1BA9 A26B7E00 E47F81A2
 8C1E22E4 C1134EF2 9843489C B50DE910 1DBC8382 EF3E3FF1
+C9E0B721 A078904B 8370A3D9 8FD91C41
 """.split()
 
 

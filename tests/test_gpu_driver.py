@@ -43,13 +43,13 @@ def _check_golden(uuid, case_dir):
         assert ok, (uuid, key, amax, worst)
 
 
-@pytest.mark.parametrize("uuid", ["2AB32975", "BCA926AC", "05D092C5", "A0B82851", "04E1CB26", "B49877F3"])
+@pytest.mark.parametrize("uuid", ["2AB32975", "BCA926AC", "05D092C5", "A0B82851", "04E1CB26", "B49877F3", "A078904B", "C9E0B721", "8370A3D9"])
 def test_cli_matches_golden(uuid, tmp_path):
     out = _run_cli(dict(CASES[uuid]["params"]), str(tmp_path))
     _check_golden(uuid, str(tmp_path))
     assert "Performance:" in out and "ns/gp/eq/rhs" in out
     assert os.path.exists(tmp_path / "time_data.dat") and os.path.exists(tmp_path / "simulation.inp")
-    assert os.path.isdir(tmp_path / "p_all" / "p0" / "50")
+    assert os.path.isdir(tmp_path / "p_all" / "p0")
 
 
 def test_segments_equal_single_steps(tmp_path):

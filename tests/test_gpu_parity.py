@@ -16,7 +16,7 @@ from mfc_b200 import driver
 
 pytestmark = pytest.mark.gpu
 
-SINGLE = sorted(u for u in CASES if CASES[u]["ppn"] == 1)
+SINGLE = sorted(u for u in CASES if CASES[u]["ppn"] == 1 and str(CASES[u]["params"].get("cfl_adap_dt", "F")) != "T")  # CFL-driven: test_gpu_driver.py
 # one representative per feature for the (slower) oracle cross-check
 ORACLE_SET = ["2AB32975", "677DAA82", "9090FC4B", "16A922E4", "C4907722", "1CCA82F5", "5EC236F2", "63CD6ADF", "70DAE9E8",
               "D6415F48", "AE3ECF01", "F0F175B2", "4129A23A", "EB6687AB", "10DBA76B", "4D7926CD", "55533234",

@@ -191,7 +191,8 @@ def test_cli_parallel_io_round_trip(tmp_path):
 
 
 class OracleCfl(OracleState):
-    """dt_min of the current state for the CFL-driven loop (the CUDA library: mfc5_reduce(what = 1)); numpy here."""
+    """dt_min of the current state for the CFL-driven loop (the CUDA library: mfc5_reduce(what = 1)); numpy here,
+    following s_compute_enthalpy / s_compute_speed_of_sound / s_compute_dt_from_cfl (m_sim_helpers.fpp:45-105,182-215)."""
 
     def reduce(self, what, dt=0.0):
         self.cons2prim()                 # what == 2 (NaN count) is only used by the driver to refresh the primitives
@@ -200,13 +201,35 @@ class OracleCfl(OracleState):
         q = self.get_prim()
         P = self.P
         nf, nd = P.num_fluids, P.num_dims
-        assert nf == 1 and nd == 1
-        rho, u, p = q[0], q[1], q[2]
-        g, pinf = P.fluid_gamma[0], P.fluid_pi_inf[0]
-        E = g * p + pinf + 0.5 * rho * u * u
+        arho = [q[f].copy() for f in range(nf)]
+        alf = [q[nf + nd + 1 + f].copy() for f in range(nf)]
+        if P.mpp_lim:
+            for _ in range(2):
+                s = np.zeros_like(alf[0])
+                for f in range(nf):
+                    arho[f] = np.maximum(0.0, arho[f])
+                    alf[f] = np.minimum(np.maximum(0.0, alf[f]), 1.0)
+                    s = s + alf[f]
+                for f in range(nf):
+                    alf[f] = alf[f] / np.maximum(s, 1e-16)
+        rho = sum(arho)
+        g = sum(alf[f] * P.fluid_gamma[f] for f in range(nf))
+        pinf = sum(alf[f] * P.fluid_pi_inf[f] for f in range(nf))
+        vel = [q[nf + a] for a in range(nd)]
+        vs = sum(v * v for v in vel)
+        p = q[nf + nd]
+        E = g * p + pinf + 0.5 * rho * vs
         H = (E + p) / rho
-        c = np.sqrt((H - 0.5 * u * u) / g)
-        return float(np.min(self._dx / (np.abs(u) + c)))
+        c = np.sqrt((H - 0.5 * vs) / g)
+        dts = [self._ds[a] / (np.abs(vel[a]) + c) for a in range(nd)]
+        return float(np.min(np.minimum.reduce(dts)))
+
+
+def _make_cfl_oracle(P, cbs, gws, dirichlet):
+    o = OracleCfl(P, cbs, ghost_widths=gws)
+    shapes = [(1, 1, -1), (1, -1, 1), (-1, 1, 1)]
+    o._ds = [np.diff(cbs[a]).reshape(shapes[a]) for a in range(P.num_dims)]
+    return o
 
 
 def test_cfl_driven_time_stepping(tmp_path):
@@ -217,11 +240,7 @@ def test_cfl_driven_time_stepping(tmp_path):
     w = SerialWorld()
     main.run_pre_process(case, str(tmp_path), w, log=lines.append)
 
-    def make(P, cbs, gws, dirichlet):
-        o = OracleCfl(P, cbs, ghost_widths=gws)
-        o._dx = np.diff(cbs[0])[None, None, :]
-        return o
-    out = main.run_simulation(case, str(tmp_path), w, make_state=make, log=lines.append)
+    out = main.run_simulation(case, str(tmp_path), w, make_state=_make_cfl_oracle, log=lines.append)
     rows = [l for l in open(tmp_path / "run_time.inf").read().split("\n") if l.strip() and l.split()[0].isdigit()]
     dts = np.array([float(r.split()[1]) for r in rows])
     icfl = np.array([float(r.split()[3]) for r in rows])
@@ -230,3 +249,20 @@ def test_cfl_driven_time_stepping(tmp_path):
     assert abs(dts.sum() - 0.02) < 1e-5
     assert os.path.isdir(tmp_path / "p_all" / "p0" / "1") and os.path.isdir(tmp_path / "p_all" / "p0" / "2")
     assert any(l.startswith(" [  0%] Time ") for l in lines)
+
+
+def test_kelvin_helmholtz_example_cfl_golden(tmp_path):
+    """The reference's example golden A078904B (2-D Kelvin-Helmholtz, HLL, cfl_adap_dt, hard-coded profile 207): every D/ file of every
+    save (selected by simulated time) through the CFL-driven loop."""
+    case = dict(CASES["A078904B"]["params"])
+    w = SerialWorld()
+    main.run_pre_process(case, str(tmp_path), w, log=lambda s: None)
+    main.run_simulation(case, str(tmp_path), w, make_state=_make_cfl_oracle, log=lambda s: None)
+    packed = data_io.pack_D(str(tmp_path))
+    g = golden("A078904B")
+    assert len(g) > 100
+    for key, want in g.items():
+        name = f"D/{key}.dat"
+        assert name in packed, name
+        ok, amax, worst = compare(packed[name], want, float(CASES["A078904B"]["tol"]))
+        assert ok, (key, amax, worst)

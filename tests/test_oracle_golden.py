@@ -12,7 +12,12 @@ from golden_util import CASES, compare, golden, golden_field, setup_case
 from mfc_b200 import driver
 from oracle_lib import Oracle
 
-SINGLE = sorted(u for u in CASES if CASES[u]["ppn"] == 1)
+def _cfl(u):
+    return str(CASES[u]["params"].get("cfl_adap_dt", "F")) == "T" or str(CASES[u]["params"].get("cfl_const_dt", "F")) == "T"
+
+
+# (CFL-driven cases save by simulated time: they go through the host driver's loop, tests/test_host_driver.py)
+SINGLE = sorted(u for u in CASES if CASES[u]["ppn"] == 1 and not _cfl(u))
 
 
 def run_oracle(uuid, omp=False):
@@ -36,6 +41,8 @@ def test_golden(uuid):
     # EF3E3FF1 (Titarev-Toro, hcid 181): the golden's step-0 profile was generated with a single-precision pi
     # (1.4e-14 from 1 + 0.1 sin(20 x pi_sp)); the current source (1dHardcodedIC.fpp:27-30) uses pi of kind wp, 8.4e-7 away
     ic_tol = 1e-6 if uuid == "EF3E3FF1" else 1e-13
+    if uuid in ("8370A3D9", "8FD91C41", "C9E0B721"):  # acoustic pulse / zero-circulation / Gresho vortex: hard-coded profiles
+        ic_tol = 1e-7                                     # with chains of single-precision literals (2dHardcodedIC.fpp)
     for v in range(q.shape[0]):
         # the regenerated initial condition must reproduce the golden's own step-0 lines
         ok0, a0, _ = compare(cons0[v], golden_field(g, "cons", v + 1, 0, 0, shape), ic_tol)
