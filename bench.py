@@ -364,6 +364,24 @@ def main():
         except (OSError, ValueError):
             pass
 
+    # the sweeps are FP64-pipe bound: the same launch times against the measured FP64 issue peak
+    fp64 = None
+    cnt_file = os.path.join(ROOT, "profiles", "fp64_counts.json")
+    if args.case == "3D_performance_test" and args.riemann == "hllc" and os.path.exists(cnt_file):
+        try:
+            with open(cnt_file) as f:
+                cnt = json.load(f)
+            sm_hz = float((clocks or {}).get("sm_mhz") or peaks.get("sm_max_mhz", 1965.0)) * 1e6
+            pk = cnt["peak_thread_inst_per_clk_per_sm"] * 148 * sm_hz
+            per = {k: cnt["thread_inst_per_cell"][k] * ncell_loc / (kern[k]["ms_per_launch"] * 1e-3) for k in cnt["thread_inst_per_cell"] if k in kern}
+            tot_inst = sum(cnt["thread_inst_per_cell"][k] for k in per) * ncell_loc
+            tot_t = sum(kern[k]["ms_per_launch"] for k in per) * 1e-3
+            fp64 = {"unit": "FP64 thread instructions/s (DFMA+DMUL+DADD)", "peak": pk, "achieved": tot_inst / tot_t, "frac": tot_inst / tot_t / pk,
+                    "per_sweep_frac": {k: v / pk for k, v in per.items()}, "thread_inst_per_cell": cnt["thread_inst_per_cell"],
+                    "stage_floor_ms": tot_inst / pk * 1e3, "source": "profiles/fp64_counts.json (ncu) + profiles/fp64_peak_r01.txt"}
+        except (OSError, KeyError, ValueError, ZeroDivisionError):
+            fp64 = None
+
     value = grind(t_stage, (case["m"], case["n"], case["p"]), N)
     out = {
         "metric": "grind_time", "value": value, "unit": "ns/gp/eq/rhs", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -378,6 +396,8 @@ def main():
         "clocks": clocks, "gpu_launches": int(launches), "nan_count": nan_count,
         "roofline": roof, "roofline_stage": roof_stage, "kernels": kern,
     }
+    if fp64 is not None:
+        out["roofline_fp64"] = fp64
     if e2e is not None:
         out["e2e"] = e2e
     # ---- CPU baseline on this box's host cores (bounded sample), N = 1 only

@@ -54,7 +54,7 @@ typedef struct mfc5_params {
     int null_weights;
     double weno_eps;
     /* Riemann solver */
-    int riemann_solver;  /* 1 = HLL, 2 = HLLC */
+    int riemann_solver;  /* 1 = HLL, 2 = HLLC, 5 = Lax-Friedrichs (m_riemann_solver_lf.fpp) */
     int hll_u_interface; /* HLL alpha transport "method 2" */
     int avg_state;       /* 1 = Roe, 2 = arithmetic */
     int wave_speeds;     /* 1 = direct, 2 = pressure based */
@@ -82,7 +82,10 @@ typedef struct mfc5_params {
     /* Riemann-solver extras; they occupy former reserved words, so the struct size is unchanged */
     int low_Mach;        /* 0 off; 1 pressure correction (HLL, HLLC); 2 velocity correction (HLLC): inline_riemann.fpp:71-93 */
     int alt_soundspeed;  /* Wood sound speed + K div(u) term in the alpha equations (2 fluids; HLLC or HLL with hll_u_interface) */
-    int reserved[4];
+    /* MUSCL reconstruction (recon_type = 2, src/simulation/m_muscl.fpp): muscl_order 0 = off (WENO), 1, 2;
+     * muscl_lim 0 unlimited, 1 minmod, 2 MC, 3 Van Albada, 4 Van Leer, 5 SUPERBEE; buff_size = muscl_order + 2 */
+    int muscl_order, muscl_lim;
+    double muscl_eps;
 } mfc5_params;
 
 #ifdef __cplusplus

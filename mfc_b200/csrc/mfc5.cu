@@ -141,8 +141,15 @@ extern "C" int mfc5_create(const mfc5_params* p, mfc5_handle** out) {
         return fail(std::string("no CUDA device available (libmfc5 has no CPU fallback): ") + cudaGetErrorString(e));
     if (p->model_eqns != 2) return fail("only model_eqns = 2 (5-equation model) is supported");
     if (p->num_fluids < 1 || p->num_fluids > 3) return fail("num_fluids must be 1..3");
+    mfc5_params pe = *p;   // effective parameters: MUSCL borrows the stencil / buffer geometry of the WENO of the same width
+    if (p->muscl_order != 0) {
+        if (p->muscl_order < 1 || p->muscl_order > 2 || p->muscl_lim < 0 || p->muscl_lim > 5) return fail("muscl_order must be 1 or 2, muscl_lim 0..5");
+        pe.weno_order = 2 * p->muscl_order + 1;   // buff_size = muscl_order + 2 (m_helper_basic.fpp:134-135)
+    }
+    p = &pe;
     if (p->weno_order != 1 && p->weno_order != 3 && p->weno_order != 5) return fail("weno_order must be 1, 3 or 5");
-    if (p->riemann_solver != 1 && p->riemann_solver != 2) return fail("riemann_solver must be 1 (HLL) or 2 (HLLC)");
+    if (p->riemann_solver != 1 && p->riemann_solver != 2 && p->riemann_solver != 5)
+        return fail("riemann_solver must be 1 (HLL), 2 (HLLC) or 5 (Lax-Friedrichs)");
     if (p->mapped_weno && p->wenoz) return fail("mapped_weno and wenoz are mutually exclusive");
     if (p->alt_soundspeed && (p->num_fluids != 2 || p->avg_state != 2 || (p->riemann_solver == 1 && !p->hll_u_interface)))
         return fail("alt_soundspeed needs 2 fluids, avg_state = 2 and a u-interface solver (HLLC, or HLL with hll_u_interface)");
@@ -150,7 +157,8 @@ extern "C" int mfc5_create(const mfc5_params* p, mfc5_handle** out) {
     if (p->time_stepper < 1 || p->time_stepper > 3) return fail("time_stepper must be 1..3");
     if (p->m < 0 || p->n < 0 || p->p < 0 || (p->n == 0 && p->p > 0)) return fail("invalid m, n, p");
     // m_checker.fpp:52-69: at least num_stcls_min*weno_order cells per direction
-    const int need = p->weno_order > 1 ? 5 * p->weno_order : 1;
+    const int recon_order = p->muscl_order > 0 ? p->muscl_order : p->weno_order;
+    const int need = recon_order > 1 ? 5 * recon_order : 1;
     const int ss[3] = {p->m, p->n, p->p};
     for (int d = 0; d < 3; d++)
         if ((d == 0 || ss[d] > 0) && ss[d] + 1 < need) return fail("too few cells for the WENO stencil (m_checker.fpp:52-69)");
@@ -165,7 +173,10 @@ extern "C" int mfc5_create(const mfc5_params* p, mfc5_handle** out) {
     h->b = h->pn + 2;  // m_helper_basic.fpp:127-132
     for (int d = 0; d < h->nd; d++)
         for (int sd = 0; sd < 2; sd++)
-            if (is_cbc(p->bc[d][sd]) && p->weno_order == 1) { delete h; return fail("characteristic BCs need weno_order >= 3"); }
+            if (is_cbc(p->bc[d][sd]) && (p->weno_order == 1 || p->muscl_order > 0)) {
+                delete h;
+                return fail("characteristic BCs need weno_order >= 3 (and are not available with MUSCL)");
+            }
     CK(cudaSetDevice(p->device));
     // HBM layout: SoA, x contiguous; interior x = 0 sits on a 128-byte boundary
     h->ox = 16; h->oy = h->nd > 1 ? h->b : 0; h->oz = h->nd > 2 ? h->b : 0;
@@ -405,8 +416,9 @@ extern "C" int mfc5_finalize_setup(mfc5_handle* h) {
     // weno_eps large enough that products of four smoothness indicators cannot underflow
     D.low_mach = h->P.low_Mach;
     D.alt_ss = h->P.alt_soundspeed;
+    D.muscl = h->P.muscl_order; D.muscl_lim = h->P.muscl_lim; D.muscl_eps = h->P.muscl_eps;
     D.fast = h->P.fast_math && h->P.wave_speeds == 1 && !h->P.null_weights && h->P.weno_eps >= 1e-30 && h->P.low_Mach == 0 &&
-             !h->P.alt_soundspeed;
+             !h->P.alt_soundspeed && h->P.riemann_solver != 5 && h->P.muscl_order == 0;
     if (getenv("MFC5_NO_FAST")) D.fast = 0;
     D.sy = h->px; D.sz = h->px * h->ey; D.fs = h->fs;
     D.base = h->ox + h->oy * D.sy + h->oz * D.sz;

@@ -47,6 +47,8 @@ struct DevP {
     int wo, wv, rs;    // weno_order; variant 0 JS / 1 M / 2 Z; riemann_solver 1 HLL / 2 HLLC
     int hll_u, avg, ws, mpp, mixerr, fast;
     int low_mach;      // 0 / 1 / 2, inline_riemann.fpp:71-93 (reference-order kernels only)
+    int muscl, muscl_lim;  // MUSCL reconstruction order (0 = WENO) and limiter, m_muscl.fpp (reference-order kernels only)
+    double muscl_eps;
     int alt_ss;        // alt_soundspeed: Wood sound speed + K div(u) term (reference-order kernels only)
     long long sy, sz, fs, base;  // strides (x stride = 1), field size, offset of cell (0,0,0)
     double eps;
@@ -341,6 +343,39 @@ __device__ __forceinline__ void weno_edges(const DevP& P, const DirTables& T, in
     const int wv = (WV < 0) ? P.wv : WV;
     const double eps = P.eps;
     if (wo == 1) { eL = f2; eR = f2; return; }
+    if (!FAST && WO < 0 && P.muscl > 0) {  // s_muscl, src/simulation/m_muscl.fpp:94-216 (generic kernels only)
+        double slope = 0.0;
+        if (P.muscl == 2) {
+            const double meps = P.muscl_eps;
+            const double slopeL = f3 - f2, slopeR = f2 - f1;
+            switch (P.muscl_lim) {
+            case 0: slope = 5e-1 * (slopeL + slopeR); break;
+            case 1:
+                if (slopeL * slopeR > meps) slope = fmin(fabs(slopeL), fabs(slopeR));
+                if (slopeL < 0.0) slope = -slope;
+                break;
+            case 2:
+                if (slopeL * slopeR > meps) {
+                    slope = fmin(2.0 * fabs(slopeL), 2.0 * fabs(slopeR));
+                    slope = fmin(slope, 5e-1 * (fabs(slopeL) + fabs(slopeR)));
+                }
+                if (slopeL < 0.0) slope = -slope;
+                break;
+            case 3:
+                if (slopeL * slopeR > meps) slope = ((slopeL + slopeR) * slopeL * slopeR) / (slopeL * slopeL + slopeR * slopeR);
+                break;
+            case 4:
+                if (slopeL * slopeR > meps) slope = 2.0 * slopeL * slopeR / (slopeL + slopeR);
+                break;
+            case 5:
+                if (slopeL * slopeR > meps) slope = -1.0 * fmin(-fmin(2.0 * fabs(slopeL), fabs(slopeR)), -fmin(fabs(slopeL), 2.0 * fabs(slopeR)));
+                break;
+            }
+        }
+        eL = f2 - (5.e-1 * slope);
+        eR = f2 + (5.e-1 * slope);
+        return;
+    }
     if (FAST) {
         const double f[1][5] = {{f0, f1, f2, f3, f4}};
         double l[1], r[1];
@@ -771,7 +806,12 @@ __device__ __forceinline__ void riemann_face(const DevP& P, double* qL, double* 
         s_R = uR + c_R * Ms_R;
         s_S = 5.e-1 * ((uL + uR) + (pres_L - pres_R) / (rho_avg * c_avg));
     }
-    const double s_M = fmin(0.0, s_L), s_P = fmax(0.0, s_R);
+    double s_M = fmin(0.0, s_L), s_P = fmax(0.0, s_R);
+    if (rs == 5) {  // Lax-Friedrichs: one symmetric speed, m_riemann_solver_lf.fpp:238-253
+        s_P = fmax(sqrt(vel_L_rms), sqrt(vel_R_rms)) + fmax(c_L, c_R);
+        s_M = -s_P;
+        s_L = s_M; s_R = s_P;
+    }
     double pcorr = 0.0;
     if (P.low_mach == 1) {
         if (rs == 2) pcorr = rho_L * rho_R * (s_L - uL) * (s_R - uR) * (uR - uL) / (rho_R * (s_R - uR) - rho_L * (s_L - uL)) * (zcoef - 1.0);
@@ -821,7 +861,9 @@ __device__ __forceinline__ void riemann_face(const DevP& P, double* qL, double* 
             for (int a = 0; a < ND; a++) F[IM + a] = F[IM + a] + (s_M / s_L) * (s_P / s_R) * pcorr * (qR[IM + a] - qL[IM + a]);
             F[IE] = F[IE] + (s_M / s_L) * (s_P / s_R) * pcorr * (vel_R_rms - vel_L_rms) / 2.0;
         }
-        if (!P.hll_u) {
+        // Lax-Friedrichs always exports the interface alphas (m_riemann_solver_lf.fpp:306-313); the RHS then reads
+        // flux_src(adv%beg) as the shared face velocity (adv_src_mode_vel_iface, m_global_parameters.fpp:903-906)
+        if (!P.hll_u || rs == 5) {
 #pragma unroll
             for (int f = 0; f < NF; f++) {
                 F[IA + f] = (qL[IA + f] - qR[IA + f]) * s_M * s_P / (s_M - s_P);

@@ -78,6 +78,15 @@ def split(s_glb, nprocs, coord):
     return (s + 1) * coord + rem, s
 
 
+def _recon_order(case):
+    """weno_order, or muscl_order for recon_type = 2 (m_checker.fpp:52-69 uses the reconstruction order)."""
+    rt = case.get("recon_type", 1)
+    if rt in (2, "muscl"):
+        mo = case.get("muscl_order", 1)
+        return {"first_order": 1, "second_order": 2}.get(mo, mo)
+    return int(case["weno_order"])
+
+
 class Block:
     """Everything one rank needs: local extents, neighbour ranks, local grid and neighbour cell widths."""
 
@@ -86,7 +95,7 @@ class Block:
         self.glb = (m, n, p)
         self.nd = 1 + (n > 0) + (p > 0)
         self.rank, self.nranks = rank, nranks
-        self.dims = tuple(dims) if dims is not None else factorize(nranks, m, n, p, int(case["weno_order"]))
+        self.dims = tuple(dims) if dims is not None else factorize(nranks, m, n, p, _recon_order(case))
         assert self.dims[0] * self.dims[1] * self.dims[2] == nranks
         self.coords = cart_coords(rank, self.dims, self.nd)
         self.start, self.s = [0, 0, 0], [m, n, p]

@@ -17,6 +17,8 @@ _NAMED = {
     "wave_speeds": {"direct": 1, "pressure": 2},
     "avg_state": {"roe": 1, "arithmetic": 2},
     "recon_type": {"weno": 1, "muscl": 2},
+    "muscl_order": {"first_order": 1, "second_order": 2},
+    "muscl_lim": {"unlimited": 0, "minmod": 1, "mc": 2, "van_albada": 3, "van_leer": 4, "superbee": 5},
 }
 
 
@@ -38,7 +40,7 @@ class Mfc5Params(C.Structure):
         ("alpha_rho_in", (C.c_double * MAX_FLUIDS) * 3), ("alpha_in", (C.c_double * MAX_FLUIDS) * 3),
         ("fluid_gamma", C.c_double * MAX_FLUIDS), ("fluid_pi_inf", C.c_double * MAX_FLUIDS),
         ("fluid_qv", C.c_double * MAX_FLUIDS),
-        ("device", C.c_int), ("fast_math", C.c_int), ("low_Mach", C.c_int), ("alt_soundspeed", C.c_int), ("reserved", C.c_int * 4),
+        ("device", C.c_int), ("fast_math", C.c_int), ("low_Mach", C.c_int), ("alt_soundspeed", C.c_int), ("muscl_order", C.c_int), ("muscl_lim", C.c_int), ("muscl_eps", C.c_double),
     ]
 
     @property
@@ -51,8 +53,14 @@ class Mfc5Params(C.Structure):
 
     @property
     def buff_size(self):
-        # src/common/m_helper_basic.fpp:127-132 (inviscid WENO)
+        # src/common/m_helper_basic.fpp:127-135 (inviscid WENO: weno_polyn + 2; MUSCL: muscl_polyn + 2 = muscl_order + 2)
+        if self.muscl_order > 0:
+            return self.muscl_order + 2
         return (self.weno_order - 1) // 2 + 2
+
+    @property
+    def recon_order(self):
+        return self.muscl_order if self.muscl_order > 0 else self.weno_order
 
     def copy(self):
         q = Mfc5Params()
@@ -103,18 +111,26 @@ def params_from_case(case, device=0, fast_math=1):
         raise UnsupportedCase("only model_eqns = 2 (5-equation) is on the hot path")
     if P.num_fluids > MAX_FLUIDS:
         raise UnsupportedCase(f"num_fluids > {MAX_FLUIDS}")
-    if int(_val(case, "recon_type", 1)) != 1:
-        raise UnsupportedCase("only recon_type = weno")
-    P.weno_order = int(case["weno_order"])
-    if P.weno_order not in (1, 3, 5):
-        raise UnsupportedCase("weno_order must be 1, 3 or 5")
+    if int(_val(case, "recon_type", 1)) == 2:  # MUSCL: m_muscl.fpp; defaults m_global_parameters.fpp:718-724
+        P.muscl_order = int(_val(case, "muscl_order", 1))
+        if P.muscl_order not in (1, 2):
+            raise UnsupportedCase("muscl_order must be 1 or 2")
+        P.muscl_lim = int(_val(case, "muscl_lim", 0) or 0)
+        if P.muscl_lim not in (0, 1, 2, 3, 4, 5):
+            raise UnsupportedCase("muscl_lim must be 0..5")
+        P.muscl_eps = float(case["muscl_eps"]) if "muscl_eps" in case else (1e-9 if P.muscl_lim <= 2 else 1e-6)
+        P.weno_order = 2 * P.muscl_order + 1   # same stencil window / buffer geometry as the WENO of that width
+    else:
+        P.weno_order = int(case["weno_order"])
+        if P.weno_order not in (1, 3, 5):
+            raise UnsupportedCase("weno_order must be 1, 3 or 5")
     P.mapped_weno = _logical(case.get("mapped_weno", "F"))
     P.wenoz = _logical(case.get("wenoz", "F"))
     P.null_weights = _logical(case.get("null_weights", "F"))
     P.weno_eps = float(case.get("weno_eps", 1e-16))
     P.riemann_solver = int(_val(case, "riemann_solver"))
-    if P.riemann_solver not in (1, 2):
-        raise UnsupportedCase("riemann_solver must be HLL (1) or HLLC (2)")
+    if P.riemann_solver not in (1, 2, 5):
+        raise UnsupportedCase("riemann_solver must be HLL (1), HLLC (2) or Lax-Friedrichs (5)")
     P.hll_u_interface = _logical(case.get("hll_u_interface", "F"))
     P.avg_state = int(_val(case, "avg_state", 2))
     P.wave_speeds = int(_val(case, "wave_speeds", 1))
@@ -166,7 +182,9 @@ def params_from_case(case, device=0, fast_math=1):
 
 def check_params(P):
     """Run-time checks of the reference: src/simulation/m_checker.fpp:52-69 (cells per rank)."""
-    need = 5 * P.weno_order if P.weno_order > 1 else 1
+    need = 5 * P.recon_order if P.recon_order > 1 else 1
+    if P.muscl_order > 0 and any(-12 <= P.bc[d][s] <= -5 for d in range(P.num_dims) for s in range(2)):
+        raise UnsupportedCase("characteristic boundary conditions with MUSCL reconstruction are outside the hot path")
     for s, name in ((P.m, "m"), (P.n, "n"), (P.p, "p")):
         if s > 0 and s + 1 < need:
             raise UnsupportedCase(f"{name}+1 must be >= num_stcls_min*weno_order = {need}")

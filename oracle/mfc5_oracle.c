@@ -62,7 +62,8 @@ orc_state* orc_create(const mfc5_params* P) {
     S->nd = 1 + (P->n > 0) + (P->p > 0);
     S->nf = P->num_fluids;
     S->N = 2 * S->nf + S->nd + 1;
-    S->polyn = (P->weno_order - 1) / 2;
+    if (P->muscl_order > 0) S->P.weno_order = 2 * P->muscl_order + 1; /* stencil / buffer geometry: buff_size = muscl_order + 2 */
+    S->polyn = (S->P.weno_order - 1) / 2;
     S->ns = S->polyn + 1;
     /* buff_size = weno_polyn + 2 for inviscid WENO: src/common/m_helper_basic.fpp:127-132 */
     S->b = S->polyn + 2;
@@ -507,6 +508,40 @@ static void weno_dir(orc_state* S, int d) {
                     double* oL = S->vL + v * S->fsz + c;
                     double* oR = S->vR + v * S->fsz + c;
                     if (pn == 0) { *oL = f[0]; *oR = f[0]; continue; }
+                    if (S->P.muscl_order > 0) { /* s_muscl, src/simulation/m_muscl.fpp:94-216 */
+                        double slope = 0.0;
+                        if (S->P.muscl_order == 2) {
+                            const double meps = S->P.muscl_eps;
+                            double slopeL = f[sd] - f[0], slopeR = f[0] - f[-sd];
+                            switch (S->P.muscl_lim) {
+                            case 0: slope = 5e-1 * (slopeL + slopeR); break;
+                            case 1:
+                                if (slopeL * slopeR > meps) slope = dmin(fabs(slopeL), fabs(slopeR));
+                                if (slopeL < 0.0) slope = -slope;
+                                break;
+                            case 2:
+                                if (slopeL * slopeR > meps) {
+                                    slope = dmin(2.0 * fabs(slopeL), 2.0 * fabs(slopeR));
+                                    slope = dmin(slope, 5e-1 * (fabs(slopeL) + fabs(slopeR)));
+                                }
+                                if (slopeL < 0.0) slope = -slope;
+                                break;
+                            case 3:
+                                if (slopeL * slopeR > meps) slope = ((slopeL + slopeR) * slopeL * slopeR) / (slopeL * slopeL + slopeR * slopeR);
+                                break;
+                            case 4:
+                                if (slopeL * slopeR > meps) slope = 2.0 * slopeL * slopeR / (slopeL + slopeR);
+                                break;
+                            case 5:
+                                if (slopeL * slopeR > meps)
+                                    slope = -1.0 * dmin(-dmin(2.0 * fabs(slopeL), fabs(slopeR)), -dmin(fabs(slopeL), 2.0 * fabs(slopeR)));
+                                break;
+                            }
+                        }
+                        *oL = f[0] - (5.e-1 * slope);
+                        *oR = f[0] + (5.e-1 * slope);
+                        continue;
+                    }
                     double dvd[4], poly[3], beta[3], alpha[3], omega[3], tau = 0.0;
                     const double* dl = &S->dL[d][(jc + b) * ns];
                     const double* dr = &S->dR[d][(jc + b) * ns];
@@ -744,6 +779,14 @@ static void riemann_dir(orc_state* S, int d) {
                     s_S = 5.e-1 * ((uL + uR) + (pres_L - pres_R) / (rho_avg * c_avg));
                 }
                 double s_M = dmin(0.0, s_L), s_P = dmax(0.0, s_R);
+                if (P->riemann_solver == 5) { /* Lax-Friedrichs: one symmetric speed, m_riemann_solver_lf.fpp:238-253 */
+                    double vl = 0.0, vr = 0.0;
+                    for (int a = 0; a < nd; a++) { vl = vl + vel_L[a] * vel_L[a]; vr = vr + vel_R[a] * vel_R[a]; }
+                    vl = sqrt(vl); vr = sqrt(vr);
+                    s_P = dmax(vl, vr) + dmax(c_L, c_R);
+                    s_M = -s_P;
+                    s_L = s_M; s_R = s_P;
+                }
                 double pcorr = 0.0;
                 if (P->low_Mach == 1) {
                     if (hllc) pcorr = rho_L * rho_R * (s_L - uL) * (s_R - uR) * (uR - uL) / (rho_R * (s_R - uR) - rho_L * (s_L - uL)) * (zcoef - 1.0);
@@ -788,7 +831,9 @@ static void riemann_dir(orc_state* S, int d) {
                     }
                     F[S->iE] = (s_M * uR * (E_R + pres_R) - s_P * uL * (E_L + pres_L) + s_M * s_P * (E_L - E_R)) / (s_M - s_P) +
                                (s_M / s_L) * (s_P / s_R) * pcorr * (vel_R_rms - vel_L_rms) / 2.0;
-                    if (!P->hll_u_interface) {
+                    /* Lax-Friedrichs always exports the interface alphas (m_riemann_solver_lf.fpp:306-313) although the RHS then
+                     * reads flux_src(adv%beg) as a shared face velocity (adv_src_mode_vel_iface, m_global_parameters.fpp:903-906) */
+                    if (!P->hll_u_interface || P->riemann_solver == 5) {
                         for (int f = 0; f < nf; f++) {
                             F[S->iadv + f] = (qL[S->iadv + f] - qR[S->iadv + f]) * s_M * s_P / (s_M - s_P);
                             Fsrc[f] = (s_M * qR[S->iadv + f] - s_P * qL[S->iadv + f]) / (s_M - s_P);

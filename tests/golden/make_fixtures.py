@@ -23,7 +23,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 REF = sys.argv[1] if len(sys.argv) > 1 else "/root/reference"
 
 # UUIDs inside the 5-eq / WENO{3,5}{JS,M,Z} / HLL|HLLC / RK3 envelope;
-# last lines: the f-4 widening (low_Mach = 1 / 2, tolerance 1e-10 by the reference's own rule; alt_soundspeed) and f-3 (elliptic smoothing, hard-coded 1-D profiles)
+# last lines: the f-4 widening (low_Mach = 1 / 2, tolerance 1e-10 by the reference's own rule; alt_soundspeed) and f-3 (elliptic smoothing, hard-coded profiles), Lax-Friedrichs, MUSCL
 UUIDS = """
 D79C3E6F 8A59E8E6 2AB32975 70DAE9E8 3AE495F4 5EC236F2 48CCE072 AED93D34 C5B79059 727F72ED A60691E7 3FC6FC4A
 2FD933A2 ED728400 9D92767D 63CD6ADF
@@ -47,6 +47,8 @@ BCA926AC 24FD489A B5F0C655 82152069 BCB15E8E 02D1E522
 7C8F1BA9 A26B7E00 E47F81A2
 8C1E22E4 C1134EF2 9843489C B50DE910 1DBC8382 EF3E3FF1
 C9E0B721 A078904B 8370A3D9 8FD91C41
+AFB46CF8 4AADC848
+F1D01264 14846B52 90D62933 A7C19B7B 4F79391A 77292B06 9BD657CB 30035426 01DC0251 24119641 F33CC4CA
 """.split()
 
 
