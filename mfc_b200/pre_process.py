@@ -51,14 +51,6 @@ def generate_grid_1d(case, x, ncells_m1, beg=None, end=None, glb=None):
     return cb
 
 
-def cell_centers(cb, stretched, beg, s):
-    """x_cc as pre_process computes it (m_grid.f90:43-44 uniform, :63 stretched)."""
-    if stretched:
-        return (cb[1:] + cb[:-1]) / 2.0
-    dx = (cb[-1] - beg) / float(s + 1) if False else None
-    return None
-
-
 def generate_grid(case, local=None):
     """Return ([x_cb, y_cb, z_cb], [x_cc, y_cc, z_cc]) for the (possibly rank-local) block.
 
