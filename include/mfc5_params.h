@@ -86,6 +86,9 @@ typedef struct mfc5_params {
      * muscl_lim 0 unlimited, 1 minmod, 2 MC, 3 Van Albada, 4 Van Leer, 5 SUPERBEE; buff_size = muscl_order + 2 */
     int muscl_order, muscl_lim;
     double muscl_eps;
+    /* TENO weights for weno_order = 5 (Fu et al. 2016; m_weno.fpp:1167-1187): cut-off teno_CT */
+    int teno, reserved2;
+    double teno_CT;
 } mfc5_params;
 
 #ifdef __cplusplus

@@ -151,6 +151,8 @@ extern "C" int mfc5_create(const mfc5_params* p, mfc5_handle** out) {
     if (p->riemann_solver != 1 && p->riemann_solver != 2 && p->riemann_solver != 5)
         return fail("riemann_solver must be 1 (HLL), 2 (HLLC) or 5 (Lax-Friedrichs)");
     if (p->mapped_weno && p->wenoz) return fail("mapped_weno and wenoz are mutually exclusive");
+    if (p->teno && (p->mapped_weno || p->wenoz || p->weno_order != 5 || p->muscl_order != 0 || !(p->teno_CT > 0.0)))
+        return fail("teno needs weno_order = 5, teno_CT > 0 and neither mapped_weno nor wenoz");
     if (p->alt_soundspeed && (p->num_fluids != 2 || p->avg_state != 2 || (p->riemann_solver == 1 && !p->hll_u_interface)))
         return fail("alt_soundspeed needs 2 fluids, avg_state = 2 and a u-interface solver (HLLC, or HLL with hll_u_interface)");
     if (p->low_Mach < 0 || p->low_Mach > 2 || (p->low_Mach == 2 && p->riemann_solver != 2)) return fail("low_Mach must be 0, 1 or 2 (2: HLLC only)");
@@ -416,9 +418,10 @@ extern "C" int mfc5_finalize_setup(mfc5_handle* h) {
     // weno_eps large enough that products of four smoothness indicators cannot underflow
     D.low_mach = h->P.low_Mach;
     D.alt_ss = h->P.alt_soundspeed;
+    D.teno = h->P.teno; D.teno_ct = h->P.teno_CT;
     D.muscl = h->P.muscl_order; D.muscl_lim = h->P.muscl_lim; D.muscl_eps = h->P.muscl_eps;
     D.fast = h->P.fast_math && h->P.wave_speeds == 1 && !h->P.null_weights && h->P.weno_eps >= 1e-30 && h->P.low_Mach == 0 &&
-             !h->P.alt_soundspeed && h->P.riemann_solver != 5 && h->P.muscl_order == 0;
+             !h->P.alt_soundspeed && h->P.riemann_solver != 5 && h->P.muscl_order == 0 && !h->P.teno;
     if (getenv("MFC5_NO_FAST")) D.fast = 0;
     D.sy = h->px; D.sz = h->px * h->ey; D.fs = h->fs;
     D.base = h->ox + h->oy * D.sy + h->oz * D.sz;

@@ -47,6 +47,8 @@ struct DevP {
     int wo, wv, rs;    // weno_order; variant 0 JS / 1 M / 2 Z; riemann_solver 1 HLL / 2 HLLC
     int hll_u, avg, ws, mpp, mixerr, fast;
     int low_mach;      // 0 / 1 / 2, inline_riemann.fpp:71-93 (reference-order kernels only)
+    int teno;          // TENO5 weights (m_weno.fpp:1167-1187), cut-off teno_ct (reference-order kernels only)
+    double teno_ct;
     int muscl, muscl_lim;  // MUSCL reconstruction order (0 = WENO) and limiter, m_muscl.fpp (reference-order kernels only)
     double muscl_eps;
     int alt_ss;        // alt_soundspeed: Wood sound speed + K div(u) term (reference-order kernels only)
@@ -453,6 +455,17 @@ __device__ __forceinline__ void weno_edges(const DevP& P, const DirTables& T, in
         }
         double tau = 0.0;
         if (wv == 2) tau = fabs(b2 - b0);
+        double td0 = 1.0, td1 = 1.0, td2 = 1.0;  // TENO cut-off flags, computed once and used on both sides
+        const bool teno = (WV < 0) && P.teno;
+        if (teno) {
+            tau = fabs(b2 - b0);
+            double g0 = 1.0 + tau / b0, g1 = 1.0 + tau / b1, g2 = 1.0 + tau / b2;
+            g0 = (g0 * g0 * g0) * (g0 * g0 * g0); g1 = (g1 * g1 * g1) * (g1 * g1 * g1); g2 = (g2 * g2 * g2) * (g2 * g2 * g2);
+            const double sum = g0 + g1 + g2;
+            td0 = (g0 / sum < P.teno_ct) ? 0.0 : 1.0;
+            td1 = (g1 / sum < P.teno_ct) ? 0.0 : 1.0;
+            td2 = (g2 / sum < P.teno_ct) ? 0.0 : 1.0;
+        }
 #pragma unroll
         for (int side = 0; side < 2; side++) {
             const double* dd = side == 0 ? dl : dr;
@@ -475,6 +488,8 @@ __device__ __forceinline__ void weno_edges(const DevP& P, const DirTables& T, in
                 a0 = dd0 * (1.0 + (tau / b0));
                 a1 = dd1 * (1.0 + (tau / b1));
                 a2 = dd2 * (1.0 + (tau / b2));
+            } else if (teno) {
+                a0 = td0 * dd0; a1 = td1 * dd1; a2 = td2 * dd2;
             } else {
                 a0 = dd0 / (b0 * b0);
                 a1 = dd1 / (b1 * b1);

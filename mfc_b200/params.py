@@ -41,6 +41,7 @@ class Mfc5Params(C.Structure):
         ("fluid_gamma", C.c_double * MAX_FLUIDS), ("fluid_pi_inf", C.c_double * MAX_FLUIDS),
         ("fluid_qv", C.c_double * MAX_FLUIDS),
         ("device", C.c_int), ("fast_math", C.c_int), ("low_Mach", C.c_int), ("alt_soundspeed", C.c_int), ("muscl_order", C.c_int), ("muscl_lim", C.c_int), ("muscl_eps", C.c_double),
+        ("teno", C.c_int), ("reserved2", C.c_int), ("teno_CT", C.c_double),
     ]
 
     @property
@@ -84,7 +85,7 @@ def _val(case, key, default=None):
 _UNSUPPORTED_TRUE = [
     "viscous", "surface_tension", "bubbles_euler", "bubbles_lagrange", "qbmm", "hypoelasticity",
     "hyperelasticity", "mhd", "relativity", "chemistry", "igr", "ib", "cyl_coord", "acoustic_source", "relax",
-    "mp_weno", "teno", "cont_damage", "hyper_cleaning",
+    "mp_weno", "cont_damage", "hyper_cleaning",
 ]
 
 
@@ -127,6 +128,15 @@ def params_from_case(case, device=0, fast_math=1):
     P.mapped_weno = _logical(case.get("mapped_weno", "F"))
     P.wenoz = _logical(case.get("wenoz", "F"))
     P.null_weights = _logical(case.get("null_weights", "F"))
+    P.teno = _logical(case.get("teno", "F"))
+    if P.teno:  # toolchain/mfc/case_validator.py:942-966
+        if P.muscl_order > 0 or P.weno_order != 5:
+            raise UnsupportedCase("teno is available for weno_order = 5 on this path (the reference: 5 or 7)")
+        if P.mapped_weno or P.wenoz:
+            raise UnsupportedCase("Only one of mapped_weno, wenoz, or teno can be set to true")
+        if "teno_CT" not in case or float(case["teno_CT"]) <= 0:
+            raise UnsupportedCase("teno requires teno_CT to be set. A typical value is 1e-6")
+        P.teno_CT = float(case["teno_CT"])
     P.weno_eps = float(case.get("weno_eps", 1e-16))
     P.riemann_solver = int(_val(case, "riemann_solver"))
     if P.riemann_solver not in (1, 2, 5):

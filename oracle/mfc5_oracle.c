@@ -542,7 +542,7 @@ static void weno_dir(orc_state* S, int d) {
                         *oR = f[0] + (5.e-1 * slope);
                         continue;
                     }
-                    double dvd[4], poly[3], beta[3], alpha[3], omega[3], tau = 0.0;
+                    double dvd[4], poly[3], beta[3], alpha[3], omega[3], tau = 0.0, teno_delta[3] = {1.0, 1.0, 1.0};
                     const double* dl = &S->dL[d][(jc + b) * ns];
                     const double* dr = &S->dR[d][(jc + b) * ns];
                     const double* cl = &S->cL[d][(jc + b) * ns * pn];
@@ -607,6 +607,18 @@ static void weno_dir(orc_state* S, int d) {
                             } else if (wz) {
                                 if (sideLR == 0) tau = fabs(beta[2] - beta[0]);
                                 for (int q = 0; q < 3; q++) alpha[q] = dd[q] * (1.0 + (tau / beta[q]));
+                            } else if (S->P.teno) { /* Fu et al. (2016), m_weno.fpp:1167-1187; the cut-off flags are reused on the right side (:1225-1229) */
+                                if (sideLR == 0) {
+                                    tau = fabs(beta[2] - beta[0]);
+                                    for (int q = 0; q < 3; q++) {
+                                        alpha[q] = 1.0 + tau / beta[q];
+                                        alpha[q] = (alpha[q] * alpha[q] * alpha[q]) * (alpha[q] * alpha[q] * alpha[q]);
+                                    }
+                                    double sum = alpha[0] + alpha[1] + alpha[2];
+                                    for (int q = 0; q < 3; q++) omega[q] = alpha[q] / sum;
+                                    for (int q = 0; q < 3; q++) teno_delta[q] = omega[q] < S->P.teno_CT ? 0.0 : 1.0;
+                                }
+                                for (int q = 0; q < 3; q++) alpha[q] = teno_delta[q] * dd[q];
                             } else {
                                 for (int q = 0; q < 3; q++) alpha[q] = dd[q] / (beta[q] * beta[q]);
                             }
