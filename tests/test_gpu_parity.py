@@ -145,6 +145,38 @@ def test_baseline_config_vs_oracle(name, mode):
     g.close()
 
 
+@pytest.mark.parametrize("name", ["C5_perf_hllc_weno5m", "C4_droplet_weno5z", "C3_bench_weno3m", "C2_shockbubble"])
+def test_100_rk3_steps_within_1e10(name):
+    """The north star's acceptance bar: conserved variables within 1e-10 max relative error after 100 RK3 steps in FP64,
+    product build (division-light arithmetic, CUDA-graph replay) against the oracle restatement of the reference
+    (the reference's own CPU build cannot be made in this image)."""
+    from mfc_b200 import pre_process
+    from mfc_b200.lib import Mfc5
+    from mfc_b200.params import params_from_case
+    from oracle_lib import Oracle
+    case = dict(_baseline_cases()[name], t_step_stop=100, t_step_save=100)
+    P = params_from_case(case)
+    cbs, ccs = pre_process.generate_grid(case)
+    _, cons = pre_process.initial_condition(case, ccs)
+    g = Mfc5(P, cbs)
+    o = Oracle(P, cbs, omp=True)
+    g.set_cons(cons)
+    o.set_cons(cons)
+    dt = float(case["dt"])
+    g.steps(dt, 100)
+    g.sync()
+    for _ in range(100):
+        o.step(dt)
+    a, b = g.get_cons(), o.get_cons()
+    assert not np.isnan(a).any() and not np.array_equal(b, cons)
+    worst = 0.0
+    for v in range(a.shape[0]):
+        scale = np.max(np.abs(b[v])) + 1e-300
+        worst = max(worst, np.max(np.abs(a[v] - b[v])) / scale)
+    assert worst <= 1e-10, f"{name}: {worst:.3e}"
+    g.close()
+
+
 @pytest.mark.parametrize("uuid", ["2AB32975", "4129A23A", "B5F0C655"])
 def test_graph_replay_is_bitwise_eager(uuid):
     """mfc5_tvd_rk_n (CUDA-graph replay of the captured step) == the same number of mfc5_tvd_rk calls."""
