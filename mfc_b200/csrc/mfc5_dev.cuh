@@ -36,9 +36,6 @@ struct DirTables {
     int uniform;       // uniform_grid(dir), m_weno.fpp:869-879
 };
 #define MFC5_TAB 48
-#ifndef MFC5_MERGE_RCP
-#define MFC5_MERGE_RCP 0  // 1: left/right reciprocals of the WENO normalisations from one reciprocal (measured slower: 0.970 vs 0.912 ms x sweep)
-#endif
 
 // Everything a kernel needs, passed by value (__grid_constant__).
 struct DevP {
@@ -177,66 +174,6 @@ __device__ __forceinline__ void weno5_fast(const DevP& P, const DirTables& T, co
             }
         }
     }
-#if MFC5_MERGE_RCP
-    // both sides together: the left and right reciprocals of each normalisation come out of ONE reciprocal of
-    // the product of the two sums (rcp_nr2).  The sums are ~ beta^4, so the product stays far inside the
-    // FP64 range for weno_eps >= 1e-30 (the fast-path guard of mfc5_finalize_setup).
-    double dq[2][3], m1[2][3], m2[2][3], m3[2][3], cf[2][6];
-#pragma unroll
-    for (int side = 0; side < 2; side++) {
-#pragma unroll
-        for (int q = 0; q < 3; q++) dq[side][q] = row[12 + side * 3 + q];
-#pragma unroll
-        for (int k = 0; k < 6; k++) cf[side][k] = row[side * 6 + k];
-        if (WV == 1) {
-#pragma unroll
-            for (int q = 0; q < 3; q++) {
-                if (ROW::kHasMapTerms) {
-                    m1[side][q] = row[27 + side * 3 + q]; m2[side][q] = row[33 + side * 3 + q]; m3[side][q] = row[39 + side * 3 + q];
-                } else {
-                    const double d = dq[side][q];
-                    m1[side][q] = fma(d, d, d); m2[side][q] = fma(-2.0, d, 1.0); m3[side][q] = d * d;
-                }
-            }
-        }
-    }
-#pragma unroll
-    for (int u = 0; u < NV; u++) {
-        const double f2 = f[u][2];
-        double a[2][3], num[2], sum[2];
-#pragma unroll
-        for (int side = 0; side < 2; side++) {
-            a[side][0] = dq[side][0] * g0[u]; a[side][1] = dq[side][1] * g1[u]; a[side][2] = dq[side][2] * g2[u];
-        }
-        if (WV == 1) {
-            double r[2];
-            rcp_nr2(a[0][0] + a[0][1] + a[0][2], a[1][0] + a[1][1] + a[1][2], r[0], r[1]);
-#pragma unroll
-            for (int side = 0; side < 2; side++) {
-                double n0, n1, n2, e0, e1, e2;
-                map_nd(dq[side][0], m1[side][0], m2[side][0], m3[side][0], a[side][0] * r[side], n0, e0);
-                map_nd(dq[side][1], m1[side][1], m2[side][1], m3[side][1], a[side][1] * r[side], n1, e1);
-                map_nd(dq[side][2], m1[side][2], m2[side][2], m3[side][2], a[side][2] * r[side], n2, e2);
-                a[side][0] = n0 * (e1 * e2);
-                a[side][1] = n1 * (e0 * e2);
-                a[side][2] = n2 * (e0 * e1);
-            }
-        }
-#pragma unroll
-        for (int side = 0; side < 2; side++) {
-            const double* c = cf[side];
-            const double p0 = fma(c[1], d0[u], fma(c[0], d1[u], f2));
-            const double p1 = fma(c[3], dm1[u], fma(c[2], d0[u], f2));
-            const double p2 = fma(c[5], dm2[u], fma(c[4], dm1[u], f2));
-            num[side] = fma(a[side][2], p2, fma(a[side][1], p1, a[side][0] * p0));
-            sum[side] = a[side][0] + a[side][1] + a[side][2];
-        }
-        double iL, iR;
-        rcp_nr2(sum[0], sum[1], iL, iR);
-        eL[u] = num[0] * iL;
-        eR[u] = num[1] * iR;
-    }
-#else
 #pragma unroll
     for (int side = 0; side < 2; side++) {
         const int cc = side * 6, dd = 12 + side * 3;
@@ -255,10 +192,13 @@ __device__ __forceinline__ void weno5_fast(const DevP& P, const DirTables& T, co
         }
 #pragma unroll
         for (int u = 0; u < NV; u++) {
+            // candidate polynomials as INCREMENTS over the cell value: the weighted increment is added to f2 at the
+            // end, so a locally constant field is reconstructed exactly (the normalised sum f2 * sum(a) / sum(a) is
+            // not, and its rounding error -- ~ ulp(p) on the pressure -- would enter the momentum flux difference)
             const double f2 = f[u][2];
-            const double p0 = fma(c1, d0[u], fma(c0, d1[u], f2));
-            const double p1 = fma(c3, dm1[u], fma(c2, d0[u], f2));
-            const double p2 = fma(c5, dm2[u], fma(c4, dm1[u], f2));
+            const double p0 = fma(c1, d0[u], c0 * d1[u]);
+            const double p1 = fma(c3, dm1[u], c2 * d0[u]);
+            const double p2 = fma(c5, dm2[u], c4 * dm1[u]);
             double a0 = dd0 * g0[u], a1 = dd1 * g1[u], a2 = dd2 * g2[u];
             if (WV == 1) {
                 const double r = rcp_nr(a0 + a1 + a2);
@@ -270,11 +210,10 @@ __device__ __forceinline__ void weno5_fast(const DevP& P, const DirTables& T, co
                 a1 = n1 * (e0 * e2);
                 a2 = n2 * (e0 * e1);
             }
-            const double val = fma(a2, p2, fma(a1, p1, a0 * p0)) * rcp_nr(a0 + a1 + a2);
+            const double val = fma(fma(a2, p2, fma(a1, p1, a0 * p0)), rcp_nr(a0 + a1 + a2), f2);
             if (side == 0) eL[u] = val; else eR[u] = val;
         }
     }
-#endif
 }
 
 template <int WV, int NV, class ROW>
@@ -315,8 +254,8 @@ __device__ __forceinline__ void weno3_fast(const DevP& P, const DirTables& T, co
 #pragma unroll
         for (int u = 0; u < NV; u++) {
             const double f2 = f[u][2];
-            const double p0 = fma(c0, d0[u], f2);
-            const double p1 = fma(c1, dm1[u], f2);
+            const double p0 = c0 * d0[u];  // increments over the cell value, see weno5_fast
+            const double p1 = c1 * dm1[u];
             double a0 = dd0 * g0[u], a1 = dd1 * g1[u];
             if (WV == 1) {
                 const double r = rcp_nr(a0 + a1);
@@ -326,7 +265,7 @@ __device__ __forceinline__ void weno3_fast(const DevP& P, const DirTables& T, co
                 a0 = n0 * e1;
                 a1 = n1 * e0;
             }
-            const double val = fma(a1, p1, a0 * p0) * rcp_nr(a0 + a1);
+            const double val = fma(fma(a1, p1, a0 * p0), rcp_nr(a0 + a1), f2);
             if (side == 0) eL[u] = val; else eR[u] = val;
         }
     }

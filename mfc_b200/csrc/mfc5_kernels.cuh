@@ -514,7 +514,11 @@ __global__ void __launch_bounds__(128, MFC5_X_MINB) k_sweep_x(const __grid_const
     double F[N], Fs[NF];
 #pragma unroll
     for (int f = 0; f < NF; f++) Fs[f] = 0.0;
+#ifdef MFC5_DEBUG_SPLIT   // accuracy bisection builds: 1 = reference-order Riemann solve with the fast WENO
+    if (FAST && MFC5_DEBUG_SPLIT != 1) riemann_face_fast<NF, ND, 0, RS>(P, eR, qR, F, Fs);
+#else
     if (FAST) riemann_face_fast<NF, ND, 0, RS>(P, eR, qR, F, Fs);
+#endif
     else riemann_face<NF, ND, 0, RS>(P, eR, qR, F, Fs);
     if (P.cbc_on[0][0] | P.cbc_on[0][1]) cbc_override<NF, ND, 0>(P, i, row, rows, F, Fs);
     double Fp[N], Fsp[NF];
@@ -704,7 +708,11 @@ __global__ void __launch_bounds__(MFC5_MARCH_THREADS, (2 * NF + ND + 1 <= 8) ? M
 #pragma unroll
                 for (int v = 0; v < N; v++) eL[v] = qL[v];
             }
+#ifdef MFC5_DEBUG_SPLIT
+            if (FAST && MFC5_DEBUG_SPLIT != 1) riemann_face_fast<NF, ND, DIR, RS>(P, qL, eL, F, Fs);
+#else
             if (FAST) riemann_face_fast<NF, ND, DIR, RS>(P, qL, eL, F, Fs);
+#endif
             else riemann_face<NF, ND, DIR, RS>(P, qL, eL, F, Fs);
             if (P.cbc_on[DIR][0] | P.cbc_on[DIR][1]) cbc_override<NF, ND, DIR>(P, face, t, plane, F, Fs);
             if (fin) {
