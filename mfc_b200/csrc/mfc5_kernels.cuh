@@ -394,7 +394,7 @@ __device__ __forceinline__ void finish_cell(const DevP& P, long long c, double d
         for (int v = 0; v < S::N; v++) {
             const double q1 = P.q1[v * P.fs + c];
             const double q2 = P.q2[v * P.fs + c];
-            if (FAST) P.qout[v * P.fs + c] = (P.rk0 * q1 + P.rk1 * q2 + P.rk2 * P.dt * r[v]) * P.irk3;
+            if (FAST) P.qout[v * P.fs + c] = div_by_const(P.rk0 * q1 + P.rk1 * q2 + P.rk2 * P.dt * r[v], P.rk3, P.irk3);
             else P.qout[v * P.fs + c] = (P.rk0 * q1 + P.rk1 * q2 + P.rk2 * P.dt * r[v]) / P.rk3;
         }
     } else {
@@ -736,7 +736,7 @@ __global__ void __launch_bounds__(MFC5_MARCH_THREADS, (2 * NF + ND + 1 <= 8) ? M
                 if (rk) {
 #pragma unroll
                     for (int v = 0; v < N; v++) {
-                        if (FAST) P.qout[v * P.fs + c] = (P.rk0 * q1in[v] + P.rk1 * q2in[v] + P.rk2 * P.dt * r[v]) * P.irk3;
+                        if (FAST) P.qout[v * P.fs + c] = div_by_const(P.rk0 * q1in[v] + P.rk1 * q2in[v] + P.rk2 * P.dt * r[v], P.rk3, P.irk3);
                         else P.qout[v * P.fs + c] = (P.rk0 * q1in[v] + P.rk1 * q2in[v] + P.rk2 * P.dt * r[v]) / P.rk3;
                     }
                 } else {

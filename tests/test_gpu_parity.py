@@ -169,19 +169,13 @@ def test_100_rk3_steps_within_1e10(name):
         o.step(dt)
     a, b = g.get_cons(), o.get_cons()
     assert not np.isnan(a).any() and not np.array_equal(b, cons)
-    nf, nd = P.num_fluids, P.num_dims
+    worst = 0.0
     for v in range(a.shape[0]):
         scale = np.max(np.abs(b[v])) + 1e-300
-        err = np.max(np.abs(a[v] - b[v])) / scale
-        if nf <= v < nf + nd:
-            # Momentum in a nearly static stiffened-gas field (C5: |m| <= 0.5 while E ~ 7e8): one ulp of E (1.2e-7), which
-            # any re-association produces in a few cells, becomes 4e-7 in p = (E - ...)/gamma and enters the momentum as
-            # ~1e-12 per stage, i.e. 6e-10 of max|m| after 100 steps.  The reference's own compare
-            # rule (abs OR rel error <= tol per value, toolchain/mfc/packer/tol.py:10-20) at 1e-10 is the bar here.
-            ok, amax, worst = compare(a[v], b[v], 1e-10)
-            assert ok, f"{name} momentum {v - nf + 1}: abs {amax:.3e}, worst min(abs, rel) {worst:.3e}, rel. to max {err:.3e}"
-        else:
-            assert err <= 1e-10, f"{name} var {v + 1}: {err:.3e}"
+        worst = max(worst, np.max(np.abs(a[v] - b[v])) / scale)
+    # measured 2.4e-15 on C5 (tools/parity_growth.py); before the RK update divided exactly by 3 (div_by_const) the momenta
+    # of this stiffened-gas case drifted to 6e-10 -- DESIGN.md section 4
+    assert worst <= 1e-10, f"{name}: {worst:.3e}"
     g.close()
 
 
