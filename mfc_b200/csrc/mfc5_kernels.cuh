@@ -362,9 +362,9 @@ __global__ void __launch_bounds__(128) k_cbc(const __grid_constant__ DevP P, con
 // (m_time_steppers.fpp:486-507).
 // -------------------------------------------------------------------------------------------------
 template <int NF, int ND, int DIR, int FAST>
-__device__ __forceinline__ void finish_cell(const DevP& P, long long c, double ds, const double* Fp, const double* Fsp, const double* Fc,
-                                            const double* Fsc) {
-    const double inv_ds = FAST ? rcp_nr(ds) : 1.0 / ds;
+__device__ __forceinline__ void finish_cell(const DevP& P, long long c, double ds, double inv_ds_tab, const double* Fp, const double* Fsp,
+                                            const double* Fc, const double* Fsc) {
+    const double inv_ds = FAST ? inv_ds_tab : 1.0 / ds;  // FAST: 1/ds from the table (host division, correctly rounded like the reference's)
     using S = Shape<NF, ND>;
     const bool alpha_iface = (P.rs == 1 && !P.hll_u);
     double r[S::N];
@@ -527,7 +527,7 @@ __global__ void __launch_bounds__(128, MFC5_X_MINB) k_sweep_x(const __grid_const
 #pragma unroll
     for (int f = 0; f < NF; f++) Fsp[f] = __shfl_up_sync(0xffffffffu, Fs[f], 1);
     if (lane >= 1 && lane <= MFC5_XW && i <= P.s[0]) {
-        finish_cell<NF, ND, 0, FAST>(P, rowbase + i, __ldg(T.ds + i + P.b), Fp, Fsp, F, Fs);
+        finish_cell<NF, ND, 0, FAST>(P, rowbase + i, __ldg(T.ds + i + P.b), FAST ? xrow[46] : 0.0, Fp, Fsp, F, Fs);
     }
 }
 
