@@ -190,21 +190,28 @@ def read_parallel_grid(case_dir, m_glb, n_glb, p_glb):
     return cbs
 
 
+def create_parallel_restart(case_dir, t_step, glb_mnp, sys_size):
+    """Create (or reset to the right size) ``restart_data/lustre_<t_step>.dat``.  ONE rank calls this, followed by a
+    barrier, before the ranks write their blocks (MPI_FILE_OPEN with MPI_MODE_CREATE is collective in the reference)."""
+    m, n, p = glb_mnp
+    path = _lustre(case_dir, f"{t_step}.dat")
+    os.makedirs(os.path.dirname(path), exist_ok=True)
+    with open(path, "ab") as f:
+        f.truncate(sys_size * (p + 1) * (n + 1) * (m + 1) * 8)
+
+
 def _parallel_map(case_dir, t_step, glb_shape, sys_size, mode):
     nz, ny, nx = glb_shape
     path = _lustre(case_dir, f"{t_step}.dat")
-    if mode == "r" and not os.path.exists(path):
+    if not os.path.exists(path):
         raise IOError(f"File {path} is missing. Exiting.")
-    os.makedirs(os.path.dirname(path), exist_ok=True)
-    if mode != "r" and not os.path.exists(path):
-        with open(path, "wb") as f:
-            f.truncate(sys_size * nz * ny * nx * 8)
     return np.memmap(path, dtype="<f8", mode="r" if mode == "r" else "r+", shape=(sys_size, nz, ny, nx))
 
 
 def write_parallel_restart(case_dir, t_step, glb_mnp, start, cons):
     """This rank's block of ``restart_data/lustre_<t_step>.dat`` (the MPI-IO subarray view, ``m_data_output.fpp:795-830``).
-    ``start`` = (i0, j0, k0) global index of the block's first cell.  Ranks write disjoint regions of one file."""
+    ``start`` = (i0, j0, k0) global index of the block's first cell.  Ranks write disjoint regions of one file, which
+    ``create_parallel_restart`` must have created first."""
     m, n, p = glb_mnp
     N, nz, ny, nx = cons.shape
     mm = _parallel_map(case_dir, t_step, (p + 1, n + 1, m + 1), N, "w")

@@ -88,6 +88,7 @@ def run_pre_process(case, case_dir, world=None, log=print):
         if world.rank == 0:
             glb_cbs, _ = pre_process.generate_grid(case)
             data_io.write_parallel_grid(case_dir, glb_cbs)
+            data_io.create_parallel_restart(case_dir, t0, blk.glb, P.sys_size)
         world.barrier()
         data_io.write_parallel_restart(case_dir, t0, blk.glb, blk.start, cons)
     else:
@@ -166,7 +167,11 @@ def run_simulation(case, case_dir, world=None, make_state=None, log=print):
         if np.isnan(q).any():                      # s_save_data, m_start_up.fpp:741-751
             raise FloatingPointError("NaN(s) in timestep output.")
         if par_io:
+            if world.rank == 0:
+                data_io.create_parallel_restart(case_dir, ts, blk.glb, P.sys_size)
+            world.barrier()
             data_io.write_parallel_restart(case_dir, ts, blk.glb, blk.start, q)
+            world.barrier()
         else:
             prim = None
             if prim_wrt or P.num_dims == 1:
@@ -272,7 +277,7 @@ def run_simulation(case, case_dir, world=None, make_state=None, log=print):
 
 
 def _next_multiple(t_step, t0, every):
-    """Last step of the segment that ends right before/at the next multiple of ``every`` counted from t0."""
+    """The first step index after ``t_step`` that is a multiple of ``every`` counted from ``t0``."""
     k = (t_step - t0) // every + 1
     return t0 + k * every
 

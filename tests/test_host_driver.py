@@ -114,6 +114,9 @@ def test_fortran_records_and_text(tmp_path):
 def test_parallel_io_blocks(tmp_path):
     rng = np.random.default_rng(3)
     glb = rng.standard_normal((4, 5, 6, 9))
+    with pytest.raises(IOError):  # the file is created collectively first
+        data_io.write_parallel_restart(str(tmp_path), 12, (8, 5, 4), (0, 0, 0), glb[:, :, :, :5])
+    data_io.create_parallel_restart(str(tmp_path), 12, (8, 5, 4), 4)
     data_io.write_parallel_restart(str(tmp_path), 12, (8, 5, 4), (0, 0, 0), glb[:, :, :, :5])
     data_io.write_parallel_restart(str(tmp_path), 12, (8, 5, 4), (5, 0, 0), glb[:, :, :, 5:])
     assert os.path.getsize(tmp_path / "restart_data" / "lustre_12.dat") == glb.size * 8
