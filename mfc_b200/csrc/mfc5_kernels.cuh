@@ -393,7 +393,7 @@ __device__ __forceinline__ void finish_cell(const DevP& P, long long c, double d
 #pragma unroll
         for (int v = 0; v < S::N; v++) {
             const double q1 = P.q1[v * P.fs + c];
-            const double q2 = P.q2[v * P.fs + c];
+            const double q2 = (P.rk1 != 0.0) ? P.q2[v * P.fs + c] : 0.0;  // rk1 = 0 in stage 1: 0 * q2 adds nothing
             if (FAST) P.qout[v * P.fs + c] = div_by_const(P.rk0 * q1 + P.rk1 * q2 + P.rk2 * P.dt * r[v], P.rk3, P.irk3);
             else P.qout[v * P.fs + c] = (P.rk0 * q1 + P.rk1 * q2 + P.rk2 * P.dt * r[v]) / P.rk3;
         }
@@ -637,7 +637,11 @@ __global__ void __launch_bounds__(MFC5_MARCH_THREADS, (2 * NF + ND + 1 <= 8) ? M
             }
             if ((DIR == ND - 1) && P.do_rk) {
 #pragma unroll
-                for (int v = 0; v < N; v++) { prefetch_l2(P.q1 + v * P.fs + c); prefetch_l2(P.q2 + v * P.fs + c); }
+                for (int v = 0; v < N; v++) prefetch_l2(P.q1 + v * P.fs + c);
+                if (P.rk1 != 0.0) {  // stage 1 has rk1 = 0: q2 is not read at all
+#pragma unroll
+                    for (int v = 0; v < N; v++) prefetch_l2(P.q2 + v * P.fs + c);
+                }
             }
         }
         // tap k (plane cc-PN+k) sits in slot (tail+k) mod NSLOT
@@ -690,7 +694,7 @@ __global__ void __launch_bounds__(MFC5_MARCH_THREADS, (2 * NF + ND + 1 <= 8) ? M
 #pragma unroll
                 for (int v = 0; v < N; v++) {
                     rin[v] = (DIR == 0) ? 0.0 : P.rhs[v * P.fs + c];
-                    if (rk) { q1in[v] = __ldg(P.q1 + v * P.fs + c); q2in[v] = __ldg(P.q2 + v * P.fs + c); }
+                    if (rk) { q1in[v] = __ldg(P.q1 + v * P.fs + c); q2in[v] = (P.rk1 != 0.0) ? __ldg(P.q2 + v * P.fs + c) : 0.0; }
                 }
 #pragma unroll
                 for (int f = 0; f < NF; f++) acoef[f] = __ldg(P.prim + (alpha_iface ? (S::IM + DIR) : (S::IA + f)) * P.fs + c);
