@@ -92,7 +92,9 @@ struct mfc5_handle {
     double* d_cbcbuf[3][2] = {};
     double* d_dirich[3][2] = {};
     long long plane[3];
-    cudaStream_t st = nullptr, st_comm = nullptr;
+    cudaStream_t st = nullptr, st_comm = nullptr, st_bc = nullptr;
+    cudaEvent_t ev_bc = nullptr;
+    int use_side_stream = 1;
     cudaEvent_t ev_stage[4] = {}, ev_comm = nullptr, ev_comp = nullptr;
     // per-kernel-class device timing of the last mfc5_tvd_rk call (events on the compute stream)
     std::vector<cudaEvent_t> ev_pool;
@@ -196,6 +198,8 @@ extern "C" int mfc5_create(const mfc5_params* p, mfc5_handle** out) {
     CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
     CK(cudaStreamCreateWithPriority(&h->st, cudaStreamNonBlocking, lo));
     CK(cudaStreamCreateWithPriority(&h->st_comm, cudaStreamNonBlocking, hi));
+    CK(cudaStreamCreateWithPriority(&h->st_bc, cudaStreamNonBlocking, hi));
+    CK(cudaEventCreateWithFlags(&h->ev_bc, cudaEventDisableTiming));
     for (auto& ev : h->ev_stage) CK(cudaEventCreate(&ev));
     CK(cudaEventCreateWithFlags(&h->ev_comm, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&h->ev_comp, cudaEventDisableTiming));
@@ -222,7 +226,8 @@ extern "C" int mfc5_destroy(mfc5_handle* h) {
     cudaEventDestroy(h->ev_prim); cudaEventDestroy(h->ev_halo);
     cudaFree(h->d_cbccoef);
     if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
-    cudaStreamDestroy(h->st); cudaStreamDestroy(h->st_comm);
+    cudaEventDestroy(h->ev_bc);
+    cudaStreamDestroy(h->st); cudaStreamDestroy(h->st_comm); cudaStreamDestroy(h->st_bc);
     delete h;
     return 0;
 }
@@ -509,6 +514,7 @@ extern "C" int mfc5_finalize_setup(mfc5_handle* h) {
     if (const char* e = getenv("MFC5_CHUNK")) D.chunk = std::max(0, atoi(e));
     D.x_march = getenv("MFC5_X_MARCH") ? 1 : 0;
     h->use_graph = getenv("MFC5_NO_GRAPH") ? 0 : 1;
+    h->use_side_stream = getenv("MFC5_NO_SIDE_STREAM") ? 0 : 1;
     h->warmed = false;
     h->setup = true;
     for (int i = 0; i < 2; i++) if (h->gexec[i]) { cudaGraphExecDestroy(h->gexec[i]); h->gexec[i] = nullptr; }
@@ -796,23 +802,48 @@ static int run_stage(mfc5_handle* h, const double* q1, const double* q2, double*
         if (exchange_halos(h, D)) return -1;
         halo_pending = true;
     }
-    if (h->any_phys) {
-        if (seg_begin(h, MFC5_K_BC_FILL)) return -1;
-        k_bc_faces<<<dim3(faces_grid_x(h, h->N), 6, 1), 256, 0, h->st>>>(D);
-        if (seg_end(h, 1)) return -1;
-    }
-    if (h->any_cbc) {
-        if (seg_begin(h, MFC5_K_CBC)) return -1;
-        long long mx = 1;
-        for (int d = 0; d < h->nd; d++) mx = std::max(mx, h->plane[d]);
-        const CbcCoef* K = h->d_cbccoef;
-        by_shape(h, [&](auto nf, auto nd) {
-            k_cbc<decltype(nf)::value, decltype(nd)::value><<<dim3((unsigned)((mx + 127) / 128), 6, 1), 128, 0, h->st>>>(D, K);
-        });
-        if (seg_end(h, 1)) return -1;
-    }
+    // Ghost fill and characteristic-BC fluxes, one launch per kind and face group.  Only the x faces are needed by the
+    // x sweep: the y / z faces (written outside everything the x sweep reads) run on a side stream concurrently with it
+    // and are joined before the y sweep.
+    bool any_phys_x = false, any_phys_yz = false, any_cbc_x = false, any_cbc_yz = false;
     for (int d = 0; d < h->nd; d++)
+        for (int sd = 0; sd < 2; sd++) {
+            if (h->P.bc[d][sd] < 0) (d == 0 ? any_phys_x : any_phys_yz) = true;
+            if (D.cbc_on[d][sd]) (d == 0 ? any_cbc_x : any_cbc_yz) = true;
+        }
+    long long mx = 1;
+    for (int d = 0; d < h->nd; d++) mx = std::max(mx, h->plane[d]);
+    const CbcCoef* K = h->d_cbccoef;
+    auto faces = [&](int face0, int nfaces, bool phys, bool cbc, cudaStream_t st) -> int {
+        if (phys) {
+            if (seg_begin(h, MFC5_K_BC_FILL, st)) return -1;
+            k_bc_faces<<<dim3(faces_grid_x(h, h->N), nfaces, 1), 256, 0, st>>>(D, face0);
+            if (seg_end(h, 1, st)) return -1;
+        }
+        if (cbc) {
+            if (seg_begin(h, MFC5_K_CBC, st)) return -1;
+            by_shape(h, [&](auto nf, auto nd) {
+                k_cbc<decltype(nf)::value, decltype(nd)::value><<<dim3((unsigned)((mx + 127) / 128), nfaces, 1), 128, 0, st>>>(D, K, face0);
+            });
+            if (seg_end(h, 1, st)) return -1;
+        }
+        return 0;
+    };
+    bool side_pending = false;
+    if (h->nd > 1 && (any_phys_yz || any_cbc_yz)) {
+        if (h->use_side_stream) {
+            if (!h->any_nb) CK(cudaEventRecord(h->ev_prim, h->st));
+            CK(cudaStreamWaitEvent(h->st_bc, h->ev_prim, 0));
+            if (faces(2, 2 * (h->nd - 1), any_phys_yz, any_cbc_yz, h->st_bc)) return -1;
+            CK(cudaEventRecord(h->ev_bc, h->st_bc));
+            side_pending = true;
+        } else if (faces(2, 2 * (h->nd - 1), any_phys_yz, any_cbc_yz, h->st)) return -1;
+    }
+    if (faces(0, 2, any_phys_x, any_cbc_x, h->st)) return -1;
+    for (int d = 0; d < h->nd; d++) {
+        if (d == 1 && side_pending) CK(cudaStreamWaitEvent(h->st, h->ev_bc, 0));
         if (launch_sweep(h, D, d, &halo_pending)) return -1;
+    }
     // the next stage's cons2prim overwrites prim: the communication stream must be done reading it (it is:
     // every sweep waited for ev_halo), and the next pack must not start before this stage's sweeps finished
     // reading the ghosts it will overwrite -- ev_prim of the next stage is recorded after them on h->st.

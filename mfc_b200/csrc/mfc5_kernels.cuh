@@ -158,9 +158,10 @@ __global__ void __launch_bounds__(256) k_bc_fill(const __grid_constant__ DevP P,
     bc_fill_face(P, d, side, full, blockIdx.x * (long long)blockDim.x + threadIdx.x, (long long)gridDim.x * blockDim.x);
 }
 
-// every physical face of the block in ONE launch: blockIdx.y = 2 * direction + side
-__global__ void __launch_bounds__(256) k_bc_faces(const __grid_constant__ DevP P) {
-    const int d = blockIdx.y >> 1, side = blockIdx.y & 1;
+// the physical faces face0 .. face0 + gridDim.y - 1 of the block in ONE launch: face = 2 * direction + side
+__global__ void __launch_bounds__(256) k_bc_faces(const __grid_constant__ DevP P, int face0) {
+    const int face = blockIdx.y + face0;
+    const int d = face >> 1, side = face & 1;
     if (d >= P.nd || P.bc[d][side] >= 0) return;
     bc_fill_face(P, d, side, 0, blockIdx.x * (long long)blockDim.x + threadIdx.x, (long long)gridDim.x * blockDim.x);
 }
@@ -183,14 +184,15 @@ struct CbcCoef {
     int grcbc_in, grcbc_out, grcbc_vel_out;
 };
 
-// every characteristic-BC face of the block in ONE launch (blockIdx.y = 2 * direction + side); Kall[6] in HBM
+// the characteristic-BC faces face0 .. of the block in ONE launch (face = 2 * direction + side); Kall[6] in HBM
 template <int NF, int ND>
-__global__ void __launch_bounds__(128) k_cbc(const __grid_constant__ DevP P, const CbcCoef* __restrict__ Kall) {
+__global__ void __launch_bounds__(128) k_cbc(const __grid_constant__ DevP P, const CbcCoef* __restrict__ Kall, int face0) {
     using S = Shape<NF, ND>;
     constexpr int N = S::N;
-    const int d = blockIdx.y >> 1, side = blockIdx.y & 1;
+    const int face = blockIdx.y + face0;
+    const int d = face >> 1, side = face & 1;
     if (d >= ND || !P.cbc_on[d][side]) return;
-    const CbcCoef& K = Kall[blockIdx.y];
+    const CbcCoef& K = Kall[face];
     const int t1 = d == 0 ? 1 : 0, t2 = d == 2 ? 1 : 2;
     const int n1 = P.s[t1] + 1, n2 = P.s[t2] + 1;
     const long long plane = (long long)n1 * n2;
