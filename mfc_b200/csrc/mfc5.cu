@@ -80,7 +80,13 @@ struct mfc5_handle {
     int ox, oy, oz;
     long long px, ey, ez, fs;
     double* d_q[2] = {nullptr, nullptr};
-    double *d_prim = nullptr, *d_rhs = nullptr;
+    // two primitive-variable buffers: the RK-fused last sweep of a stage writes the primitives of the new state into the
+    // other one, so that the next stage needs no cons -> prim pass (prim_valid: d_prim[pp] matches the current state)
+    double* d_prim[2] = {nullptr, nullptr};
+    double* d_rhs = nullptr;
+    int pp = 0;
+    bool prim_valid = false;
+    int fuse_c2p = 0;
     int cur = 0;
     // host grid (ghosted): scb[d][i + 1 + b], ds[d][i + b]
     std::vector<double> scb[3], ds[3];
@@ -114,9 +120,11 @@ struct mfc5_handle {
     CbcCoef* d_cbccoef = nullptr;  // [6], index 2*dir + side
     cudaEvent_t ev_prim = nullptr, ev_halo = nullptr;
     // graph replay of a whole step, keyed by (cur, dt)
-    cudaGraphExec_t gexec[2] = {nullptr, nullptr};
-    double gdt[2] = {0, 0};
-    long long glaunches[2] = {0, 0};  // kernel launches inside each captured step
+    cudaGraphExec_t gexec[4] = {nullptr, nullptr, nullptr, nullptr};  // key = 2 * cur + pp
+    double gdt[4] = {0, 0, 0, 0};
+    long long glaunches[4] = {0, 0, 0, 0};  // kernel launches inside each captured step
+    int gcur1[4] = {0, 0, 0, 0}, gpp1[4] = {0, 0, 0, 0};  // buffer parities after the captured step
+    long long launches_captured = 0;
     bool warmed = false;              // one step has run uncaptured (lazy allocations, function attributes)
     int use_graph = 1;
 };
@@ -190,9 +198,9 @@ extern "C" int mfc5_create(const mfc5_params* p, mfc5_handle** out) {
     h->fs = h->px * h->ey * h->ez;
     const size_t nb = (size_t)h->N * h->fs * sizeof(double);
     CK(cudaMalloc(&h->d_q[0], nb)); CK(cudaMalloc(&h->d_q[1], nb));
-    CK(cudaMalloc(&h->d_prim, nb)); CK(cudaMalloc(&h->d_rhs, nb));
+    CK(cudaMalloc(&h->d_prim[0], nb)); CK(cudaMalloc(&h->d_rhs, nb));  // d_prim[1]: only with MFC5_FUSE_C2P (finalize_setup)
     CK(cudaMemset(h->d_q[0], 0, nb)); CK(cudaMemset(h->d_q[1], 0, nb));
-    CK(cudaMemset(h->d_prim, 0, nb)); CK(cudaMemset(h->d_rhs, 0, nb));
+    CK(cudaMemset(h->d_prim[0], 0, nb)); CK(cudaMemset(h->d_rhs, 0, nb));
     CK(cudaMalloc(&h->d_red, 4 * sizeof(unsigned long long)));
     int lo, hi;
     CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
@@ -214,8 +222,9 @@ extern "C" int mfc5_destroy(mfc5_handle* h) {
     if (!h) return 0;
     cudaSetDevice(h->P.device);
     cudaDeviceSynchronize();
-    for (int i = 0; i < 2; i++) { cudaFree(h->d_q[i]); if (h->gexec[i]) cudaGraphExecDestroy(h->gexec[i]); }
-    cudaFree(h->d_prim); cudaFree(h->d_rhs); cudaFree(h->d_red);
+    for (int i = 0; i < 2; i++) cudaFree(h->d_q[i]);
+    for (int i = 0; i < 4; i++) if (h->gexec[i]) cudaGraphExecDestroy(h->gexec[i]);
+    cudaFree(h->d_prim[0]); cudaFree(h->d_prim[1]); cudaFree(h->d_rhs); cudaFree(h->d_red);
     for (int d = 0; d < 3; d++) {
         for (int k = 0; k < 9; k++) cudaFree(h->d_tab[d][k]);
         for (int k = 0; k < 2; k++) { cudaFree(h->d_cbcbuf[d][k]); cudaFree(h->d_dirich[d][k]); cudaFree(h->d_send[d][k]); cudaFree(h->d_recv[d][k]); }
@@ -517,7 +526,15 @@ extern "C" int mfc5_finalize_setup(mfc5_handle* h) {
     h->use_side_stream = getenv("MFC5_NO_SIDE_STREAM") ? 0 : 1;
     h->warmed = false;
     h->setup = true;
-    for (int i = 0; i < 2; i++) if (h->gexec[i]) { cudaGraphExecDestroy(h->gexec[i]); h->gexec[i] = nullptr; }
+    for (int i = 0; i < 4; i++) if (h->gexec[i]) { cudaGraphExecDestroy(h->gexec[i]); h->gexec[i] = nullptr; }
+    h->prim_valid = false;
+    h->pp = 0;
+    h->fuse_c2p = getenv("MFC5_FUSE_C2P") ? 1 : 0;   // opt-in, see store_next_prim
+    if (h->fuse_c2p && !h->d_prim[1]) {
+        const size_t nb = (size_t)h->N * h->fs * sizeof(double);
+        CK(cudaMalloc(&h->d_prim[1], nb));
+        CK(cudaMemset(h->d_prim[1], 0, nb));
+    }
     return 0;
 }
 
@@ -588,6 +605,7 @@ static int copy_fields(mfc5_handle* h, double* dev, const double* const* hostc, 
 
 extern "C" int mfc5_upload_cons(mfc5_handle* h, const double* const* q, int ghosted) {
     if (!h || !q) return fail("mfc5_upload_cons: null argument");
+    h->prim_valid = false;
     return copy_fields(h, h->d_q[h->cur], q, nullptr, ghosted, true);
 }
 extern "C" int mfc5_download_cons(mfc5_handle* h, double* const* q, int ghosted) {
@@ -599,10 +617,10 @@ extern "C" int mfc5_download_prim(mfc5_handle* h, double* const* q, int ghosted)
     if (ghosted && h->setup) {  // edges and corners as the reference fills them (the sweeps do not need them)
         CK(cudaSetDevice(h->P.device));
         DevP D = h->D;
-        D.prim = h->d_prim; D.primw = h->d_prim;
+        D.prim = h->d_prim[h->pp]; D.primw = h->d_prim[h->pp];
         if (fill_full(h, D)) return -1;
     }
-    return copy_fields(h, h->d_prim, nullptr, q, ghosted, false);
+    return copy_fields(h, h->d_prim[h->pp], nullptr, q, ghosted, false);
 }
 extern "C" int mfc5_download_rhs(mfc5_handle* h, double* const* q, int ghosted) {
     if (!h || !q) return fail("mfc5_download_rhs: null argument");
@@ -787,15 +805,18 @@ static int launch_sweep(mfc5_handle* h, const DevP& D0, int dir, bool* halo_pend
 // one RHS evaluation (+ fused RK update when do_rk): q1 = state read, q2 = stage-1 copy, qout = target
 static int run_stage(mfc5_handle* h, const double* q1, const double* q2, double* qout, int do_rk, const double rk[4], double dt) {
     DevP D = h->D;
-    D.prim = h->d_prim; D.primw = h->d_prim; D.q1 = q1; D.q2 = q2; D.qout = qout; D.rhs = h->d_rhs;
+    D.prim = h->d_prim[h->pp]; D.primw = h->d_prim[h->pp]; D.q1 = q1; D.q2 = q2; D.qout = qout; D.rhs = h->d_rhs;
+    D.prim_next = (do_rk && h->fuse_c2p) ? h->d_prim[h->pp ^ 1] : nullptr;
     D.rk0 = rk[0]; D.rk1 = rk[1]; D.rk2 = rk[2]; D.rk3 = rk[3]; D.irk3 = 1.0 / rk[3]; D.dt = dt; D.do_rk = do_rk;
     const long long ncell = (long long)(h->s[0] + 1) * (h->s[1] + 1) * (h->s[2] + 1);
-    if (seg_begin(h, MFC5_K_CONS2PRIM)) return -1;
-    int rc = by_shape(h, [&](auto nf, auto nd) {
-        k_cons2prim<decltype(nf)::value, decltype(nd)::value><<<grid_for(ncell, 256), 256, 0, h->st>>>(D);
-    });
-    if (rc) return rc;
-    if (seg_end(h, 1)) return -1;
+    if (!h->prim_valid) {  // with MFC5_FUSE_C2P only after an upload: the previous stage wrote them
+        if (seg_begin(h, MFC5_K_CONS2PRIM)) return -1;
+        int rc = by_shape(h, [&](auto nf, auto nd) {
+            k_cons2prim<decltype(nf)::value, decltype(nd)::value><<<grid_for(ncell, 256), 256, 0, h->st>>>(D);
+        });
+        if (rc) return rc;
+        if (seg_end(h, 1)) return -1;
+    }
     bool halo_pending = false;
     if (h->any_nb) {
         CK(cudaEventRecord(h->ev_prim, h->st));
@@ -848,6 +869,12 @@ static int run_stage(mfc5_handle* h, const double* q1, const double* q2, double*
     // every sweep waited for ev_halo), and the next pack must not start before this stage's sweeps finished
     // reading the ghosts it will overwrite -- ev_prim of the next stage is recorded after them on h->st.
     CK(cudaGetLastError());
+    if (do_rk) {
+        if (D.prim_next) { h->pp ^= 1; h->prim_valid = true; }   // primitives of the new state are in the other buffer
+        else h->prim_valid = false;
+    } else {
+        h->prim_valid = true;                                     // d_prim[pp] holds the primitives of the (unchanged) state
+    }
     return 0;
 }
 
@@ -917,15 +944,18 @@ extern "C" int mfc5_tvd_rk_n(mfc5_handle* h, double dt, int nsteps) {
     if (!h || !h->setup) return fail("mfc5_tvd_rk_n: handle not set up");
     CK(cudaSetDevice(h->P.device));
     for (int i = 0; i < nsteps; i++) {
-        if (!h->use_graph || !h->warmed) {
+        // eager: the first step (lazy allocations, function attributes) and any step that has to start with a
+        // cons -> prim pass (right after an upload), which the captured sequence does not contain
+        if (!h->use_graph || !h->warmed || (h->fuse_c2p && !h->prim_valid)) {
             if (enqueue_step(h, dt, false)) return -1;
             h->warmed = true;
             continue;
         }
-        const int par = h->cur;
-        if (!h->gexec[par] || h->gdt[par] != dt) {
-            if (h->gexec[par]) { cudaGraphExecDestroy(h->gexec[par]); h->gexec[par] = nullptr; }
+        const int cur0 = h->cur, pp0 = h->pp, key = 2 * cur0 + pp0;  // buffer parities the captured pointers depend on
+        if (!h->gexec[key] || h->gdt[key] != dt) {
+            if (h->gexec[key]) { cudaGraphExecDestroy(h->gexec[key]); h->gexec[key] = nullptr; }
             const long long l0 = h->launches;
+            const bool pv0 = h->prim_valid;
             cudaGraph_t graph = nullptr;
             cudaError_t e = cudaStreamBeginCapture(h->st, cudaStreamCaptureModeRelaxed);
             int rc = 0;
@@ -933,26 +963,28 @@ extern "C" int mfc5_tvd_rk_n(mfc5_handle* h, double dt, int nsteps) {
                 rc = enqueue_step(h, dt, false);
                 e = cudaStreamEndCapture(h->st, &graph);
             }
-            if (e == cudaSuccess && rc == 0 && graph) e = cudaGraphInstantiate(&h->gexec[par], graph, 0);
+            const int cur1 = h->cur, pp1 = h->pp;  // where a step leaves the parities
+            h->launches_captured = h->launches - l0;
+            if (e == cudaSuccess && rc == 0 && graph) e = cudaGraphInstantiate(&h->gexec[key], graph, 0);
             if (graph) cudaGraphDestroy(graph);
-            if (e != cudaSuccess || rc != 0 || !h->gexec[par]) {
+            h->launches = l0;
+            h->cur = cur0; h->pp = pp0; h->prim_valid = pv0;  // the captured enqueue only did the bookkeeping, nothing ran
+            if (e != cudaSuccess || rc != 0 || !h->gexec[key]) {
                 // capture not possible here (e.g. an NCCL build without graph support): run eagerly from now on
                 cudaGetLastError();
-                h->gexec[par] = nullptr;
+                h->gexec[key] = nullptr;
                 h->use_graph = 0;
-                h->launches = l0;
-                if (rc == 0 && h->cur != par) h->cur = par;  // the captured enqueue flipped the parity without running
                 if (enqueue_step(h, dt, false)) return -1;
                 continue;
             }
-            h->glaunches[par] = h->launches - l0;
-            h->gdt[par] = dt;
-            h->launches = l0;
-            h->cur = par;  // enqueue_step flipped it while capturing; the replay below flips it for real
+            h->glaunches[key] = h->launches_captured;
+            h->gdt[key] = dt;
+            h->gcur1[key] = cur1; h->gpp1[key] = pp1;
         }
-        CK(cudaGraphLaunch(h->gexec[par], h->st));
-        h->launches += h->glaunches[par];
-        if (h->P.time_stepper > 1) h->cur ^= 1;
+        CK(cudaGraphLaunch(h->gexec[key], h->st));
+        h->launches += h->glaunches[key];
+        h->cur = h->gcur1[key]; h->pp = h->gpp1[key];
+        h->prim_valid = h->fuse_c2p != 0;
     }
     return 0;
 }
@@ -971,7 +1003,8 @@ extern "C" int mfc5_reduce(mfc5_handle* h, int what, double dt, double* out) {
     CK(cudaSetDevice(h->P.device));
     // primitive variables of the current state
     DevP D = h->D;
-    D.prim = h->d_prim; D.primw = h->d_prim; D.q1 = h->d_q[h->cur]; D.q2 = D.q1; D.qout = nullptr; D.rhs = h->d_rhs;
+    D.prim = h->d_prim[h->pp]; D.primw = h->d_prim[h->pp]; D.q1 = h->d_q[h->cur]; D.q2 = D.q1; D.qout = nullptr; D.rhs = h->d_rhs;
+    h->prim_valid = true;  // the cons -> prim pass below refreshes d_prim[pp] for the current state
     const long long ncell = (long long)(h->s[0] + 1) * (h->s[1] + 1) * (h->s[2] + 1);
     const unsigned long long init[4] = {0ull, 0x7FEFFFFFFFFFFFFFull, 0ull, 0ull};
     CK(cudaMemcpyAsync(h->d_red, init, sizeof(init), cudaMemcpyHostToDevice, h->st));

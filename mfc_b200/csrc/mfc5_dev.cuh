@@ -63,6 +63,7 @@ struct DevP {
     // per launch
     const double* prim;
     double* primw;
+    double* prim_next;  // != nullptr: the RK-fused last sweep also writes the primitive variables of the new state here
     const double* q1;   // conservative state read by this stage
     const double* q2;   // stage-1 copy (q_cons_ts(2))
     double* qout;       // where the fused RK update writes

@@ -179,6 +179,32 @@ def test_100_rk3_steps_within_1e10(name):
     g.close()
 
 
+@pytest.mark.parametrize("uuid", ["2AB32975", "4129A23A", "A0B82851"])
+def test_opt_in_fused_cons2prim_is_bitwise(uuid, monkeypatch):
+    """MFC5_FUSE_C2P=1 (the RK-fused last sweep also writes the primitives of the new state; second primitive buffer,
+    graphs keyed by both buffer parities): same bits as the default path, eager and graph replay, strict build vs oracle."""
+    case, P, cbs, cons, dbuf, g0 = _gpu(uuid, strict=True)
+    monkeypatch.setenv("MFC5_FUSE_C2P", "1")
+    _, _, _, _, _, g1 = _gpu(uuid, strict=True)
+    _, _, _, _, _, g2 = _gpu(uuid, strict=True)
+    o = _oracle(P, cbs, cons, dbuf)
+    dt = float(case["dt"])
+    for _ in range(6):
+        g0.step(dt)
+        g1.step(dt)
+        o.step(dt)
+    g2.steps(dt, 6)
+    g2.sync()
+    a = g0.get_cons()
+    np.testing.assert_array_equal(a, o.get_cons())
+    np.testing.assert_array_equal(g1.get_cons(), a)
+    np.testing.assert_array_equal(g2.get_cons(), a)
+    assert g1.icfl_max(dt) == g0.icfl_max(dt)
+    g1.compute_rhs()
+    g0.compute_rhs()
+    np.testing.assert_array_equal(g1.get_rhs(), g0.get_rhs())
+
+
 @pytest.mark.parametrize("uuid", ["2AB32975", "4129A23A", "B5F0C655"])
 def test_graph_replay_is_bitwise_eager(uuid):
     """mfc5_tvd_rk_n (CUDA-graph replay of the captured step) == the same number of mfc5_tvd_rk calls."""
