@@ -79,6 +79,11 @@ MFC5_API int mfc5_tvd_rk(mfc5_handle* h, double dt, double* stage_time_min);
 MFC5_API int mfc5_tvd_rk_n(mfc5_handle* h, double dt, int nsteps);
 MFC5_API int mfc5_sync(mfc5_handle* h);
 
+/* Simulation time of the state (the reference's `mytime`, GPU_UPDATE(device=[mytime]) m_time_steppers.fpp:532); only the
+ * body-force acceleration g + k sin(w t - p) depends on it.  mfc5_tvd_rk / mfc5_tvd_rk_n add dt after every step, like
+ * s_perform_time_step (m_start_up.fpp:634). */
+MFC5_API int mfc5_set_time(mfc5_handle* h, double mytime);
+
 /* reductions over the interior, using the primitive variables of the current state:
  * what = 0: ICFL max  = max dt/min_d(ds_d/(|u_d|+c))  (m_sim_helpers.fpp:108-130, m_data_output.fpp:159-224)
  * what = 1: dt min    = min_d(ds_d/(|u_d|+c)) (caller multiplies by cfl_target; m_sim_helpers.fpp:182-249)

@@ -89,6 +89,10 @@ typedef struct mfc5_params {
     /* TENO weights for weno_order = 5 (Fu et al. 2016; m_weno.fpp:1167-1187): cut-off teno_CT */
     int teno, reserved2;
     double teno_CT;
+    /* body forces (m_body_forces.fpp:206-218,294-385; applied after every RK stage update, m_time_steppers.fpp:533,713-737):
+     * acceleration of direction d = bf_g[d] + bf_k[d] * sin(bf_w[d] * t - bf_p[d]) when bf[d] is set */
+    int bf[3], reserved3;
+    double bf_k[3], bf_w[3], bf_p[3], bf_g[3];
 } mfc5_params;
 
 #ifdef __cplusplus

@@ -86,6 +86,7 @@ struct mfc5_handle {
     double* d_rhs = nullptr;
     int pp = 0;
     bool prim_valid = false;
+    double mytime = 0.0;   // simulation time of the state (body forces); advanced by dt after every step
     int fuse_c2p = 0;
     int cur = 0;
     // host grid (ghosted): scb[d][i + 1 + b], ds[d][i + b]
@@ -524,6 +525,8 @@ extern "C" int mfc5_finalize_setup(mfc5_handle* h) {
     D.x_march = getenv("MFC5_X_MARCH") ? 1 : 0;
     h->use_graph = getenv("MFC5_NO_GRAPH") ? 0 : 1;
     h->use_side_stream = getenv("MFC5_NO_SIDE_STREAM") ? 0 : 1;
+    for (int d = 0; d < h->nd; d++)
+        if (h->P.bf[d] && h->P.bf_k[d] != 0.0) h->use_graph = 0;   // time-dependent acceleration: kernel arguments change every step
     h->warmed = false;
     h->setup = true;
     for (int i = 0; i < 4; i++) if (h->gexec[i]) { cudaGraphExecDestroy(h->gexec[i]); h->gexec[i] = nullptr; }
@@ -807,6 +810,13 @@ static int run_stage(mfc5_handle* h, const double* q1, const double* q2, double*
     DevP D = h->D;
     D.prim = h->d_prim[h->pp]; D.primw = h->d_prim[h->pp]; D.q1 = q1; D.q2 = q2; D.qout = qout; D.rhs = h->d_rhs;
     D.prim_next = (do_rk && h->fuse_c2p) ? h->d_prim[h->pp ^ 1] : nullptr;
+    D.bf_on = 0;
+    if (do_rk && (h->P.bf[0] || h->P.bf[1] || h->P.bf[2])) {   // s_compute_acceleration(mytime), m_body_forces.fpp:206-218
+        D.bf_on = 1;
+        for (int d = 0; d < 3; d++)
+            D.bf_a[d] = (d < h->nd && h->P.bf[d]) ? h->P.bf_g[d] + h->P.bf_k[d] * std::sin(h->P.bf_w[d] * h->mytime - h->P.bf_p[d]) : 0.0;
+        D.bf_ldt = rk[2] * dt / rk[3];
+    }
     D.rk0 = rk[0]; D.rk1 = rk[1]; D.rk2 = rk[2]; D.rk3 = rk[3]; D.irk3 = 1.0 / rk[3]; D.dt = dt; D.do_rk = do_rk;
     const long long ncell = (long long)(h->s[0] + 1) * (h->s[1] + 1) * (h->s[2] + 1);
     if (!h->prim_valid) {  // with MFC5_FUSE_C2P only after an upload: the previous stage wrote them
@@ -902,6 +912,7 @@ static int enqueue_step(mfc5_handle* h, double dt, bool timed) {
     if (timed) CK(cudaEventRecord(h->ev_stage[ns], h->st));
     h->timing = false;
     if (ns > 1) h->cur ^= 1;
+    h->mytime = h->mytime + dt;   // m_start_up.fpp:634
     return 0;
 }
 
@@ -956,6 +967,7 @@ extern "C" int mfc5_tvd_rk_n(mfc5_handle* h, double dt, int nsteps) {
             if (h->gexec[key]) { cudaGraphExecDestroy(h->gexec[key]); h->gexec[key] = nullptr; }
             const long long l0 = h->launches;
             const bool pv0 = h->prim_valid;
+            const double t0 = h->mytime;
             cudaGraph_t graph = nullptr;
             cudaError_t e = cudaStreamBeginCapture(h->st, cudaStreamCaptureModeRelaxed);
             int rc = 0;
@@ -968,7 +980,7 @@ extern "C" int mfc5_tvd_rk_n(mfc5_handle* h, double dt, int nsteps) {
             if (e == cudaSuccess && rc == 0 && graph) e = cudaGraphInstantiate(&h->gexec[key], graph, 0);
             if (graph) cudaGraphDestroy(graph);
             h->launches = l0;
-            h->cur = cur0; h->pp = pp0; h->prim_valid = pv0;  // the captured enqueue only did the bookkeeping, nothing ran
+            h->cur = cur0; h->pp = pp0; h->prim_valid = pv0; h->mytime = t0;  // the captured enqueue only did the bookkeeping, nothing ran
             if (e != cudaSuccess || rc != 0 || !h->gexec[key]) {
                 // capture not possible here (e.g. an NCCL build without graph support): run eagerly from now on
                 cudaGetLastError();
@@ -985,7 +997,14 @@ extern "C" int mfc5_tvd_rk_n(mfc5_handle* h, double dt, int nsteps) {
         h->launches += h->glaunches[key];
         h->cur = h->gcur1[key]; h->pp = h->gpp1[key];
         h->prim_valid = h->fuse_c2p != 0;
+        h->mytime = h->mytime + dt;
     }
+    return 0;
+}
+
+extern "C" int mfc5_set_time(mfc5_handle* h, double mytime) {
+    if (!h) return fail("null handle");
+    h->mytime = mytime;
     return 0;
 }
 

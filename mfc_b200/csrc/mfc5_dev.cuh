@@ -48,6 +48,8 @@ struct DevP {
     double teno_ct;
     int muscl, muscl_lim;  // MUSCL reconstruction order (0 = WENO) and limiter, m_muscl.fpp (reference-order kernels only)
     double muscl_eps;
+    int bf_on;         // body forces after the RK update of this stage (m_time_steppers.fpp:533): accelerations bf_a (0 where off)
+    double bf_a[3], bf_ldt;  // bf_ldt = rk_coef(s,3) * dt / rk_coef(s,4)
     int alt_ss;        // alt_soundspeed: Wood sound speed + K div(u) term (reference-order kernels only)
     long long sy, sz, fs, base;  // strides (x stride = 1), field size, offset of cell (0,0,0)
     double eps;

@@ -377,6 +377,24 @@ __global__ void __launch_bounds__(128) k_cbc(const __grid_constant__ DevP P, con
 // cell less HBM traffic, one launch less per stage).  Same arithmetic as k_cons2prim, so the bits are the same.  Measured
 // on C5: z sweep 0.955 -> 1.150 ms against 0.215 ms of k_cons2prim saved, 8.95 -> 8.88 ms per step, for a fifth state-sized
 // buffer -- not worth it by default (a reciprocal-based conversion gets 8.80 ms but costs 1e-11 of parity).
+// body forces, operator-split after the stage update of one cell (s_apply_bodyforces m_time_steppers.fpp:713-737 with
+// s_compute_body_forces_rhs m_body_forces.fpp:294-385): rhoM and the momenta of the UPDATED state enter the source
+template <int NF, int ND>
+__device__ __forceinline__ void apply_body_forces(const DevP& P, double* qn) {
+    using S = Shape<NF, ND>;
+    double rhoM = 0.0, rhs_E = 0.0, rhs_m[ND];
+#pragma unroll
+    for (int f = 0; f < NF; f++) rhoM = rhoM + qn[f];
+#pragma unroll
+    for (int d = 0; d < ND; d++) {
+        rhs_m[d] = rhoM * P.bf_a[d];
+        rhs_E = rhs_E + qn[S::IM + d] * P.bf_a[d];
+    }
+#pragma unroll
+    for (int d = 0; d < ND; d++) qn[S::IM + d] = qn[S::IM + d] + P.bf_ldt * rhs_m[d];
+    qn[S::IE] = qn[S::IE] + P.bf_ldt * rhs_E;
+}
+
 template <int NF, int ND, int FAST>
 __device__ __forceinline__ void store_next_prim(const DevP& P, long long c, const double* qn) {
     if (!P.prim_next) return;
@@ -422,8 +440,10 @@ __device__ __forceinline__ void finish_cell(const DevP& P, long long c, double d
             const double q2 = (P.rk1 != 0.0) ? P.q2[v * P.fs + c] : 0.0;  // rk1 = 0 in stage 1: 0 * q2 adds nothing
             if (FAST) qn[v] = div_by_const(P.rk0 * q1 + P.rk1 * q2 + P.rk2 * P.dt * r[v], P.rk3, P.irk3);
             else qn[v] = (P.rk0 * q1 + P.rk1 * q2 + P.rk2 * P.dt * r[v]) / P.rk3;
-            P.qout[v * P.fs + c] = qn[v];
         }
+        if (P.bf_on) apply_body_forces<NF, ND>(P, qn);
+#pragma unroll
+        for (int v = 0; v < S::N; v++) P.qout[v * P.fs + c] = qn[v];
         store_next_prim<NF, ND, FAST>(P, c, qn);
     } else {
 #pragma unroll
@@ -770,8 +790,10 @@ __global__ void __launch_bounds__(MFC5_MARCH_THREADS, (2 * NF + ND + 1 <= 8) ? M
                     for (int v = 0; v < N; v++) {
                         if (FAST) r[v] = div_by_const(P.rk0 * q1in[v] + P.rk1 * q2in[v] + P.rk2 * P.dt * r[v], P.rk3, P.irk3);
                         else r[v] = (P.rk0 * q1in[v] + P.rk1 * q2in[v] + P.rk2 * P.dt * r[v]) / P.rk3;
-                        P.qout[v * P.fs + c] = r[v];
                     }
+                    if (P.bf_on) apply_body_forces<NF, ND>(P, r);
+#pragma unroll
+                    for (int v = 0; v < N; v++) P.qout[v * P.fs + c] = r[v];
                     store_next_prim<NF, ND, FAST>(P, c, r);
                 } else {
 #pragma unroll

@@ -45,6 +45,7 @@ def load(strict=False):
     L.mfc5_tvd_rk.argtypes = [vp, C.c_double, _dp]
     L.mfc5_tvd_rk_n.argtypes = [vp, C.c_double, C.c_int]
     L.mfc5_sync.argtypes = [vp]
+    L.mfc5_set_time.argtypes = [vp, C.c_double]
     L.mfc5_reduce.argtypes = [vp, C.c_int, C.c_double, _dp]
     L.mfc5_nccl_unique_id.argtypes = [C.c_char_p]
     L.mfc5_comm_init.argtypes = [vp, C.c_char_p, C.c_int, C.c_int]
@@ -65,7 +66,7 @@ def load(strict=False):
 EXPORTED_SYMBOLS = [
     "mfc5_create", "mfc5_destroy", "mfc5_set_grid", "mfc5_finalize_setup", "mfc5_set_dirichlet", "mfc5_upload_cons",
     "mfc5_download_cons", "mfc5_download_prim", "mfc5_download_rhs", "mfc5_compute_rhs", "mfc5_tvd_rk", "mfc5_tvd_rk_n",
-    "mfc5_sync", "mfc5_reduce", "mfc5_nccl_unique_id", "mfc5_comm_init", "mfc5_sys_size", "mfc5_buff_size",
+    "mfc5_sync", "mfc5_set_time", "mfc5_reduce", "mfc5_nccl_unique_id", "mfc5_comm_init", "mfc5_sys_size", "mfc5_buff_size",
     "mfc5_kernel_launches", "mfc5_last_kernel_ms", "mfc5_compute_stream", "mfc5_last_error", "mfc5_version",
 ]
 
@@ -157,6 +158,10 @@ class Mfc5:
 
     def sync(self):
         self._ck(self.L.mfc5_sync(self.h))
+
+    def set_time(self, mytime):
+        """The reference's ``mytime`` (only the body-force acceleration depends on it); steps advance it by dt."""
+        self._ck(self.L.mfc5_set_time(self.h, mytime))
 
     def reduce(self, what, dt=0.0):
         out = C.c_double()

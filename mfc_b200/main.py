@@ -202,6 +202,8 @@ def run_simulation(case, case_dir, world=None, make_state=None, log=print):
                 if rti is not None:
                     rti.write(t_step, dt, mytime, icfl)
             ws = time.perf_counter()
+            if hasattr(state, "set_time"):
+                state.set_time(mytime)
             state.step(dt)
             wall = time.perf_counter() - ws
             if timed_api:
@@ -237,6 +239,8 @@ def run_simulation(case, case_dir, world=None, make_state=None, log=print):
                 nseg += 1
             nseg = max(1, nseg)
         ws = time.perf_counter()
+        if hasattr(state, "set_time"):
+            state.set_time(mytime)   # GPU_UPDATE(device=[mytime]); steps advance it by dt themselves
         if nseg == 1:
             state.step(dt)
             if timed_api:

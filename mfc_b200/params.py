@@ -42,6 +42,8 @@ class Mfc5Params(C.Structure):
         ("fluid_qv", C.c_double * MAX_FLUIDS),
         ("device", C.c_int), ("fast_math", C.c_int), ("low_Mach", C.c_int), ("alt_soundspeed", C.c_int), ("muscl_order", C.c_int), ("muscl_lim", C.c_int), ("muscl_eps", C.c_double),
         ("teno", C.c_int), ("reserved2", C.c_int), ("teno_CT", C.c_double),
+        ("bf", C.c_int * 3), ("reserved3", C.c_int),
+        ("bf_k", C.c_double * 3), ("bf_w", C.c_double * 3), ("bf_p", C.c_double * 3), ("bf_g", C.c_double * 3),
     ]
 
     @property
@@ -184,6 +186,15 @@ def params_from_case(case, device=0, fast_math=1):
         P.fluid_gamma[f] = float(case[f"fluid_pp({f + 1})%gamma"])
         P.fluid_pi_inf[f] = float(case.get(f"fluid_pp({f + 1})%pi_inf", 0.0))
         P.fluid_qv[f] = float(case.get(f"fluid_pp({f + 1})%qv", 0.0))
+    for d, x in enumerate("xyz"):  # body forces, m_body_forces.fpp:206-218 (a direction beyond num_dims is a checker error there)
+        P.bf[d] = _logical(case.get(f"bf_{x}", "F"))
+        if P.bf[d]:
+            if d >= nd:
+                raise UnsupportedCase(f"bf_{x} needs a {x} direction")
+            P.bf_k[d], P.bf_w[d] = float(case.get(f"k_{x}", 0.0)), float(case.get(f"w_{x}", 0.0))
+            P.bf_p[d], P.bf_g[d] = float(case.get(f"p_{x}", 0.0)), float(case.get(f"g_{x}", 0.0))
+    if _logical(case.get("bf_spatial_support", "F")) or _logical(case.get("synthetic_turbulence", "F")):
+        raise UnsupportedCase("bf_spatial_support / synthetic_turbulence are outside the hot path")
     P.device = device
     P.fast_math = fast_math
     check_params(P)

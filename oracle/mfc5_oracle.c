@@ -18,6 +18,7 @@
 #define MAXN MFC5_MAX_EQ
 
 struct orc_state {
+    double mytime; /* simulation time of the state (body forces) */
     mfc5_params P;
     int nd, nf, N, b, polyn, ns; /* ns = weno_num_stencils + 1 */
     int s[3];                    /* m, n, p */
@@ -1139,7 +1140,32 @@ void orc_rk_update(orc_state* S, int stage, double dt) {
                     double q2 = nstage > 1 ? S->q2[a] : S->q1[a];
                     S->q1[a] = (rk[0] * S->q1[a] + rk[1] * q2 + rk[2] * dt * S->rhs[a]) / rk[3];
                 }
+    /* body forces, operator-split after the stage update: s_apply_bodyforces m_time_steppers.fpp:533,713-737 with
+     * s_compute_body_forces_rhs m_body_forces.fpp:294-385 (acceleration at mytime, :206-218) */
+    if (S->P.bf[0] || S->P.bf[1] || S->P.bf[2]) {
+        double accel[3] = {0, 0, 0};
+        for (int d = 0; d < 3; d++)
+            if (S->P.bf[d]) accel[d] = S->P.bf_g[d] + S->P.bf_k[d] * sin(S->P.bf_w[d] * S->mytime - S->P.bf_p[d]);
+        const double ldt = rk[2] * dt / rk[3];
+#pragma omp parallel for collapse(2)
+        for (int k = 0; k <= S->s[2]; k++)
+            for (int j = 0; j <= S->s[1]; j++)
+                for (int i = 0; i <= S->s[0]; i++) {
+                    long c = IDX(S, i, j, k);
+                    double rhoM = 0.0, rhs_m[3] = {0, 0, 0}, rhs_E = 0.0;
+                    for (int f = 0; f < S->nf; f++) rhoM = rhoM + S->q1[f * S->fsz + c];
+                    for (int d = 0; d < S->nd; d++)
+                        if (S->P.bf[d]) {
+                            rhs_m[d] = rhs_m[d] + rhoM * accel[d];
+                            rhs_E = rhs_E + S->q1[(S->imom + d) * S->fsz + c] * accel[d];
+                        }
+                    for (int d = 0; d < S->nd; d++) S->q1[(S->imom + d) * S->fsz + c] = S->q1[(S->imom + d) * S->fsz + c] + ldt * rhs_m[d];
+                    S->q1[S->iE * S->fsz + c] = S->q1[S->iE * S->fsz + c] + ldt * rhs_E;
+                }
+    }
 }
+
+void orc_set_time(orc_state* S, double t) { S->mytime = t; }
 
 void orc_compute_rhs(orc_state* S) {
     orc_cons2prim(S);
@@ -1152,6 +1178,7 @@ void orc_tvd_rk_step(orc_state* S, double dt) {
         orc_compute_rhs(S);
         orc_rk_update(S, st, dt);
     }
+    S->mytime = S->mytime + dt; /* m_start_up.fpp:634 */
 }
 
 /* ICFL: m_data_output.fpp:159-224 with s_compute_enthalpy (m_sim_helpers.fpp:45-105) and

@@ -49,6 +49,7 @@ void orc_rk_update(orc_state* S, int stage, double dt);
 /* single-rank convenience: one full RK stage / step with physical BCs on every side */
 void orc_compute_rhs(orc_state* S);
 void orc_tvd_rk_step(orc_state* S, double dt);
+void orc_set_time(orc_state* S, double mytime);
 
 /* max over interior cells of dt / min_d(ds_d / (|u_d| + c)) (m_sim_helpers.fpp:108-180) */
 double orc_icfl_max(orc_state* S, double dt);

@@ -42,6 +42,7 @@ def load(omp=False):
     L.orc_rk_update.argtypes = [C.c_void_p, C.c_int, C.c_double]
     L.orc_compute_rhs.argtypes = [C.c_void_p]
     L.orc_tvd_rk_step.argtypes = [C.c_void_p, C.c_double]
+    L.orc_set_time.argtypes = [C.c_void_p, C.c_double]
     L.orc_icfl_max.argtypes = [C.c_void_p, C.c_double]
     L.orc_icfl_max.restype = C.c_double
     L.orc_num_threads.restype = C.c_int
@@ -107,6 +108,9 @@ class Oracle:
 
     def step(self, dt):
         self.L.orc_tvd_rk_step(self.h, dt)
+
+    def set_time(self, mytime):
+        self.L.orc_set_time(self.h, mytime)
 
     def icfl_max(self, dt):
         return self.L.orc_icfl_max(self.h, dt)

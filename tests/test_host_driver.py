@@ -254,18 +254,20 @@ def test_cfl_driven_time_stepping(tmp_path):
     assert any(l.startswith(" [  0%] Time ") for l in lines)
 
 
-def test_kelvin_helmholtz_example_cfl_golden(tmp_path):
-    """The reference's example golden A078904B (2-D Kelvin-Helmholtz, HLL, cfl_adap_dt, hard-coded profile 207): every D/ file of every
-    save (selected by simulated time) through the CFL-driven loop."""
-    case = dict(CASES["A078904B"]["params"])
+@pytest.mark.parametrize("uuid", ["A078904B", "B54BB9D8"])
+def test_cfl_driven_goldens(uuid, tmp_path):
+    """Reference goldens of CFL-driven runs through the driver loop: A078904B (2-D Kelvin-Helmholtz example, HLL, hard-coded
+    profile 207; every D/ file of every save, selected by simulated time) and B54BB9D8 (3-D body forces with cfl_adap_dt:
+    the acceleration follows the accumulated time)."""
+    case = dict(CASES[uuid]["params"])
     w = SerialWorld()
     main.run_pre_process(case, str(tmp_path), w, log=lambda s: None)
     main.run_simulation(case, str(tmp_path), w, make_state=_make_cfl_oracle, log=lambda s: None)
     packed = data_io.pack_D(str(tmp_path))
-    g = golden("A078904B")
-    assert len(g) > 100
+    g = golden(uuid)
+    assert len(g) > (100 if uuid == "A078904B" else 10)
     for key, want in g.items():
         name = f"D/{key}.dat"
         assert name in packed, name
-        ok, amax, worst = compare(packed[name], want, float(CASES["A078904B"]["tol"]))
+        ok, amax, worst = compare(packed[name], want, float(CASES[uuid]["tol"]))
         assert ok, (key, amax, worst)
