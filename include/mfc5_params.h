@@ -93,6 +93,10 @@ typedef struct mfc5_params {
      * acceleration of direction d = bf_g[d] + bf_k[d] * sin(bf_w[d] * t - bf_p[d]) when bf[d] is set */
     int bf[3], reserved3;
     double bf_k[3], bf_w[3], bf_p[3], bf_g[3];
+    /* interface compression: 0 off, 1 THINC (m_thinc.fpp:295-406, applied to the reconstructed alpha / alpha-rho of the two
+     * fluids after WENO or MUSCL); ic_eps / ic_beta default to 1e-4 / 1.6 (m_constants.fpp:53-54) */
+    int int_comp, reserved4;
+    double ic_eps, ic_beta;
 } mfc5_params;
 
 #ifdef __cplusplus

@@ -48,6 +48,8 @@ struct DevP {
     double teno_ct;
     int muscl, muscl_lim;  // MUSCL reconstruction order (0 = WENO) and limiter, m_muscl.fpp (reference-order kernels only)
     double muscl_eps;
+    int int_comp;      // 1: THINC interface compression after the reconstruction (m_thinc.fpp:319-401; reference-order kernels only)
+    double ic_eps, ic_beta, ic_cosh, ic_tanh;  // cosh / tanh of ic_beta from the host
     int bf_on;         // body forces after the RK update of this stage (m_time_steppers.fpp:533): accelerations bf_a (0 where off)
     double bf_a[3], bf_ldt;  // bf_ldt = rk_coef(s,3) * dt / rk_coef(s,4)
     int alt_ss;        // alt_soundspeed: Wood sound speed + K div(u) term (reference-order kernels only)
@@ -476,6 +478,34 @@ __device__ __forceinline__ void weno_edges_nv(const DevP& P, const DirTables& T,
     }
 #pragma unroll
     for (int u = 0; u < NV; u++) weno_edges<WO, WV, 0>(P, T, slot, row, f[u][0], f[u][1], f[u][2], f[u][3], f[u][4], eL[u], eR[u]);
+}
+
+// THINC (s_thinc_compression, m_thinc.fpp:319-401) for one cell: aCL / aC / aCR = alpha_1 of cells j-1, j, j+1, rb / re =
+// alpha-rho of the first / last fluid of cell j.  Returns false where the reconstruction is left alone; otherwise
+// L[0..3] / R[0..3] = (alpha-rho_1, alpha-rho_NF, alpha_1, alpha_NF) on the left / right face of the cell.
+__device__ __forceinline__ bool thinc_cell(const DevP& P, double aCL, double aC, double aCR, double rb, double re, double* L, double* R) {
+    const double ic_eps = P.ic_eps;
+    if (!(aC >= ic_eps && aC <= 1.0 - ic_eps)) return false;
+    const double moncon = (aCR - aC) * (aC - aCL);
+    if (!(moncon > 1e-8)) return false;  // moncon_cutoff, m_constants.fpp:55
+    const double sgn = (aCR - aCL > 0.0) ? 1.0 : -1.0;
+    const double beta_eff = P.ic_beta;
+    const double qmin = fmin(aCR, aCL);
+    const double qmax = fmax(aCR, aCL) - qmin;
+    const double C = (aC - qmin + MFC5_SGM_EPS) / (qmax + MFC5_SGM_EPS);
+    const double B = exp(sgn * beta_eff * (2.0 * C - 1.0));
+    const double A = (B / P.ic_cosh - 1.0) / P.ic_tanh;
+    const double rho_b = rb / aC;
+    const double rho_e = re / (1.0 - aC);
+    double aT = qmin + 5e-1 * qmax * (1.0 + sgn * A);
+    if (aT < ic_eps) aT = ic_eps;
+    if (aT > 1.0 - ic_eps) aT = 1.0 - ic_eps;
+    L[0] = rho_b * aT; L[1] = rho_e * (1.0 - aT); L[2] = aT; L[3] = 1.0 - aT;
+    aT = qmin + 5e-1 * qmax * (1.0 + sgn * (P.ic_tanh + A) / (1.0 + A * P.ic_tanh));
+    if (aT < ic_eps) aT = ic_eps;
+    if (aT > 1.0 - ic_eps) aT = 1.0 - ic_eps;
+    R[0] = rho_b * aT; R[1] = rho_e * (1.0 - aT); R[2] = aT; R[3] = 1.0 - aT;
+    return true;
 }
 
 // s_compute_speed_of_sound, 5-eq branch: src/common/m_variables_conversion.fpp:1233-1260

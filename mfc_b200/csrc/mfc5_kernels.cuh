@@ -547,6 +547,20 @@ __global__ void __launch_bounds__(128, MFC5_X_MINB) k_sweep_x(const __grid_const
             myQ[vv[u]][lane] = __shfl_down_sync(0xffffffffu, l[u], 1);
         }
     }
+    if (!FAST && WO < 0 && NF >= 2 && P.int_comp == 1) {  // THINC on my cell: my right edge, and my left edge = lane-1's qR
+        double tl[4], tr[4];
+        const bool on = thinc_cell(P, my[S::IA][lane + 1], my[S::IA][lane + 2], my[S::IA][lane + 3], my[0][lane + 2], my[NF - 1][lane + 2], tl, tr);
+        __syncwarp();
+        if (on) {
+            const int vi[4] = {0, NF - 1, S::IA, S::IA + NF - 1};
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                myR[vi[q]][lane] = tr[q];
+                if (lane > 0) myQ[vi[q]][lane - 1] = tl[q];
+            }
+        }
+        __syncwarp();
+    }
     double eR[N], qR[N];
 #pragma unroll
     for (int v = 0; v < N; v++) { eR[v] = myR[v][lane]; qR[v] = myQ[v][lane]; }
@@ -722,6 +736,15 @@ __global__ void __launch_bounds__(MFC5_MARCH_THREADS, (2 * NF + ND + 1 <= 8) ? M
                 weno_edges_nv<WO, WV, FAST, NV>(P, T, cc + P.b, mrow, f, l, r);
 #pragma unroll
                 for (int u = 0; u < NV; u++) { sEL[vv[u] * NT + tid] = l[u]; sERc[vv[u] * NT] = r[u]; }
+            }
+            if (!FAST && WO < 0 && NF >= 2 && PN >= 1 && P.int_comp == 1) {  // THINC on cell cc (a thread only touches its own column)
+                double tl[4], tr[4];
+                const int om = off[PN >= 1 ? PN - 1 : 0], oc = off[PN], op = off[PN >= 1 ? PN + 1 : 0];
+                if (thinc_cell(P, ring[om + S::IA * NT], ring[oc + S::IA * NT], ring[op + S::IA * NT], ring[oc], ring[oc + (NF - 1) * NT], tl, tr)) {
+                    const int vi[4] = {0, NF - 1, S::IA, S::IA + NF - 1};
+#pragma unroll
+                    for (int q = 0; q < 4; q++) { sEL[vi[q] * NT + tid] = tl[q]; sERc[vi[q] * NT] = tr[q]; }
+                }
             }
         }
         if (cc <= c1) {       // plane cc+1+PN enters the window in the slot of plane cc-PN; lands during the Riemann solve

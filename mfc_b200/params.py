@@ -19,6 +19,7 @@ _NAMED = {
     "recon_type": {"weno": 1, "muscl": 2},
     "muscl_order": {"first_order": 1, "second_order": 2},
     "muscl_lim": {"unlimited": 0, "minmod": 1, "mc": 2, "van_albada": 3, "van_leer": 4, "superbee": 5},
+    "int_comp": {"off": 0, "thinc": 1, "mthinc": 2},
 }
 
 
@@ -44,6 +45,7 @@ class Mfc5Params(C.Structure):
         ("teno", C.c_int), ("reserved2", C.c_int), ("teno_CT", C.c_double),
         ("bf", C.c_int * 3), ("reserved3", C.c_int),
         ("bf_k", C.c_double * 3), ("bf_w", C.c_double * 3), ("bf_p", C.c_double * 3), ("bf_g", C.c_double * 3),
+        ("int_comp", C.c_int), ("reserved4", C.c_int), ("ic_eps", C.c_double), ("ic_beta", C.c_double),
     ]
 
     @property
@@ -103,9 +105,6 @@ def params_from_case(case, device=0, fast_math=1):
     for k in _UNSUPPORTED_TRUE:
         if _logical(case.get(k, "F")):
             raise UnsupportedCase(f"{k}=T is outside the 5-equation inviscid hot path")
-    ic = case.get("int_comp", 0)
-    if (_logical(ic) if isinstance(ic, str) else int(ic or 0) != 0):
-        raise UnsupportedCase("interface compression is not supported")
     P = Mfc5Params()
     P.m, P.n, P.p = int(case["m"]), int(case.get("n", 0)), int(case.get("p", 0))
     P.num_fluids = int(case["num_fluids"])
@@ -186,6 +185,18 @@ def params_from_case(case, device=0, fast_math=1):
         P.fluid_gamma[f] = float(case[f"fluid_pp({f + 1})%gamma"])
         P.fluid_pi_inf[f] = float(case.get(f"fluid_pp({f + 1})%pi_inf", 0.0))
         P.fluid_qv[f] = float(case.get(f"fluid_pp({f + 1})%qv", 0.0))
+    ic = _val(case, "int_comp", 0)
+    ic = (1 if _logical(ic) else 0) if isinstance(ic, str) and ic.strip().upper() in ("T", "F") else int(ic or 0)
+    if ic not in (0, 1):
+        raise UnsupportedCase("int_comp = 2 (MTHINC) is outside the hot path; 0 (off) and 1 (THINC) are available")
+    if ic == 1:  # toolchain/mfc/case_validator.py:426-444
+        if P.num_fluids != 2:
+            raise UnsupportedCase("int_comp > 0 requires num_fluids = 2")
+        if P.recon_order == 1:
+            raise UnsupportedCase("int_comp must be 0 (off) when weno_order = 1 / muscl_order = 1")
+    P.int_comp = ic
+    P.ic_eps = float(case.get("ic_eps", 1e-4))
+    P.ic_beta = float(case.get("ic_beta", 1.6))
     for d, x in enumerate("xyz"):  # body forces, m_body_forces.fpp:206-218 (a direction beyond num_dims is a checker error there)
         P.bf[d] = _logical(case.get(f"bf_{x}", "F"))
         if P.bf[d]:

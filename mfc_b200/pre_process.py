@@ -154,8 +154,8 @@ def initial_condition(case, ccs, ds_min=None):
     for ip in range(1, int(case["num_patches"]) + 1):
         geom = int(_patch(case, ip, "geometry"))
         smooth = _logical(_patch(case, ip, "smoothen", "F"))
-        if smooth and geom != 8:
-            raise NotImplementedError("patch smoothing is implemented for the sphere only")
+        if smooth and geom not in (2, 8):
+            raise NotImplementedError("patch smoothing is implemented for the circle and the sphere only")
         if _patch(case, ip, "hcid") is not None and smooth:
             raise NotImplementedError("hard-coded profile on a smoothed patch")
         xc = float(_patch(case, ip, "x_centroid", 0.0))
@@ -176,6 +176,11 @@ def initial_condition(case, ccs, ds_min=None):
         elif geom == 2:
             r = float(_patch(case, ip, "radius"))
             inside = ((X - xc) ** 2 + (Y - yc) ** 2 <= r ** 2) & (Z == Z)
+            if smooth:  # m_icpp_patches.fpp:317-321
+                coeff = float(_patch(case, ip, "smooth_coeff"))
+                if ds_min is None:
+                    ds_min = grid_minima(case)
+                eta = np.tanh(coeff / min(ds_min[:2]) * (np.sqrt((X - xc) ** 2 + (Y - yc) ** 2) - r)) * (-0.5) + 0.5 + 0.0 * Z
         elif geom == 8:
             r = float(_patch(case, ip, "radius"))
             inside = (X - xc) ** 2 + (Y - yc) ** 2 + (Z - zc) ** 2 <= r ** 2

@@ -631,6 +631,37 @@ static void weno_dir(orc_state* S, int d) {
                         }
                     }
                 }
+                /* interface compression (THINC), s_thinc_compression m_thinc.fpp:319-401: overwrites the reconstructed
+                 * alpha / alpha-rho of the two fluids in interface cells where alpha_1 is monotone across the stencil */
+                if (S->P.int_comp == 1 && pn > 0) {
+                    const int nf = S->nf;
+                    const double ic_eps = S->P.ic_eps, ic_beta = S->P.ic_beta;
+                    const long ia = (long)S->iadv * S->fsz + c, ib = (long)(S->iadv + nf - 1) * S->fsz + c;
+                    const long r0 = c, r1 = (long)(nf - 1) * S->fsz + c;
+                    double aCL = S->prim[ia - sd], aC = S->prim[ia], aCR = S->prim[ia + sd];
+                    if (aC >= ic_eps && aC <= 1.0 - ic_eps) {
+                        double moncon = (aCR - aC) * (aC - aCL);
+                        if (moncon > 1e-8) { /* moncon_cutoff, m_constants.fpp:55 */
+                            double sgn = (aCR - aCL > 0.0) ? 1.0 : -1.0;
+                            double beta_eff = ic_beta;
+                            double qmin = dmin(aCR, aCL);
+                            double qmax = dmax(aCR, aCL) - qmin;
+                            double C = (aC - qmin + SGM_EPS) / (qmax + SGM_EPS);
+                            double B = exp(sgn * beta_eff * (2.0 * C - 1.0));
+                            double A = (B / cosh(beta_eff) - 1.0) / tanh(beta_eff);
+                            double rho_b = S->prim[r0] / aC;
+                            double rho_e = S->prim[r1] / (1.0 - aC);
+                            double aT = qmin + 5e-1 * qmax * (1.0 + sgn * A);
+                            if (aT < ic_eps) aT = ic_eps;
+                            if (aT > 1.0 - ic_eps) aT = 1.0 - ic_eps;
+                            S->vL[r0] = rho_b * aT; S->vL[r1] = rho_e * (1.0 - aT); S->vL[ia] = aT; S->vL[ib] = 1.0 - aT;
+                            aT = qmin + 5e-1 * qmax * (1.0 + sgn * (tanh(beta_eff) + A) / (1.0 + A * tanh(beta_eff)));
+                            if (aT < ic_eps) aT = ic_eps;
+                            if (aT > 1.0 - ic_eps) aT = 1.0 - ic_eps;
+                            S->vR[r0] = rho_b * aT; S->vR[r1] = rho_e * (1.0 - aT); S->vR[ia] = aT; S->vR[ib] = 1.0 - aT;
+                        }
+                    }
+                }
             }
 }
 

@@ -50,6 +50,7 @@ C9E0B721 A078904B 8370A3D9 8FD91C41
 AFB46CF8 4AADC848
 F1D01264 14846B52 90D62933 A7C19B7B 4F79391A 77292B06 9BD657CB 30035426 01DC0251 24119641 F33CC4CA
 7BCDC8E7 10041BB7 B54BB9D8
+516A2067 A089CE54 10DE58AA
 """.split()
 
 

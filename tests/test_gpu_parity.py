@@ -58,6 +58,30 @@ def test_rhs_strict_matches_oracle(uuid):
     assert np.max(np.abs(r_g - r_o)) <= 1e-13 * scale, np.max(np.abs(r_g - r_o)) / scale
 
 
+# the widening of SURVEY.md 8 f-4 (reference-order kernels): one or two goldens per feature
+F4_SET = ["07C1FECC", "C462AA3E", "F9E0BE95", "7C8F1BA9", "A26B7E00", "4AADC848", "F1D01264", "01DC0251", "7BCDC8E7", "10041BB7",
+          "516A2067", "A089CE54"]
+
+
+@pytest.mark.parametrize("uuid", F4_SET)
+def test_f4_features_strict_vs_oracle(uuid):
+    """low_Mach, alt_soundspeed, Lax-Friedrichs, MUSCL, TENO5, body forces: strict build == oracle, bit for bit, after 10 steps.
+    THINC (516A2067, A089CE54) evaluates exp() on the device (CUDA libm vs glibc: last-bit differences), hence 1e-13 there."""
+    case, P, cbs, cons, dbuf, g = _gpu(uuid, strict=True)
+    o = _oracle(P, cbs, cons, dbuf)
+    dt = float(case["dt"])
+    for _ in range(10):
+        g.step(dt)
+        o.step(dt)
+    a, b = g.get_cons(), o.get_cons()
+    assert not np.array_equal(b, cons)
+    if int(case.get("int_comp", 0) or 0):
+        for v in range(a.shape[0]):
+            assert np.max(np.abs(a[v] - b[v])) <= 1e-13 * (np.max(np.abs(b[v])) + 1e-300)
+    else:
+        np.testing.assert_array_equal(a, b)
+
+
 @pytest.mark.parametrize("fast", [1, 0])
 @pytest.mark.parametrize("uuid", ORACLE_SET)
 def test_50_steps_vs_oracle(uuid, fast):
