@@ -480,6 +480,27 @@ __device__ __forceinline__ void weno_edges_nv(const DevP& P, const DirTables& T,
     for (int u = 0; u < NV; u++) weno_edges<WO, WV, 0>(P, T, slot, row, f[u][0], f[u][1], f[u][2], f[u][3], f[u][4], eL[u], eR[u]);
 }
 
+// exp() of the THINC profile.  The strict build evaluates the same fdlibm-style sequence as the oracle (oracle/mfc5_oracle.c
+// orc_exp: Cody-Waite reduction, degree-5 Remez polynomial, < 1 ulp) so that the two agree bit for bit; the product build uses
+// CUDA's exp.
+__device__ __forceinline__ double thinc_exp(double x) {
+#ifdef MFC5_STRICT
+    const double ln2hi = 6.93147180369123816490e-01, ln2lo = 1.90821492927058770002e-10, invln2 = 1.44269504088896338700e+00,
+                 P1 = 1.66666666666666019037e-01, P2 = -2.77777777770155933842e-03, P3 = 6.61375632143793436117e-05,
+                 P4 = -1.65339022054652515390e-06, P5 = 4.13813679705723846039e-08;
+    if (!(fabs(x) < 700.0)) return exp(x);
+    const int k = (int)(invln2 * x + (x < 0.0 ? -0.5 : 0.5));
+    const double hi = x - (double)k * ln2hi, lo = (double)k * ln2lo;
+    const double r = hi - lo;
+    const double t = r * r;
+    const double c = r - t * (P1 + t * (P2 + t * (P3 + t * (P4 + t * P5))));
+    const double y = 1.0 - ((lo - (r * c) / (2.0 - c)) - hi);
+    return ldexp(y, k);
+#else
+    return exp(x);
+#endif
+}
+
 // THINC (s_thinc_compression, m_thinc.fpp:319-401) for one cell: aCL / aC / aCR = alpha_1 of cells j-1, j, j+1, rb / re =
 // alpha-rho of the first / last fluid of cell j.  Returns false where the reconstruction is left alone; otherwise
 // L[0..3] / R[0..3] = (alpha-rho_1, alpha-rho_NF, alpha_1, alpha_NF) on the left / right face of the cell.
@@ -493,7 +514,7 @@ __device__ __forceinline__ bool thinc_cell(const DevP& P, double aCL, double aC,
     const double qmin = fmin(aCR, aCL);
     const double qmax = fmax(aCR, aCL) - qmin;
     const double C = (aC - qmin + MFC5_SGM_EPS) / (qmax + MFC5_SGM_EPS);
-    const double B = exp(sgn * beta_eff * (2.0 * C - 1.0));
+    const double B = thinc_exp(sgn * beta_eff * (2.0 * C - 1.0));
     const double A = (B / P.ic_cosh - 1.0) / P.ic_tanh;
     const double rho_b = rb / aC;
     const double rho_e = re / (1.0 - aC);

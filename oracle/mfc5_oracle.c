@@ -44,6 +44,28 @@ static inline long IDX(const orc_state* S, int i, int j, int k) {
 }
 static inline double sq(double x) { return x * x; }
 static inline double dmin(double a, double b) { return a < b ? a : b; }
+
+/* exp() for THINC, restated from the published fdlibm algorithm (Sun's e_exp.c: Cody-Waite reduction x = k ln2 + r,
+ * |r| <= 0.5 ln2, exp(r) = 1 + 2r/(R(r^2) - r) with a degree-5 Remez polynomial; error < 1 ulp) instead of libm's, so that
+ * the strict CUDA build (same operations, no FMA contraction) reproduces the oracle bit for bit: CUDA's exp and glibc's
+ * differ in the last bit for some arguments, and THINC's thresholds amplify that.  Arguments here are |x| <= ~2 ic_beta. */
+#ifndef ORC_LIBM_EXP
+static double orc_exp(double x) {
+    static const double ln2hi = 6.93147180369123816490e-01, ln2lo = 1.90821492927058770002e-10, invln2 = 1.44269504088896338700e+00,
+                        P1 = 1.66666666666666019037e-01, P2 = -2.77777777770155933842e-03, P3 = 6.61375632143793436117e-05,
+                        P4 = -1.65339022054652515390e-06, P5 = 4.13813679705723846039e-08;
+    if (!(fabs(x) < 700.0)) return exp(x); /* outside the range THINC can produce */
+    int k = (int)(invln2 * x + (x < 0.0 ? -0.5 : 0.5));
+    double hi = x - (double)k * ln2hi, lo = (double)k * ln2lo;
+    double r = hi - lo;
+    double t = r * r;
+    double c = r - t * (P1 + t * (P2 + t * (P3 + t * (P4 + t * P5))));
+    double y = 1.0 - ((lo - (r * c) / (2.0 - c)) - hi);
+    return ldexp(y, k);
+}
+#else
+#define orc_exp exp
+#endif
 static inline double dmax(double a, double b) { return a > b ? a : b; }
 /* Fortran sign(a, b): |a| with the sign of b (b = +0 -> +, b = -0 -> -) */
 static inline double fsign(double a, double b) { return copysign(fabs(a), b); }
@@ -647,7 +669,7 @@ static void weno_dir(orc_state* S, int d) {
                             double qmin = dmin(aCR, aCL);
                             double qmax = dmax(aCR, aCL) - qmin;
                             double C = (aC - qmin + SGM_EPS) / (qmax + SGM_EPS);
-                            double B = exp(sgn * beta_eff * (2.0 * C - 1.0));
+                            double B = orc_exp(sgn * beta_eff * (2.0 * C - 1.0));
                             double A = (B / cosh(beta_eff) - 1.0) / tanh(beta_eff);
                             double rho_b = S->prim[r0] / aC;
                             double rho_e = S->prim[r1] / (1.0 - aC);

@@ -65,8 +65,10 @@ F4_SET = ["07C1FECC", "C462AA3E", "F9E0BE95", "7C8F1BA9", "A26B7E00", "4AADC848"
 
 @pytest.mark.parametrize("uuid", F4_SET)
 def test_f4_features_strict_vs_oracle(uuid):
-    """low_Mach, alt_soundspeed, Lax-Friedrichs, MUSCL, TENO5, body forces: strict build == oracle, bit for bit, after 10 steps.
-    THINC (516A2067, A089CE54) evaluates exp() on the device (CUDA libm vs glibc: last-bit differences), hence 1e-13 there."""
+    """low_Mach, alt_soundspeed, Lax-Friedrichs, MUSCL, TENO5, body forces, THINC: strict build == oracle, bit for bit, after 10
+    steps.  THINC (516A2067, A089CE54) needs exp(): the oracle and the strict build evaluate the same fdlibm-style sequence
+    (orc_exp / thinc_exp) -- with libm's exp on one side and CUDA's on the other, last-bit differences flip THINC's thresholds and
+    show up at full size in the noise-level transverse momenta of these symmetric cases."""
     case, P, cbs, cons, dbuf, g = _gpu(uuid, strict=True)
     o = _oracle(P, cbs, cons, dbuf)
     dt = float(case["dt"])
@@ -75,11 +77,7 @@ def test_f4_features_strict_vs_oracle(uuid):
         o.step(dt)
     a, b = g.get_cons(), o.get_cons()
     assert not np.array_equal(b, cons)
-    if int(case.get("int_comp", 0) or 0):
-        for v in range(a.shape[0]):
-            assert np.max(np.abs(a[v] - b[v])) <= 1e-13 * (np.max(np.abs(b[v])) + 1e-300)
-    else:
-        np.testing.assert_array_equal(a, b)
+    np.testing.assert_array_equal(a, b)
 
 
 @pytest.mark.parametrize("fast", [1, 0])
