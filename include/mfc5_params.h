@@ -87,7 +87,8 @@ typedef struct mfc5_params {
     int muscl_order, muscl_lim;
     double muscl_eps;
     /* TENO weights for weno_order = 5 (Fu et al. 2016; m_weno.fpp:1167-1187): cut-off teno_CT */
-    int teno, reserved2;
+    int teno;
+    int mp_weno;         /* monotonicity-preserving bounds on the WENO5 edge values (m_weno.fpp:1495-1601); reference-order kernels */
     double teno_CT;
     /* body forces (m_body_forces.fpp:206-218,294-385; applied after every RK stage update, m_time_steppers.fpp:533,713-737):
      * acceleration of direction d = bf_g[d] + bf_k[d] * sin(bf_w[d] * t - bf_p[d]) when bf[d] is set */

@@ -164,6 +164,7 @@ extern "C" int mfc5_create(const mfc5_params* p, mfc5_handle** out) {
     if (p->mapped_weno && p->wenoz) return fail("mapped_weno and wenoz are mutually exclusive");
     if (p->int_comp != 0 && (p->int_comp != 1 || p->num_fluids != 2 || (p->muscl_order > 0 ? p->muscl_order : p->weno_order) == 1))
         return fail("int_comp: only THINC (1), with num_fluids = 2 and a reconstruction order above 1");
+    if (p->mp_weno && (p->weno_order != 5 || p->muscl_order != 0)) return fail("mp_weno requires weno_order = 5");
     if (p->teno && (p->mapped_weno || p->wenoz || p->weno_order != 5 || p->muscl_order != 0 || !(p->teno_CT > 0.0)))
         return fail("teno needs weno_order = 5, teno_CT > 0 and neither mapped_weno nor wenoz");
     if (p->alt_soundspeed && (p->num_fluids != 2 || p->avg_state != 2 || (p->riemann_solver == 1 && !p->hll_u_interface)))
@@ -435,12 +436,12 @@ extern "C" int mfc5_finalize_setup(mfc5_handle* h) {
     // weno_eps large enough that products of four smoothness indicators cannot underflow
     D.low_mach = h->P.low_Mach;
     D.alt_ss = h->P.alt_soundspeed;
-    D.teno = h->P.teno; D.teno_ct = h->P.teno_CT;
+    D.teno = h->P.teno; D.teno_ct = h->P.teno_CT; D.mp_weno = h->P.mp_weno;
     D.int_comp = h->P.int_comp; D.ic_eps = h->P.ic_eps; D.ic_beta = h->P.ic_beta;
     D.ic_cosh = std::cosh(h->P.ic_beta); D.ic_tanh = std::tanh(h->P.ic_beta);
     D.muscl = h->P.muscl_order; D.muscl_lim = h->P.muscl_lim; D.muscl_eps = h->P.muscl_eps;
     D.fast = h->P.fast_math && h->P.wave_speeds == 1 && !h->P.null_weights && h->P.weno_eps >= 1e-30 && h->P.low_Mach == 0 &&
-             !h->P.alt_soundspeed && h->P.riemann_solver != 5 && h->P.muscl_order == 0 && !h->P.teno && h->P.int_comp == 0;
+             !h->P.alt_soundspeed && h->P.riemann_solver != 5 && h->P.muscl_order == 0 && !h->P.teno && !h->P.mp_weno && h->P.int_comp == 0;
     if (getenv("MFC5_NO_FAST")) D.fast = 0;
     D.sy = h->px; D.sz = h->px * h->ey; D.fs = h->fs;
     D.base = h->ox + h->oy * D.sy + h->oz * D.sz;

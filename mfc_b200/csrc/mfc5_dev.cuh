@@ -46,6 +46,7 @@ struct DevP {
     int low_mach;      // 0 / 1 / 2, inline_riemann.fpp:71-93 (reference-order kernels only)
     int teno;          // TENO5 weights (m_weno.fpp:1167-1187), cut-off teno_ct (reference-order kernels only)
     double teno_ct;
+    int mp_weno;       // monotonicity-preserving bounds on the WENO5 edge values (m_weno.fpp:1495-1601; reference-order kernels only)
     int muscl, muscl_lim;  // MUSCL reconstruction order (0 = WENO) and limiter, m_muscl.fpp (reference-order kernels only)
     double muscl_eps;
     int int_comp;      // 1: THINC interface compression after the reconstruction (m_thinc.fpp:319-401; reference-order kernels only)
@@ -286,6 +287,34 @@ __device__ __forceinline__ void weno3_fast(const DevP& P, const DirTables& T, co
     }
 }
 
+// Monotonicity-preserving bounds on the WENO5 edge values (mp_weno), s_preserve_monotonicity m_weno.fpp:1495-1601; same
+// operation order as oracle/mfc5_oracle.c mp_limit (explicit comparisons, so that the sign of a zero is decided the same way).
+__device__ __forceinline__ double mp_min(double a, double b) { return a < b ? a : b; }
+__device__ __forceinline__ double mp_max(double a, double b) { return a > b ? a : b; }
+__device__ __forceinline__ double mp_md(double a, double b) {
+    const double s = copysign(1.0, 4.0 * a - b);
+    const double mn = mp_min(mp_min(mp_min(fabs(4.0 * a - b), fabs(a)), fabs(4.0 * b - a)), fabs(b));
+    return (s + copysign(1.0, 4.0 * b - a)) * fabs((s + copysign(1.0, a)) * (s + copysign(1.0, b))) * mn / 8.0;
+}
+__device__ __forceinline__ void mp_limit(double vm2, double vm1, double vp0, double vp1, double vp2, double& vL, double& vR) {
+    const double alpha_mp = 2.0, beta_mp = 4.0 / 3.0;
+    const double dm = vp0 + vm2 - vm1 * 2.0, d0 = vp1 + vm1 - vp0 * 2.0, dp = vp2 + vp0 - vp1 * 2.0;
+    double d_MD = mp_md(dm, d0), d_LC = mp_md(d0, dp);
+    double UL = vp0 - (vp1 - vp0) * alpha_mp;
+    double MD = (vp0 + vm1 - d_MD) * 5.e-1;
+    double LC = vp0 - (vp1 - vp0) * 5.e-1 + beta_mp * d_LC;
+    double vmin = mp_max(mp_min(mp_min(vp0, vm1), MD), mp_min(mp_min(vp0, UL), LC));
+    double vmax = mp_min(mp_max(mp_max(vp0, vm1), MD), mp_max(mp_max(vp0, UL), LC));
+    vL = vL + (copysign(5.e-1, vmin - vL) + copysign(5.e-1, vmax - vL)) * mp_min(fabs(vmin - vL), fabs(vmax - vL));
+    d_MD = mp_md(d0, dp); d_LC = mp_md(dm, d0);
+    UL = vp0 + (vp0 - vm1) * alpha_mp;
+    MD = (vp0 + vp1 - d_MD) * 5.e-1;
+    LC = vp0 + (vp0 - vm1) * 5.e-1 + beta_mp * d_LC;
+    vmin = mp_max(mp_min(mp_min(vp0, vp1), MD), mp_min(mp_min(vp0, UL), LC));
+    vmax = mp_min(mp_max(mp_max(vp0, vp1), MD), mp_max(mp_max(vp0, UL), LC));
+    vR = vR + (copysign(5.e-1, vmin - vR) + copysign(5.e-1, vmax - vR)) * mp_min(fabs(vmin - vR), fabs(vmax - vR));
+}
+
 // -------------------------------------------------------------------------------------------------
 // WENO reconstruction of one variable in one cell: left- and right-boundary values.
 // reference: s_weno, src/simulation/m_weno.fpp:1007-1085 (WENO3), :1098-1239 (WENO5), :952-993 (1).
@@ -454,6 +483,7 @@ __device__ __forceinline__ void weno_edges(const DevP& P, const DirTables& T, in
             const double val = w0 * p0 + w1 * p1 + w2 * p2;
             if (side == 0) eL = val; else eR = val;
         }
+        if ((WV < 0) && P.mp_weno) mp_limit(f0, f1, f2, f3, f4, eL, eR);  // m_weno.fpp:1241-1243
     }
 }
 

@@ -42,7 +42,7 @@ class Mfc5Params(C.Structure):
         ("fluid_gamma", C.c_double * MAX_FLUIDS), ("fluid_pi_inf", C.c_double * MAX_FLUIDS),
         ("fluid_qv", C.c_double * MAX_FLUIDS),
         ("device", C.c_int), ("fast_math", C.c_int), ("low_Mach", C.c_int), ("alt_soundspeed", C.c_int), ("muscl_order", C.c_int), ("muscl_lim", C.c_int), ("muscl_eps", C.c_double),
-        ("teno", C.c_int), ("reserved2", C.c_int), ("teno_CT", C.c_double),
+        ("teno", C.c_int), ("mp_weno", C.c_int), ("teno_CT", C.c_double),
         ("bf", C.c_int * 3), ("reserved3", C.c_int),
         ("bf_k", C.c_double * 3), ("bf_w", C.c_double * 3), ("bf_p", C.c_double * 3), ("bf_g", C.c_double * 3),
         ("int_comp", C.c_int), ("reserved4", C.c_int), ("ic_eps", C.c_double), ("ic_beta", C.c_double),
@@ -89,7 +89,7 @@ def _val(case, key, default=None):
 _UNSUPPORTED_TRUE = [
     "viscous", "surface_tension", "bubbles_euler", "bubbles_lagrange", "qbmm", "hypoelasticity",
     "hyperelasticity", "mhd", "relativity", "chemistry", "igr", "ib", "cyl_coord", "acoustic_source", "relax",
-    "mp_weno", "cont_damage", "hyper_cleaning",
+    "cont_damage", "hyper_cleaning",
 ]
 
 
@@ -138,6 +138,9 @@ def params_from_case(case, device=0, fast_math=1):
         if "teno_CT" not in case or float(case["teno_CT"]) <= 0:
             raise UnsupportedCase("teno requires teno_CT to be set. A typical value is 1e-6")
         P.teno_CT = float(case["teno_CT"])
+    P.mp_weno = _logical(case.get("mp_weno", "F"))
+    if P.mp_weno and (P.muscl_order > 0 or P.weno_order != 5):  # toolchain/mfc/case_validator.py:967
+        raise UnsupportedCase("mp_weno requires weno_order = 5")
     P.weno_eps = float(case.get("weno_eps", 1e-16))
     P.riemann_solver = int(_val(case, "riemann_solver"))
     if P.riemann_solver not in (1, 2, 5):

@@ -44,6 +44,7 @@ static inline long IDX(const orc_state* S, int i, int j, int k) {
 }
 static inline double sq(double x) { return x * x; }
 static inline double dmin(double a, double b) { return a < b ? a : b; }
+static inline double dmax(double a, double b) { return a > b ? a : b; }
 
 /* exp() for THINC, restated from the published fdlibm algorithm (Sun's e_exp.c: Cody-Waite reduction x = k ln2 + r,
  * |r| <= 0.5 ln2, exp(r) = 1 + 2r/(R(r^2) - r) with a degree-5 Remez polynomial; error < 1 ulp) instead of libm's, so that
@@ -66,7 +67,33 @@ static double orc_exp(double x) {
 #else
 #define orc_exp exp
 #endif
-static inline double dmax(double a, double b) { return a > b ? a : b; }
+
+/* Monotonicity-preserving bounds on the WENO5 edge values (mp_weno), s_preserve_monotonicity m_weno.fpp:1495-1601.
+ * mp_md(a, b): the reference's median/curvature expression on two neighbouring second differences. */
+static inline double fsgn1(double b) { return copysign(1.0, b); }
+static inline double mp_md(double a, double b) {
+    double s = fsgn1(4.0 * a - b);
+    double mn = dmin(dmin(dmin(fabs(4.0 * a - b), fabs(a)), fabs(4.0 * b - a)), fabs(b));
+    return (s + fsgn1(4.0 * b - a)) * fabs((s + fsgn1(a)) * (s + fsgn1(b))) * mn / 8.0;
+}
+static void mp_limit(double vm2, double vm1, double vp0, double vp1, double vp2, double* vL, double* vR) {
+    const double alpha_mp = 2.0, beta_mp = 4.0 / 3.0;
+    double dm = vp0 + vm2 - vm1 * 2.0, d0 = vp1 + vm1 - vp0 * 2.0, dp = vp2 + vp0 - vp1 * 2.0;
+    double d_MD = mp_md(dm, d0), d_LC = mp_md(d0, dp);
+    double UL = vp0 - (vp1 - vp0) * alpha_mp;
+    double MD = (vp0 + vm1 - d_MD) * 5.e-1;
+    double LC = vp0 - (vp1 - vp0) * 5.e-1 + beta_mp * d_LC;
+    double vmin = dmax(dmin(dmin(vp0, vm1), MD), dmin(dmin(vp0, UL), LC));
+    double vmax = dmin(dmax(dmax(vp0, vm1), MD), dmax(dmax(vp0, UL), LC));
+    *vL = *vL + (copysign(5.e-1, vmin - *vL) + copysign(5.e-1, vmax - *vL)) * dmin(fabs(vmin - *vL), fabs(vmax - *vL));
+    d_MD = mp_md(d0, dp); d_LC = mp_md(dm, d0);
+    UL = vp0 + (vp0 - vm1) * alpha_mp;
+    MD = (vp0 + vp1 - d_MD) * 5.e-1;
+    LC = vp0 + (vp0 - vm1) * 5.e-1 + beta_mp * d_LC;
+    vmin = dmax(dmin(dmin(vp0, vp1), MD), dmin(dmin(vp0, UL), LC));
+    vmax = dmin(dmax(dmax(vp0, vp1), MD), dmax(dmax(vp0, UL), LC));
+    *vR = *vR + (copysign(5.e-1, vmin - *vR) + copysign(5.e-1, vmax - *vR)) * dmin(fabs(vmin - *vR), fabs(vmax - *vR));
+}
 /* Fortran sign(a, b): |a| with the sign of b (b = +0 -> +, b = -0 -> -) */
 static inline double fsign(double a, double b) { return copysign(fabs(a), b); }
 
@@ -651,6 +678,7 @@ static void weno_dir(orc_state* S, int d) {
                             double val = omega[0] * poly[0] + omega[1] * poly[1] + omega[2] * poly[2];
                             if (sideLR == 0) *oL = val; else *oR = val;
                         }
+                        if (S->P.mp_weno) mp_limit(f[-2 * sd], f[-sd], f[0], f[sd], f[2 * sd], oL, oR); /* m_weno.fpp:1241-1243 */
                     }
                 }
                 /* interface compression (THINC), s_thinc_compression m_thinc.fpp:319-401: overwrites the reconstructed

@@ -52,6 +52,7 @@ F1D01264 14846B52 90D62933 A7C19B7B 4F79391A 77292B06 9BD657CB 30035426 01DC0251
 7BCDC8E7 10041BB7 B54BB9D8
 516A2067 A089CE54 10DE58AA
 48D5C130 E719C5F2 EDADA16E
+B3E70A3A 0ACB1F16 A3EC9BD7
 3F0FA534 D78D6B12 6FA80DE9 3EE4302C F4E54FC0 F207F0FE B46CEFF3 28D9A304 71258175
 F883F4EE 743D6D71 84A12B88 6B227FF5 D68EDC50 5EC347F2 42848784 374C9B16 347964C3
 AFE4994E 66CB22E3 7B21681C CB76A5E1 96AF00B3 9DAC4DDC F5512823 F28381D9 0288BDAD

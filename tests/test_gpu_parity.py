@@ -60,12 +60,12 @@ def test_rhs_strict_matches_oracle(uuid):
 
 # the widening of SURVEY.md 8 f-4 (reference-order kernels): one or two goldens per feature
 F4_SET = ["07C1FECC", "C462AA3E", "F9E0BE95", "7C8F1BA9", "A26B7E00", "4AADC848", "F1D01264", "01DC0251", "7BCDC8E7", "10041BB7",
-          "516A2067", "A089CE54"]
+          "516A2067", "A089CE54", "DC97B66D", "0ACB1F16", "A3EC9BD7", "EDADA16E"]
 
 
 @pytest.mark.parametrize("uuid", F4_SET)
 def test_f4_features_strict_vs_oracle(uuid):
-    """low_Mach, alt_soundspeed, Lax-Friedrichs, MUSCL, TENO5, body forces, THINC: strict build == oracle, bit for bit, after 10
+    """low_Mach, alt_soundspeed, Lax-Friedrichs, MUSCL, TENO5, body forces, THINC, mp_weno: strict build == oracle, bit for bit, after 10
     steps.  THINC (516A2067, A089CE54) needs exp(): the oracle and the strict build evaluate the same fdlibm-style sequence
     (orc_exp / thinc_exp) -- with libm's exp on one side and CUDA's on the other, last-bit differences flip THINC's thresholds and
     show up at full size in the noise-level transverse momenta of these symmetric cases."""
