@@ -76,6 +76,7 @@ struct DevP {
     double rk0, rk1, rk2, rk3, irk3, dt;
     int do_rk;
     int chunk;          // marching chunk length (<= 0: chosen per launch)
+    int x_sw;          // x kernel: warps of a block along the segments (4) or along y (1); set by sweep_grid_x
     int xseg_lo, xseg_n;  // x kernel: this launch covers segments [xseg_lo, xseg_lo + xseg_n) (xseg_n = 0: all)
     int x_march;        // x sweep with the marching kernel (lanes along y) instead of the warp-shuffle kernel
 };
@@ -588,6 +589,26 @@ __device__ __forceinline__ double k_term(const DevP& P, double pres, double alph
 // the star state on the upwind side of the contact is evaluated (the reference evaluates both and
 // multiplies one by xi_M / xi_P = 0; identical unless the discarded side is non-finite).
 // -------------------------------------------------------------------------------------------------
+// min / max by one comparison and a select (DSETP + 2 SEL).  fmin / fmax carry IEEE NaN handling that costs ~6 more
+// integer-pipe instructions each, and every non-FP64 instruction takes an issue slot from the FP64 pipe;
+// the operands here are never NaN unless the state already is.
+#ifdef MFC5_IEEE_MINMAX
+__device__ __forceinline__ double sel_min(double a, double b) { return fmin(a, b); }
+__device__ __forceinline__ double sel_max(double a, double b) { return fmax(a, b); }
+#else
+// (inline PTX: nvcc turns the C++ conditional back into the IEEE max / min expansion)
+__device__ __forceinline__ double sel_min(double a, double b) {
+    double r;
+    asm("{\n\t.reg .pred p;\n\tsetp.lt.f64 p, %1, %2;\n\tselp.f64 %0, %1, %2, p;\n\t}" : "=d"(r) : "d"(a), "d"(b));
+    return r;
+}
+__device__ __forceinline__ double sel_max(double a, double b) {
+    double r;
+    asm("{\n\t.reg .pred p;\n\tsetp.gt.f64 p, %1, %2;\n\tselp.f64 %0, %1, %2, p;\n\t}" : "=d"(r) : "d"(a), "d"(b));
+    return r;
+}
+#endif
+
 template <int NF, int ND, int DIR, int RS>
 __device__ __forceinline__ void riemann_face_fast(const DevP& P, double* qL, double* qR, double* F, double* Fs) {
     constexpr int IM = NF, IE = NF + ND, IA = NF + ND + 1;
@@ -609,15 +630,15 @@ __device__ __forceinline__ void riemann_face_fast(const DevP& P, double* qL, dou
         double sL = 0.0, sR = 0.0;
 #pragma unroll
         for (int f = 0; f < NF; f++) {
-            arho_L[f] = fmax(0.0, arho_L[f]);
-            alf_L[f] = fmin(fmax(0.0, alf_L[f]), 1.0);
+            arho_L[f] = sel_max(arho_L[f], 0.0);
+            alf_L[f] = sel_min(sel_max(alf_L[f], 0.0), 1.0);
             sL = sL + alf_L[f];
-            arho_R[f] = fmax(0.0, arho_R[f]);
-            alf_R[f] = fmin(fmax(0.0, alf_R[f]), 1.0);
+            arho_R[f] = sel_max(arho_R[f], 0.0);
+            alf_R[f] = sel_min(sel_max(alf_R[f], 0.0), 1.0);
             sR = sR + alf_R[f];
         }
         double iL, iR;
-        rcp_nr2(fmax(sL, MFC5_SGM_EPS), fmax(sR, MFC5_SGM_EPS), iL, iR);
+        rcp_nr2(sel_max(sL, MFC5_SGM_EPS), sel_max(sR, MFC5_SGM_EPS), iL, iR);
 #pragma unroll
         for (int f = 0; f < NF; f++) { alf_L[f] = alf_L[f] * iL; alf_R[f] = alf_R[f] * iR; }
         if (rs == 2) {  // HLLC limits the face states in place (hllc.fpp:938-958); HLL only local copies
@@ -649,9 +670,9 @@ __device__ __forceinline__ void riemann_face_fast(const DevP& P, double* qL, dou
     c_L = (P.mixerr && c_L < 0.0) ? 100.0 * MFC5_SGM_EPS : sqrt(c_L);
     c_R = (P.mixerr && c_R < 0.0) ? 100.0 * MFC5_SGM_EPS : sqrt(c_R);
     const double uL = qL[IM + DIR], uR = qR[IM + DIR];
-    const double s_L = fmin(uL - c_L, uR - c_R);
-    const double s_R = fmax(uR + c_R, uL + c_L);
-    const double s_M = fmin(0.0, s_L), s_P = fmax(0.0, s_R);
+    const double s_L = sel_min(uL - c_L, uR - c_R);
+    const double s_R = sel_max(uR + c_R, uL + c_L);
+    const double s_M = sel_min(s_L, 0.0), s_P = sel_max(s_R, 0.0);
     if (rs == 2) {
         const double mL = rho_L * (s_L - uL), mR = rho_R * (s_R - uR);
         // s_S = A / B.  Its sign (which selects the upwind side) is known before the division, and

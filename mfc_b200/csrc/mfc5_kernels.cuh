@@ -490,14 +490,18 @@ __global__ void __launch_bounds__(128, MFC5_X_MINB) k_sweep_x(const __grid_const
     using S = Shape<NF, ND>;
     constexpr int N = S::N;
     const int lane = threadIdx.x & 31;
-    const long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+    // 3-D grid, no integer division: blockIdx.z = k; the 4 warps of a block take 4 consecutive rows j of one segment
+    // (P.x_sw = 1; blockIdx.x = segment) or, for thin domains, 4 consecutive segments of one row (P.x_sw = 4)
+    const int w = threadIdx.x >> 5;
     const int nx = P.s[0] + 1;
     const int segs = P.xseg_n > 0 ? P.xseg_n : (nx + MFC5_XW - 1) / MFC5_XW;  // segments of this launch
+    const int sidx = (P.x_sw == 4) ? (int)blockIdx.x * 4 + w : (int)blockIdx.x;
+    const int j = (P.x_sw == 4) ? (int)blockIdx.y : (int)blockIdx.y * 4 + w;
+    const int k = blockIdx.z;
+    if (sidx >= segs || j > P.s[1]) return;  // warp-uniform
+    const int seg = P.xseg_lo + sidx;
     const long long rows = (long long)(P.s[1] + 1) * (P.s[2] + 1);
-    if (warp >= rows * segs) return;  // warp-uniform
-    const int seg = P.xseg_lo + (int)(warp % segs);
-    const long long row = warp / segs;
-    const int j = (int)(row % (P.s[1] + 1)), k = (int)(row / (P.s[1] + 1));
+    const long long row = j + (long long)(P.s[1] + 1) * k;
     const int i0 = seg * MFC5_XW;
     int i = i0 - 1 + lane;                    // my cell
     const int ic = min(i, P.s[0] + 1);        // clamp loads (cells beyond m+1 are never used)

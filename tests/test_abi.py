@@ -67,12 +67,15 @@ def test_out_of_envelope_cases_are_rejected():
     from golden_util import CASES
     base = dict(CASES["2AB32975"]["params"])
     for key, val in (("viscous", "T"), ("bubbles_euler", "T"), ("model_eqns", 3), ("riemann_solver", 4), ("weno_order", 7),
-                     ("igr", "T"), ("alt_soundspeed", "T"), ("low_Mach", 3), ("mp_weno", "T")):
+                     ("igr", "T"), ("alt_soundspeed", "T"), ("low_Mach", 3), ("cont_damage", "T")):
         with pytest.raises(UnsupportedCase):  # (alt_soundspeed: the base case has one fluid)
             params_from_case(dict(base, **{key: val}))
     two = dict(CASES["A0B82851"]["params"])
     assert params_from_case(dict(two, alt_soundspeed="T")).alt_soundspeed == 1
     assert params_from_case(dict(base, low_Mach=1)).low_Mach == 1
+    assert params_from_case(dict(base, mp_weno="T")).mp_weno == 1
+    with pytest.raises(UnsupportedCase):  # case_validator.py:967
+        params_from_case(dict(base, mp_weno="T", weno_order=3))
     with pytest.raises(UnsupportedCase):  # HLL with interface alphas + alt_soundspeed: no nc_iface_vel on this path
         params_from_case(dict(two, alt_soundspeed="T", riemann_solver=1))
     with pytest.raises(UnsupportedCase):  # low_Mach = 2 is HLLC only
