@@ -76,7 +76,6 @@ struct DevP {
     double rk0, rk1, rk2, rk3, irk3, dt;
     int do_rk;
     int chunk;          // marching chunk length (<= 0: chosen per launch)
-    int x_sw;          // x kernel: warps of a block along the segments (4) or along y (1); set by sweep_grid_x
     int xseg_lo, xseg_n;  // x kernel: this launch covers segments [xseg_lo, xseg_lo + xseg_n) (xseg_n = 0: all)
     int x_march;        // x sweep with the marching kernel (lanes along y) instead of the warp-shuffle kernel
 };

@@ -16,13 +16,13 @@ bool launch_sweep_generic_nf2(const DevP& P, int dir, cudaStream_t st);
 bool launch_sweep_generic_nf3(const DevP& P, int dir, cudaStream_t st);
 
 // x-sweep, warp-shuffle kernel: used when there are too few pencils for the marching kernel (1-D, thin 2-D)
-inline void sweep_grid_x(DevP& P, dim3& grid, dim3& block) {
-    block = dim3(128, 1, 1);
+inline void sweep_grid_x(const DevP& P, dim3& grid, dim3& block) {
     const long long segs = P.xseg_n > 0 ? P.xseg_n : (P.s[0] + 1 + MFC5_XW - 1) / MFC5_XW;
     const int ny = P.s[1] + 1, nz = P.s[2] + 1;
-    P.x_sw = (ny >= 4) ? 1 : 4;  // warps of a block: 4 rows of one segment, or 4 segments of one row (k_sweep_x)
-    if (P.x_sw == 1) grid = dim3((unsigned)segs, (unsigned)((ny + 3) / 4), (unsigned)nz);
-    else grid = dim3((unsigned)((segs + 3) / 4), (unsigned)ny, (unsigned)nz);
+    const int nw = (ny >= 4) ? 4 : 1;  // warps per block (k_sweep_x): 4 rows of one segment at a time, 1 for thin domains
+    block = dim3(32 * nw, 1, 1);
+    const int rows_per_block = MFC5_X_RPB * nw;
+    grid = dim3((unsigned)segs, (unsigned)((ny + rows_per_block - 1) / rows_per_block), (unsigned)nz);
 }
 
 inline long long march_pencils(const DevP& P, int dir) {
@@ -80,9 +80,8 @@ inline bool launch_sweep_t(const DevP& P, int dir, cudaStream_t st) {
     if (dir == 0) {
         if (march_pencils(P, 0) < 4096 || !P.x_march) {
             dim3 grid, block;
-            DevP Px = P;
-            sweep_grid_x(Px, grid, block);
-            k_sweep_x<NF, ND, WO, WV, RS, FAST><<<grid, block, 0, st>>>(Px);
+            sweep_grid_x(P, grid, block);
+            k_sweep_x<NF, ND, WO, WV, RS, FAST><<<grid, block, 0, st>>>(P);
             return true;
         }
         if constexpr (ND >= 2) return launch_march<NF, ND, 0, WO, WV, RS, FAST>(P, st);

@@ -485,115 +485,152 @@ __device__ __forceinline__ void cbc_override(const DevP& P, int face, long long 
 #ifndef MFC5_X_MINB
 #define MFC5_X_MINB 4   // 128 registers: 16 warps per SM (measured best of 3, 4, 5 blocks)
 #endif
+#ifndef MFC5_X_RPB
+#define MFC5_X_RPB 8    // rows a warp handles in turn (the next row's window is in flight while the current one is computed)
+#endif
+#ifndef MFC5_X_STAB
+#define MFC5_X_STAB 1   // 1: the segment's WENO table tile is staged in shared memory once per block
+#endif
+__device__ __forceinline__ void cp_async_wait_1() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
+
+// One segment's tile of DirTables::tabX in shared memory: element k of lane l at p[k * 32] (p = tile + l)
+struct RowTile {
+    static constexpr bool kHasMapTerms = true;
+    const double* p;
+    __device__ __forceinline__ double operator[](int k) const { return p[k * 32]; }
+};
+
+// Grid: blockIdx.x = segment, blockIdx.z = k, blockIdx.y = group of MFC5_X_RPB * (warps per block) rows j; warp w of the
+// block takes rows j0 + w, j0 + w + nw, ... (no integer division anywhere).  All warps of a block work on the same segment,
+// so its 48 x 32 table tile is read from HBM / L2 once per block and then from shared memory.  blockDim.x = 128, or 32 for
+// thin domains (sweep_grid_x).
 template <int NF, int ND, int WO, int WV, int RS, int FAST>
 __global__ void __launch_bounds__(128, MFC5_X_MINB) k_sweep_x(const __grid_constant__ DevP P) {
     using S = Shape<NF, ND>;
     constexpr int N = S::N;
-    const int lane = threadIdx.x & 31;
-    // 3-D grid, no integer division: blockIdx.z = k; the 4 warps of a block take 4 consecutive rows j of one segment
-    // (P.x_sw = 1; blockIdx.x = segment) or, for thin domains, 4 consecutive segments of one row (P.x_sw = 4)
-    const int w = threadIdx.x >> 5;
-    const int nx = P.s[0] + 1;
-    const int segs = P.xseg_n > 0 ? P.xseg_n : (nx + MFC5_XW - 1) / MFC5_XW;  // segments of this launch
-    const int sidx = (P.x_sw == 4) ? (int)blockIdx.x * 4 + w : (int)blockIdx.x;
-    const int j = (P.x_sw == 4) ? (int)blockIdx.y : (int)blockIdx.y * 4 + w;
-    const int k = blockIdx.z;
-    if (sidx >= segs || j > P.s[1]) return;  // warp-uniform
-    const int seg = P.xseg_lo + sidx;
-    const long long rows = (long long)(P.s[1] + 1) * (P.s[2] + 1);
-    const long long row = j + (long long)(P.s[1] + 1) * k;
-    const int i0 = seg * MFC5_XW;
-    int i = i0 - 1 + lane;                    // my cell
-    const int ic = min(i, P.s[0] + 1);        // clamp loads (cells beyond m+1 are never used)
-    const long long rowbase = P.base + j * P.sy + k * P.sz;
-    const long long c = rowbase + ic;
-    const DirTables& T = P.T[0];
-    const int slot = ic + P.b;
-    // stage the warp's 36-cell window of every variable in shared memory with cp.async (one batched
-    // wait instead of one exposed load latency per variable); lane l then reads cells l .. l+4
     constexpr int XT = 40;
     constexpr int NV = MFC5_WENO_NV;
-    __shared__ double sx[4][N][XT];
+    constexpr int NB = (MFC5_X_RPB > 1 && N <= 8) ? 2 : 1;  // window buffers per warp (static shared memory: 48 KB)
+    const int lane = threadIdx.x & 31;
+    const int w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const int seg = P.xseg_lo + (int)blockIdx.x;
+    const int k = blockIdx.z;
+    const long long rows = (long long)(P.s[1] + 1) * (P.s[2] + 1);
+    const int i0 = seg * MFC5_XW;
+    const int i = i0 - 1 + lane;              // my cell
+    const int ic = min(i, P.s[0] + 1);        // clamp loads (cells beyond m+1 are never used)
+    const DirTables& T = P.T[0];
+    const int slot = ic + P.b;
+    // the warp's 36-cell window of every variable is staged in shared memory with cp.async; lane l reads cells l .. l+4
+    __shared__ double sx[4][NB][N][XT];
     __shared__ double sedge[4][2][N][32];  // per lane: right edge of my cell, left edge of cell +1 (spill space of the rolled loop)
-    double(*my)[XT] = sx[(threadIdx.x >> 5) & 3];
-    double(*myR)[32] = sedge[(threadIdx.x >> 5) & 3][0];
-    double(*myQ)[32] = sedge[(threadIdx.x >> 5) & 3][1];
-    {
-        const int hi = P.s[0] + P.b;
-        const int ca = min(i0 - 3 + lane, hi), cb = min(i0 - 3 + 32 + lane, hi);
+    __shared__ double stab[(FAST && MFC5_X_STAB) ? MFC5_TAB * 32 : 32];
+    double(*myR)[32] = sedge[w][0];
+    double(*myQ)[32] = sedge[w][1];
+    const int hi = P.s[0] + P.b;
+    const int ca = min(i0 - 3 + lane, hi), cb = min(i0 - 3 + 32 + lane, hi);
+    auto load_window = [&](int buf, int jj) {
+        const long long rb = P.base + jj * P.sy + k * P.sz;
 #pragma unroll
         for (int v = 0; v < N; v++) {
-            cp_async8(&my[v][lane], P.prim + v * P.fs + rowbase + ca);
-            if (lane < 4) cp_async8(&my[v][32 + lane], P.prim + v * P.fs + rowbase + cb);
+            cp_async8(&sx[w][buf][v][lane], P.prim + v * P.fs + rb + ca);
+            if (lane < 4) cp_async8(&sx[w][buf][v][32 + lane], P.prim + v * P.fs + rb + cb);
         }
         cp_async_commit();
-        cp_async_wait_all();
-        __syncwarp();
+    };
+    int j = (int)blockIdx.y * (MFC5_X_RPB * nw) + w;
+    if (j <= P.s[1]) load_window(0, j);  // warp-uniform
+    if (FAST && MFC5_X_STAB) {           // every thread of the block takes part before any leaves
+        const double* src = T.tabX + (long long)seg * (MFC5_TAB * 32);
+        for (int q = threadIdx.x; q < MFC5_TAB * 32; q += blockDim.x) stab[q] = __ldg(src + q);
+        __syncthreads();
     }
-    // WENO of NV variables per iteration of a ROLLED loop (code size: the instruction cache, not the
-    // register file, is what the fully unrolled version ran out of); the left edge of cell i+1 arrives by
-    // warp shuffle; edge states wait in shared memory for the Riemann solve
+#if MFC5_X_STAB
+    const RowTile xrow{stab + lane};
+#else
     const RowSeg xrow{T.tabX + (long long)seg * (MFC5_TAB * 32) + lane};
+#endif
+    const double ds_i = __ldg(T.ds + ic + P.b);
 #pragma unroll 1
-    for (int v0 = 0; v0 < N; v0 += NV) {
-        double f[NV][5], l[NV], r[NV];
-        int vv[NV];
-#pragma unroll
-        for (int u = 0; u < NV; u++) {
-            vv[u] = min(v0 + u, N - 1);
-#pragma unroll
-            for (int k = 0; k < 5; k++) f[u][k] = my[vv[u]][lane + k];
+    for (int it = 0; it < MFC5_X_RPB; it++, j += nw) {
+        if (j > P.s[1]) break;  // warp-uniform; no block-wide synchronisation below
+        const int buf = it & (NB - 1);
+        if (NB > 1 && it + 1 < MFC5_X_RPB && j + nw <= P.s[1]) {
+            load_window(buf ^ 1, j + nw);  // the next row's window travels while this one is computed
+            cp_async_wait_1();
+        } else {
+            if (NB == 1 && it > 0) load_window(0, j);
+            cp_async_wait_all();
         }
-        weno_edges_nv<WO, WV, FAST, NV>(P, T, slot, xrow, f, l, r);
-#pragma unroll
-        for (int u = 0; u < NV; u++) {
-            myR[vv[u]][lane] = r[u];
-            myQ[vv[u]][lane] = __shfl_down_sync(0xffffffffu, l[u], 1);
-        }
-    }
-    if (!FAST && WO < 0 && NF >= 2 && P.int_comp == 1) {  // THINC on my cell: my right edge, and my left edge = lane-1's qR
-        double tl[4], tr[4];
-        const bool on = thinc_cell(P, my[S::IA][lane + 1], my[S::IA][lane + 2], my[S::IA][lane + 3], my[0][lane + 2], my[NF - 1][lane + 2], tl, tr);
         __syncwarp();
-        if (on) {
-            const int vi[4] = {0, NF - 1, S::IA, S::IA + NF - 1};
+        double(*my)[XT] = sx[w][buf];
+        const long long row = j + (long long)(P.s[1] + 1) * k;
+        const long long rowbase = P.base + j * P.sy + k * P.sz;
+        // WENO of NV variables per iteration of a ROLLED loop (code size: the instruction cache, not the
+        // register file, is what the fully unrolled version ran out of); the left edge of cell i+1 arrives by
+        // warp shuffle; edge states wait in shared memory for the Riemann solve
+#pragma unroll 1
+        for (int v0 = 0; v0 < N; v0 += NV) {
+            double f[NV][5], l[NV], r[NV];
+            int vv[NV];
 #pragma unroll
-            for (int q = 0; q < 4; q++) {
-                myR[vi[q]][lane] = tr[q];
-                if (lane > 0) myQ[vi[q]][lane - 1] = tl[q];
+            for (int u = 0; u < NV; u++) {
+                vv[u] = min(v0 + u, N - 1);
+#pragma unroll
+                for (int q = 0; q < 5; q++) f[u][q] = my[vv[u]][lane + q];
+            }
+            weno_edges_nv<WO, WV, FAST, NV>(P, T, slot, xrow, f, l, r);
+#pragma unroll
+            for (int u = 0; u < NV; u++) {
+                myR[vv[u]][lane] = r[u];
+                myQ[vv[u]][lane] = __shfl_down_sync(0xffffffffu, l[u], 1);
             }
         }
-        __syncwarp();
-    }
-    double eR[N], qR[N];
+        if (!FAST && WO < 0 && NF >= 2 && P.int_comp == 1) {  // THINC on my cell: my right edge, and my left edge = lane-1's qR
+            double tl[4], tr[4];
+            const bool on = thinc_cell(P, my[S::IA][lane + 1], my[S::IA][lane + 2], my[S::IA][lane + 3], my[0][lane + 2], my[NF - 1][lane + 2], tl, tr);
+            __syncwarp();
+            if (on) {
+                const int vi[4] = {0, NF - 1, S::IA, S::IA + NF - 1};
 #pragma unroll
-    for (int v = 0; v < N; v++) { eR[v] = myR[v][lane]; qR[v] = myQ[v][lane]; }
-    // BC -4 (Riemann extrapolation), m_riemann_state.fpp:149-206
-    if (P.bc[0][0] == MFC5_BC_RIEMANN_EXTRAP && i == -1) {
+                for (int q = 0; q < 4; q++) {
+                    myR[vi[q]][lane] = tr[q];
+                    if (lane > 0) myQ[vi[q]][lane - 1] = tl[q];
+                }
+            }
+            __syncwarp();
+        }
+        double eR[N], qR[N];
 #pragma unroll
-        for (int v = 0; v < N; v++) eR[v] = qR[v];
-    }
-    if (P.bc[0][1] == MFC5_BC_RIEMANN_EXTRAP && i == P.s[0]) {
+        for (int v = 0; v < N; v++) { eR[v] = myR[v][lane]; qR[v] = myQ[v][lane]; }
+        // BC -4 (Riemann extrapolation), m_riemann_state.fpp:149-206
+        if (P.bc[0][0] == MFC5_BC_RIEMANN_EXTRAP && i == -1) {
 #pragma unroll
-        for (int v = 0; v < N; v++) qR[v] = eR[v];
-    }
-    double F[N], Fs[NF];
+            for (int v = 0; v < N; v++) eR[v] = qR[v];
+        }
+        if (P.bc[0][1] == MFC5_BC_RIEMANN_EXTRAP && i == P.s[0]) {
 #pragma unroll
-    for (int f = 0; f < NF; f++) Fs[f] = 0.0;
+            for (int v = 0; v < N; v++) qR[v] = eR[v];
+        }
+        double F[N], Fs[NF];
+#pragma unroll
+        for (int f = 0; f < NF; f++) Fs[f] = 0.0;
 #ifdef MFC5_DEBUG_SPLIT   // accuracy bisection builds: 1 = reference-order Riemann solve with the fast WENO
-    if (FAST && MFC5_DEBUG_SPLIT != 1) riemann_face_fast<NF, ND, 0, RS>(P, eR, qR, F, Fs);
+        if (FAST && MFC5_DEBUG_SPLIT != 1) riemann_face_fast<NF, ND, 0, RS>(P, eR, qR, F, Fs);
 #else
-    if (FAST) riemann_face_fast<NF, ND, 0, RS>(P, eR, qR, F, Fs);
+        if (FAST) riemann_face_fast<NF, ND, 0, RS>(P, eR, qR, F, Fs);
 #endif
-    else riemann_face<NF, ND, 0, RS>(P, eR, qR, F, Fs);
-    if (P.cbc_on[0][0] | P.cbc_on[0][1]) cbc_override<NF, ND, 0>(P, i, row, rows, F, Fs);
-    double Fp[N], Fsp[NF];
+        else riemann_face<NF, ND, 0, RS>(P, eR, qR, F, Fs);
+        if (P.cbc_on[0][0] | P.cbc_on[0][1]) cbc_override<NF, ND, 0>(P, i, row, rows, F, Fs);
+        double Fp[N], Fsp[NF];
 #pragma unroll
-    for (int v = 0; v < N; v++) Fp[v] = __shfl_up_sync(0xffffffffu, F[v], 1);
+        for (int v = 0; v < N; v++) Fp[v] = __shfl_up_sync(0xffffffffu, F[v], 1);
 #pragma unroll
-    for (int f = 0; f < NF; f++) Fsp[f] = __shfl_up_sync(0xffffffffu, Fs[f], 1);
-    if (lane >= 1 && lane <= MFC5_XW && i <= P.s[0]) {
-        finish_cell<NF, ND, 0, FAST>(P, rowbase + i, __ldg(T.ds + i + P.b), FAST ? xrow[46] : 0.0, Fp, Fsp, F, Fs);
+        for (int f = 0; f < NF; f++) Fsp[f] = __shfl_up_sync(0xffffffffu, Fs[f], 1);
+        if (lane >= 1 && lane <= MFC5_XW && i <= P.s[0]) {
+            finish_cell<NF, ND, 0, FAST>(P, rowbase + i, ds_i, FAST ? xrow[46] : 0.0, Fp, Fsp, F, Fs);
+        }
+        __syncwarp();  // the window buffer and the edge arrays are rewritten by the next rows
     }
 }
 
