@@ -486,7 +486,7 @@ __device__ __forceinline__ void cbc_override(const DevP& P, int face, long long 
 #define MFC5_X_MINB 4   // 128 registers: 16 warps per SM (measured best of 3, 4, 5 blocks)
 #endif
 #ifndef MFC5_X_RPB
-#define MFC5_X_RPB 8    // rows a warp handles in turn (the next row's window is in flight while the current one is computed)
+#define MFC5_X_RPB 4    // rows a warp handles in turn; measured 4: 0.818, 8: 0.823, 16: 0.838, 32: 0.887 ms (the next row's window is in flight while the current one is computed)
 #endif
 #ifndef MFC5_X_STAB
 #define MFC5_X_STAB 1   // 1: the segment's WENO table tile is staged in shared memory once per block
@@ -650,6 +650,9 @@ __global__ void __launch_bounds__(128, MFC5_X_MINB) k_sweep_x(const __grid_const
 // cc-1, finishes cell cc-1 with the carried flux of face cc-2 (flux difference, alpha source, fused RK).
 // The WENO tables are indexed by the marching position, i.e. uniform over the block.
 // -------------------------------------------------------------------------------------------------
+#ifndef MFC5_PF_MASK
+#define MFC5_PF_MASK 7   // L2 prefetches of the marching kernel: 1 = next primitive plane, 2 = rhs, 4 = q1 / q2 of the cell to finish
+#endif
 #ifndef MFC5_MARCH_THREADS
 #define MFC5_MARCH_THREADS 192
 #endif
@@ -727,18 +730,18 @@ __global__ void __launch_bounds__(MFC5_MARCH_THREADS, (2 * NF + ND + 1 <= 8) ? M
     constexpr int NV = MFC5_WENO_NV;
     for (int cc = c0 - 1; cc <= c1 + 1; cc++) {
         cp_async_wait_all();  // the window of cell cc is complete
-        if (cc < c1) {        // the plane requested after the NEXT reconstruction: pull it into L2 now
+        if ((MFC5_PF_MASK & 1) && cc < c1) {        // the plane requested after the NEXT reconstruction: pull it into L2 now
             const int pl = min(max(cc + 2 + PN, lo), hi);
 #pragma unroll
             for (int v = 0; v < N; v++) prefetch_l2(P.prim + v * P.fs + colbase + pl * sd);
         }
         if (cc >= c0 + 1) {   // inputs of the finishing step of cell cc-1: pull them into L2 now
             const long long c = colbase + (long long)(cc - 1) * sd;
-            if (DIR != 0) {
+            if ((MFC5_PF_MASK & 2) && DIR != 0) {
 #pragma unroll
                 for (int v = 0; v < N; v++) prefetch_l2(P.rhs + v * P.fs + c);
             }
-            if ((DIR == ND - 1) && P.do_rk) {
+            if ((MFC5_PF_MASK & 4) && (DIR == ND - 1) && P.do_rk) {
 #pragma unroll
                 for (int v = 0; v < N; v++) prefetch_l2(P.q1 + v * P.fs + c);
                 if (P.rk1 != 0.0) {  // stage 1 has rk1 = 0: q2 is not read at all
