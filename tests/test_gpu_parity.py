@@ -201,6 +201,114 @@ def test_100_rk3_steps_within_1e10(name):
     g.close()
 
 
+# ---- BASELINE.json's full size (examples/3D_performance_test, 201^3 cells): one step against the oracle, and the
+# ---- size-independent properties of the scheme ----------------------------------------------------------------------
+def _full_size_c5(fast, strict, **over):
+    from mfc_b200 import cases, pre_process
+    from mfc_b200.lib import Mfc5
+    from mfc_b200.params import params_from_case
+    case = dict(cases.perf_test_3d(m=200, steps=1), **over)
+    P = params_from_case(case, fast_math=fast)
+    cbs, ccs = pre_process.generate_grid(case)
+    _, cons = pre_process.initial_condition(case, ccs)
+    g = Mfc5(P, cbs, strict=strict)
+    return case, P, cbs, cons, g
+
+
+@pytest.mark.parametrize("mode", ["strict", "fast"])
+def test_full_size_c5_one_step_vs_oracle(mode):
+    """The bench workload itself (201^3 cells, stretched grid, WENO5-M + HLLC + mpp_lim, BC -2/-6): one RK3 step through the C
+    ABI against the oracle on the same input.  Strict build: bit for bit; product build (case-optimised kernels, CUDA
+    graph): the reference's golden rule at 1e-12 (abs or rel), and 1e-13 of max|q| per variable."""
+    from oracle_lib import Oracle
+    case, P, cbs, cons, g = _full_size_c5(fast=0 if mode == "strict" else 1, strict=(mode == "strict"))
+    o = Oracle(P, cbs, omp=True)
+    g.set_cons(cons)
+    o.set_cons(cons)
+    dt = float(case["dt"])
+    g.step(dt)
+    o.step(dt)
+    a, b = g.get_cons(), o.get_cons()
+    g.close()
+    assert not np.array_equal(b, cons)
+    if mode == "strict":
+        np.testing.assert_array_equal(a, b)
+    else:
+        for v in range(a.shape[0]):
+            ok, mabs, worst = compare(a[v], b[v], 1e-12)
+            assert ok, f"var {v + 1}: worst min(abs, rel) err {worst:.3e}"
+            assert np.max(np.abs(a[v] - b[v])) <= 1e-13 * np.max(np.abs(b[v])) + 1e-300
+
+
+@pytest.mark.parametrize("ends", ["extrapolation", "case"])
+def test_full_size_uniform_state_is_preserved(ends):
+    """Free-stream preservation at full size: a uniform two-fluid state at rest on the stretched 201^3 grid has equal fluxes
+    on every face, so three RK3 steps leave it unchanged (product build; its WENO adds weighted increments to the cell
+    value, which is exact for constant data).  With ghost-cell boundaries (-2 reflective, -3 extrapolation) the momenta stay
+    exactly zero and the rest moves by at most the rounding of the RK combination (one ulp per step); with
+    the case's own characteristic boundaries (-6) the boundary flux is an interpolation of cell-centre fluxes, which may
+    round the pressure by an ulp: momenta stay below 1e-12, everything else is unchanged to 1e-14 relative."""
+    over = {f"bc_{d}%end": -3 for d in "xyz"} if ends == "extrapolation" else {}
+    case, P, cbs, cons, g = _full_size_c5(fast=1, strict=False, **over)
+    q = np.empty_like(cons)
+    for v in range(cons.shape[0]):
+        q[v] = cons[v, -1, -1, -1]           # the far-field corner state everywhere
+    nf = P.num_fluids
+    q[nf:nf + 3] = 0.0                       # at rest
+    g.set_cons(q)
+    g.steps(float(case["dt"]), 3)
+    g.sync()
+    a = g.get_cons()
+    g.close()
+    if ends == "extrapolation":
+        # no spurious motion at all: the momenta stay exactly zero; the other variables only see the rounding of the RK
+        # combination itself ((2 q + q) / 3 is one ulp off q for q = 0.1 -- in the reference's arithmetic as well)
+        assert not a[nf:nf + 3].any()
+        assert np.all(np.abs(a - q) <= 3 * np.spacing(np.abs(q)))
+    else:
+        assert np.max(np.abs(a[nf:nf + 3])) <= 1e-12
+        for v in list(range(nf)) + list(range(nf + 3, a.shape[0])):
+            assert np.max(np.abs(a[v] - q[v])) <= 1e-14 * np.max(np.abs(q[v]))
+
+
+def test_full_size_periodic_conservation():
+    """Conservation at full size: with periodic boundaries on a uniform 201^3 grid the flux differences telescope, so the sums
+    of the partial densities, momenta and energy over the domain change only by rounding (the volume fractions obey a
+    non-conservative equation and are not checked).  Smooth two-fluid field, 3 RK3 steps, product build."""
+    over = {"stretch_x": "F", "stretch_y": "F", "stretch_z": "F"}
+    for d in "xyz":
+        over[f"bc_{d}%beg"] = -1
+        over[f"bc_{d}%end"] = -1
+    case, P, cbs, cons, g = _full_size_c5(fast=1, strict=False, **over)
+    nz, ny, nx = cons.shape[1:]
+    z, y, x = np.meshgrid(np.arange(nz) / nz, np.arange(ny) / ny, np.arange(nx) / nx, indexing="ij")
+    two_pi = 2.0 * np.pi
+    a1 = 0.5 + 0.3 * np.sin(two_pi * x) * np.cos(two_pi * y) * np.cos(two_pi * z)
+    rho1, rho2 = 1000.0, 1.0
+    u = [5.0 * np.sin(two_pi * (x + y)), 3.0 * np.cos(two_pi * (y - z)), 2.0 * np.sin(two_pi * (z + x))]
+    pres = 1.0e5 * (1.0 + 0.1 * np.cos(two_pi * (x + y + z)))
+    nf = P.num_fluids
+    q = np.empty_like(cons)
+    q[0], q[1] = a1 * rho1, (1.0 - a1) * rho2
+    rho = q[0] + q[1]
+    for d in range(3):
+        q[nf + d] = rho * u[d]
+    gam = a1 * P.fluid_gamma[0] + (1.0 - a1) * P.fluid_gamma[1]
+    pinf = a1 * P.fluid_pi_inf[0] + (1.0 - a1) * P.fluid_pi_inf[1]
+    q[nf + 3] = gam * pres + pinf + 0.5 * rho * (u[0] ** 2 + u[1] ** 2 + u[2] ** 2)
+    q[nf + 4], q[nf + 5] = a1, 1.0 - a1
+    g.set_cons(q)
+    g.steps(float(case["dt"]), 3)
+    g.sync()
+    a = g.get_cons()
+    g.close()
+    assert not np.isnan(a).any() and not np.array_equal(a, q)
+    for v in range(nf + 4):
+        s0, s1 = np.sum(q[v], dtype=np.longdouble), np.sum(a[v], dtype=np.longdouble)
+        scale = np.sum(np.abs(q[v]), dtype=np.longdouble) + 1e-300
+        assert abs(s1 - s0) <= 1e-13 * scale, f"var {v + 1}: sum drifted by {float(abs(s1 - s0) / scale):.3e}"
+
+
 @pytest.mark.parametrize("uuid", ["2AB32975", "4129A23A", "A0B82851"])
 def test_opt_in_fused_cons2prim_is_bitwise(uuid, monkeypatch):
     """MFC5_FUSE_C2P=1 (the RK-fused last sweep also writes the primitives of the new state; second primitive buffer,
