@@ -13,6 +13,10 @@
 
 namespace mfc5 {
 
+// index type of the sweep kernels' field accesses (see k_sweep_march)
+template <bool NARROW> struct SweepIdx { using type = long long; };
+template <> struct SweepIdx<true> { using type = unsigned; };
+
 template <int NF, int ND>
 struct Shape {
     static constexpr int N = 2 * NF + ND + 1;
@@ -404,31 +408,32 @@ __device__ __forceinline__ void store_next_prim(const DevP& P, long long c, cons
     for (int v = 0; v < Shape<NF, ND>::N; v++) P.prim_next[v * P.fs + c] = pr[v];
 }
 
-template <int NF, int ND, int DIR, int FAST>
-__device__ __forceinline__ void finish_cell(const DevP& P, long long c, double ds, double inv_ds_tab, const double* Fp, const double* Fsp,
+template <int NF, int ND, int DIR, int FAST, class ix = long long>
+__device__ __forceinline__ void finish_cell(const DevP& P, ix c, double ds, double inv_ds_tab, const double* Fp, const double* Fsp,
                                             const double* Fc, const double* Fsc) {
     const double inv_ds = FAST ? inv_ds_tab : 1.0 / ds;  // FAST: 1/ds from the table (host division, correctly rounded like the reference's)
     using S = Shape<NF, ND>;
+    const ix fs = (ix)P.fs;
     const bool alpha_iface = (P.rs == 1 && !P.hll_u);
     double r[S::N];
 #pragma unroll
     for (int v = 0; v < S::N; v++) {
         if (DIR == 0) r[v] = inv_ds * (Fp[v] - Fc[v]);
-        else r[v] = P.rhs[v * P.fs + c] + inv_ds * (Fp[v] - Fc[v]);
+        else r[v] = P.rhs[(ix)((ix)v * fs + c)] + inv_ds * (Fp[v] - Fc[v]);
     }
     if (alpha_iface) {
-        const double coeff = __ldg(P.prim + (S::IM + DIR) * P.fs + c);
+        const double coeff = __ldg(P.prim + (ix)((ix)(S::IM + DIR) * fs + c));
 #pragma unroll
         for (int f = 0; f < NF; f++) r[S::IA + f] = r[S::IA + f] + inv_ds * coeff * (Fsp[f] - Fsc[f]);
     } else {
 #pragma unroll
         for (int f = 0; f < NF; f++) {
-            const double coeff = __ldg(P.prim + (S::IA + f) * P.fs + c);  // q_cons(adv) == q_prim(adv)
+            const double coeff = __ldg(P.prim + (ix)((ix)(S::IA + f) * fs + c));  // q_cons(adv) == q_prim(adv)
             r[S::IA + f] = r[S::IA + f] + inv_ds * coeff * (Fsc[0] - Fsp[0]);
         }
     }
     if (!FAST && P.alt_ss) {  // K div(u) correction, u-interface form (m_rhs.fpp:1489-1503)
-        const double K = k_term(P, __ldg(P.prim + S::IE * P.fs + c), __ldg(P.prim + S::IA * P.fs + c), __ldg(P.prim + (S::IA + NF - 1) * P.fs + c));
+        const double K = k_term(P, __ldg(P.prim + (ix)((ix)S::IE * fs + c)), __ldg(P.prim + (ix)((ix)S::IA * fs + c)), __ldg(P.prim + (ix)((ix)(S::IA + NF - 1) * fs + c)));
         r[S::IA] = r[S::IA] + K * inv_ds * (Fsc[0] - Fsp[0]);
         r[S::IA + NF - 1] = r[S::IA + NF - 1] - K * inv_ds * (Fsc[0] - Fsp[0]);
     }
@@ -436,18 +441,18 @@ __device__ __forceinline__ void finish_cell(const DevP& P, long long c, double d
         double qn[S::N];
 #pragma unroll
         for (int v = 0; v < S::N; v++) {
-            const double q1 = P.q1[v * P.fs + c];
-            const double q2 = (P.rk1 != 0.0) ? P.q2[v * P.fs + c] : 0.0;  // rk1 = 0 in stage 1: 0 * q2 adds nothing
+            const double q1 = P.q1[(ix)((ix)v * fs + c)];
+            const double q2 = (P.rk1 != 0.0) ? P.q2[(ix)((ix)v * fs + c)] : 0.0;  // rk1 = 0 in stage 1: 0 * q2 adds nothing
             if (FAST) qn[v] = div_by_const(P.rk0 * q1 + P.rk1 * q2 + P.rk2 * P.dt * r[v], P.rk3, P.irk3);
             else qn[v] = (P.rk0 * q1 + P.rk1 * q2 + P.rk2 * P.dt * r[v]) / P.rk3;
         }
         if (P.bf_on) apply_body_forces<NF, ND>(P, qn);
 #pragma unroll
-        for (int v = 0; v < S::N; v++) P.qout[v * P.fs + c] = qn[v];
-        store_next_prim<NF, ND, FAST>(P, c, qn);
+        for (int v = 0; v < S::N; v++) P.qout[(ix)((ix)v * fs + c)] = qn[v];
+        store_next_prim<NF, ND, FAST>(P, (long long)c, qn);
     } else {
 #pragma unroll
-        for (int v = 0; v < S::N; v++) P.rhs[v * P.fs + c] = r[v];
+        for (int v = 0; v < S::N; v++) P.rhs[(ix)((ix)v * fs + c)] = r[v];
     }
 }
 
@@ -529,12 +534,14 @@ __global__ void __launch_bounds__(128, MFC5_X_MINB) k_sweep_x(const __grid_const
     double(*myQ)[32] = sedge[w][1];
     const int hi = P.s[0] + P.b;
     const int ca = min(i0 - 3 + lane, hi), cb = min(i0 - 3 + 32 + lane, hi);
+    using ix = typename SweepIdx<(WO >= 0)>::type;  // 32-bit element indices in the case-optimised kernels (k_sweep_march)
+    const ix fs = (ix)P.fs;
     auto load_window = [&](int buf, int jj) {
-        const long long rb = P.base + jj * P.sy + k * P.sz;
+        const ix rb = (ix)P.base + (ix)jj * (ix)P.sy + (ix)k * (ix)P.sz;
 #pragma unroll
         for (int v = 0; v < N; v++) {
-            cp_async8(&sx[w][buf][v][lane], P.prim + v * P.fs + rb + ca);
-            if (lane < 4) cp_async8(&sx[w][buf][v][32 + lane], P.prim + v * P.fs + rb + cb);
+            cp_async8(&sx[w][buf][v][lane], P.prim + (ix)((ix)v * fs + rb + (ix)ca));
+            if (lane < 4) cp_async8(&sx[w][buf][v][32 + lane], P.prim + (ix)((ix)v * fs + rb + (ix)cb));
         }
         cp_async_commit();
     };
@@ -565,7 +572,7 @@ __global__ void __launch_bounds__(128, MFC5_X_MINB) k_sweep_x(const __grid_const
         __syncwarp();
         double(*my)[XT] = sx[w][buf];
         const long long row = j + (long long)(P.s[1] + 1) * k;
-        const long long rowbase = P.base + j * P.sy + k * P.sz;
+        const ix rowbase = (ix)P.base + (ix)j * (ix)P.sy + (ix)k * (ix)P.sz;
         // WENO of NV variables per iteration of a ROLLED loop (code size: the instruction cache, not the
         // register file, is what the fully unrolled version ran out of); the left edge of cell i+1 arrives by
         // warp shuffle; edge states wait in shared memory for the Riemann solve
@@ -628,7 +635,7 @@ __global__ void __launch_bounds__(128, MFC5_X_MINB) k_sweep_x(const __grid_const
 #pragma unroll
         for (int f = 0; f < NF; f++) Fsp[f] = __shfl_up_sync(0xffffffffu, Fs[f], 1);
         if (lane >= 1 && lane <= MFC5_XW && i <= P.s[0]) {
-            finish_cell<NF, ND, 0, FAST>(P, rowbase + i, ds_i, FAST ? xrow[46] : 0.0, Fp, Fsp, F, Fs);
+            finish_cell<NF, ND, 0, FAST, ix>(P, rowbase + (ix)i, ds_i, FAST ? xrow[46] : 0.0, Fp, Fsp, F, Fs);
         }
         __syncwarp();  // the window buffer and the edge arrays are rewritten by the next rows
     }
@@ -701,10 +708,15 @@ __global__ void __launch_bounds__(MFC5_MARCH_THREADS, (2 * NF + ND + 1 <= 8) ? M
     const long long t = blockIdx.x * (long long)NT + tid;
     if (t >= plane) return;
     const int a = (int)(t % n_a), bb = (int)(t / n_a);
-    const long long sa = (DIR == 0) ? P.sy : 1;
-    const long long sb = (DIR == 2) ? P.sy : P.sz;
-    const long long sd = (DIR == 0) ? 1 : (DIR == 1 ? P.sy : P.sz);
-    const long long colbase = P.base + a * sa + bb * sb;
+    // element indices into the field arrays: 32-bit (one IMAD.WIDE per access, the per-variable index shared by all arrays)
+    // in the case-optimised kernels, whose launcher checks that N * field size fits; 64-bit in the generic ones.  Plane
+    // numbers below zero wrap around in unsigned arithmetic and come out right because the final index is non-negative.
+    using ix = typename SweepIdx<(WO >= 0)>::type;
+    const ix fs = (ix)P.fs;
+    const ix sa = (DIR == 0) ? (ix)P.sy : (ix)1;
+    const ix sb = (DIR == 2) ? (ix)P.sy : (ix)P.sz;
+    const ix sd = (DIR == 0) ? (ix)1 : (DIR == 1 ? (ix)P.sy : (ix)P.sz);
+    const ix colbase = (ix)P.base + (ix)a * sa + (ix)bb * sb;
     const int s = P.s[DIR];
     const int c0 = blockIdx.y * P.chunk;
     const int c1 = min(c0 + P.chunk - 1, s);
@@ -716,7 +728,7 @@ __global__ void __launch_bounds__(MFC5_MARCH_THREADS, (2 * NF + ND + 1 <= 8) ? M
     for (int k = 0; k < R; k++) {
         const int pl = min(max(c0 - 1 - PN + k, lo), hi);
 #pragma unroll
-        for (int v = 0; v < N; v++) cp_async8(ring + (k * N + v) * NT + tid, P.prim + v * P.fs + colbase + pl * sd);
+        for (int v = 0; v < N; v++) cp_async8(ring + (k * N + v) * NT + tid, P.prim + (ix)((ix)v * fs + colbase + (ix)pl * sd));
     }
     cp_async_commit();
     int tail = 0;  // slot of the oldest plane of the window (cc - PN)
@@ -733,20 +745,20 @@ __global__ void __launch_bounds__(MFC5_MARCH_THREADS, (2 * NF + ND + 1 <= 8) ? M
         if ((MFC5_PF_MASK & 1) && cc < c1) {        // the plane requested after the NEXT reconstruction: pull it into L2 now
             const int pl = min(max(cc + 2 + PN, lo), hi);
 #pragma unroll
-            for (int v = 0; v < N; v++) prefetch_l2(P.prim + v * P.fs + colbase + pl * sd);
+            for (int v = 0; v < N; v++) prefetch_l2(P.prim + (ix)((ix)v * fs + colbase + (ix)pl * sd));
         }
         if (cc >= c0 + 1) {   // inputs of the finishing step of cell cc-1: pull them into L2 now
-            const long long c = colbase + (long long)(cc - 1) * sd;
+            const ix c = colbase + (ix)(cc - 1) * sd;
             if ((MFC5_PF_MASK & 2) && DIR != 0) {
 #pragma unroll
-                for (int v = 0; v < N; v++) prefetch_l2(P.rhs + v * P.fs + c);
+                for (int v = 0; v < N; v++) prefetch_l2(P.rhs + (ix)((ix)v * fs + c));
             }
             if ((MFC5_PF_MASK & 4) && (DIR == ND - 1) && P.do_rk) {
 #pragma unroll
-                for (int v = 0; v < N; v++) prefetch_l2(P.q1 + v * P.fs + c);
+                for (int v = 0; v < N; v++) prefetch_l2(P.q1 + (ix)((ix)v * fs + c));
                 if (P.rk1 != 0.0) {  // stage 1 has rk1 = 0: q2 is not read at all
 #pragma unroll
-                    for (int v = 0; v < N; v++) prefetch_l2(P.q2 + v * P.fs + c);
+                    for (int v = 0; v < N; v++) prefetch_l2(P.q2 + (ix)((ix)v * fs + c));
                 }
             }
         }
@@ -794,12 +806,12 @@ __global__ void __launch_bounds__(MFC5_MARCH_THREADS, (2 * NF + ND + 1 <= 8) ? M
         if (cc <= c1) {       // plane cc+1+PN enters the window in the slot of plane cc-PN; lands during the Riemann solve
             const int pl = min(max(cc + 1 + PN, lo), hi);
 #pragma unroll
-            for (int v = 0; v < N; v++) cp_async8(ring + (tail * N + v) * NT + tid, P.prim + v * P.fs + colbase + pl * sd);
+            for (int v = 0; v < N; v++) cp_async8(ring + (tail * N + v) * NT + tid, P.prim + (ix)((ix)v * fs + colbase + (ix)pl * sd));
             cp_async_commit();
         }
         if (cc >= c0) {
             const int face = cc - 1;
-            const long long c = colbase + (long long)(cc - 1) * sd;  // the cell finished in this iteration
+            const ix c = colbase + (ix)(cc - 1) * sd;  // the cell finished in this iteration
             const bool fin = cc >= c0 + 1;
             // inputs of the finishing step, requested before the Riemann solve so that their latency is covered
             double rin[N], q1in[N], q2in[N], acoef[NF];
@@ -807,12 +819,20 @@ __global__ void __launch_bounds__(MFC5_MARCH_THREADS, (2 * NF + ND + 1 <= 8) ? M
             const bool alpha_iface = (P.rs == 1 && !P.hll_u);
             if (fin) {
 #pragma unroll
-                for (int v = 0; v < N; v++) {
-                    rin[v] = (DIR == 0) ? 0.0 : P.rhs[v * P.fs + c];
-                    if (rk) { q1in[v] = __ldg(P.q1 + v * P.fs + c); q2in[v] = (P.rk1 != 0.0) ? __ldg(P.q2 + v * P.fs + c) : 0.0; }
+                for (int v = 0; v < N; v++) rin[v] = (DIR == 0) ? 0.0 : P.rhs[(ix)((ix)v * fs + c)];
+                if (rk) {   // kernel-uniform branches, outside the variable loop
+#pragma unroll
+                    for (int v = 0; v < N; v++) q1in[v] = __ldg(P.q1 + (ix)((ix)v * fs + c));
+                    if (P.rk1 != 0.0) {
+#pragma unroll
+                        for (int v = 0; v < N; v++) q2in[v] = __ldg(P.q2 + (ix)((ix)v * fs + c));
+                    } else {
+#pragma unroll
+                        for (int v = 0; v < N; v++) q2in[v] = 0.0;
+                    }
                 }
 #pragma unroll
-                for (int f = 0; f < NF; f++) acoef[f] = __ldg(P.prim + (alpha_iface ? (S::IM + DIR) : (S::IA + f)) * P.fs + c);
+                for (int f = 0; f < NF; f++) acoef[f] = __ldg(P.prim + (ix)((ix)(alpha_iface ? (S::IM + DIR) : (S::IA + f)) * fs + c));
             }
             double qL[N], eL[N], F[N], Fs[NF];
 #pragma unroll
@@ -848,7 +868,7 @@ __global__ void __launch_bounds__(MFC5_MARCH_THREADS, (2 * NF + ND + 1 <= 8) ? M
                     else r[S::IA + f] = r[S::IA + f] + inv_ds * acoef[f] * (Fs[0] - Fsp[0]);
                 }
                 if (!FAST && P.alt_ss) {  // K div(u) correction, u-interface form (m_rhs.fpp:1568-1582,1714-1728)
-                    const double K = k_term(P, __ldg(P.prim + S::IE * P.fs + c), __ldg(P.prim + S::IA * P.fs + c), __ldg(P.prim + (S::IA + NF - 1) * P.fs + c));
+                    const double K = k_term(P, __ldg(P.prim + (ix)((ix)S::IE * fs + c)), __ldg(P.prim + (ix)((ix)S::IA * fs + c)), __ldg(P.prim + (ix)((ix)(S::IA + NF - 1) * fs + c)));
                     r[S::IA] = r[S::IA] + K * inv_ds * (Fs[0] - Fsp[0]);
                     r[S::IA + NF - 1] = r[S::IA + NF - 1] - K * inv_ds * (Fs[0] - Fsp[0]);
                 }
@@ -860,11 +880,11 @@ __global__ void __launch_bounds__(MFC5_MARCH_THREADS, (2 * NF + ND + 1 <= 8) ? M
                     }
                     if (P.bf_on) apply_body_forces<NF, ND>(P, r);
 #pragma unroll
-                    for (int v = 0; v < N; v++) P.qout[v * P.fs + c] = r[v];
-                    store_next_prim<NF, ND, FAST>(P, c, r);
+                    for (int v = 0; v < N; v++) P.qout[(ix)((ix)v * fs + c)] = r[v];
+                    if constexpr (WO < 0) store_next_prim<NF, ND, FAST>(P, (long long)c, r);  // opt-in MFC5_FUSE_C2P: generic kernels only
                 } else {
 #pragma unroll
-                    for (int v = 0; v < N; v++) P.rhs[v * P.fs + c] = r[v];
+                    for (int v = 0; v < N; v++) P.rhs[(ix)((ix)v * fs + c)] = r[v];
                 }
             }
 #pragma unroll
