@@ -164,6 +164,72 @@ def perf_test_3d(m=200, riemann="hllc", steps=30):
     return case
 
 
+def _convergence_scheme(order, muscl, muscl_lim, teno, teno_ct, no_mapped=False):
+    """The scheme block shared by the reference's convergence cases (examples/1D_euler_convergence/case.py:46-65,
+    examples/2D_advection_convergence, 3D_advection_convergence, 1D_sod_convergence: identical)."""
+    if muscl:
+        return {"recon_type": "muscl", "muscl_order": "second_order", "muscl_lim": muscl_lim}
+    sp = {"recon_type": "weno", "weno_order": order, "weno_eps": 1.0e-40, "weno_Re_flux": "F", "weno_avg": "F",
+          "mapped_weno": "F" if (order == 1 or no_mapped or teno) else "T", "null_weights": "F", "mp_weno": "F",
+          "teno": "T" if teno else "F"}
+    if teno:
+        sp["teno_CT"] = teno_ct
+    return sp
+
+
+def advection_convergence(ndim, N=64, order=5, muscl=False, muscl_lim=0, teno=False, teno_ct=1e-6, cfl=0.4, no_mapped=False,
+                          time_stepper=3, t_end=None):
+    """The reference's smooth-advection known-answer cases: examples/1D_euler_convergence/case.py (rho = 1 + 0.2 sin(2 pi x),
+    u = 1, p = 1, period 1), examples/2D_advection_convergence/case.py (diagonal, period 1/2) and
+    examples/3D_advection_convergence/case.py (period 1/3); single fluid, periodic, HLLC.  Arguments = the case files' own
+    command-line options (-N, --order, --muscl, --muscl-lim, --teno, --teno-ct, --cfl, --no-mapped, --time-stepper, --t-end)."""
+    import math
+    gamma = 1.4
+    L = 1.0
+    dx = L / N
+    c_max = (math.sqrt(gamma) if ndim == 1 else math.sqrt(gamma / 0.8)) + 1.0
+    dt = cfl * dx / c_max
+    T_end = t_end if t_end is not None else 1.0 / ndim
+    Nt = max(1, math.ceil(T_end / dt))
+    dt = T_end / Nt
+    m = N - 1
+    case = {"run_time_info": "F", "m": m, "n": m if ndim > 1 else 0, "p": m if ndim > 2 else 0, "dt": dt, "t_step_start": 0,
+            "t_step_stop": Nt, "t_step_save": Nt, "num_patches": 1, "model_eqns": "5eq", "alt_soundspeed": "F", "num_fluids": 1,
+            "mpp_lim": "F", "mixture_err": "F", "time_stepper": time_stepper, "riemann_solver": "hllc", "wave_speeds": "direct",
+            "avg_state": "arithmetic", "format": "silo", "precision": "double", "prim_vars_wrt": "T", "parallel_io": "F",
+            "patch_icpp(1)%geometry": {1: 1, 2: 3, 3: 9}[ndim], "patch_icpp(1)%pres": 1.0, "patch_icpp(1)%alpha(1)": 1.0,
+            "fluid_pp(1)%gamma": 1.0 / (gamma - 1.0), "fluid_pp(1)%pi_inf": 0.0}
+    phase = {1: "x / lx", 2: "(x / lx + y / ly)", 3: "(x / lx + y / ly + z / lz)"}[ndim]
+    case["patch_icpp(1)%alpha_rho(1)"] = f"1.0 + 0.2 * sin(2.0 * pi * {phase})"
+    for d, x in enumerate("xyz"[:ndim]):
+        case.update({f"{x}_domain%beg": 0.0, f"{x}_domain%end": L, f"bc_{x}%beg": -1, f"bc_{x}%end": -1,
+                     f"patch_icpp(1)%{x}_centroid": 0.5, f"patch_icpp(1)%length_{x}": L, f"patch_icpp(1)%vel({d + 1})": 1.0})
+    case.update(_convergence_scheme(order, muscl, muscl_lim, teno, teno_ct, no_mapped))
+    return case
+
+
+def sod_convergence(N=128, order=5, muscl=False, muscl_lim=1, teno=False, teno_ct=1e-6, cfl=0.3):
+    """examples/1D_sod_convergence/case.py: the Sod problem on [0, 1] to T = 0.2 with outflow ends, for the L1
+    self-convergence study."""
+    import math
+    gamma = 1.4
+    dx = 1.0 / N
+    dt = cfl * dx / (math.sqrt(gamma) + 1.0)
+    Nt = max(4, math.ceil(0.2 / dt))
+    dt = 0.2 / Nt
+    case = {"run_time_info": "F", "x_domain%beg": 0.0, "x_domain%end": 1.0, "m": N - 1, "n": 0, "p": 0, "dt": dt, "t_step_start": 0,
+            "t_step_stop": Nt, "t_step_save": Nt, "num_patches": 2, "model_eqns": "5eq", "alt_soundspeed": "F", "num_fluids": 1,
+            "mpp_lim": "F", "mixture_err": "F", "time_stepper": "rk3", "riemann_solver": "hllc", "wave_speeds": "direct",
+            "avg_state": "arithmetic", "bc_x%beg": -3, "bc_x%end": -3, "format": "silo", "precision": "double", "prim_vars_wrt": "T",
+            "parallel_io": "F", "fluid_pp(1)%gamma": 1.0 / (gamma - 1.0), "fluid_pp(1)%pi_inf": 0.0}
+    for i, (xc, pres, rho) in enumerate(((0.25, 1.0, 1.0), (0.75, 0.1, 0.125)), start=1):
+        case.update({f"patch_icpp({i})%geometry": 1, f"patch_icpp({i})%x_centroid": xc, f"patch_icpp({i})%length_x": 0.5,
+                     f"patch_icpp({i})%vel(1)": 0.0, f"patch_icpp({i})%pres": pres, f"patch_icpp({i})%alpha_rho(1)": rho,
+                     f"patch_icpp({i})%alpha(1)": 1.0})
+    case.update(_convergence_scheme(order, muscl, muscl_lim, teno, teno_ct))
+    return case
+
+
 CONFIGS = {
     "1D_sodshocktube": sod_1d,
     "2D_shockbubble": shockbubble_2d,
