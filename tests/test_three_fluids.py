@@ -110,3 +110,47 @@ def test_gpu_three_fluids_vs_two_fluid_golden(uuid, fast):
         ok, a, w = compare(q[i3], golden_field(gold, "cons", i2 + 1, 0, nstep, q.shape[1:]), CASES[uuid]["tol"])
         assert ok, f"{uuid} var {i2 + 1}: worst min(abs, rel) err {w:.3e}"
     assert np.max(np.abs(q[2])) <= 1e-300 and np.max(np.abs(q[5 + nd + 1])) <= 1e-300
+
+
+# ---- the same invariance one level down: an empty SECOND fluid on the single-fluid boundary-condition goldens ----------------
+# The reference's goldens for the characteristic (-5 .. -12, GRCBC), slip / no-slip (-15 / -16) and Dirichlet (-17) boundaries are
+# single-fluid, while every BASELINE configuration that uses them (C2 - C5: -6) has two fluids.  The 2-fluid CUDA path is held
+# bit for bit to the 2-fluid oracle on those configurations (tests/test_gpu_parity.py::test_baseline_config_vs_oracle); this test
+# closes the chain to the goldens: the 2-fluid oracle with an empty second fluid == the golden-pinned 1-fluid oracle, bit for bit.
+BC_UUIDS = ["727F72ED", "A60691E7", "3FC6FC4A", "2FD933A2", "ED728400", "9D92767D", "3AE495F4", "5EC236F2", "48CCE072", "AED93D34",
+            "C5B79059",                                                                # 1-D: -10 -11 -12 -15 -16 -17 -5 .. -9
+            "B96AC58F", "4D7926CD", "98081DA3", "10DBA76B", "A6E65782", "4129A23A", "E84967E7", "5F877BC9", "16C03D8E",  # 2-D
+            "9DCBE54F", "5010B814", "730DFD6D"]                                        # 3-D: -17, -6, -7
+# (GRCBC inflow is NOT invariant, in the reference itself: every fluid's wave amplitude carries the pressure-relaxation term
+#  - c Ma (p - p_in) / Del whatever its partial density, m_cbc.fpp:739-742, so an empty fluid is filled at the inflow face.)
+
+
+def with_empty_second_fluid(case):
+    c = dict(case)
+    c["num_fluids"] = 2
+    for key in ("gamma", "pi_inf", "qv", "cv", "qvp"):
+        if f"fluid_pp(1)%{key}" in c:
+            c[f"fluid_pp(2)%{key}"] = c[f"fluid_pp(1)%{key}"]
+    for i in range(1, int(c["num_patches"]) + 1):
+        c[f"patch_icpp({i})%alpha_rho(2)"] = 0.0
+        c[f"patch_icpp({i})%alpha(2)"] = 0.0
+    return c
+
+
+@pytest.mark.parametrize("uuid", BC_UUIDS)
+def test_oracle_empty_second_fluid_on_boundary_goldens(uuid):
+    case1 = CASES[uuid]["params"]
+    case2 = with_empty_second_fluid(case1)
+    out = []
+    for case in (case1, case2):
+        P, cbs, cons, dbuf = _setup(case)
+        o = _oracle(P, cbs, cons, dbuf, omp=P.num_dims == 3)
+        driver.run(o, case)
+        out.append((P, o.get_cons()))
+    (P1, q1), (P2, q2) = out
+    nd = P1.num_dims
+    # 1-fluid layout: [arho, mom(nd), E, alpha]; 2-fluid: [arho1, arho2, mom(nd), E, alpha1, alpha2]
+    pairs = [(0, 0)] + [(2 + d, 1 + d) for d in range(nd)] + [(2 + nd, 1 + nd), (3 + nd, 2 + nd)]
+    for i2, i1 in pairs:
+        np.testing.assert_array_equal(q2[i2], q1[i1])
+    assert not q2[1].any() and not q2[4 + nd].any()
