@@ -98,6 +98,9 @@ typedef struct mfc5_params {
      * fluids after WENO or MUSCL); ic_eps / ic_beta default to 1e-4 / 1.6 (m_constants.fpp:53-54) */
     int int_comp, reserved4;
     double ic_eps, ic_beta;
+    /* WENO-Z power of order 7, alpha = d (1 + (tau / beta)^wenoz_q) (m_weno.fpp:1381-1389); the CPU oracle only so far: the CUDA
+     * library rejects weno_order = 7 */
+    double wenoz_q;
 } mfc5_params;
 
 #ifdef __cplusplus

@@ -181,6 +181,9 @@ void orc_set_grid(orc_state* S, int d, const double* s_cb_in, const double* gbeg
  * WENO coefficient tables: src/simulation/m_weno.fpp:196-215 (WENO3), :233-341 (WENO5),
  * null_weights :219-229,345-361, uniform-grid detection :869-879.
  * ------------------------------------------------------------------------------------------- */
+#define GK_MAX 4
+static void g_weno_tables(int k, const double* xb, double cLo[][GK_MAX - 1], double cRo[][GK_MAX - 1], double* dLo, double* dRo,
+                          double bto[][6]);
 static void weno_coefficients(orc_state* S, int d) {
     int s = S->s[d], b = S->b, pn = S->polyn, ns = S->ns;
     int nslot = s + 1 + 2 * b;
@@ -188,7 +191,7 @@ static void weno_coefficients(orc_state* S, int d) {
     S->cR[d] = (double*)calloc((size_t)nslot * ns * (pn > 0 ? pn : 1), sizeof(double));
     S->dL[d] = (double*)calloc((size_t)nslot * ns, sizeof(double));
     S->dR[d] = (double*)calloc((size_t)nslot * ns, sizeof(double));
-    S->bt[d] = (double*)calloc((size_t)nslot * ns * 3, sizeof(double));
+    S->bt[d] = (double*)calloc((size_t)nslot * ns * (pn == 3 ? 6 : 3), sizeof(double));
     const double* scb = S->scb[d];
 #define C(k) scb[i + (k)]
 #define CL(j, q, r) S->cL[d][(((j) + b) * ns + (q)) * pn + (r)]
@@ -281,6 +284,21 @@ static void weno_coefficients(orc_state* S, int d) {
             }
         }
     }
+    if (S->P.weno_order == 7) { /* m_weno.fpp:362-851, by the general construction (g_weno_tables, defined below) */
+        for (int j = -b + pn; j <= s + b - pn; j++) {
+            double xb[8], cl[GK_MAX][GK_MAX - 1], cr[GK_MAX][GK_MAX - 1], dl[GK_MAX], dr[GK_MAX], bt[GK_MAX][6];
+            for (int m = 0; m < 8; m++) xb[m] = scb[j - 4 + m];
+            g_weno_tables(4, xb, cl, cr, dl, dr, bt);
+            for (int q = 0; q < 4; q++) {
+                for (int r = 0; r < 3; r++) { CL(j, q, r) = cl[q][r]; CR(j, q, r) = cr[q][r]; }
+                /* the reference numbers the ideal weights, polynomials and betas of order 7 from the LEFTMOST stencil (d_cb(0) =
+                 * 1/35 on a uniform grid) while poly_coef / beta_coef keep the rightmost-first index: d(q) belongs to sidx 3 - q */
+                DL(q, j) = dl[3 - q];
+                DR(q, j) = dr[3 - q];
+                for (int r = 0; r < 6; r++) S->bt[d][(((j) + b) * ns + q) * 6 + r] = bt[q][r];
+            }
+        }
+    }
     /* uniform-grid detection, m_weno.fpp:869-879 (epsilon(h0) = 2^-52) */
     S->uniform[d] = 1;
     if (s > 0) {
@@ -289,6 +307,144 @@ static void weno_coefficients(orc_state* S, int d) {
             if (fabs((scb[i + 1] - scb[i]) - h0) > sqrt(2.220446049250313e-16) * fabs(h0)) { S->uniform[d] = 0; break; }
     }
 #undef C
+}
+
+
+/* ---------------------------------------------------------------------------------------------
+ * WENO tables by the general construction, used for weno_order = 7 (m_weno.fpp:362-851 lists the same quantities as ~500
+ * lines of closed forms; restated here from the published definitions they come from):
+ *   - candidate polynomials: Shu (1997), eq. 2.20 -- the degree-(k-1) polynomial whose cell averages match k cells is the
+ *     derivative of the Lagrange interpolant of the primitive function through the k+1 cell boundaries;
+ *   - written, like the reference, on the cell-value differences dvd(t) = v(i+t+1) - v(i+t):  p = v(i) + sum_t a_t dvd(t);
+ *   - ideal weights: the combination of the k candidates that reproduces the (2k-1)-cell polynomial at the cell boundary;
+ *   - smoothness indicators: Jiang & Shu / Shu eq. 2.61, beta = sum_{l=1}^{k-1} dx_i^(2l-1) int_cell (d^l p / dx^l)^2 dx, as
+ *     the quadratic form in the stencil's dvd's (beta_coef: squares and doubled cross terms, highest dvd first).
+ * Checked against the transcribed WENO5 closed forms on a stretched grid (orc_selftest_weno_generic: 1e-13) and pinned by
+ * the reference's WENO7 goldens.  Stencil index sidx = 0 is the rightmost one (cells i .. i+k-1), as in poly_coef_cb.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct { double c[8]; int n; } gpoly; /* c[0] + c[1] x + ..., n = number of coefficients */
+static gpoly gp_mul_lin(gpoly a, double r, double scale) { /* a * (x - r) * scale */
+    gpoly o; o.n = a.n + 1;
+    for (int i = 0; i < o.n; i++) o.c[i] = 0.0;
+    for (int i = 0; i < a.n; i++) { o.c[i + 1] += a.c[i] * scale; o.c[i] -= a.c[i] * r * scale; }
+    return o;
+}
+static gpoly gp_deriv(gpoly a) {
+    gpoly o; o.n = a.n > 1 ? a.n - 1 : 1; o.c[0] = 0.0;
+    for (int i = 1; i < a.n; i++) o.c[i - 1] = a.c[i] * (double)i;
+    return o;
+}
+static gpoly gp_axpy(gpoly y, double a, gpoly x) { /* y + a x */
+    gpoly o; o.n = y.n > x.n ? y.n : x.n;
+    for (int i = 0; i < o.n; i++) o.c[i] = (i < y.n ? y.c[i] : 0.0) + a * (i < x.n ? x.c[i] : 0.0);
+    return o;
+}
+static double gp_eval(gpoly a, double x) { double v = 0.0; for (int i = a.n - 1; i >= 0; i--) v = v * x + a.c[i]; return v; }
+static double gp_int_prod(gpoly a, gpoly b, double L) { /* int_0^L a b dx */
+    double prod[16]; int n = a.n + b.n - 1;
+    for (int i = 0; i < n; i++) prod[i] = 0.0;
+    for (int i = 0; i < a.n; i++) for (int j = 0; j < b.n; j++) prod[i + j] += a.c[i] * b.c[j];
+    double v = 0.0, Lp = L;
+    for (int i = 0; i < n; i++) { v += prod[i] * Lp / (double)(i + 1); Lp *= L; }
+    return v;
+}
+/* c_j(x), j = 0..kk-1: weights of the cell averages in the reconstruction polynomial over the cells bounded by X[0..kk] */
+static void g_cell_weights(const double* X, int kk, gpoly* cj) {
+    gpoly dL[2 * GK_MAX]; /* L_m'(x), m = 0..kk */
+    for (int m = 0; m <= kk; m++) {
+        gpoly l; l.n = 1; l.c[0] = 1.0;
+        for (int n = 0; n <= kk; n++) if (n != m) l = gp_mul_lin(l, X[n], 1.0 / (X[m] - X[n]));
+        dL[m] = gp_deriv(l);
+    }
+    for (int j = 0; j < kk; j++) {
+        gpoly acc; acc.n = 1; acc.c[0] = 0.0;
+        for (int m = j + 1; m <= kk; m++) acc = gp_axpy(acc, 1.0, dL[m]);
+        for (int i = 0; i < acc.n; i++) acc.c[i] *= (X[j + 1] - X[j]);
+        cj[j] = acc;
+    }
+}
+/* tables of cell i for order 2k-1; xb = boundaries x_{i-k+1-1/2} .. x_{i+k-1+1/2} (2k values) relative to any origin.
+ * out: cL/cR[sidx][r] (r = 0: highest dvd), dL/dR[sidx], bt[sidx][0..k(k-1)/2-1] */
+static void g_weno_tables(int k, const double* xb, double cLo[][GK_MAX - 1], double cRo[][GK_MAX - 1], double* dLo, double* dRo,
+                          double bto[][6]) {
+    double X[2 * GK_MAX];
+    const double x0 = xb[k - 1];              /* left boundary of cell i */
+    for (int m = 0; m < 2 * k; m++) X[m] = xb[m] - x0;
+    const double dxi = X[k] - X[k - 1];       /* = X[k] */
+    gpoly cw[GK_MAX][GK_MAX];                 /* cw[sidx][local cell] */
+    for (int sidx = 0; sidx < k; sidx++) {
+        const int l = sidx;                   /* cell i is local cell l of the stencil starting at global cell i - l ...      */
+        (void)l;
+    }
+    /* stencil with cell i at local position l covers boundaries X[k-1-l .. 2k-1-l]; sidx = 0 <-> l = 0 (rightmost) */
+    for (int l = 0; l < k; l++) {
+        g_cell_weights(X + (k - 1 - l), k, cw[l]);
+        gpoly a[GK_MAX - 1];                  /* a[e]: coefficient polynomial of the local difference v(e+1) - v(e) */
+        for (int e = 0; e < k - 1; e++) {
+            gpoly acc; acc.n = 1; acc.c[0] = 0.0;
+            if (e >= l) { for (int j = e + 1; j < k; j++) acc = gp_axpy(acc, 1.0, cw[l][j]); }
+            else        { for (int j = 0; j <= e; j++) acc = gp_axpy(acc, -1.0, cw[l][j]); }
+            a[e] = acc;
+        }
+        for (int r = 0; r < k - 1; r++) {     /* r = 0 <-> highest difference e = k-2 */
+            const int e = k - 2 - r;
+            cLo[l][r] = gp_eval(a[e], 0.0);
+            cRo[l][r] = gp_eval(a[e], dxi);
+        }
+        /* beta quadratic form */
+        double B[GK_MAX - 1][GK_MAX - 1];
+        for (int e = 0; e < k - 1; e++) for (int f = 0; f < k - 1; f++) B[e][f] = 0.0;
+        gpoly da[GK_MAX - 1];
+        for (int e = 0; e < k - 1; e++) da[e] = a[e];
+        double w = dxi;                       /* dx^(2l-1) */
+        for (int ord = 1; ord <= k - 1; ord++) {
+            for (int e = 0; e < k - 1; e++) da[e] = gp_deriv(da[e]);
+            for (int e = 0; e < k - 1; e++) for (int f = 0; f < k - 1; f++) B[e][f] += w * gp_int_prod(da[e], da[f], dxi);
+            w *= dxi * dxi;
+        }
+        int n = 0;
+        for (int r = 0; r < k - 1; r++) for (int r2 = r; r2 < k - 1; r2++) {
+            const int e = k - 2 - r, f = k - 2 - r2;
+            bto[l][n++] = (r == r2) ? B[e][e] : 2.0 * B[e][f];
+        }
+    }
+    /* ideal weights from the (2k-1)-cell polynomial */
+    gpoly cbig[2 * GK_MAX];
+    g_cell_weights(X, 2 * k - 1, cbig);
+    for (int side = 0; side < 2; side++) {
+        const double xe = side == 0 ? 0.0 : dxi;
+        double* dd = side == 0 ? dLo : dRo;
+        /* global cell g = 0 .. 2k-2 (g = k-1 is cell i); stencil l covers g = k-1-l .. 2k-2-l */
+        for (int l = k - 1; l >= 0; l--) {
+            const int g = k - 1 - l;          /* the leftmost cell of stencil l; stencils l' > l also contain it */
+            double rhs = gp_eval(cbig[g], xe);
+            for (int l2 = k - 1; l2 > l; l2--) rhs -= dd[l2] * gp_eval(cw[l2][g - (k - 1 - l2)], xe);
+            dd[l] = rhs / gp_eval(cw[l][0], xe);
+        }
+    }
+}
+
+/* self-test: the general construction for k = 3 against the transcribed WENO5 closed forms of direction d; returns the largest
+ * deviation relative to the largest table entry of each kind */
+double orc_selftest_weno_generic(orc_state* S, int d) {
+    if (S->P.weno_order != 5) return -1.0;
+    const int s = S->s[d], b = S->b, pn = S->polyn, ns = S->ns;
+    double worst = 0.0;
+    for (int j = -b + pn; j <= s + b - pn; j++) {
+        double xb[6], cl[GK_MAX][GK_MAX - 1], cr[GK_MAX][GK_MAX - 1], dl[GK_MAX], dr[GK_MAX], bt[GK_MAX][6];
+        for (int m = 0; m < 6; m++) xb[m] = S->scb[d][j - 3 + m];
+        g_weno_tables(3, xb, cl, cr, dl, dr, bt);
+        for (int q = 0; q < 3; q++) {
+            for (int r = 0; r < 2; r++) {
+                worst = fmax(worst, fabs(cl[q][r] - S->cL[d][((j + b) * ns + q) * pn + r]));
+                worst = fmax(worst, fabs(cr[q][r] - S->cR[d][((j + b) * ns + q) * pn + r]));
+            }
+            worst = fmax(worst, fabs(dl[q] - S->dL[d][(j + b) * ns + q]));
+            worst = fmax(worst, fabs(dr[q] - S->dR[d][(j + b) * ns + q]));
+            for (int r = 0; r < 3; r++) worst = fmax(worst, fabs(bt[q][r] - S->bt[d][((j + b) * ns + q) * 3 + r]) / 10.0);
+        }
+    }
+    return worst;
 }
 
 /* CBC coefficients: src/simulation/m_cbc.fpp:327-408 (fd_coef, pi_coef), :410-461 (ds), Del :312-313 */
@@ -533,6 +689,92 @@ void orc_halo_unpack(orc_state* S, int d, int side, const double* buf) {
     halo_copy(S, d, side == 0 ? -S->b : S->s[d] + 1, (double*)buf, 0);
 }
 
+
+/* WENO7 / TENO7 reconstruction of one variable in one cell, s_weno m_weno.fpp:1248-1490 (same operation order).
+ * f points at v(i); sd = stride along the sweep.  Tables: cL/cR(sidx, r), bt(sidx, 0..5) with sidx = 0 the rightmost stencil;
+ * dL/dR(q), poly(q), beta(q) numbered from the leftmost one. */
+static void weno7_cell(const orc_state* S, int d, int jc, const double* f, long sd, double* oL, double* oR) {
+    const int b = S->b, ns = S->ns, pn = 3;
+    const double eps = S->P.weno_eps;
+    const double* dl = &S->dL[d][(jc + b) * ns];
+    const double* dr = &S->dR[d][(jc + b) * ns];
+    const double* cl = &S->cL[d][(jc + b) * ns * pn];
+    const double* cr = &S->cR[d][(jc + b) * ns * pn];
+    const double* bt = &S->bt[d][(jc + b) * ns * 6];
+    const double vp0 = f[0], vm1 = f[-sd], vm2 = f[-2 * sd], vm3 = f[-3 * sd], vp1 = f[sd], vp2 = f[2 * sd], vp3 = f[3 * sd];
+    double poly[5], beta[5], alpha[5] = {0, 0, 0, 0, 0}, omega[5], delta[5] = {1, 1, 1, 1, 1}, tau = 0.0;
+    if (!S->P.teno) {
+        /* dvd(2) .. dvd(-3) */
+        const double e2 = vp3 - vp2, e1 = vp2 - vp1, e0 = vp1 - vp0, em1 = vp0 - vm1, em2 = vm1 - vm2, em3 = vm2 - vm3;
+        beta[3] = bt[0] * e2 * e2 + bt[1] * e2 * e1 + bt[2] * e2 * e0 + bt[3] * e1 * e1 + bt[4] * e1 * e0 + bt[5] * e0 * e0 + eps;
+        beta[2] = bt[6] * e1 * e1 + bt[7] * e1 * e0 + bt[8] * e1 * em1 + bt[9] * e0 * e0 + bt[10] * e0 * em1 + bt[11] * em1 * em1 + eps;
+        beta[1] = bt[12] * e0 * e0 + bt[13] * e0 * em1 + bt[14] * e0 * em2 + bt[15] * em1 * em1 + bt[16] * em1 * em2 + bt[17] * em2 * em2 + eps;
+        beta[0] = bt[18] * em1 * em1 + bt[19] * em1 * em2 + bt[20] * em1 * em3 + bt[21] * em2 * em2 + bt[22] * em2 * em3 + bt[23] * em3 * em3 + eps;
+        for (int side = 0; side < 2; side++) {
+            const double* cc = side == 0 ? cl : cr;
+            const double* dd = side == 0 ? dl : dr;
+            poly[3] = vp0 + cc[0] * e2 + cc[1] * e1 + cc[2] * e0;
+            poly[2] = vp0 + cc[3] * e1 + cc[4] * e0 + cc[5] * em1;
+            poly[1] = vp0 + cc[6] * e0 + cc[7] * em1 + cc[8] * em2;
+            poly[0] = vp0 + cc[9] * em1 + cc[10] * em2 + cc[11] * em3;
+            if (S->P.mapped_weno) {
+                for (int q = 0; q < 4; q++) alpha[q] = dd[q] / (beta[q] * beta[q]);
+                double sum = alpha[0] + alpha[1] + alpha[2] + alpha[3];
+                for (int q = 0; q < 4; q++) omega[q] = alpha[q] / sum;
+                for (int q = 0; q < 4; q++)
+                    alpha[q] = (dd[q] * (1.0 + dd[q] - 3.0 * omega[q]) + omega[q] * omega[q]) *
+                               (omega[q] / (dd[q] * dd[q] + omega[q] * (1.0 - 2.0 * dd[q])));
+            } else if (S->P.wenoz) {
+                if (side == 0) tau = fabs(beta[3] - beta[0]);
+                for (int q = 0; q < 4; q++) alpha[q] = dd[q] * (1.0 + pow(tau / beta[q], S->P.wenoz_q));
+            } else {
+                for (int q = 0; q < 4; q++) alpha[q] = dd[q] / (beta[q] * beta[q]);
+            }
+            double sum = alpha[0] + alpha[1] + alpha[2] + alpha[3];
+            for (int q = 0; q < 4; q++) omega[q] = alpha[q] / sum;
+            const double val = omega[0] * poly[0] + omega[1] * poly[1] + omega[2] * poly[2] + omega[3] * poly[3];
+            if (side == 0) *oL = val; else *oR = val;
+        }
+        return;
+    }
+    /* TENO7 (Fu et al. 2016; Fu & Tang 2019): five uniform-grid stencils, m_weno.fpp:1303-1313,1355-1372,1427-1456 */
+    static const double dLt[5] = {18.0 / 35.0, 3.0 / 35.0, 9.0 / 35.0, 1.0 / 35.0, 4.0 / 35.0};
+    static const double dRt[5] = {18.0 / 35.0, 9.0 / 35.0, 3.0 / 35.0, 4.0 / 35.0, 1.0 / 35.0};
+    beta[0] = 13.0 / 12.0 * sq(vm1 - 2.0 * vp0 + vp1) + sq(vm1 - vp1) / 4.0 + eps;
+    beta[1] = 13.0 / 12.0 * sq(vp0 - 2.0 * vp1 + vp2) + sq(3.0 * vp0 - 4.0 * vp1 + vp2) / 4.0 + eps;
+    beta[2] = 13.0 / 12.0 * sq(vm2 - 2.0 * vm1 + vp0) + sq(vm2 - 4.0 * vm1 + 3.0 * vp0) / 4.0 + eps;
+    beta[3] = (vp0 * (2107.0 * vp0 - 9402.0 * vp1 + 7042.0 * vp2 - 1854.0 * vp3) + vp1 * (11003.0 * vp1 - 17246.0 * vp2 + 4642.0 * vp3) +
+               vp2 * (7043.0 * vp2 - 3882.0 * vp3) + vp3 * (547.0 * vp3)) / 240.0 + eps;
+    beta[4] = (vm3 * (547.0 * vm3 - 3882.0 * vm2 + 4642.0 * vm1 - 1854.0 * vp0) + vm2 * (7043.0 * vm2 - 17246.0 * vm1 + 7042.0 * vp0) +
+               vm1 * (11003.0 * vm1 - 9402.0 * vp0) + vp0 * (2107.0 * vp0)) / 240.0 + eps;
+    for (int side = 0; side < 2; side++) {
+        const double* dd = side == 0 ? dLt : dRt;
+        if (side == 0) {
+            poly[0] = (2.0 * vm1 + 5.0 * vp0 - 1.0 * vp1) / 6.0;
+            poly[1] = (11.0 * vp0 - 7.0 * vp1 + 2.0 * vp2) / 6.0;
+            poly[2] = (-1.0 * vm2 + 5.0 * vm1 + 2.0 * vp0) / 6.0;
+            poly[3] = (25.0 * vp0 - 23.0 * vp1 + 13.0 * vp2 - 3.0 * vp3) / 12.0;
+            poly[4] = (1.0 * vm3 - 5.0 * vm2 + 13.0 * vm1 + 3.0 * vp0) / 12.0;
+            tau = fabs(beta[4] - beta[3]);
+            for (int q = 0; q < 5; q++) { alpha[q] = 1.0 + tau / beta[q]; alpha[q] = (alpha[q] * alpha[q] * alpha[q]) * (alpha[q] * alpha[q] * alpha[q]); }
+            double sum = alpha[0] + alpha[1] + alpha[2] + alpha[3] + alpha[4];
+            for (int q = 0; q < 5; q++) { omega[q] = alpha[q] / sum; delta[q] = omega[q] < S->P.teno_CT ? 0.0 : 1.0; }
+        } else {
+            poly[0] = (-1.0 * vm1 + 5.0 * vp0 + 2.0 * vp1) / 6.0;
+            poly[1] = (2.0 * vp0 + 5.0 * vp1 - 1.0 * vp2) / 6.0;
+            poly[2] = (2.0 * vm2 - 7.0 * vm1 + 11.0 * vp0) / 6.0;
+            poly[3] = (3.0 * vp0 + 13.0 * vp1 - 5.0 * vp2 + 1.0 * vp3) / 12.0;
+            poly[4] = (-3.0 * vm3 + 13.0 * vm2 - 23.0 * vm1 + 25.0 * vp0) / 12.0;
+        }
+        for (int q = 0; q < 5; q++) alpha[q] = delta[q] * dd[q];
+        double sum = alpha[0] + alpha[1] + alpha[2] + alpha[3] + alpha[4];
+        for (int q = 0; q < 5; q++) omega[q] = alpha[q] / sum;
+        double val = omega[0] * poly[0] + omega[1] * poly[1] + omega[2] * poly[2] + omega[3] * poly[3];
+        val = val + omega[4] * poly[4];
+        if (side == 0) *oL = val; else *oR = val;
+    }
+}
+
 /* ---------------------------------------------------------------------------------------------
  * WENO reconstruction along direction d: s_weno, m_weno.fpp:1007-1085 (WENO3), :1098-1239 (WENO5),
  * :952-993 (order 1).  vL = left-boundary value of cell j, vR = right-boundary value.  Only cells
@@ -592,6 +834,7 @@ static void weno_dir(orc_state* S, int d) {
                         *oR = f[0] + (5.e-1 * slope);
                         continue;
                     }
+                    if (pn == 3) { weno7_cell(S, d, jc, f, sd, oL, oR); continue; }
                     double dvd[4], poly[3], beta[3], alpha[3], omega[3], tau = 0.0, teno_delta[3] = {1.0, 1.0, 1.0};
                     const double* dl = &S->dL[d][(jc + b) * ns];
                     const double* dr = &S->dR[d][(jc + b) * ns];

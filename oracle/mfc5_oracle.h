@@ -56,6 +56,8 @@ double orc_icfl_max(orc_state* S, double dt);
 
 /* timing hook for bench.py's cpu baseline: OpenMP threads used by the sweeps (1 if built without) */
 int orc_num_threads(void);
+/* general WENO table construction (k = 3) against the transcribed WENO5 closed forms of direction dir: largest deviation */
+double orc_selftest_weno_generic(orc_state* S, int dir);
 
 #ifdef __cplusplus
 }

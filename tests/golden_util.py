@@ -11,7 +11,10 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 GOLD = os.path.join(HERE, "golden")
 
 with open(os.path.join(GOLD, "cases.json")) as _f:
-    CASES = json.load(_f)
+    _ALL = json.load(_f)
+# weno_order = 7 exists in the CPU oracle only so far (tests/test_weno7_oracle.py); every other list of cases is the product's
+ORACLE_ONLY = {u: c for u, c in _ALL.items() if int(c["params"].get("weno_order", 0) or 0) == 7}
+CASES = {u: c for u, c in _ALL.items() if u not in ORACLE_ONLY}
 
 
 def golden(uuid):
