@@ -126,7 +126,7 @@ def params_from_case(case, device=0, fast_math=1, oracle_only=False):
     else:
         P.weno_order = int(case["weno_order"])
         if P.weno_order not in (1, 3, 5) and not (oracle_only and P.weno_order == 7):
-            # weno_order = 7: restated in the CPU oracle and pinned by the reference's goldens (tests/test_weno7_oracle.py); the CUDA
+            # weno_order = 7: restated in the CPU oracle and pinned by the reference's goldens (tests/test_oracle_next.py); the CUDA
             # kernels do not have it yet, so the product path rejects it
             raise UnsupportedCase("weno_order must be 1, 3 or 5")
     P.mapped_weno = _logical(case.get("mapped_weno", "F"))
@@ -196,9 +196,12 @@ def params_from_case(case, device=0, fast_math=1, oracle_only=False):
         P.fluid_qv[f] = float(case.get(f"fluid_pp({f + 1})%qv", 0.0))
     ic = _val(case, "int_comp", 0)
     ic = (1 if _logical(ic) else 0) if isinstance(ic, str) and ic.strip().upper() in ("T", "F") else int(ic or 0)
-    if ic not in (0, 1):
+    if ic not in (0, 1) and not (oracle_only and ic == 2):
+        # MTHINC: in the CPU oracle and pinned by the reference's goldens (tests/test_oracle_next.py), not yet in the CUDA kernels
         raise UnsupportedCase("int_comp = 2 (MTHINC) is outside the hot path; 0 (off) and 1 (THINC) are available")
-    if ic == 1:  # toolchain/mfc/case_validator.py:426-444
+    if ic == 2 and P.n == 0:
+        raise UnsupportedCase("int_comp = 2 (MTHINC) requires at least 2D (n > 0)")
+    if ic >= 1:  # toolchain/mfc/case_validator.py:426-444
         if P.num_fluids != 2:
             raise UnsupportedCase("int_comp > 0 requires num_fluids = 2")
         if P.recon_order == 1:

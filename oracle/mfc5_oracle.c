@@ -37,6 +37,8 @@ struct orc_state {
     double *q1, *q2, *prim, *rhs, *vL, *vR, *flux, *fsrc;
     /* Dirichlet (-17) face values, bc_buffers of m_boundary_common.fpp:46-65: [v][t2][t1] over the transverse interior */
     double* dirich[3][2];
+    /* MTHINC (int_comp = 2): unit normal and interface position per cell, m_thinc.fpp:36-38 */
+    double *mth_n[3], *mth_d;
 };
 
 static inline long IDX(const orc_state* S, int i, int j, int k) {
@@ -135,10 +137,10 @@ void orc_destroy(orc_state* S) {
     if (!S) return;
     for (int d = 0; d < 3; d++) {
         free(S->scb_store[d]); free(S->ds_store[d]);
-        free(S->cL[d]); free(S->cR[d]); free(S->dL[d]); free(S->dR[d]); free(S->bt[d]);
+        free(S->cL[d]); free(S->cR[d]); free(S->dL[d]); free(S->dR[d]); free(S->bt[d]); free(S->mth_n[d]);
     }
     for (int d = 0; d < 3; d++) { free(S->dirich[d][0]); free(S->dirich[d][1]); }
-    free(S->q1); free(S->q2); free(S->prim); free(S->rhs); free(S->vL); free(S->vR); free(S->flux); free(S->fsrc);
+    free(S->q1); free(S->q2); free(S->prim); free(S->rhs); free(S->vL); free(S->vR); free(S->flux); free(S->fsrc); free(S->mth_d);
     free(S);
 }
 int orc_sys_size(const orc_state* S) { return S->N; }
@@ -690,6 +692,132 @@ void orc_halo_unpack(orc_state* S, int d, int side, const double* buf) {
 }
 
 
+/* ---------------------------------------------------------------------------------------------
+ * MTHINC (int_comp = 2), src/simulation/m_thinc.fpp:28-291: multi-dimensional THINC with the interface normal from the
+ * central difference of alpha_1 and the interface position d from a Newton solve of the cell's volume integral
+ * (3-point Gauss-Legendre in the transverse directions, analytic along the first).
+ * ------------------------------------------------------------------------------------------- */
+static const double GQ3_PTS[3] = {-5e-1 * 0.7745966692414834, 0.0, 5e-1 * 0.7745966692414834};
+static const double GQ3_WTS[3] = {5.0 / 18.0, 8.0 / 18.0, 5.0 / 18.0};
+#define VERYSMALL 1.e-12        /* m_constants.fpp:16 */
+#define MTHINC_ALIGN_TOL 1.e-8  /* m_constants.fpp:56 */
+static double log_cosh_diff(double a, double h) {
+    double t = tanh(a) * tanh(h);
+    return 2.0 * atanh(copysign(dmin(fabs(t), 1.0 - 2.220446049250313e-16), t));
+}
+static double thinc_integral_1d(double a, double bb) {
+    if (fabs(bb) < VERYSMALL) return 5e-1 * (1.0 + tanh(a));
+    return 5e-1 + log_cosh_diff(a, 5e-1 * bb) / (2.0 * bb);
+}
+static double mthinc_volume_integral(double n1, double n2, double n3, double dd, double beta, int ndim) {
+    double res = 0.0;
+    if (ndim == 1) return thinc_integral_1d(beta * dd, beta * n1);
+    if (ndim == 2) {
+        for (int q1 = 0; q1 < 3; q1++) res = res + GQ3_WTS[q1] * thinc_integral_1d(beta * (n2 * GQ3_PTS[q1] + dd), beta * n1);
+        return res;
+    }
+    for (int q1 = 0; q1 < 3; q1++)
+        for (int q2 = 0; q2 < 3; q2++)
+            res = res + GQ3_WTS[q1] * GQ3_WTS[q2] * thinc_integral_1d(beta * (n2 * GQ3_PTS[q1] + n3 * GQ3_PTS[q2] + dd), beta * n1);
+    return res;
+}
+static double mthinc_volume_integral_dd(double n1, double n2, double n3, double dd, double beta, int ndim) {
+    double res = 0.0, th;
+    if (ndim == 1) {
+        for (int q1 = 0; q1 < 3; q1++) { th = tanh(beta * (n1 * GQ3_PTS[q1] + dd)); res = res + GQ3_WTS[q1] * (1.0 - th * th); }
+    } else if (ndim == 2) {
+        for (int q1 = 0; q1 < 3; q1++)
+            for (int q2 = 0; q2 < 3; q2++) {
+                th = tanh(beta * (n1 * GQ3_PTS[q1] + n2 * GQ3_PTS[q2] + dd));
+                res = res + GQ3_WTS[q1] * GQ3_WTS[q2] * (1.0 - th * th);
+            }
+    } else {
+        for (int q1 = 0; q1 < 3; q1++)
+            for (int q2 = 0; q2 < 3; q2++)
+                for (int q3 = 0; q3 < 3; q3++) {
+                    th = tanh(beta * (n1 * GQ3_PTS[q1] + n2 * GQ3_PTS[q2] + n3 * GQ3_PTS[q3] + dd));
+                    res = res + GQ3_WTS[q1] * GQ3_WTS[q2] * GQ3_WTS[q3] * (1.0 - th * th);
+                }
+    }
+    return 5e-1 * beta * res;
+}
+static double mthinc_solve_d(double n1, double n2, double n3, double beta, double alpha_cell, int ndim) {
+    double dd = 0.0;
+    for (int iter = 1; iter <= 30; iter++) {
+        double V = mthinc_volume_integral(n1, n2, n3, dd, beta, ndim);
+        double residual = V - alpha_cell;
+        if (fabs(residual) < VERYSMALL) break;
+        double dV = mthinc_volume_integral_dd(n1, n2, n3, dd, beta, ndim);
+        if (fabs(dV) < VERYSMALL) break;
+        dd = dd - residual / dV;
+    }
+    return dd;
+}
+static double mthinc_face_average(double n1, double n2, double n3, double dd, double beta, int face_dir, double face_pos, int ndim) {
+    double n_face, n_t0, n_t1, res;
+    if (ndim == 1) return 5e-1 * (1.0 + tanh(beta * (n1 * face_pos + dd)));
+    if (ndim == 2) {
+        if (face_dir == 1) { n_face = n1; n_t0 = n2; } else { n_face = n2; n_t0 = n1; }
+        return thinc_integral_1d(beta * (n_face * face_pos + dd), beta * n_t0);
+    }
+    if (face_dir == 1) { n_face = n1; n_t0 = n2; n_t1 = n3; }
+    else if (face_dir == 2) { n_face = n2; n_t0 = n1; n_t1 = n3; }
+    else { n_face = n3; n_t0 = n1; n_t1 = n2; }
+    res = 0.0;
+    for (int q = 0; q < 3; q++) res = res + GQ3_WTS[q] * thinc_integral_1d(beta * (n_face * face_pos + n_t0 * GQ3_PTS[q] + dd), beta * n_t1);
+    return res;
+}
+/* s_compute_mthinc_normals, m_thinc.fpp:207-291; called once per RHS on the ghost-filled primitive variables (m_rhs.fpp:674) */
+static void mthinc_normals(orc_state* S) {
+    const int b = S->b, nd = S->nd;
+    if (!S->mth_d) {
+        for (int a = 0; a < 3; a++) S->mth_n[a] = (double*)calloc((size_t)S->fsz, sizeof(double));
+        S->mth_d = (double*)calloc((size_t)S->fsz, sizeof(double));
+    }
+    for (int a = 0; a < 3; a++) memset(S->mth_n[a], 0, (size_t)S->fsz * sizeof(double));
+    memset(S->mth_d, 0, (size_t)S->fsz * sizeof(double));
+    /* cell centres with ghosts: x_cc(0:m) = x_cb(-1:m-1) + dx/2 (m_start_up.fpp), ghosts by s_populate_grid_variables_buffers */
+    double* xcc[3] = {0, 0, 0};
+    for (int d = 0; d < nd; d++) {
+        const int s = S->s[d];
+        double* st = (double*)calloc((size_t)(s + 1 + 2 * b), sizeof(double));
+        double* cc = st + b;
+        for (int i = 0; i <= s; i++) cc[i] = S->scb[d][i - 1] + S->ds[d][i] / 2.0;
+        for (int i = 1; i <= b; i++) cc[-i] = cc[1 - i] - (S->ds[d][1 - i] + S->ds[d][-i]) / 2.0;
+        for (int i = 1; i <= b; i++) cc[s + i] = cc[s + i - 1] + (S->ds[d][s + i - 1] + S->ds[d][s + i]) / 2.0;
+        xcc[d] = cc;
+    }
+    int lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0};
+    for (int d = 0; d < nd; d++) { lo[d] = -b + 1; hi[d] = S->s[d] + b - 1; }
+    const double* al = S->prim + (long)S->iadv * S->fsz;
+    const double ic_eps = S->P.ic_eps;
+#pragma omp parallel for collapse(2)
+    for (int k = lo[2]; k <= hi[2]; k++)
+        for (int j = lo[1]; j <= hi[1]; j++)
+            for (int i = lo[0]; i <= hi[0]; i++) {
+                const long c = IDX(S, i, j, k);
+                const double ac = al[c];
+                if (!(ac >= ic_eps && ac <= 1.0 - ic_eps)) continue;
+                const int ijk[3] = {i, j, k};
+                double nr[3] = {0.0, 0.0, 0.0};
+                for (int d = 0; d < nd; d++) {
+                    const long sd = S->stride[d];
+                    const int q = ijk[d];
+                    nr[d] = (al[c + sd] - al[c - sd]) * (S->scb[d][q] - S->scb[d][q - 1]) / (xcc[d][q + 1] - xcc[d][q - 1]);
+                }
+                double nmag = sqrt(nr[0] * nr[0] + nr[1] * nr[1] + nr[2] * nr[2]);
+                if (!(nmag > VERYSMALL)) continue;
+                for (int d = 0; d < 3; d++) nr[d] = nr[d] / nmag;
+                const double nmax = dmax(dmax(fabs(nr[0]), fabs(nr[1])), fabs(nr[2]));
+                for (int d = 0; d < 3; d++) if (fabs(nr[d]) < MTHINC_ALIGN_TOL * nmax) nr[d] = 0.0;
+                nmag = sqrt(nr[0] * nr[0] + nr[1] * nr[1] + nr[2] * nr[2]);
+                if (!(nmag > VERYSMALL)) continue;
+                for (int d = 0; d < 3; d++) { nr[d] = nr[d] / nmag; S->mth_n[d][c] = nr[d]; }
+                S->mth_d[c] = mthinc_solve_d(nr[0], nr[1], nr[2], S->P.ic_beta, ac, nd);
+            }
+    for (int d = 0; d < nd; d++) free(xcc[d] - b);
+}
+
 /* WENO7 / TENO7 reconstruction of one variable in one cell, s_weno m_weno.fpp:1248-1490 (same operation order).
  * f points at v(i); sd = stride along the sweep.  Tables: cL/cR(sidx, r), bt(sidx, 0..5) with sidx = 0 the rightmost stencil;
  * dL/dR(q), poly(q), beta(q) numbered from the leftmost one. */
@@ -926,7 +1054,27 @@ static void weno_dir(orc_state* S, int d) {
                 }
                 /* interface compression (THINC), s_thinc_compression m_thinc.fpp:319-401: overwrites the reconstructed
                  * alpha / alpha-rho of the two fluids in interface cells where alpha_1 is monotone across the stencil */
-                if (S->P.int_comp == 1 && pn > 0) {
+                if (S->P.int_comp == 2 && S->nd > 1 && pn > 0) { /* MTHINC, m_thinc.fpp:323-355 */
+                    const int nf = S->nf;
+                    const double ic_eps = S->P.ic_eps;
+                    const long ia = (long)S->iadv * S->fsz + c, ib = (long)(S->iadv + nf - 1) * S->fsz + c;
+                    const long r0 = c, r1 = (long)(nf - 1) * S->fsz + c;
+                    const double aC = S->prim[ia];
+                    if (aC >= ic_eps && aC <= 1.0 - ic_eps) {
+                        const double nh1 = S->mth_n[0][c], nh2 = S->mth_n[1][c], nh3 = S->mth_n[2][c], dloc = S->mth_d[c];
+                        if (nh1 * nh1 + nh2 * nh2 + nh3 * nh3 > 5e-1) {
+                            const double rho1 = S->prim[r0] / aC, rho2 = S->prim[r1] / (1.0 - aC);
+                            double aT = mthinc_face_average(nh1, nh2, nh3, dloc, S->P.ic_beta, d + 1, -5e-1, S->nd);
+                            if (aT < ic_eps) aT = ic_eps;
+                            if (aT > 1.0 - ic_eps) aT = 1.0 - ic_eps;
+                            S->vL[r0] = rho1 * aT; S->vL[r1] = rho2 * (1.0 - aT); S->vL[ia] = aT; S->vL[ib] = 1.0 - aT;
+                            aT = mthinc_face_average(nh1, nh2, nh3, dloc, S->P.ic_beta, d + 1, 5e-1, S->nd);
+                            if (aT < ic_eps) aT = ic_eps;
+                            if (aT > 1.0 - ic_eps) aT = 1.0 - ic_eps;
+                            S->vR[r0] = rho1 * aT; S->vR[r1] = rho2 * (1.0 - aT); S->vR[ia] = aT; S->vR[ib] = 1.0 - aT;
+                        }
+                    }
+                } else if (S->P.int_comp >= 1 && pn > 0) { /* THINC (also int_comp = 2 in 1-D, m_thinc.fpp:324) */
                     const int nf = S->nf;
                     const double ic_eps = S->P.ic_eps, ic_beta = S->P.ic_beta;
                     const long ia = (long)S->iadv * S->fsz + c, ib = (long)(S->iadv + nf - 1) * S->fsz + c;
@@ -1438,6 +1586,7 @@ static void flux_difference(orc_state* S, int d) {
 }
 
 void orc_sweeps(orc_state* S) {
+    if (S->P.int_comp == 2 && S->nd > 1) mthinc_normals(S);
     for (int d = 0; d < S->nd; d++) {
         weno_dir(S, d);
         riemann_dir(S, d);

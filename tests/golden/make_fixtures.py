@@ -23,7 +23,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 REF = sys.argv[1] if len(sys.argv) > 1 else "/root/reference"
 
 # UUIDs inside the 5-eq / WENO{3,5}{JS,M,Z} / HLL|HLLC / RK3 envelope;
-# (weno_order = 7: the CPU oracle only so far, tests/test_weno7_oracle.py)
+# (weno_order = 7 and int_comp = 2 (MTHINC): the CPU oracle only so far, tests/test_oracle_next.py)
 # last lines: the f-4 widening (low_Mach = 1 / 2, tolerance 1e-10 by the reference's own rule; alt_soundspeed) and f-3 (elliptic smoothing, hard-coded profiles), Lax-Friedrichs, MUSCL
 UUIDS = """
 D79C3E6F 8A59E8E6 2AB32975 70DAE9E8 3AE495F4 5EC236F2 48CCE072 AED93D34 C5B79059 727F72ED A60691E7 3FC6FC4A
@@ -55,6 +55,7 @@ F1D01264 14846B52 90D62933 A7C19B7B 4F79391A 77292B06 9BD657CB 30035426 01DC0251
 48D5C130 E719C5F2 EDADA16E
 B3E70A3A 0ACB1F16 A3EC9BD7
 7B71820F 56BB8D80 0347811A 5D68B0F5 A72F7006 B8BF00C9 9E9DA539 448EA9A4 4A15969C E3EB6065 CD6C83A2 0F6DB678 6247B427
+5126B21F 4E4FECA9 4F3722DB 4C4F339C 7A1719C6
 3F0FA534 D78D6B12 6FA80DE9 3EE4302C F4E54FC0 F207F0FE B46CEFF3 28D9A304 71258175
 F883F4EE 743D6D71 84A12B88 6B227FF5 D68EDC50 5EC347F2 42848784 374C9B16 347964C3
 AFE4994E 66CB22E3 7B21681C CB76A5E1 96AF00B3 9DAC4DDC F5512823 F28381D9 0288BDAD

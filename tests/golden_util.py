@@ -12,8 +12,9 @@ GOLD = os.path.join(HERE, "golden")
 
 with open(os.path.join(GOLD, "cases.json")) as _f:
     _ALL = json.load(_f)
-# weno_order = 7 exists in the CPU oracle only so far (tests/test_weno7_oracle.py); every other list of cases is the product's
-ORACLE_ONLY = {u: c for u, c in _ALL.items() if int(c["params"].get("weno_order", 0) or 0) == 7}
+# weno_order = 7 and MTHINC (int_comp = 2) exist in the CPU oracle only so far (tests/test_oracle_next.py); every other list of cases is the product's
+ORACLE_ONLY = {u: c for u, c in _ALL.items()
+               if int(c["params"].get("weno_order", 0) or 0) == 7 or str(c["params"].get("int_comp", 0)) in ("2", "mthinc")}
 CASES = {u: c for u, c in _ALL.items() if u not in ORACLE_ONLY}
 
 

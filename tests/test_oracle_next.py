@@ -1,8 +1,12 @@
-"""weno_order = 7 (WENO7-JS / -M / -Z with wenoz_q, TENO7) in the CPU oracle, pinned by the reference's own goldens and by its
-convergence suite's 7th-order cases.  The CUDA library does not have order 7 yet and rejects it: this file
-is the checker waiting for that kernel.  The tables are not transcribed from m_weno.fpp:362-851 but built by the general
-construction those closed forms come from (oracle/mfc5_oracle.c g_weno_tables), which reproduces the transcribed WENO5 tables
-to 1e-13 on stretched grids (first test)."""
+"""Features the CPU oracle already has and the CUDA library does not yet -- the checker waiting for those
+kernels; the product path (``params_from_case`` without ``oracle_only``, ``mfc5_create``) rejects them.
+
+* weno_order = 7: WENO7-JS / -M / -Z with wenoz_q, TENO7 (m_weno.fpp:362-851,1248-1490), pinned by the reference's 13 order-7
+  goldens and its 7th-order convergence cases.  The tables are not transcribed from the reference's ~500 lines of closed forms
+  but built by the general construction those come from (oracle/mfc5_oracle.c g_weno_tables), which reproduces the transcribed
+  WENO5 tables to 1e-13 on stretched grids (first test).
+* int_comp = 2: MTHINC (m_thinc.fpp:28-291,323-355), pinned by the reference's 5 goldens.
+"""
 import ctypes as C
 import math
 
@@ -47,7 +51,7 @@ def test_product_path_rejects_order_7():
 
 
 @pytest.mark.parametrize("uuid", sorted(ORACLE_ONLY))
-def test_weno7_golden(uuid):
+def test_oracle_only_golden(uuid):
     entry = ORACLE_ONLY[uuid]
     case = entry["params"]
     P, cons0, q = _oracle_run(case)
