@@ -132,7 +132,7 @@ def test_oracle_spatial_order_2d(label, scheme, expected, tol, res):
     h_sweep("oracle", 2, res, expected, tol, **scheme)
 
 
-@pytest.mark.parametrize("label,ts,expected,tol,cfls", TEMPORAL, ids=_ids(TEMPORAL))
+@pytest.mark.parametrize("label,ts,expected,tol,cfls", TEMPORAL[1:], ids=_ids(TEMPORAL[1:]))  # RK1 (33 k steps): GPU leg only
 def test_oracle_temporal_order(label, ts, expected, tol, cfls):
     dt_sweep("oracle", cfls, expected, tol, ts)
 
