@@ -11,7 +11,10 @@
  *   - host field arguments are `sys_size` pointers, one per equation, exactly like
  *     q_cons_vf(1:sys_size)%sf (reference src/common/m_derived_types.fpp:21-24).  `ghosted` = 1:
  *     each array has the reference's buffered bounds (-b:m+b, -b:n+b, -b:p+b) (collapsed dims 0:0),
- *     x fastest; `ghosted` = 0: interior only (0:m,0:n,0:p).  Only the interior is read/written.
+ *     x fastest; `ghosted` = 0: interior only (0:m,0:n,0:p).  Uploads read the interior only.  Downloads with
+ *     `ghosted` = 1 write the whole array like the reference's GPU_UPDATE(host=...): q_prim_vf gets its ghost cells
+ *     filled (faces, edges, corners, x -> y -> z order), q_cons_vf / rhs_vf get zeros in theirs (never meaningful in
+ *     the reference either: boundary conditions act on the primitive variables, m_rhs.fpp:641-645).
  *   - all device memory is owned by the library; state persists in the handle between calls so a
  *     steady-state step moves no bytes between host and device.
  */
@@ -78,6 +81,9 @@ MFC5_API int mfc5_tvd_rk(mfc5_handle* h, double dt, double* stage_time_min);
  * the captured step); returns after enqueue.  mfc5_sync waits. */
 MFC5_API int mfc5_tvd_rk_n(mfc5_handle* h, double dt, int nsteps);
 MFC5_API int mfc5_sync(mfc5_handle* h);
+/* how mfc5_tvd_rk_n runs its steps: 1 = CUDA-graph replay, 0 = eager launches by request, -1 = a graph capture failed and
+ * the handle fell back to eager launches (a performance cliff on small grids, never a correctness issue) */
+MFC5_API int mfc5_graph_state(const mfc5_handle* h);
 
 /* Simulation time of the state (the reference's `mytime`, GPU_UPDATE(device=[mytime]) m_time_steppers.fpp:532); only the
  * body-force acceleration g + k sin(w t - p) depends on it.  mfc5_tvd_rk / mfc5_tvd_rk_n add dt after every step, like

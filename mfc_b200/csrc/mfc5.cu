@@ -14,11 +14,24 @@
 #include <string>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>   // header-only; a no-op unless a profiler is attached
+
 #include "../../include/mfc5.h"
 #define MFC5_HOST_TU
 #include "mfc5_host.cuh"
 
 using namespace mfc5;
+
+// NVTX ranges with the reference's names (m_time_steppers.fpp:453 TIMESTEP, m_rhs.fpp:594 COMPUTE-RHS, :640 RHS-CONVERT,
+// :635/:644 RHS-COMMUNICATION, :912 RHS-RECONSTRUCTION, :1030 RHS-RIEMANN-SOLVER, :1041 RHS-ADVECTION-SRC -- the last three
+// are one fused kernel per direction here, so they share one range).  Host-side enqueue ranges: under CUDA-graph replay a
+// whole step is one launch inside TIMESTEP.
+struct NvtxRange {
+    bool open = true;
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    void end() { if (open) { nvtxRangePop(); open = false; } }
+    ~NvtxRange() { end(); }
+};
 
 static thread_local std::string g_err;
 static int fail(const std::string& m) { g_err = m; return -1; }
@@ -39,6 +52,7 @@ struct NcclApi {
     int (*Send)(const void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
     int (*Recv)(void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
     int (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    int (*AllGather)(const void*, void*, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
     int (*GroupStart)() = nullptr;
     int (*GroupEnd)() = nullptr;
     const char* (*GetErrorString)(int) = nullptr;
@@ -59,6 +73,7 @@ static int nccl_load() {
     SYM(Send, "ncclSend");
     SYM(Recv, "ncclRecv");
     SYM(AllReduce, "ncclAllReduce");
+    SYM(AllGather, "ncclAllGather");
     SYM(GroupStart, "ncclGroupStart");
     SYM(GroupEnd, "ncclGroupEnd");
     SYM(GetErrorString, "ncclGetErrorString");
@@ -110,6 +125,7 @@ struct mfc5_handle {
     long long cls_launches[MFC5_NUM_KCLASS] = {};
     bool timing = false;
     unsigned long long* d_red = nullptr;
+    unsigned long long* d_red_all = nullptr;   // [nranks][4]: every rank's partial results (one ncclAllGather per reduction)
     long long launches = 0;
     DevP D;
     // multi-GPU
@@ -128,6 +144,7 @@ struct mfc5_handle {
     long long launches_captured = 0;
     bool warmed = false;              // one step has run uncaptured (lazy allocations, function attributes)
     int use_graph = 1;
+    bool graph_fallback = false;      // a capture failed and the handle fell back to eager launches
 };
 
 static bool is_cbc(int bc) { return bc <= MFC5_BC_CHAR_SLIP_WALL && bc >= MFC5_BC_CHAR_SUP_OUTFLOW; }
@@ -174,7 +191,7 @@ extern "C" int mfc5_create(const mfc5_params* p, mfc5_handle** out) {
     if (p->m < 0 || p->n < 0 || p->p < 0 || (p->n == 0 && p->p > 0)) return fail("invalid m, n, p");
     // m_checker.fpp:52-69: at least num_stcls_min*weno_order cells per direction
     const int recon_order = p->muscl_order > 0 ? p->muscl_order : p->weno_order;
-    const int need = recon_order > 1 ? 5 * recon_order : 1;
+    const int need = 5 * recon_order;   // num_stcls_min * weno_order for every order, 1 included (s_check_inputs_weno)
     const int ss[3] = {p->m, p->n, p->p};
     for (int d = 0; d < 3; d++)
         if ((d == 0 || ss[d] > 0) && ss[d] + 1 < need) return fail("too few cells for the WENO stencil (m_checker.fpp:52-69)");
@@ -228,7 +245,7 @@ extern "C" int mfc5_destroy(mfc5_handle* h) {
     cudaDeviceSynchronize();
     for (int i = 0; i < 2; i++) cudaFree(h->d_q[i]);
     for (int i = 0; i < 4; i++) if (h->gexec[i]) cudaGraphExecDestroy(h->gexec[i]);
-    cudaFree(h->d_prim[0]); cudaFree(h->d_prim[1]); cudaFree(h->d_rhs); cudaFree(h->d_red);
+    cudaFree(h->d_prim[0]); cudaFree(h->d_prim[1]); cudaFree(h->d_rhs); cudaFree(h->d_red); cudaFree(h->d_red_all);
     for (int d = 0; d < 3; d++) {
         for (int k = 0; k < 9; k++) cudaFree(h->d_tab[d][k]);
         for (int k = 0; k < 2; k++) { cudaFree(h->d_cbcbuf[d][k]); cudaFree(h->d_dirich[d][k]); cudaFree(h->d_send[d][k]); cudaFree(h->d_recv[d][k]); }
@@ -551,8 +568,13 @@ extern "C" int mfc5_set_dirichlet(mfc5_handle* h, int d, int side, const double*
     CK(cudaSetDevice(h->P.device));
     const int t1 = d == 0 ? 1 : 0, t2 = d == 2 ? 1 : 2;
     const size_t n = (size_t)h->N * (h->s[t1] + 1) * (h->s[t2] + 1);
-    if (h->d_dirich[d][side]) cudaFree(h->d_dirich[d][side]);
-    CK(cudaMalloc(&h->d_dirich[d][side], n * sizeof(double)));
+    CK(cudaStreamSynchronize(h->st));
+    if (!h->d_dirich[d][side]) {
+        // first call for this face: the kernel argument changes from nullptr to the new buffer, so steps captured
+        // before it (they hold DevP by value) must be re-captured.  Later calls reuse the allocation (its size is fixed).
+        CK(cudaMalloc(&h->d_dirich[d][side], n * sizeof(double)));
+        for (int i = 0; i < 4; i++) if (h->gexec[i]) { cudaGraphExecDestroy(h->gexec[i]); h->gexec[i] = nullptr; }
+    }
     CK(cudaMemcpy(h->d_dirich[d][side], values, n * sizeof(double), cudaMemcpyHostToDevice));
     h->D.dirich[d][side] = h->d_dirich[d][side];
     return 0;
@@ -568,7 +590,9 @@ static int copy_fields(mfc5_handle* h, double* dev, const double* const* hostc, 
     const int gx = ghosted ? h->b : 0, gy = (ghosted && h->nd > 1) ? h->b : 0, gz = (ghosted && h->nd > 2) ? h->b : 0;
     // host extents
     const size_t hx = h->s[0] + 1 + 2 * gx, hy = h->s[1] + 1 + 2 * gy, hz = h->s[2] + 1 + 2 * gz;
-    // copy region: upload -> interior only; download -> everything the host array holds
+    // copy region: upload -> interior only (ghost conserved values are never valid in the reference either); download ->
+    // everything the host array holds, like GPU_UPDATE(host=...) of the whole sf array: the ghost cells of q_prim_vf are part
+    // of its contract (m_rhs.fpp:884-898), those of q_cons_vf / rhs_vf receive the device's own (unused, zero) ghost cells
     const int cgx = to_dev ? 0 : gx, cgy = to_dev ? 0 : gy, cgz = to_dev ? 0 : gz;
     const size_t wx = h->s[0] + 1 + 2 * cgx, wy = h->s[1] + 1 + 2 * cgy, wz = h->s[2] + 1 + 2 * cgz;
     // Staging image = the other ping-pong state buffer: between calls it only holds the stale previous state
@@ -620,13 +644,19 @@ extern "C" int mfc5_download_cons(mfc5_handle* h, double* const* q, int ghosted)
     if (!h || !q) return fail("mfc5_download_cons: null argument");
     return copy_fields(h, h->d_q[h->cur], nullptr, q, ghosted, false);
 }
+static int refresh_prim(mfc5_handle* h);
+static long long halo_count(const mfc5_handle* h, int d);
 extern "C" int mfc5_download_prim(mfc5_handle* h, double* const* q, int ghosted) {
     if (!h || !q) return fail("mfc5_download_prim: null argument");
-    if (ghosted && h->setup) {  // edges and corners as the reference fills them (the sweeps do not need them)
+    if (h->setup) {
         CK(cudaSetDevice(h->P.device));
-        DevP D = h->D;
-        D.prim = h->d_prim[h->pp]; D.primw = h->d_prim[h->pp];
-        if (fill_full(h, D)) return -1;
+        // after a time step the primitive buffer still holds the last STAGE's input: convert the current state first
+        if (!h->prim_valid && refresh_prim(h)) return -1;
+        if (ghosted) {  // edges and corners as the reference fills them (the sweeps do not need them)
+            DevP D = h->D;
+            D.prim = h->d_prim[h->pp]; D.primw = h->d_prim[h->pp];
+            if (fill_full(h, D)) return -1;
+        }
     }
     return copy_fields(h, h->d_prim[h->pp], nullptr, q, ghosted, false);
 }
@@ -812,6 +842,7 @@ static int launch_sweep(mfc5_handle* h, const DevP& D0, int dir, bool* halo_pend
 
 // one RHS evaluation (+ fused RK update when do_rk): q1 = state read, q2 = stage-1 copy, qout = target
 static int run_stage(mfc5_handle* h, const double* q1, const double* q2, double* qout, int do_rk, const double rk[4], double dt) {
+    NvtxRange nv_rhs("COMPUTE-RHS");
     DevP D = h->D;
     D.prim = h->d_prim[h->pp]; D.primw = h->d_prim[h->pp]; D.q1 = q1; D.q2 = q2; D.qout = qout; D.rhs = h->d_rhs;
     D.prim_next = (do_rk && h->fuse_c2p) ? h->d_prim[h->pp ^ 1] : nullptr;
@@ -825,6 +856,7 @@ static int run_stage(mfc5_handle* h, const double* q1, const double* q2, double*
     D.rk0 = rk[0]; D.rk1 = rk[1]; D.rk2 = rk[2]; D.rk3 = rk[3]; D.irk3 = 1.0 / rk[3]; D.dt = dt; D.do_rk = do_rk;
     const long long ncell = (long long)(h->s[0] + 1) * (h->s[1] + 1) * (h->s[2] + 1);
     if (!h->prim_valid) {  // with MFC5_FUSE_C2P only after an upload: the previous stage wrote them
+        NvtxRange nv("RHS-CONVERT");
         if (seg_begin(h, MFC5_K_CONS2PRIM)) return -1;
         int rc = by_shape(h, [&](auto nf, auto nd) {
             k_cons2prim<decltype(nf)::value, decltype(nd)::value><<<grid_for(ncell, 256), 256, 0, h->st>>>(D);
@@ -833,6 +865,7 @@ static int run_stage(mfc5_handle* h, const double* q1, const double* q2, double*
         if (seg_end(h, 1)) return -1;
     }
     bool halo_pending = false;
+    NvtxRange nv_comm("RHS-COMMUNICATION");
     if (h->any_nb) {
         CK(cudaEventRecord(h->ev_prim, h->st));
         if (exchange_halos(h, D)) return -1;
@@ -876,7 +909,11 @@ static int run_stage(mfc5_handle* h, const double* q1, const double* q2, double*
         } else if (faces(2, 2 * (h->nd - 1), any_phys_yz, any_cbc_yz, h->st)) return -1;
     }
     if (faces(0, 2, any_phys_x, any_cbc_x, h->st)) return -1;
+    nv_comm.end();
+    static const char* sweep_names[3] = {"RHS-RECONSTRUCTION+RIEMANN-SOLVER+ADVECTION-SRC x", "RHS-RECONSTRUCTION+RIEMANN-SOLVER+ADVECTION-SRC y",
+                                         "RHS-RECONSTRUCTION+RIEMANN-SOLVER+ADVECTION-SRC z"};
     for (int d = 0; d < h->nd; d++) {
+        NvtxRange nv(sweep_names[d]);
         if (d == 1 && side_pending) CK(cudaStreamWaitEvent(h->st, h->ev_bc, 0));
         if (launch_sweep(h, D, d, &halo_pending)) return -1;
     }
@@ -893,6 +930,22 @@ static int run_stage(mfc5_handle* h, const double* q1, const double* q2, double*
     return 0;
 }
 
+// primitive variables of the CURRENT conservative state into d_prim[pp] (interior; physical ghost faces are filled by the
+// callers that need them)
+static int refresh_prim(mfc5_handle* h) {
+    DevP D = h->D;
+    D.prim = h->d_prim[h->pp]; D.primw = h->d_prim[h->pp]; D.q1 = h->d_q[h->cur]; D.q2 = D.q1; D.qout = nullptr; D.rhs = h->d_rhs;
+    const long long ncell = (long long)(h->s[0] + 1) * (h->s[1] + 1) * (h->s[2] + 1);
+    int rc = by_shape(h, [&](auto nf, auto nd) {
+        k_cons2prim<decltype(nf)::value, decltype(nd)::value><<<grid_for(ncell, 256), 256, 0, h->st>>>(D);
+    });
+    if (rc) return rc;
+    h->launches += 1;
+    CK(cudaGetLastError());
+    h->prim_valid = true;
+    return 0;
+}
+
 static const double RK3[3][4] = {{1, 0, 1, 1}, {1, 3, 1, 4}, {2, 1, 2, 3}};  // m_time_steppers.fpp:421-432
 static const double RK2[2][4] = {{1, 0, 1, 1}, {1, 1, 1, 2}};
 static const double RK1[1][4] = {{1, 0, 1, 1}};
@@ -900,6 +953,7 @@ static const double RK1[1][4] = {{1, 0, 1, 1}};
 // enqueue one full step on h->st.  Ping-pong: stage 1 reads A (which thereby *is* q_cons_ts(2)) and
 // writes B; later stages update B in place.  For time_stepper = 1 the update is in place.
 static int enqueue_step(mfc5_handle* h, double dt, bool timed) {
+    NvtxRange nv_step("TIMESTEP");
     const int ns = h->P.time_stepper;
     double* A = h->d_q[h->cur];
     double* B = ns > 1 ? h->d_q[h->cur ^ 1] : A;
@@ -934,6 +988,7 @@ extern "C" int mfc5_tvd_rk(mfc5_handle* h, double dt, double* stage_time_min) {
     if (!h || !h->setup) return fail("mfc5_tvd_rk: handle not set up");
     CK(cudaSetDevice(h->P.device));
     if (enqueue_step(h, dt, true)) return -1;
+    h->warmed = true;
     CK(cudaStreamSynchronize(h->st));
     const int ns = h->P.time_stepper;
     for (int st = 0; st < ns; st++) {
@@ -967,6 +1022,10 @@ extern "C" int mfc5_tvd_rk_n(mfc5_handle* h, double dt, int nsteps) {
             h->warmed = true;
             continue;
         }
+        // Outside MFC5_FUSE_C2P mode a captured step must always start with its cons -> prim pass: whether stage 1 launches
+        // it depends on prim_valid at CAPTURE time (mfc5_reduce / mfc5_compute_rhs leave it true), and a graph captured
+        // without it would replay on stale primitive variables.  The pass is redundant right after those calls, but correct.
+        if (!h->fuse_c2p) h->prim_valid = false;
         const int cur0 = h->cur, pp0 = h->pp, key = 2 * cur0 + pp0;  // buffer parities the captured pointers depend on
         if (!h->gexec[key] || h->gdt[key] != dt) {
             if (h->gexec[key]) { cudaGraphExecDestroy(h->gexec[key]); h->gexec[key] = nullptr; }
@@ -988,9 +1047,12 @@ extern "C" int mfc5_tvd_rk_n(mfc5_handle* h, double dt, int nsteps) {
             h->cur = cur0; h->pp = pp0; h->prim_valid = pv0; h->mytime = t0;  // the captured enqueue only did the bookkeeping, nothing ran
             if (e != cudaSuccess || rc != 0 || !h->gexec[key]) {
                 // capture not possible here (e.g. an NCCL build without graph support): run eagerly from now on
+                g_err = std::string("mfc5_tvd_rk_n: CUDA graph capture failed (") + (e != cudaSuccess ? cudaGetErrorString(e) : "enqueue error") +
+                        "); running eagerly from now on";   // not fatal: readable through mfc5_last_error / mfc5_graph_state
                 cudaGetLastError();
                 h->gexec[key] = nullptr;
                 h->use_graph = 0;
+                h->graph_fallback = true;
                 if (enqueue_step(h, dt, false)) return -1;
                 continue;
             }
@@ -1005,6 +1067,13 @@ extern "C" int mfc5_tvd_rk_n(mfc5_handle* h, double dt, int nsteps) {
         h->mytime = h->mytime + dt;
     }
     return 0;
+}
+
+// 1: steps enqueued by mfc5_tvd_rk_n replay a captured CUDA graph; 0: eager by request (MFC5_NO_GRAPH, time-dependent body
+// force); -1: a capture failed and the handle fell back to eager launches (the reason is in mfc5_last_error at that time)
+extern "C" int mfc5_graph_state(const mfc5_handle* h) {
+    if (!h) return 0;
+    return h->graph_fallback ? -1 : (h->use_graph ? 1 : 0);
 }
 
 extern "C" int mfc5_set_time(mfc5_handle* h, double mytime) {
@@ -1038,14 +1107,24 @@ extern "C" int mfc5_reduce(mfc5_handle* h, int what, double dt, double* out) {
     });
     if (rc) return rc;
     h->launches += 2;
-    if (h->comm) {
-        NK(g_nccl.AllReduce(h->d_red + 0, h->d_red + 0, 1, NCCL_FLOAT64, NCCL_MAX, h->comm, h->st));
-        NK(g_nccl.AllReduce(h->d_red + 1, h->d_red + 1, 1, NCCL_FLOAT64, NCCL_MIN, h->comm, h->st));
-        NK(g_nccl.AllReduce(h->d_red + 2, h->d_red + 2, 1, NCCL_UINT64, NCCL_SUM, h->comm, h->st));
-    }
     unsigned long long res[4];
-    CK(cudaMemcpyAsync(res, h->d_red, sizeof(res), cudaMemcpyDeviceToHost, h->st));
-    CK(cudaStreamSynchronize(h->st));
+    if (h->comm) {
+        // max / min / sum of three scalars in ONE collective: gather every rank's 4 words, combine on the host (the three
+        // separate 1-element all-reduces cost three NCCL latencies per cfl_adap_dt step)
+        NK(g_nccl.AllGather(h->d_red, h->d_red_all, 4, NCCL_UINT64, h->comm, h->st));
+        std::vector<unsigned long long> all((size_t)4 * h->nranks);
+        CK(cudaMemcpyAsync(all.data(), h->d_red_all, all.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->st));
+        CK(cudaStreamSynchronize(h->st));
+        res[0] = 0ull; res[1] = 0x7FEFFFFFFFFFFFFFull; res[2] = 0ull; res[3] = 0ull;
+        for (int r = 0; r < h->nranks; r++) {   // non-negative doubles order like their bit patterns
+            res[0] = std::max(res[0], all[4 * r + 0]);
+            res[1] = std::min(res[1], all[4 * r + 1]);
+            res[2] += all[4 * r + 2];
+        }
+    } else {
+        CK(cudaMemcpyAsync(res, h->d_red, sizeof(res), cudaMemcpyDeviceToHost, h->st));
+        CK(cudaStreamSynchronize(h->st));
+    }
     if (what == 2) { *out = (double)res[2]; return 0; }
     double v;
     std::memcpy(&v, &res[what], sizeof(double));
@@ -1071,5 +1150,15 @@ extern "C" int mfc5_comm_init(mfc5_handle* h, const char id_in[128], int rank, i
     std::memcpy(id.internal, id_in, 128);
     NK(g_nccl.CommInitRank(&h->comm, nranks, id, rank));
     h->rank = rank; h->nranks = nranks;
+    if (h->d_red_all) cudaFree(h->d_red_all);
+    CK(cudaMalloc(&h->d_red_all, (size_t)4 * nranks * sizeof(unsigned long long)));
+    // packed halo faces: allocated here, not lazily inside the first stage
+    for (int d = 0; d < h->nd; d++)
+        for (int sd = 0; sd < 2; sd++)
+            if (h->P.bc[d][sd] >= 0 && !h->d_send[d][sd]) {
+                const size_t nb = (size_t)halo_count(h, d) * sizeof(double);
+                CK(cudaMalloc(&h->d_send[d][sd], nb));
+                CK(cudaMalloc(&h->d_recv[d][sd], nb));
+            }
     return 0;
 }

@@ -55,13 +55,16 @@ template <int NF, int ND, int DIR, int WO, int WV, int RS, int FAST>
 inline bool launch_march(const DevP& P0, cudaStream_t st) {
     constexpr int bps = (2 * NF + ND + 1 <= 8) ? MFC5_MARCH_MINB : 1;  // resident blocks per SM the kernel is built for
     auto kern = k_sweep_march<NF, ND, DIR, WO, WV, RS, FAST>;
-    static bool attr_done = false;
-    if (!attr_done) {
+    // the attribute is per device (a process may hold handles on several): once per (kernel, device ordinal)
+    static bool attr_done[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64 || !attr_done[dev]) {
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024) != cudaSuccess) {
             cudaGetLastError();
             return false;
         }
-        attr_done = true;
+        if (dev >= 0 && dev < 64) attr_done[dev] = true;
     }
     DevP P = P0;
     // longest chunk whose table rows still let `bps` blocks share the 227 KB of an SM

@@ -45,6 +45,7 @@ def load(strict=False):
     L.mfc5_tvd_rk.argtypes = [vp, C.c_double, _dp]
     L.mfc5_tvd_rk_n.argtypes = [vp, C.c_double, C.c_int]
     L.mfc5_sync.argtypes = [vp]
+    L.mfc5_graph_state.argtypes = [vp]
     L.mfc5_set_time.argtypes = [vp, C.c_double]
     L.mfc5_reduce.argtypes = [vp, C.c_int, C.c_double, _dp]
     L.mfc5_nccl_unique_id.argtypes = [C.c_char_p]
@@ -66,7 +67,7 @@ def load(strict=False):
 EXPORTED_SYMBOLS = [
     "mfc5_create", "mfc5_destroy", "mfc5_set_grid", "mfc5_finalize_setup", "mfc5_set_dirichlet", "mfc5_upload_cons",
     "mfc5_download_cons", "mfc5_download_prim", "mfc5_download_rhs", "mfc5_compute_rhs", "mfc5_tvd_rk", "mfc5_tvd_rk_n",
-    "mfc5_sync", "mfc5_set_time", "mfc5_reduce", "mfc5_nccl_unique_id", "mfc5_comm_init", "mfc5_sys_size", "mfc5_buff_size",
+    "mfc5_sync", "mfc5_graph_state", "mfc5_set_time", "mfc5_reduce", "mfc5_nccl_unique_id", "mfc5_comm_init", "mfc5_sys_size", "mfc5_buff_size",
     "mfc5_kernel_launches", "mfc5_last_kernel_ms", "mfc5_compute_stream", "mfc5_last_error", "mfc5_version",
 ]
 
@@ -138,10 +139,32 @@ class Mfc5:
         return self._get(self.L.mfc5_download_cons)
 
     def get_prim(self):
+        """Primitive variables of the CURRENT state (the library converts first if its buffer is stale, e.g. after a step)."""
         return self._get(self.L.mfc5_download_prim)
 
     def get_rhs(self):
         return self._get(self.L.mfc5_download_rhs)
+
+    # ---- the layout the Fortran host passes: q_cons_vf(i)%sf(-b:m+b, -b:n+b, -b:p+b) (``ghosted = 1``) ----
+    @property
+    def box_shape(self):
+        """(N, p+1+2bz, n+1+2by, m+1+2b): the buffered box of every field (collapsed dimensions have no ghosts)."""
+        P, b = self.P, self.b
+        return (self.N, P.p + 1 + (2 * b if P.p > 0 else 0), P.n + 1 + (2 * b if P.n > 0 else 0), P.m + 1 + 2 * b)
+
+    def set_cons_box(self, q):
+        """Upload from buffered arrays (only the interior is read, like GPU_UPDATE of q_cons_ts(1))."""
+        q = np.ascontiguousarray(q, dtype=np.float64)
+        assert q.shape == self.box_shape, (q.shape, self.box_shape)
+        self._ck(self.L.mfc5_upload_cons(self.h, self._field_ptrs(q), 1))
+
+    def get_box(self, which, out=None):
+        """Download into buffered arrays: 'cons' / 'rhs' (interior + whatever the device ghosts hold) or 'prim'
+        (ghost cells filled in the reference's x -> y -> z order, edges and corners included, m_rhs.fpp:884-898)."""
+        fn = {"cons": self.L.mfc5_download_cons, "prim": self.L.mfc5_download_prim, "rhs": self.L.mfc5_download_rhs}[which]
+        q = np.zeros(self.box_shape) if out is None else out
+        self._ck(fn(self.h, self._field_ptrs(q), 1))
+        return q
 
     def compute_rhs(self):
         """``s_compute_rhs`` (reference m_rhs.fpp:574): RHS of the current state, no update."""
@@ -158,6 +181,11 @@ class Mfc5:
 
     def sync(self):
         self._ck(self.L.mfc5_sync(self.h))
+
+    @property
+    def graph_state(self):
+        """1: ``steps`` replays a CUDA graph; 0: eager by request; -1: graph capture failed, eager fallback."""
+        return int(self.L.mfc5_graph_state(self.h))
 
     def set_time(self, mytime):
         """The reference's ``mytime`` (only the body-force acceleration depends on it); steps advance it by dt."""

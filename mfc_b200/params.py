@@ -226,7 +226,7 @@ def params_from_case(case, device=0, fast_math=1, oracle_only=False):
 
 def check_params(P):
     """Run-time checks of the reference: src/simulation/m_checker.fpp:52-69 (cells per rank)."""
-    need = 5 * P.recon_order if P.recon_order > 1 else 1
+    need = 5 * P.recon_order   # num_stcls_min * weno_order (or muscl_order), order 1 included: m_checker.fpp:52-90
     if P.muscl_order > 0 and any(-12 <= P.bc[d][s] <= -5 for d in range(P.num_dims) for s in range(2)):
         raise UnsupportedCase("characteristic boundary conditions with MUSCL reconstruction are outside the hot path")
     for s, name in ((P.m, "m"), (P.n, "n"), (P.p, "p")):

@@ -524,6 +524,14 @@ void orc_set_cons(orc_state* S, const double* q) { copy_interior(S, q, S->q1, 1)
 void orc_get_cons(const orc_state* S, double* q) { copy_interior(S, q, S->q1, 0); }
 void orc_get_prim(const orc_state* S, double* q) { copy_interior(S, q, S->prim, 0); }
 void orc_get_rhs(const orc_state* S, double* q) { copy_interior(S, q, S->rhs, 0); }
+/* the buffered boxes themselves, sf(-b:m+b, -b:n+b, -b:p+b) per variable (collapsed dimensions 0:0), x fastest -- the layout
+ * of q_cons_vf / q_prim_vf at the module boundary (m_time_steppers.fpp:179-185); which = 0 cons, 1 prim, 2 rhs */
+long orc_box_size(const orc_state* S) { return S->fsz; }
+void orc_get_box(const orc_state* S, int which, double* q) {
+    const double* src = which == 0 ? S->q1 : which == 1 ? S->prim : S->rhs;
+    memcpy(q, src, (size_t)S->N * S->fsz * sizeof(double));
+}
+void orc_set_cons_box(orc_state* S, const double* q) { memcpy(S->q1, q, (size_t)S->N * S->fsz * sizeof(double)); }
 
 /* mixture rule shared by cons->prim, CBC and ICFL:
  * s_compute_species_fraction (m_variables_conversion.fpp:1140-1188) followed by

@@ -36,6 +36,10 @@ void orc_set_cons(orc_state* S, const double* q);
 void orc_get_cons(const orc_state* S, double* q);
 void orc_get_prim(const orc_state* S, double* q);
 void orc_get_rhs(const orc_state* S, double* q);
+/* the buffered boxes sf(-b:m+b,-b:n+b,-b:p+b) per variable (collapsed dims 0:0): which = 0 cons, 1 prim, 2 rhs */
+long orc_box_size(const orc_state* S);
+void orc_get_box(const orc_state* S, int which, double* q);
+void orc_set_cons_box(orc_state* S, const double* q);
 
 /* phases of one RK stage (m_rhs.fpp:574-902, m_time_steppers.fpp:458-507) */
 void orc_cons2prim(orc_state* S);

@@ -32,6 +32,10 @@ def load(omp=False):
     L.orc_set_dirichlet.argtypes = [C.c_void_p, C.c_int, C.c_int, _dp]
     for f in ("orc_set_cons", "orc_get_cons", "orc_get_prim", "orc_get_rhs"):
         getattr(L, f).argtypes = [C.c_void_p, _dp]
+    L.orc_box_size.argtypes = [C.c_void_p]
+    L.orc_box_size.restype = C.c_long
+    L.orc_get_box.argtypes = [C.c_void_p, C.c_int, _dp]
+    L.orc_set_cons_box.argtypes = [C.c_void_p, _dp]
     L.orc_cons2prim.argtypes = [C.c_void_p]
     L.orc_bc_fill.argtypes = [C.c_void_p, C.c_int, C.c_int]
     L.orc_halo_count.argtypes = [C.c_void_p, C.c_int]
@@ -102,6 +106,24 @@ class Oracle:
 
     def get_rhs(self):
         return self._get(self.L.orc_get_rhs)
+
+    @property
+    def box_shape(self):
+        """(N, p+1+2bz, n+1+2by, m+1+2b): the buffered box sf(-b:m+b, -b:n+b, -b:p+b), collapsed dims 0:0."""
+        P, b = self.P, self.b
+        return (self.N, P.p + 1 + (2 * b if P.p > 0 else 0), P.n + 1 + (2 * b if P.n > 0 else 0), P.m + 1 + 2 * b)
+
+    def get_box(self, which):
+        """which = 'cons' | 'prim' | 'rhs': the buffered box as the reference holds it (ghost cells as last filled)."""
+        q = np.empty(self.box_shape)
+        assert q.size == self.N * self.L.orc_box_size(self.h)
+        self.L.orc_get_box(self.h, {"cons": 0, "prim": 1, "rhs": 2}[which], _ptr(q))
+        return q
+
+    def set_cons_box(self, q):
+        q = np.ascontiguousarray(q, dtype=np.float64)
+        assert q.shape == self.box_shape
+        self.L.orc_set_cons_box(self.h, _ptr(q))
 
     def compute_rhs(self):
         self.L.orc_compute_rhs(self.h)

@@ -82,3 +82,14 @@ def test_out_of_envelope_cases_are_rejected():
         params_from_case(dict(base, low_Mach=2, riemann_solver=1))
     with pytest.raises(UnsupportedCase):  # m_checker.fpp:52-69
         params_from_case(dict(base, m=10))
+
+
+def test_c_host_program_compiles_and_links_against_the_header(tmp_path):
+    """tests/c_driver/abi_driver.c (the shim's call sequence in plain C) builds with gcc -Wall -Werror against include/mfc5.h
+    and links with libmfc5.so; its compute path runs in tests/test_gpu_abi.py."""
+    exe = str(tmp_path / "abi_driver")
+    libdir = os.path.join(ROOT, "mfc_b200")
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "tests", "c_driver", "abi_driver.c"), "-L", libdir, "-lmfc5", f"-Wl,-rpath,{libdir}", "-o", exe])
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 1 and "usage" in r.stderr
