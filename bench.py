@@ -144,6 +144,75 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def config_dict(name, ncell_loc, ncell_glb, N, dims, world):
+    """The `config` object, identical for both arms (the driver compares them key by key)."""
+    return {"workload": name, "cells_per_gpu": ncell_loc, "cells_global": ncell_glb, "sys_size": N, "proc_grid": list(dims),
+            "l2": "inputs larger than L2 (state 4 x %.0f MB per GPU)" % (N * ncell_loc * 8 / 1e6),
+            "vs_baseline_ref": "0.38 ns/gp/eq/rhs published for H100 SXM5 (BASELINE.md); nothing published for B200",
+            "parallelism": "block domain decomposition %dx%dx%d, NCCL halo" % tuple(dims) if world > 1 else "single GPU"}
+
+
+def reference_toolchain():
+    """the reference's own CPU build needs gfortran (or nvfortran), an MPI, fypp and cmake.  Probe the box
+    and say what is there; without them the CPU arm is the C restatement (`kind: "port"`)."""
+    import shutil
+    tools = {t: shutil.which(t) for t in ("gfortran", "nvfortran", "mpirun", "mpif90", "fypp", "cmake")}
+    have = bool((tools["gfortran"] or tools["nvfortran"]) and tools["mpirun"] and tools["fypp"] and tools["cmake"])
+    return {"found": {k: v for k, v in tools.items() if v}, "missing": sorted(k for k, v in tools.items() if not v),
+            "mfc_cpu_build_possible": have}
+
+
+def multi_gpu_parity(args, rank, world, local_rank):
+    """Driver-visible multi-GPU result check (run before the timed region): 5 RK3 steps of the bench case at 60^3 cells per GPU,
+    decomposed over `world` GPUs with NCCL halo exchange, gathered to rank 0 and compared with rank 0's own single-GPU run of
+    the same global case; bar 1e-12 of max|q| per variable (the halo values are copies; only the ghost cell-boundary coordinates
+    are rebuilt per rank, an ulp-level change of the WENO tables on the stretched grid).  Reference: s_mpi_sendrecv_variables_buffers
+    m_mpi_common.fpp:620-1065."""
+    import torch
+    import torch.distributed as dist
+    from mfc_b200 import decomp, lib
+    from mfc_b200.lib import Mfc5
+    sargs = argparse.Namespace(**vars(args))
+    sargs.case, sargs.m, sargs.scaling = "3D_performance_test", 59, "weak"
+    case, dims, _ = build_case(sargs, world)
+    nsteps, dt = 5, None
+    blk, lcase, P, cbs, gws, cons = setup_rank(case, rank, world, dims)
+    dt = float(case["dt"])
+    P.device = local_rank
+    g = Mfc5(P, cbs, ghost_widths=gws)
+    uid = [lib.nccl_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(uid, src=0)
+    g.comm_init(uid[0], rank, world)
+    g.set_cons(cons)
+    g.steps(dt, nsteps)
+    g.sync()
+    loc = torch.from_numpy(g.get_cons()).cuda()
+    parts = [torch.empty_like(loc) for _ in range(world)]
+    dist.all_gather(parts, loc)
+    launches = g.kernel_launches
+    g.close()
+    if rank != 0:
+        return None
+    _, _, Pg, cbg, _, cong = setup_rank(case, 0, 1, (1, 1, 1))
+    Pg.device = local_rank
+    s = Mfc5(Pg, cbg)
+    s.set_cons(cong)
+    s.steps(dt, nsteps)
+    s.sync()
+    full = s.get_cons()
+    s.close()
+    worst = 0.0
+    for r in range(world):
+        ref = decomp.Block(case, r, world, dims).slab(full)
+        a = parts[r].cpu().numpy()
+        for v in range(a.shape[0]):
+            worst = max(worst, float(np.abs(a[v] - ref[v]).max() / (np.abs(full[v]).max() + 1e-300)))
+    moved = float(np.abs(full - cong).max() / np.abs(cong).max())
+    return {"what": "decomposed run == single-GPU run of the same global case, 3D_performance_test at 60^3 cells per GPU, %d RK3 steps" % nsteps,
+            "cells_global": int((case["m"] + 1) * (case["n"] + 1) * (case["p"] + 1)), "proc_grid": list(dims), "max_rel": worst, "tol": 1e-12,
+            "ok": bool(worst <= 1e-12 and moved > 0.0), "state_change": moved, "kernel_launches_per_rank": int(launches)}
+
+
 def cpu_arm(case, P, cbs, cons, nsteps, warm):
     """Time the oracle (reference algorithm restated in C, OpenMP) on this box's host cores."""
     # all host cores, also under torchrun (which exports OMP_NUM_THREADS=1); must be set before libgomp starts
@@ -171,10 +240,12 @@ def grind(t_stage_s, P_glb_mnp, sys_size):
 def run_reference(args, rank, world):
     if rank != 0:
         return
-    # the CPU arm runs the single-GPU workload (per-cell cost is size independent)
+    # the workload named in `config` is the native arm's (N GPUs: N x the per-GPU block); the CPU arm times a bounded sample of
+    # it -- one per-GPU block, or a 100^3 cube of it -- and reports the intensive metric (ns per cell per equation per RHS)
+    gcase, gdims, gname = build_case(args, max(1, args.gpus))
     case, dims, name = build_case(args, 1)
-    full_m = case["m"]
-    sample = "one RK3 step of the full single-GPU workload per timed step"
+    full_cells = (case["m"] + 1) * (case["n"] + 1) * (case["p"] + 1)
+    sample = "one RK3 step of one GPU's block of the workload (%d cells) per timed step" % full_cells
     blk, lcase, P, cbs, gws, cons = setup_rank(case, 0, 1, (1, 1, 1))
     t = time.perf_counter()
     ts, threads, o = cpu_arm(lcase, P, cbs, cons, 1, 0)
@@ -187,7 +258,7 @@ def run_reference(args, rank, world):
         sargs.m = msmall
         case, dims, _ = build_case(sargs, 1)
         blk, lcase, P, cbs, gws, cons = setup_rank(case, 0, 1, (1, 1, 1))
-        sample = f"one RK3 step of a {msmall + 1}^3 sub-sample of the workload per timed step (full size projected at {est:.0f} s)"
+        sample = f"one RK3 step of a {msmall + 1}^3 cube of the same case per timed step (one GPU's block projected at {est:.0f} s for the run)"
     else:
         del o
     ts, threads, _ = cpu_arm(lcase, P, cbs, cons, args.steps, args.warmup)
@@ -199,10 +270,11 @@ def run_reference(args, rank, world):
         "impl": "reference", "metric": "grind_time", "value": g, "unit": "ns/gp/eq/rhs", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": t_step * 1e3, "higher_is_better": False, "scaling": args.scaling, "vs_baseline": g / PUBLISHED_H100,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": name, "cells_timed": ncell, "sys_size": P.sys_size,
-                   "note": "reference algorithm as the CPU oracle restatement (gfortran/MPI/fypp absent: MFC itself cannot be built here)"},
-        "cells_steps_per_s": ncell / t_step,
-        "cpu_baseline": {"value": g, "unit": "ns/gp/eq/rhs", "cores": threads, "kind": "port", "sample": sample},
+        "config": config_dict(gname, full_cells, (gcase["m"] + 1) * (gcase["n"] + 1) * (gcase["p"] + 1), P.sys_size, gdims, max(1, args.gpus)),
+        "cells_steps_per_s": ncell / t_step, "cells_timed": ncell,
+        "note": "reference algorithm as the CPU oracle restatement (kind: port): MFC's Fortran cannot be built in this image",
+        "cpu_baseline": {"value": g, "unit": "ns/gp/eq/rhs", "cores": threads, "kind": "port", "sample": sample,
+                         "reference_toolchain": reference_toolchain()},
         "e2e": {"value": g, "unit": "ns/gp/eq/rhs", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -231,6 +303,16 @@ def main():
     from mfc_b200 import lib
     from mfc_b200.lib import Mfc5
 
+    parity = None
+    if world > 1:
+        parity = multi_gpu_parity(args, rank, world, local_rank)
+        ok = [parity["ok"] if rank == 0 else None]
+        dist.broadcast_object_list(ok, src=0)
+        if not ok[0]:
+            if rank == 0:
+                print(json.dumps({"metric": "grind_time", "n_gpus": world, "error": "multi-GPU parity check failed", "parity_check": parity}), flush=True)
+            dist.destroy_process_group()
+            raise SystemExit(3)
     case, dims, name = build_case(args, world)
     blk, lcase, P, cbs, gws, cons = setup_rank(case, rank, world, dims)
     P.device = local_rank
@@ -273,6 +355,7 @@ def main():
     barrier()
     t1 = time.time()
     launches = g.kernel_launches - l0
+    graph_state = g.graph_state   # 1: the timed steps were CUDA-graph replays; -1: capture failed, eager fallback
     ms = e0.elapsed_time(e1)
     clocks = sampler.stop(t0, t1, busy0) if sampler else None
     if world > 1:
@@ -386,7 +469,9 @@ def main():
     if os.path.exists(prof_file):
         try:
             with open(prof_file) as f:
-                roof["traffic"] = json.load(f).get(dom)
+                tj = json.load(f)
+            roof["traffic"] = tj.get(dom)
+            roof["traffic_source"] = tj.get("_source", "committed ncu capture (profiles/traffic.json), not measured in this run")
         except (OSError, ValueError):
             pass
 
@@ -413,15 +498,15 @@ def main():
         "metric": "grind_time", "value": value, "unit": "ns/gp/eq/rhs", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_step, "higher_is_better": False, "scaling": args.scaling, "vs_baseline": value / PUBLISHED_H100,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": name, "cells_per_gpu": ncell_loc, "cells_global": ncell_glb, "sys_size": N, "proc_grid": list(dims),
-                   "l2": "inputs larger than L2 (state 4 x %.0f MB per GPU)" % (N * ncell_loc * 8 / 1e6),
-                   "vs_baseline_ref": "0.38 ns/gp/eq/rhs published for H100 SXM5 (BASELINE.md); nothing published for B200",
-                   "parallelism": "block domain decomposition %dx%dx%d, NCCL halo" % dims if world > 1 else "single GPU"},
+        "config": config_dict(name, ncell_loc, ncell_glb, N, dims, world),
         "cells_steps_per_s": ncell_glb / (ms_step * 1e-3),
         "grind_min_stage": grind(stage_min_s, (case["m"], case["n"], case["p"]), N),
         "clocks": clocks, "gpu_launches": int(launches), "nan_count": nan_count,
         "roofline": roof, "roofline_stage": roof_stage, "kernels": kern,
     }
+    if parity is not None:
+        out["parity_check"] = parity
+    out["graph_replay"] = graph_state
     if fp64 is not None:
         out["roofline_fp64"] = fp64
     if e2e is not None:
@@ -442,7 +527,8 @@ def main():
             sample = f"{args.cpu_steps} RK3 steps (after 1 warm-up) of the full workload"
         ts, threads, _ = cpu_arm(blcase, bP, bcbs, bcons, args.cpu_steps, 1)
         gcpu = grind(float(np.mean(ts)) / ns, (bcase["m"], bcase["n"], bcase["p"]), N)
-        out["cpu_baseline"] = {"value": gcpu, "unit": "ns/gp/eq/rhs", "cores": threads, "kind": "port", "sample": sample}
+        out["cpu_baseline"] = {"value": gcpu, "unit": "ns/gp/eq/rhs", "cores": threads, "kind": "port", "sample": sample,
+                               "reference_toolchain": reference_toolchain()}
     print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -99,6 +99,9 @@ struct mfc5_handle {
     // other one, so that the next stage needs no cons -> prim pass (prim_valid: d_prim[pp] matches the current state)
     double* d_prim[2] = {nullptr, nullptr};
     double* d_rhs = nullptr;
+    // case-optimised path: the rhs buffer doubles as the second primitive buffer (d_prim[1] == d_rhs): the RK-fused last sweep
+    // stores the primitive variables of the new state over the rhs entries it has consumed, and the two buffers swap roles
+    bool alias = false;
     int pp = 0;
     bool prim_valid = false;
     double mytime = 0.0;   // simulation time of the state (body forces); advanced by dt after every step
@@ -146,6 +149,8 @@ struct mfc5_handle {
     int use_graph = 1;
     bool graph_fallback = false;      // a capture failed and the handle fell back to eager launches
 };
+
+static double* rhs_ptr(const mfc5_handle* h) { return h->alias ? h->d_prim[h->pp ^ 1] : h->d_rhs; }
 
 static bool is_cbc(int bc) { return bc <= MFC5_BC_CHAR_SLIP_WALL && bc >= MFC5_BC_CHAR_SUP_OUTFLOW; }
 
@@ -245,7 +250,7 @@ extern "C" int mfc5_destroy(mfc5_handle* h) {
     cudaDeviceSynchronize();
     for (int i = 0; i < 2; i++) cudaFree(h->d_q[i]);
     for (int i = 0; i < 4; i++) if (h->gexec[i]) cudaGraphExecDestroy(h->gexec[i]);
-    cudaFree(h->d_prim[0]); cudaFree(h->d_prim[1]); cudaFree(h->d_rhs); cudaFree(h->d_red); cudaFree(h->d_red_all);
+    cudaFree(h->d_prim[0]); if (!h->alias) cudaFree(h->d_prim[1]); cudaFree(h->d_rhs); cudaFree(h->d_red); cudaFree(h->d_red_all);
     for (int d = 0; d < 3; d++) {
         for (int k = 0; k < 9; k++) cudaFree(h->d_tab[d][k]);
         for (int k = 0; k < 2; k++) { cudaFree(h->d_cbcbuf[d][k]); cudaFree(h->d_dirich[d][k]); cudaFree(h->d_send[d][k]); cudaFree(h->d_recv[d][k]); }
@@ -504,13 +509,13 @@ extern "C" int mfc5_finalize_setup(mfc5_handle* h) {
             if (upload(&h->d_tab[d][7], rowsT)) return -1;
             D.T[d].tabT = h->d_tab[d][7];
             D.T[d].nslot = nslot;
-            if (d == 0) {  // x kernel: [segment][MFC5_TAB][lane], lane l of segment g = cell 30 g - 1 + l (clamped to s + 1)
+            if (d == 0) {  // x kernel: [segment][MFC5_TAB / 2][lane][2], lane l of segment g = cell 30 g - 1 + l (clamped to s + 1)
                 const int nseg = (h->s[0] + 1 + MFC5_XW - 1) / MFC5_XW;
                 std::vector<double> rowsX((size_t)nseg * MFC5_TAB * 32);
                 for (int g = 0; g < nseg; g++)
                     for (int l = 0; l < 32; l++) {
                         const int sl = std::min(MFC5_XW * g - 1 + l, h->s[0] + 1) + h->b;
-                        for (int k = 0; k < MFC5_TAB; k++) rowsX[((size_t)g * MFC5_TAB + k) * 32 + l] = rows[(size_t)sl * MFC5_TAB + k];
+                        for (int k = 0; k < MFC5_TAB; k++) rowsX[(size_t)g * MFC5_TAB * 32 + (size_t)(k >> 1) * 64 + 2 * l + (k & 1)] = rows[(size_t)sl * MFC5_TAB + k];
                     }
                 if (upload(&h->d_tab[d][8], rowsX)) return -1;
                 D.T[d].tabX = h->d_tab[d][8];
@@ -554,8 +559,27 @@ extern "C" int mfc5_finalize_setup(mfc5_handle* h) {
     for (int i = 0; i < 4; i++) if (h->gexec[i]) { cudaGraphExecDestroy(h->gexec[i]); h->gexec[i] = nullptr; }
     h->prim_valid = false;
     h->pp = 0;
-    h->fuse_c2p = getenv("MFC5_FUSE_C2P") ? 1 : 0;   // opt-in, see store_next_prim
-    if (h->fuse_c2p && !h->d_prim[1]) {
+    // Case-optimised path with the second-generation marching kernels: extrapolation / reflective / periodic ghost cells are
+    // read by the sweep loaders straight from the interior (no ghost-fill kernel for those faces), and the last sweep of a
+    // stage writes the next stage's primitive variables over the rhs buffer (no cons -> prim pass, no extra buffer).
+    const bool m2 = opt_march2(D);
+    std::memset(D.gmode, 0, sizeof(D.gmode));
+    if (m2 && !getenv("MFC5_NO_FOLD"))
+        for (int d = 0; d < h->nd; d++)
+            for (int sd = 0; sd < 2; sd++) {
+                const int bc = h->P.bc[d][sd];
+                if (bc == MFC5_BC_PERIODIC) D.gmode[d][sd] = MFC5_GM_WRAP;
+                else if (bc == MFC5_BC_REFLECTIVE) D.gmode[d][sd] = MFC5_GM_MIRROR;
+                else if (bc == MFC5_BC_GHOST_EXTRAP || is_cbc(bc)) D.gmode[d][sd] = MFC5_GM_CLAMP;   // ghost extrapolation; the CBC faces rewrite their fluxes
+            }
+    const bool was_alias = h->alias;
+    h->alias = m2 && !getenv("MFC5_NO_FUSE_C2P");
+    if (was_alias && !h->alias) h->d_prim[1] = nullptr;
+    h->fuse_c2p = (h->alias || getenv("MFC5_FUSE_C2P")) ? 1 : 0;   // generic kernels: opt-in, separate buffer (see store_next_prim)
+    if (h->alias) {
+        if (h->d_prim[1] && h->d_prim[1] != h->d_rhs) cudaFree(h->d_prim[1]);
+        h->d_prim[1] = h->d_rhs;
+    } else if (h->fuse_c2p && !h->d_prim[1]) {
         const size_t nb = (size_t)h->N * h->fs * sizeof(double);
         CK(cudaMalloc(&h->d_prim[1], nb));
         CK(cudaMemset(h->d_prim[1], 0, nb));
@@ -584,9 +608,8 @@ static int fill_full(mfc5_handle* h, const DevP& D);
 static unsigned grid_for(long long n, int block) { return (unsigned)std::min<long long>((n + block - 1) / block, 148LL * 16); }
 
 // ---- host <-> device field copies ------------------------------------------------------------------
-static int copy_fields(mfc5_handle* h, double* dev, const double* const* hostc, double* const* hostm, int ghosted, bool to_dev) {
+static int copy_fields(mfc5_handle* h, double* dev, const double* const* hostc, double* const* hostm, int ghosted, bool to_dev, bool ghosts_valid = false) {
     CK(cudaSetDevice(h->P.device));
-    CK(cudaStreamSynchronize(h->st));
     const int gx = ghosted ? h->b : 0, gy = (ghosted && h->nd > 1) ? h->b : 0, gz = (ghosted && h->nd > 2) ? h->b : 0;
     // host extents
     const size_t hx = h->s[0] + 1 + 2 * gx, hy = h->s[1] + 1 + 2 * gy, hz = h->s[2] + 1 + 2 * gz;
@@ -609,6 +632,7 @@ static int copy_fields(mfc5_handle* h, double* dev, const double* const* hostc, 
     G.sy = h->px; G.sz = h->px * h->ey; G.fs = h->fs;
     G.st_off = (gx - cgx) + (long long)(gy - cgy) * hx + (long long)(gz - cgz) * hx * hy;
     G.hx = hx; G.hxy = hx * hy; G.hfs = hfs;
+    G.gx = cgx; G.gy = cgy; G.gz = cgz; G.zero_ghosts = (!to_dev && !ghosts_valid) ? 1 : 0;   // device ghost cells of q / rhs hold nothing meaningful
     bool adjacent = true;
     for (int v = 0; v < h->N; v++) {
         const double* hp = to_dev ? hostc[v] : hostm[v];
@@ -658,11 +682,11 @@ extern "C" int mfc5_download_prim(mfc5_handle* h, double* const* q, int ghosted)
             if (fill_full(h, D)) return -1;
         }
     }
-    return copy_fields(h, h->d_prim[h->pp], nullptr, q, ghosted, false);
+    return copy_fields(h, h->d_prim[h->pp], nullptr, q, ghosted, false, true);
 }
 extern "C" int mfc5_download_rhs(mfc5_handle* h, double* const* q, int ghosted) {
     if (!h || !q) return fail("mfc5_download_rhs: null argument");
-    return copy_fields(h, h->d_rhs, nullptr, q, ghosted, false);
+    return copy_fields(h, rhs_ptr(h), nullptr, q, ghosted, false);
 }
 
 // ---- stage orchestration ---------------------------------------------------------------------------
@@ -844,8 +868,8 @@ static int launch_sweep(mfc5_handle* h, const DevP& D0, int dir, bool* halo_pend
 static int run_stage(mfc5_handle* h, const double* q1, const double* q2, double* qout, int do_rk, const double rk[4], double dt) {
     NvtxRange nv_rhs("COMPUTE-RHS");
     DevP D = h->D;
-    D.prim = h->d_prim[h->pp]; D.primw = h->d_prim[h->pp]; D.q1 = q1; D.q2 = q2; D.qout = qout; D.rhs = h->d_rhs;
-    D.prim_next = (do_rk && h->fuse_c2p) ? h->d_prim[h->pp ^ 1] : nullptr;
+    D.prim = h->d_prim[h->pp]; D.primw = h->d_prim[h->pp]; D.q1 = q1; D.q2 = q2; D.qout = qout; D.rhs = rhs_ptr(h);
+    D.prim_next = (do_rk && h->fuse_c2p) ? h->d_prim[h->pp ^ 1] : nullptr;   // alias mode: == D.rhs
     D.bf_on = 0;
     if (do_rk && (h->P.bf[0] || h->P.bf[1] || h->P.bf[2])) {   // s_compute_acceleration(mytime), m_body_forces.fpp:206-218
         D.bf_on = 1;
@@ -877,7 +901,7 @@ static int run_stage(mfc5_handle* h, const double* q1, const double* q2, double*
     bool any_phys_x = false, any_phys_yz = false, any_cbc_x = false, any_cbc_yz = false;
     for (int d = 0; d < h->nd; d++)
         for (int sd = 0; sd < 2; sd++) {
-            if (h->P.bc[d][sd] < 0) (d == 0 ? any_phys_x : any_phys_yz) = true;
+            if (h->P.bc[d][sd] < 0 && D.gmode[d][sd] == MFC5_GM_MEM) (d == 0 ? any_phys_x : any_phys_yz) = true;
             if (D.cbc_on[d][sd]) (d == 0 ? any_cbc_x : any_cbc_yz) = true;
         }
     long long mx = 1;
@@ -934,7 +958,7 @@ static int run_stage(mfc5_handle* h, const double* q1, const double* q2, double*
 // callers that need them)
 static int refresh_prim(mfc5_handle* h) {
     DevP D = h->D;
-    D.prim = h->d_prim[h->pp]; D.primw = h->d_prim[h->pp]; D.q1 = h->d_q[h->cur]; D.q2 = D.q1; D.qout = nullptr; D.rhs = h->d_rhs;
+    D.prim = h->d_prim[h->pp]; D.primw = h->d_prim[h->pp]; D.q1 = h->d_q[h->cur]; D.q2 = D.q1; D.qout = nullptr; D.rhs = rhs_ptr(h);
     const long long ncell = (long long)(h->s[0] + 1) * (h->s[1] + 1) * (h->s[2] + 1);
     int rc = by_shape(h, [&](auto nf, auto nd) {
         k_cons2prim<decltype(nf)::value, decltype(nd)::value><<<grid_for(ncell, 256), 256, 0, h->st>>>(D);
@@ -1096,7 +1120,7 @@ extern "C" int mfc5_reduce(mfc5_handle* h, int what, double dt, double* out) {
     CK(cudaSetDevice(h->P.device));
     // primitive variables of the current state
     DevP D = h->D;
-    D.prim = h->d_prim[h->pp]; D.primw = h->d_prim[h->pp]; D.q1 = h->d_q[h->cur]; D.q2 = D.q1; D.qout = nullptr; D.rhs = h->d_rhs;
+    D.prim = h->d_prim[h->pp]; D.primw = h->d_prim[h->pp]; D.q1 = h->d_q[h->cur]; D.q2 = D.q1; D.qout = nullptr; D.rhs = rhs_ptr(h);
     h->prim_valid = true;  // the cons -> prim pass below refreshes d_prim[pp] for the current state
     const long long ncell = (long long)(h->s[0] + 1) * (h->s[1] + 1) * (h->s[2] + 1);
     const unsigned long long init[4] = {0ull, 0x7FEFFFFFFFFFFFFFull, 0ull, 0ull};

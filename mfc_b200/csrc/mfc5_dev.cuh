@@ -29,8 +29,8 @@ struct DirTables {
     //   [27,30) dL+dL^2  [30,33) dR+dR^2  [33,36) 1-2dL  [36,39) 1-2dR  [39,42) dL^2  [42,45) dR^2  [45] ds  [46] 1/ds
     const double* tab;
     const double* tabT;  // the same, transposed: [MFC5_TAB][nslot]
-    // x kernel: per 30-cell warp segment, [segment][MFC5_TAB][32 lanes]; lane l holds the row of cell
-    // 30*segment - 1 + l (clamped to s+1): lane-contiguous loads at immediate offsets
+    // x kernel: per 30-cell warp segment, [segment][MFC5_TAB / 2][32 lanes][2]; lane l holds the row of cell
+    // 30*segment - 1 + l (clamped to s+1), entries in adjacent pairs: lane-contiguous 16-byte loads at immediate offsets
     const double* tabX;
     int nslot;
     int uniform;       // uniform_grid(dir), m_weno.fpp:869-879
@@ -78,6 +78,39 @@ struct DevP {
     int chunk;          // marching chunk length (<= 0: chosen per launch)
     int xseg_lo, xseg_n;  // x kernel: this launch covers segments [xseg_lo, xseg_lo + xseg_n) (xseg_n = 0: all)
     int x_march;        // x sweep with the marching kernel (lanes along y) instead of the warp-shuffle kernel
+    // Ghost modes [direction][side] (case-optimised kernels): how a sweep loader obtains the primitive variables of a ghost
+    // cell.  MEM: from memory (filled by k_bc_faces or the halo exchange); CLAMP / MIRROR / WRAP: straight from the interior
+    // cell the boundary condition copies (m_boundary_primitives.fpp:27-135 extrapolation -3, -5..-12; :114-335 reflective -2
+    // with the normal velocity negated; :338-494 periodic -1), so that no ghost-fill kernel runs for those faces.
+    int gmode[3][2];
+};
+#define MFC5_GM_MEM 0
+#define MFC5_GM_CLAMP 1
+#define MFC5_GM_MIRROR 2
+#define MFC5_GM_WRAP 3
+
+// index pl in [-b, s+b] along direction d -> the cell whose stored value the (ghost) cell pl holds under the ghost mode of its
+// side; flip: the normal velocity changes sign (reflective wall).  Every mode is an affine map of pl, so a kernel computes the
+// two (slope, offset, flip) triples once and the per-plane cost is a couple of selects, not a chain of branches.
+struct GhostMap {
+    int a_lo, b_lo, a_hi, b_hi, s;
+    bool f_lo, f_hi;
+    __device__ __forceinline__ GhostMap(const DevP& P, int d) {
+        s = P.s[d];
+        const int g0 = P.gmode[d][0], g1 = P.gmode[d][1];
+        a_lo = g0 == MFC5_GM_CLAMP ? 0 : g0 == MFC5_GM_MIRROR ? -1 : 1;
+        b_lo = g0 == MFC5_GM_MIRROR ? -1 : g0 == MFC5_GM_WRAP ? s + 1 : 0;
+        a_hi = g1 == MFC5_GM_CLAMP ? 0 : g1 == MFC5_GM_MIRROR ? -1 : 1;
+        b_hi = g1 == MFC5_GM_CLAMP ? s : g1 == MFC5_GM_MIRROR ? 2 * s + 1 : g1 == MFC5_GM_WRAP ? -s - 1 : 0;
+        f_lo = g0 == MFC5_GM_MIRROR;
+        f_hi = g1 == MFC5_GM_MIRROR;
+    }
+    __device__ __forceinline__ int src(int pl, bool& flip) const {
+        const bool lo = pl < 0, hi = pl > s;
+        flip = (lo & f_lo) | (hi & f_hi);
+        const int a = lo ? a_lo : hi ? a_hi : 1, b = lo ? b_lo : hi ? b_hi : 0;
+        return a * pl + b;
+    }
 };
 
 __device__ __forceinline__ double sq(double x) { return x * x; }
@@ -112,6 +145,13 @@ __device__ __forceinline__ double div_by_const(double t, double d, double id) {
     return fma(r, id, q);
 }
 
+// a / b with one reciprocal and a residual correction (Markstein): the correctly rounded quotient whenever r is within an
+// ulp of 1/b, i.e. the reference's division bit for bit in all but rare cases, for 3 FP64 operations once r is at hand
+__device__ __forceinline__ double div_r(double a, double b, double r) {
+    const double q = a * r;
+    return fma(fma(-b, q, a), r, q);
+}
+
 // 1/a and 1/b from ONE reciprocal: r = 1/(a b), 1/a = r b, 1/b = r a  (8 FP64 operations instead of 10, one
 // MUFU instead of two).  Callers guarantee that a b neither overflows nor underflows.
 __device__ __forceinline__ void rcp_nr2(double a, double b, double& ia, double& ib) {
@@ -124,11 +164,20 @@ __device__ __forceinline__ void rcp_nr2(double a, double b, double& ia, double& 
 // shared memory, block-uniform).  RowSoA: element k at p[k * stride] (x kernel: lanes own consecutive
 // cells, so consecutive lanes read consecutive addresses of the transposed table).
 struct RowAoS {
+    static constexpr bool kAlwaysTable = false;  // uniform grids take the closed-form smoothness indicators
     static constexpr bool kHasMapTerms = true;   // read d + d^2, 1 - 2d, d^2 from the row
     const double* __restrict__ p;
     __device__ __forceinline__ double operator[](int k) const { return p[k]; }
 };
+// the same row for kernels that always evaluate the tabulated smoothness indicators (no run-time uniform-grid branch in the loop)
+struct RowAoST {
+    static constexpr bool kAlwaysTable = true;
+    static constexpr bool kHasMapTerms = true;
+    const double* __restrict__ p;
+    __device__ __forceinline__ double operator[](int k) const { return p[k]; }
+};
 struct RowSoA {
+    static constexpr bool kAlwaysTable = false;
     static constexpr bool kHasMapTerms = false;  // per-lane loads are dearer than 3 flops: recompute them
     const double* __restrict__ p;
     long long stride;
@@ -136,9 +185,10 @@ struct RowSoA {
 };
 
 struct RowSeg {
+    static constexpr bool kAlwaysTable = false;
     static constexpr bool kHasMapTerms = true;
-    const double* __restrict__ p;                // tabX + segment * MFC5_TAB * 32 + lane
-    __device__ __forceinline__ double operator[](int k) const { return __ldg(p + k * 32); }
+    const double* __restrict__ p;                // tabX + segment * MFC5_TAB * 32 + 2 * lane
+    __device__ __forceinline__ double operator[](int k) const { return __ldg(p + (k >> 1) * 64 + (k & 1)); }
 };
 
 // WENO-M map of a normalised weight w with ideal weight d (m_weno.fpp:1150-1156), as numerator and
@@ -159,7 +209,7 @@ __device__ __forceinline__ void weno5_fast(const DevP& P, const DirTables& T, co
     for (int u = 0; u < NV; u++) { d1[u] = f[u][4] - f[u][3]; d0[u] = f[u][3] - f[u][2]; dm1[u] = f[u][2] - f[u][1]; dm2[u] = f[u][1] - f[u][0]; }
     {
         double b0[NV], b1[NV], b2[NV];
-        if (T.uniform) {
+        if (!ROW::kAlwaysTable && T.uniform) {
 #pragma unroll
             for (int u = 0; u < NV; u++) {
                 b0[u] = 13.0 / 12.0 * sq(d1[u] - d0[u]) + 0.25 * sq(d1[u] - 3.0 * d0[u]) + eps;

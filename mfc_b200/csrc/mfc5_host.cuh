@@ -2,9 +2,32 @@
 #pragma once
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include "mfc5_kernels.cuh"
 
 namespace mfc5 {
+
+// Does the case-optimised path (mfc5_sweep_opt.cu) take this configuration?  The host asks the same question to decide
+// whether ghost cells are folded into the sweep loaders (DevP::gmode) and the cons -> prim pass into the last sweep.
+inline bool opt_config(const DevP& P) {
+#ifdef MFC5_STRICT
+    return false;
+#else
+    if (getenv("MFC5_NO_OPT")) return false;
+    if (P.nf != 2 || P.nd != 3 || !P.fast) return false;
+    if ((unsigned long long)P.fs * (unsigned long long)(2 * P.nf + P.nd + 1) >= (1ull << 32)) return false;  // 32-bit field indices
+    for (int d = 0; d < 3; d++)
+        for (int sd = 0; sd < 2; sd++)
+            if (P.bc[d][sd] == MFC5_BC_RIEMANN_EXTRAP) return false;   // BC -4 lives in the generic kernels
+    if (P.rs == 2) return (P.wo == 5 && (P.wv == 1 || P.wv == 2)) || (P.wo == 3 && P.wv == 1);
+    if (P.rs == 1) return P.wo == 5 && P.wv == 1;
+    return false;
+#endif
+}
+// ... and are its y / z sweeps the second-generation marching kernel (which is the one that implements gmode and prim_next)?
+inline bool opt_march2(const DevP& P) {
+    return opt_config(P) && !getenv("MFC5_MARCH_V1");
+}
 
 // Launch the fused sweep of direction `dir` for the shape / scheme in P on `st`.
 // Returns false if this translation unit has no kernel for P (caller tries the next one).
@@ -94,6 +117,50 @@ inline bool launch_sweep_t(const DevP& P, int dir, cudaStream_t st) {
     }
     if constexpr (ND >= 3) {
         if (dir == 2) return launch_march<NF, ND, 2, WO, WV, RS, FAST>(P, st);
+    }
+    return false;
+}
+
+// second-generation marching kernel (case-optimised configurations; k_march2)
+template <int NF, int ND, int DIR, int WO, int WV, int RS>
+inline bool launch_march2(const DevP& P0, cudaStream_t st) {
+    constexpr int bps = MFC5_M2_MINB;
+    auto kern = k_march2<NF, ND, DIR, WO, WV, RS>;
+    static bool attr_done[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64 || !attr_done[dev]) {
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024) != cudaSuccess) {
+            cudaGetLastError();
+            return false;
+        }
+        if (dev >= 0 && dev < 64) attr_done[dev] = true;
+    }
+    DevP P = P0;
+    // longest chunk whose table rows still let `bps` blocks share the 228 KB of an SM (1 KB per block is reserved by the system)
+    const long long budget = (228LL * 1024 - bps * 1024) / bps - (long long)march2_smem_bytes<NF, ND, WO>(-2);
+    int max_chunk = P.s[DIR] + 1;
+    if (MFC5_M2_TABS) {
+        if (budget < (long long)(6 * MFC5_TAB * sizeof(double))) return false;
+        max_chunk = (int)(budget / (MFC5_TAB * (long long)sizeof(double)) - 2);
+    }
+    const long long lanes_blocks = (march_pencils(P, DIR) + MFC5_M2_THREADS - 1) / MFC5_M2_THREADS;
+    if (P.chunk <= 0) P.chunk = march_chunk_n(P.s[DIR] + 1, lanes_blocks, bps, max_chunk, 2);
+    P.chunk = std::min(P.chunk, max_chunk);
+    const int chunks = (P.s[DIR] + 1 + P.chunk - 1) / P.chunk;
+    kern<<<dim3((unsigned)lanes_blocks, (unsigned)chunks, 1), MFC5_M2_THREADS, march2_smem_bytes<NF, ND, WO>(P.chunk), st>>>(P);
+    return true;
+}
+
+// case-optimised sweep: warp-shuffle kernel along x, second-generation marching kernel along y / z
+template <int NF, int ND, int WO, int WV, int RS>
+inline bool launch_sweep_opt_t(const DevP& P, int dir, cudaStream_t st) {
+    if (dir == 0 || !opt_march2(P)) return launch_sweep_t<NF, ND, WO, WV, RS, 1>(P, dir, st);
+    if constexpr (ND >= 2) {
+        if (dir == 1) return launch_march2<NF, ND, 1, WO, WV, RS>(P, st);
+    }
+    if constexpr (ND >= 3) {
+        if (dir == 2) return launch_march2<NF, ND, 2, WO, WV, RS>(P, st);
     }
     return false;
 }

@@ -175,7 +175,7 @@ __global__ void __launch_bounds__(256) k_bc_fill(const __grid_constant__ DevP P,
 __global__ void __launch_bounds__(256) k_bc_faces(const __grid_constant__ DevP P, int face0) {
     const int face = blockIdx.y + face0;
     const int d = face >> 1, side = face & 1;
-    if (d >= P.nd || P.bc[d][side] >= 0) return;
+    if (d >= P.nd || P.bc[d][side] >= 0 || P.gmode[d][side] != MFC5_GM_MEM) return;   // folded faces: the sweep loaders do it
     bc_fill_face(P, d, side, 0, blockIdx.x * (long long)blockDim.x + threadIdx.x, (long long)gridDim.x * blockDim.x);
 }
 
@@ -498,11 +498,13 @@ __device__ __forceinline__ void cbc_override(const DevP& P, int face, long long 
 #endif
 __device__ __forceinline__ void cp_async_wait_1() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
 
-// One segment's tile of DirTables::tabX in shared memory: element k of lane l at p[k * 32] (p = tile + l)
+// One segment's tile of DirTables::tabX in shared memory: element k of lane l at tile[(k / 2) * 64 + 2 * l + (k & 1)]
+// (pairs of consecutive entries are adjacent, [k / 2][lane][2], so that the compiler fetches two of them per 16-byte LDS)
 struct RowTile {
+    static constexpr bool kAlwaysTable = false;
     static constexpr bool kHasMapTerms = true;
-    const double* p;
-    __device__ __forceinline__ double operator[](int k) const { return p[k * 32]; }
+    const double* p;   // tile + 2 * lane
+    __device__ __forceinline__ double operator[](int k) const { return p[(k >> 1) * 64 + (k & 1)]; }
 };
 
 // Grid: blockIdx.x = segment, blockIdx.z = k, blockIdx.y = group of MFC5_X_RPB * (warps per block) rows j; warp w of the
@@ -529,11 +531,15 @@ __global__ void __launch_bounds__(128, MFC5_X_MINB) k_sweep_x(const __grid_const
     // the warp's 36-cell window of every variable is staged in shared memory with cp.async; lane l reads cells l .. l+4
     __shared__ double sx[4][NB][N][XT];
     __shared__ double sedge[4][2][N][32];  // per lane: right edge of my cell, left edge of cell +1 (spill space of the rolled loop)
-    __shared__ double stab[(FAST && MFC5_X_STAB) ? MFC5_TAB * 32 : 32];
+    __shared__ __align__(16) double stab[(FAST && MFC5_X_STAB) ? MFC5_TAB * 32 : 32];
     double(*myR)[32] = sedge[w][0];
     double(*myQ)[32] = sedge[w][1];
     const int hi = P.s[0] + P.b;
-    const int ca = min(i0 - 3 + lane, hi), cb = min(i0 - 3 + 32 + lane, hi);
+    // window cells of this lane (clamped to the ghost region), through the ghost modes of the x boundaries (DevP::gmode)
+    bool fa, fb;
+    const GhostMap gmap(P, 0);
+    const int ca = gmap.src(min(i0 - 3 + lane, hi), fa), cb = gmap.src(min(i0 - 3 + 32 + lane, hi), fb);
+    const bool any_flip = (P.gmode[0][0] == MFC5_GM_MIRROR) | (P.gmode[0][1] == MFC5_GM_MIRROR);   // kernel-uniform
     using ix = typename SweepIdx<(WO >= 0)>::type;  // 32-bit element indices in the case-optimised kernels (k_sweep_march)
     const ix fs = (ix)P.fs;
     auto load_window = [&](int buf, int jj) {
@@ -553,9 +559,9 @@ __global__ void __launch_bounds__(128, MFC5_X_MINB) k_sweep_x(const __grid_const
         __syncthreads();
     }
 #if MFC5_X_STAB
-    const RowTile xrow{stab + lane};
+    const RowTile xrow{stab + 2 * lane};
 #else
-    const RowSeg xrow{T.tabX + (long long)seg * (MFC5_TAB * 32) + lane};
+    const RowSeg xrow{T.tabX + (long long)seg * (MFC5_TAB * 32) + 2 * lane};
 #endif
     const double ds_i = __ldg(T.ds + ic + P.b);
 #pragma unroll 1
@@ -571,6 +577,11 @@ __global__ void __launch_bounds__(128, MFC5_X_MINB) k_sweep_x(const __grid_const
         }
         __syncwarp();
         double(*my)[XT] = sx[w][buf];
+        if (any_flip) {   // reflective wall: the mirrored cells carry -u_x
+            if (fa) my[S::IM][lane] = -my[S::IM][lane];
+            if (lane < 4 && fb) my[S::IM][32 + lane] = -my[S::IM][32 + lane];
+            __syncwarp();
+        }
         const long long row = j + (long long)(P.s[1] + 1) * k;
         const ix rowbase = (ix)P.base + (ix)j * (ix)P.sy + (ix)k * (ix)P.sz;
         // WENO of NV variables per iteration of a ROLLED loop (code size: the instruction cache, not the
@@ -610,12 +621,13 @@ __global__ void __launch_bounds__(128, MFC5_X_MINB) k_sweep_x(const __grid_const
         double eR[N], qR[N];
 #pragma unroll
         for (int v = 0; v < N; v++) { eR[v] = myR[v][lane]; qR[v] = myQ[v][lane]; }
-        // BC -4 (Riemann extrapolation), m_riemann_state.fpp:149-206
-        if (P.bc[0][0] == MFC5_BC_RIEMANN_EXTRAP && i == -1) {
+        // BC -4 (Riemann extrapolation), m_riemann_state.fpp:149-206 (the case-optimised kernels are not dispatched for it)
+        constexpr bool kExtrap = !(FAST && WO >= 0);
+        if (kExtrap && P.bc[0][0] == MFC5_BC_RIEMANN_EXTRAP && i == -1) {
 #pragma unroll
             for (int v = 0; v < N; v++) eR[v] = qR[v];
         }
-        if (P.bc[0][1] == MFC5_BC_RIEMANN_EXTRAP && i == P.s[0]) {
+        if (kExtrap && P.bc[0][1] == MFC5_BC_RIEMANN_EXTRAP && i == P.s[0]) {
 #pragma unroll
             for (int v = 0; v < N; v++) qR[v] = eR[v];
         }
@@ -898,6 +910,289 @@ __global__ void __launch_bounds__(MFC5_MARCH_THREADS, (2 * NF + ND + 1 <= 8) ? M
 }
 
 // -------------------------------------------------------------------------------------------------
+// Marching sweep, second generation (case-optimised configurations only: division-light arithmetic, compile-time scheme, 32-bit
+// field indices, no Riemann-extrapolation boundary).  Same algorithm and data flow as k_sweep_march; what changed is
+// everything that is not FP64 arithmetic, because an FP64 warp instruction holds the issue port for two cycles and every other
+// instruction for one (time ~ 2 F + O per warp; profiles/sass_budget_r02.md):
+//   * shared memory per thread: the window ring has ONE extra slot that carries the right-edge states of the previous cell --
+//     the right edges of cell cc are written over the plane that leaves the window (cc - PN), variable pair by variable pair
+//     as the rolled WENO loop retires it -- instead of a two-slot ping-pong: (R + 2) slots instead of (R + 3);
+//   * L2 prefetches are issued per 128-byte line, not per lane: lane l of a warp covers variable l & 7 at the column of one of
+//     four sample lanes, so one instruction per array replaces eight;
+//   * the inputs of the finishing step (rhs, q1, q2) are loaded after the Riemann solve (they are in L2 by then), which frees
+//     ~48 registers across it;
+//   * ghost planes of extrapolation / reflective / periodic boundaries are read straight from the interior plane the boundary
+//     condition copies (DevP::gmode), so no ghost-fill kernel runs for them;
+//   * the RK-fused last sweep converts the new state to primitive variables in registers and stores them over the rhs entry it
+//     has just consumed (DevP::prim_next == rhs): the next stage starts without a cons -> prim pass and without a fifth buffer.
+// -------------------------------------------------------------------------------------------------
+#ifndef MFC5_M2_THREADS
+#define MFC5_M2_THREADS 192
+#endif
+#ifndef MFC5_M2_MINB
+#define MFC5_M2_MINB 2
+#endif
+#ifndef MFC5_M2_TABS
+#define MFC5_M2_TABS 1      // 1: the chunk's table rows are staged in shared memory; 0: read through L1 (uniform-address loads)
+#endif
+#ifndef MFC5_M2_LATE
+#define MFC5_M2_LATE 0      // 1: finishing inputs are loaded after the Riemann solve (fewer live registers, exposed L2 latency; measured: z 0.937 vs 0.913 ms)
+#endif
+#ifndef MFC5_M2_NV
+#define MFC5_M2_NV MFC5_WENO_NV   // variables per iteration of the rolled WENO loop
+#endif
+
+template <int NF, int ND, int WO>
+inline size_t march2_smem_bytes(int chunk) {
+    constexpr int R = 2 * ((WO - 1) / 2) + 1;
+    return ((size_t)(R + 2) * (2 * NF + ND + 1) * MFC5_M2_THREADS + (MFC5_M2_TABS ? (size_t)(chunk + 2) * MFC5_TAB : 0)) * sizeof(double);
+}
+
+// cons -> prim of one cell with reciprocals + residual-corrected quotients (same formulas and order as cons2prim_cell)
+template <int NF, int ND>
+__device__ __forceinline__ void cons2prim_cell_fast(const DevP& P, const double* q, double* pr) {
+    using S = Shape<NF, ND>;
+    double arho[NF], alf[NF];
+#pragma unroll
+    for (int f = 0; f < NF; f++) { arho[f] = q[f]; alf[f] = q[S::IA + f]; }
+    if (P.mpp) {
+#pragma unroll
+        for (int pass = 0; pass < 2; pass++) {
+            double sum = 0.0;
+#pragma unroll
+            for (int i = 0; i < NF; i++) {
+                arho[i] = sel_max(arho[i], 0.0);
+                alf[i] = sel_min(sel_max(alf[i], 0.0), 1.0);
+                sum = sum + alf[i];
+            }
+            const double den = sel_max(sum, MFC5_SGM_EPS), r = rcp_nr(den);
+#pragma unroll
+            for (int i = 0; i < NF; i++) alf[i] = div_r(alf[i], den, r);
+        }
+    }
+    double rho = 0, gam = 0, pinf = 0, qv = 0;
+#pragma unroll
+    for (int i = 0; i < NF; i++) {
+        rho = rho + arho[i];
+        gam = fma(alf[i], P.gam[i], gam);
+        pinf = fma(alf[i], P.pinf[i], pinf);
+        qv = fma(arho[i], P.qv[i], qv);
+    }
+    rho = sel_max(rho, MFC5_SGM_EPS);
+    const double irho = rcp_nr(rho);
+    double dyn = 0.0;
+#pragma unroll
+    for (int a = 0; a < ND; a++) {
+        const double u = div_r(q[S::IM + a], rho, irho);
+        dyn = fma(5.e-1 * q[S::IM + a], u, dyn);
+        pr[S::IM + a] = u;
+    }
+    pr[S::IE] = div_r(q[S::IE] - dyn - pinf - qv, gam, rcp_nr(gam));
+#pragma unroll
+    for (int f = 0; f < NF; f++) {
+        pr[f] = q[f];
+        pr[S::IA + f] = q[S::IA + f];
+    }
+}
+
+template <int NF, int ND, int DIR, int WO, int WV, int RS>
+__global__ void __launch_bounds__(MFC5_M2_THREADS, MFC5_M2_MINB) k_march2(const __grid_constant__ DevP P) {
+    using S = Shape<NF, ND>;
+    constexpr int N = S::N;
+    constexpr int PN = (WO - 1) / 2, R = 2 * PN + 1, NSLOT = R + 1;
+    constexpr int NT = MFC5_M2_THREADS;
+    constexpr int NV = MFC5_M2_NV;
+    static_assert(N == 8, "the line-wise prefetch pattern assumes 8 variables");
+    extern __shared__ double smem[];
+    double* ring = smem;                   // [NSLOT][N][NT]: R window planes + the right-edge states of the previous cell
+    double* sEL = smem + NSLOT * N * NT;   // [N][NT] left-edge states of the cell reconstructed in this iteration
+    double* srow = sEL + N * NT;           // [chunk + 2][MFC5_TAB] table rows of cells c0-1 .. c1+1
+    const int tid = threadIdx.x;
+    const int s = P.s[DIR];
+    const int c0 = blockIdx.y * P.chunk;
+    const int c1 = min(c0 + P.chunk - 1, s);
+    const DirTables& T = P.T[DIR];
+    if (MFC5_M2_TABS) {  // cooperative, coalesced copy; every thread of the block takes part before any returns
+        const double* src = T.tab + (long long)(c0 - 1 + P.b) * MFC5_TAB;
+        const int nrow = (c1 - c0 + 3) * MFC5_TAB;
+        for (int k = tid; k < nrow; k += NT) srow[k] = __ldg(src + k);
+        __syncthreads();
+    }
+    const int n_a = (DIR == 0) ? P.s[1] + 1 : P.s[0] + 1;
+    const int n_b = (DIR == 2) ? P.s[1] + 1 : P.s[2] + 1;
+    const long long plane = (long long)n_a * n_b;
+    const long long t = blockIdx.x * (long long)NT + tid;
+    const long long tc = min(t, plane - 1);  // out-of-range threads still take part in the warp shuffles below
+    const int a = (int)(tc % n_a), bb = (int)(tc / n_a);
+    using ix = unsigned;
+    const ix fs = (ix)P.fs;
+    const ix sa = (DIR == 0) ? (ix)P.sy : (ix)1;
+    const ix sb = (DIR == 2) ? (ix)P.sy : (ix)P.sz;
+    const ix sd = (DIR == 0) ? (ix)1 : (DIR == 1 ? (ix)P.sy : (ix)P.sz);
+    const ix colbase = (ix)P.base + (ix)a * sa + (ix)bb * sb;
+    // line-wise L2 prefetch: lane l covers variable l & 7 in the column of sample lane {0, 10, 21, 31}[l >> 3]
+    const int lane = tid & 31;
+    const int samp = (lane >> 3) == 0 ? 0 : (lane >> 3) == 1 ? 10 : (lane >> 3) == 2 ? 21 : 31;
+    const ix pfbase = (ix)(lane & 7) * fs + (ix)__shfl_sync(0xffffffffu, colbase, samp);
+    if (t >= plane) return;
+    const int lo = -P.b, hi = s + P.b;
+    const bool rk = (DIR == ND - 1) && P.do_rk;
+    const bool alpha_iface = (RS == 1 && !P.hll_u);
+    const GhostMap gmap(P, DIR);
+
+    // plane pl of the primitive variables -> ring slot k (this thread's column)
+    auto load_plane = [&](int k, int pl) {
+        bool flip;
+        const int ps = gmap.src(min(max(pl, lo), hi), flip);
+        const ix c = colbase + (ix)ps * sd;
+#pragma unroll
+        for (int v = 0; v < N; v++) {
+            if (v == S::IM + DIR && flip) ring[(k * N + v) * NT + tid] = -P.prim[(ix)((ix)v * fs + c)];   // reflective wall: -u_n of the mirror cell
+            else cp_async8(ring + (k * N + v) * NT + tid, P.prim + (ix)((ix)v * fs + c));
+        }
+    };
+    auto pf_plane = [&](const double* arr, int pl) { prefetch_l2(arr + (ix)(pfbase + (ix)pl * sd)); };
+
+    // prologue: the window of cell c0-1, planes c0-1-PN .. c0-1+PN -> slots 0 .. R-1, and already the plane that enters next
+    // (c0+PN) in slot R, which holds "the previous right edge" from the second iteration on
+#pragma unroll
+    for (int k = 0; k < NSLOT; k++) load_plane(k, c0 - 1 - PN + k);
+    cp_async_commit();
+    int tail = 0;  // slot of the oldest plane of the window (cc - PN)
+
+    double Fp[N], Fsp[NF];  // flux of the previous face
+#pragma unroll
+    for (int v = 0; v < N; v++) Fp[v] = 0.0;
+#pragma unroll
+    for (int f = 0; f < NF; f++) Fsp[f] = 0.0;
+
+    for (int cc = c0 - 1; cc <= c1 + 1; cc++) {
+        cp_async_wait_all();  // the window of cell cc is complete
+        {   // pull into L2 what the NEXT iteration will ask for
+            bool flip;
+            if (cc < c1) pf_plane(P.prim, gmap.src(min(max(cc + 2 + PN, lo), hi), flip));
+            if (cc >= c0 && cc <= c1) {   // the cell finished in the next iteration is cc
+                if (DIR != 0) pf_plane(P.rhs, cc);
+                if (rk) {
+                    pf_plane(P.q1, cc);
+                    if (P.rk1 != 0.0) pf_plane(P.q2, cc);
+                }
+            }
+        }
+        // tap k (plane cc-PN+k) sits in slot (tail+k) mod NSLOT; the previous right edge in slot tail-1
+        int off[R];
+#pragma unroll
+        for (int k = 0; k < R; k++) {
+            int sl = tail + k;
+            if (sl >= NSLOT) sl -= NSLOT;
+            off[k] = sl * N * NT + tid;
+        }
+        const int slR = (tail == 0 ? NSLOT - 1 : tail - 1);
+        {
+            const RowAoST mrow{MFC5_M2_TABS ? srow + (cc - (c0 - 1)) * MFC5_TAB : T.tab + (long long)(cc + P.b) * MFC5_TAB};
+#pragma unroll 1
+            for (int v0 = 0; v0 < N; v0 += NV) {
+                double f[NV][5], l[NV], r[NV];
+                int vv[NV];
+#pragma unroll
+                for (int u = 0; u < NV; u++) {
+                    vv[u] = min(v0 + u, N - 1);
+#pragma unroll
+                    for (int k = 0; k < 5; k++) f[u][k] = 0.0;
+                    f[u][2] = ring[off[PN] + vv[u] * NT];
+                    if (PN >= 1) { f[u][1] = ring[off[PN - 1] + vv[u] * NT]; f[u][3] = ring[off[PN + (PN >= 1 ? 1 : 0)] + vv[u] * NT]; }
+                    if (PN >= 2) { f[u][0] = ring[off[0] + vv[u] * NT]; f[u][4] = ring[off[R - 1] + vv[u] * NT]; }
+                }
+                weno_edges_nv<WO, WV, 1, NV>(P, T, cc + P.b, mrow, f, l, r);
+                // the right edge of cell cc replaces plane cc-PN of the same variable, which this iteration has just read for the last time
+#pragma unroll
+                for (int u = 0; u < NV; u++) { sEL[vv[u] * NT + tid] = l[u]; ring[off[0] + vv[u] * NT] = r[u]; }
+            }
+        }
+        if (cc >= c0) {
+            const int face = cc - 1;
+            const ix c = colbase + (ix)(cc - 1) * sd;  // the cell finished in this iteration
+            const bool fin = cc >= c0 + 1;
+            double qL[N], eL[N], F[N], Fs[NF];
+#pragma unroll
+            for (int v = 0; v < N; v++) { qL[v] = ring[(slR * N + v) * NT + tid]; eL[v] = sEL[v * NT + tid]; }
+            if (cc <= c1) {       // plane cc+1+PN enters the window in the slot the previous right edge has just left
+                load_plane(slR, cc + 1 + PN);
+                cp_async_commit();
+            }
+#if !MFC5_M2_LATE
+            double rin[N], q1in[N], q2in[N], acoef[NF];
+            if (fin) {
+#pragma unroll
+                for (int v = 0; v < N; v++) rin[v] = (DIR == 0) ? 0.0 : P.rhs[(ix)((ix)v * fs + c)];
+                if (rk) {
+#pragma unroll
+                    for (int v = 0; v < N; v++) q1in[v] = __ldg(P.q1 + (ix)((ix)v * fs + c));
+#pragma unroll
+                    for (int v = 0; v < N; v++) q2in[v] = (P.rk1 != 0.0) ? __ldg(P.q2 + (ix)((ix)v * fs + c)) : 0.0;
+                }
+#pragma unroll
+                for (int f = 0; f < NF; f++) acoef[f] = __ldg(P.prim + (ix)((ix)(alpha_iface ? (S::IM + DIR) : (S::IA + f)) * fs + c));
+            }
+#endif
+#pragma unroll
+            for (int f = 0; f < NF; f++) Fs[f] = 0.0;
+            riemann_face_fast<NF, ND, DIR, RS>(P, qL, eL, F, Fs);
+            if (P.cbc_on[DIR][0] | P.cbc_on[DIR][1]) cbc_override<NF, ND, DIR>(P, face, t, plane, F, Fs);
+            if (fin) {
+                const double inv_ds = MFC5_M2_TABS ? srow[(cc - 1 - (c0 - 1)) * MFC5_TAB + 46] : __ldg(T.tab + (long long)(cc - 1 + P.b) * MFC5_TAB + 46);
+#if MFC5_M2_LATE
+                double rin[N], q1in[N], q2in[N], acoef[NF];
+#pragma unroll
+                for (int v = 0; v < N; v++) rin[v] = (DIR == 0) ? 0.0 : P.rhs[(ix)((ix)v * fs + c)];
+                if (rk) {
+#pragma unroll
+                    for (int v = 0; v < N; v++) q1in[v] = __ldg(P.q1 + (ix)((ix)v * fs + c));
+#pragma unroll
+                    for (int v = 0; v < N; v++) q2in[v] = (P.rk1 != 0.0) ? __ldg(P.q2 + (ix)((ix)v * fs + c)) : 0.0;
+                }
+#pragma unroll
+                for (int f = 0; f < NF; f++) acoef[f] = __ldg(P.prim + (ix)((ix)(alpha_iface ? (S::IM + DIR) : (S::IA + f)) * fs + c));
+#endif
+                double r[N];
+#pragma unroll
+                for (int v = 0; v < N; v++) {
+                    if (DIR == 0) r[v] = inv_ds * (Fp[v] - F[v]);
+                    else r[v] = rin[v] + inv_ds * (Fp[v] - F[v]);
+                }
+#pragma unroll
+                for (int f = 0; f < NF; f++) {
+                    if (alpha_iface) r[S::IA + f] = r[S::IA + f] + inv_ds * acoef[f] * (Fsp[f] - Fs[f]);
+                    else r[S::IA + f] = r[S::IA + f] + inv_ds * acoef[f] * (Fs[0] - Fsp[0]);
+                }
+                if (rk) {
+#pragma unroll
+                    for (int v = 0; v < N; v++) r[v] = div_by_const(P.rk0 * q1in[v] + P.rk1 * q2in[v] + P.rk2 * P.dt * r[v], P.rk3, P.irk3);
+                    if (P.bf_on) apply_body_forces<NF, ND>(P, r);
+#pragma unroll
+                    for (int v = 0; v < N; v++) P.qout[(ix)((ix)v * fs + c)] = r[v];
+                    if (P.prim_next) {   // primitive variables of the new state for the next stage (over the consumed rhs entry)
+                        double pr[N];
+                        cons2prim_cell_fast<NF, ND>(P, r, pr);
+#pragma unroll
+                        for (int v = 0; v < N; v++) P.prim_next[(ix)((ix)v * fs + c)] = pr[v];
+                    }
+                } else {
+#pragma unroll
+                    for (int v = 0; v < N; v++) P.rhs[(ix)((ix)v * fs + c)] = r[v];
+                }
+            }
+#pragma unroll
+            for (int v = 0; v < N; v++) Fp[v] = F[v];
+#pragma unroll
+            for (int f = 0; f < NF; f++) Fsp[f] = Fs[f];
+        }
+        tail = tail + 1;
+        if (tail >= NSLOT) tail = 0;
+    }
+}
+
+// -------------------------------------------------------------------------------------------------
 // Reductions: ICFL max (m_data_output.fpp:159-224, m_sim_helpers.fpp:45-130), dt min
 // (m_sim_helpers.fpp:182-249) and NaN count.  Warp shuffle reduction + one atomic per warp.
 // out[0] = max icfl (as ordered-uint bits), out[1] = min dt_local bits, out[2] = nan count.
@@ -986,6 +1281,7 @@ struct RepackGeom {
     int N, wx, wy, wz;          // copy region
     long long dev_off, sy, sz, fs;      // device: offset of the region's first cell inside a field, strides, field size
     long long st_off, hx, hxy, hfs;     // staging: the same for the host-shaped image
+    int gx, gy, gz, zero_ghosts;        // download: region cells outside [g, w - g) per direction are written as zeros
 };
 __global__ void __launch_bounds__(256) k_repack(double* __restrict__ dev, double* __restrict__ stage, const __grid_constant__ RepackGeom G, int to_dev) {
     const long long per = (long long)G.wx * G.wy * G.wz, tot = per * G.N;
@@ -997,7 +1293,9 @@ __global__ void __launch_bounds__(256) k_repack(double* __restrict__ dev, double
         const int k = (int)(r / G.wy);
         double* d = dev + v * G.fs + G.dev_off + i + j * G.sy + k * G.sz;
         double* s = stage + v * G.hfs + G.st_off + i + j * G.hx + k * G.hxy;
-        if (to_dev) *d = *s; else *s = *d;
+        if (to_dev) *d = *s;
+        else if (G.zero_ghosts && (i < G.gx || i >= G.wx - G.gx || j < G.gy || j >= G.wy - G.gy || k < G.gz || k >= G.wz - G.gz)) *s = 0.0;
+        else *s = *d;
     }
 }
 #endif  // MFC5_HOST_TU

@@ -7,15 +7,13 @@ bool launch_sweep_opt(const DevP& P, int dir, cudaStream_t st) {
 #ifdef MFC5_STRICT
     return false;
 #else
-    if (P.nf != 2 || P.nd != 3 || !P.fast) return false;
-    if ((unsigned long long)P.fs * (unsigned long long)(2 * P.nf + P.nd + 1) >= (1ull << 32)) return false;  // these kernels index the fields with 32 bits
-    if (P.prim_next) return false;  // the opt-in fused cons2prim (MFC5_FUSE_C2P, measured slower) lives in the generic kernels only
+    if (!opt_config(P)) return false;
     if (P.rs == 2) {
-        if (P.wo == 5 && P.wv == 1) return launch_sweep_t<2, 3, 5, 1, 2, 1>(P, dir, st);  // 3D_performance_test (WENO5-M, HLLC)
-        if (P.wo == 5 && P.wv == 2) return launch_sweep_t<2, 3, 5, 2, 2, 1>(P, dir, st);  // WENO5-Z override of 3D_shockdroplet
-        if (P.wo == 3 && P.wv == 1) return launch_sweep_t<2, 3, 3, 1, 2, 1>(P, dir, st);  // benchmarks/5eq_rk3_weno3_hllc, 3D_shockdroplet
+        if (P.wo == 5 && P.wv == 1) return launch_sweep_opt_t<2, 3, 5, 1, 2>(P, dir, st);  // 3D_performance_test (WENO5-M, HLLC)
+        if (P.wo == 5 && P.wv == 2) return launch_sweep_opt_t<2, 3, 5, 2, 2>(P, dir, st);  // WENO5-Z override of 3D_shockdroplet
+        if (P.wo == 3 && P.wv == 1) return launch_sweep_opt_t<2, 3, 3, 1, 2>(P, dir, st);  // benchmarks/5eq_rk3_weno3_hllc, 3D_shockdroplet
     } else if (P.rs == 1) {
-        if (P.wo == 5 && P.wv == 1) return launch_sweep_t<2, 3, 5, 1, 1, 1>(P, dir, st);  // 3D_performance_test HLL variant
+        if (P.wo == 5 && P.wv == 1) return launch_sweep_opt_t<2, 3, 5, 1, 1>(P, dir, st);  // 3D_performance_test HLL variant
     }
     return false;
 #endif

@@ -161,8 +161,9 @@ def test_c_program_drives_the_abi_like_the_fortran_shim(uuid, use_n, tmp_path):
     assert np.isfinite(q).all()   # the NaN the caller left in its ghost cells was never read, and is overwritten by zeros
     o.compute_rhs()
     pb = o.get_box("prim")
-    scale = np.max(np.abs(pb), axis=(1, 2, 3), keepdims=True) + 1e-300
-    assert np.max(np.abs(pr - pb) / scale) <= 1e-10
+    for v in range(pb.shape[0]):   # abs-or-rel like the reference's packer: the transverse velocities of this case are 1e-18 noise
+        ok, mabs, worst = compare(pr[v], pb[v], 1e-10)
+        assert ok, f"q_prim_vf var {v + 1} (ghost cells included): {worst:.3e}"
     assert abs(icfl - o.icfl_max(dt)) <= 1e-9 * o.icfl_max(dt)
     assert use_n == 1 or tavg > 0.0
 
