@@ -180,15 +180,17 @@ extern "C" int mfc5_create(const mfc5_params* p, mfc5_handle** out) {
         pe.weno_order = 2 * p->muscl_order + 1;   // buff_size = muscl_order + 2 (m_helper_basic.fpp:134-135)
     }
     p = &pe;
-    if (p->weno_order != 1 && p->weno_order != 3 && p->weno_order != 5) return fail("weno_order must be 1, 3 or 5");
+    if (p->weno_order != 1 && p->weno_order != 3 && p->weno_order != 5 && p->weno_order != 7) return fail("weno_order must be 1, 3, 5 or 7");
+    if (p->weno_order == 7 && p->wenoz && !(p->wenoz_q == 2.0 || p->wenoz_q == 3.0 || p->wenoz_q == 4.0)) return fail("wenoz at weno_order = 7 needs wenoz_q = 2, 3 or 4");
+    if (p->weno_order == 7 && (p->int_comp != 0 || p->null_weights)) return fail("weno_order = 7: int_comp and null_weights are not available");
     if (p->riemann_solver != 1 && p->riemann_solver != 2 && p->riemann_solver != 5)
         return fail("riemann_solver must be 1 (HLL), 2 (HLLC) or 5 (Lax-Friedrichs)");
     if (p->mapped_weno && p->wenoz) return fail("mapped_weno and wenoz are mutually exclusive");
     if (p->int_comp != 0 && (p->int_comp != 1 || p->num_fluids != 2 || (p->muscl_order > 0 ? p->muscl_order : p->weno_order) == 1))
         return fail("int_comp: only THINC (1), with num_fluids = 2 and a reconstruction order above 1");
     if (p->mp_weno && (p->weno_order != 5 || p->muscl_order != 0)) return fail("mp_weno requires weno_order = 5");
-    if (p->teno && (p->mapped_weno || p->wenoz || p->weno_order != 5 || p->muscl_order != 0 || !(p->teno_CT > 0.0)))
-        return fail("teno needs weno_order = 5, teno_CT > 0 and neither mapped_weno nor wenoz");
+    if (p->teno && (p->mapped_weno || p->wenoz || (p->weno_order != 5 && p->weno_order != 7) || p->muscl_order != 0 || !(p->teno_CT > 0.0)))
+        return fail("teno needs weno_order = 5 or 7, teno_CT > 0 and neither mapped_weno nor wenoz");
     if (p->alt_soundspeed && (p->num_fluids != 2 || p->avg_state != 2 || (p->riemann_solver == 1 && !p->hll_u_interface)))
         return fail("alt_soundspeed needs 2 fluids, avg_state = 2 and a u-interface solver (HLLC, or HLL with hll_u_interface)");
     if (p->low_Mach < 0 || p->low_Mach > 2 || (p->low_Mach == 2 && p->riemann_solver != 2)) return fail("low_Mach must be 0, 1 or 2 (2: HLLC only)");
@@ -211,9 +213,9 @@ extern "C" int mfc5_create(const mfc5_params* p, mfc5_handle** out) {
     h->b = h->pn + 2;  // m_helper_basic.fpp:127-132
     for (int d = 0; d < h->nd; d++)
         for (int sd = 0; sd < 2; sd++)
-            if (is_cbc(p->bc[d][sd]) && (p->weno_order == 1 || p->muscl_order > 0)) {
+            if (is_cbc(p->bc[d][sd]) && (p->weno_order == 1 || p->weno_order == 7 || p->muscl_order > 0)) {
                 delete h;
-                return fail("characteristic BCs need weno_order >= 3 (and are not available with MUSCL)");
+                return fail("characteristic BCs need weno_order 3 or 5 (and are not available with MUSCL)");
             }
     CK(cudaSetDevice(p->device));
     // HBM layout: SoA, x contiguous; interior x = 0 sits on a 128-byte boundary
@@ -292,6 +294,109 @@ extern "C" int mfc5_set_grid(mfc5_handle* h, int d, const double* s_cb, const do
     return 0;
 }
 
+// ---- WENO tables of order 7 (k = 4): s_compute_weno_coefficients m_weno.fpp:362-851 -------------------------------------
+// The reference lists these as ~500 lines of closed forms; here they come from the definitions those forms expand
+// (Shu 1997, eq. 2.20: the candidate polynomial of a k-cell stencil is the derivative of the Lagrange interpolant of the
+// primitive function through its k + 1 cell boundaries, written on the cell-value differences dvd; ideal weights: the
+// combination that reproduces the (2k-1)-cell polynomial at the cell boundary; smoothness indicators: Jiang & Shu,
+// beta = sum_l dx^(2l-1) int (d^l p / dx^l)^2 dx as a quadratic form in the dvd's).  Same operations in the same order as
+// the CPU oracle's construction, which is pinned by the reference's WENO7 goldens, so the two tables are bit-identical.
+namespace wgen {
+constexpr int KM = 4;
+struct Poly { double c[8]; int n; };
+static Poly mul_lin(const Poly& a, double r, double scale) {   // a * (x - r) * scale
+    Poly o; o.n = a.n + 1;
+    for (int i = 0; i < o.n; i++) o.c[i] = 0.0;
+    for (int i = 0; i < a.n; i++) { o.c[i + 1] += a.c[i] * scale; o.c[i] -= a.c[i] * r * scale; }
+    return o;
+}
+static Poly deriv(const Poly& a) {
+    Poly o; o.n = a.n > 1 ? a.n - 1 : 1; o.c[0] = 0.0;
+    for (int i = 1; i < a.n; i++) o.c[i - 1] = a.c[i] * (double)i;
+    return o;
+}
+static Poly axpy(const Poly& y, double a, const Poly& x) {      // y + a x
+    Poly o; o.n = y.n > x.n ? y.n : x.n;
+    for (int i = 0; i < o.n; i++) o.c[i] = (i < y.n ? y.c[i] : 0.0) + a * (i < x.n ? x.c[i] : 0.0);
+    return o;
+}
+static double eval(const Poly& a, double x) { double v = 0.0; for (int i = a.n - 1; i >= 0; i--) v = v * x + a.c[i]; return v; }
+static double int_prod(const Poly& a, const Poly& b, double L) {   // int_0^L a b dx
+    double prod[16]; const int n = a.n + b.n - 1;
+    for (int i = 0; i < n; i++) prod[i] = 0.0;
+    for (int i = 0; i < a.n; i++) for (int j = 0; j < b.n; j++) prod[i + j] += a.c[i] * b.c[j];
+    double v = 0.0, Lp = L;
+    for (int i = 0; i < n; i++) { v += prod[i] * Lp / (double)(i + 1); Lp *= L; }
+    return v;
+}
+// c_j(x), j = 0..kk-1: weights of the cell averages in the reconstruction polynomial over the cells bounded by X[0..kk]
+static void cell_weights(const double* X, int kk, Poly* cj) {
+    Poly dL[2 * KM];
+    for (int m = 0; m <= kk; m++) {
+        Poly l; l.n = 1; l.c[0] = 1.0;
+        for (int n = 0; n <= kk; n++) if (n != m) l = mul_lin(l, X[n], 1.0 / (X[m] - X[n]));
+        dL[m] = deriv(l);
+    }
+    for (int j = 0; j < kk; j++) {
+        Poly acc; acc.n = 1; acc.c[0] = 0.0;
+        for (int m = j + 1; m <= kk; m++) acc = axpy(acc, 1.0, dL[m]);
+        for (int i = 0; i < acc.n; i++) acc.c[i] *= (X[j + 1] - X[j]);
+        cj[j] = acc;
+    }
+}
+// tables of cell i for order 2k-1; xb = the 2k cell boundaries around it.  cL / cR[sidx][r] (r = 0: highest dvd; sidx = 0: the
+// rightmost stencil), dL / dR[sidx], bt[sidx][0 .. k(k-1)/2 - 1]
+static void tables(int k, const double* xb, double cLo[][KM - 1], double cRo[][KM - 1], double* dLo, double* dRo, double bto[][6]) {
+    double X[2 * KM];
+    const double x0 = xb[k - 1];
+    for (int m = 0; m < 2 * k; m++) X[m] = xb[m] - x0;
+    const double dxi = X[k] - X[k - 1];
+    Poly cw[KM][KM];
+    for (int l = 0; l < k; l++) {
+        cell_weights(X + (k - 1 - l), k, cw[l]);
+        Poly a[KM - 1];
+        for (int e = 0; e < k - 1; e++) {
+            Poly acc; acc.n = 1; acc.c[0] = 0.0;
+            if (e >= l) { for (int j = e + 1; j < k; j++) acc = axpy(acc, 1.0, cw[l][j]); }
+            else        { for (int j = 0; j <= e; j++) acc = axpy(acc, -1.0, cw[l][j]); }
+            a[e] = acc;
+        }
+        for (int r = 0; r < k - 1; r++) {
+            const int e = k - 2 - r;
+            cLo[l][r] = eval(a[e], 0.0);
+            cRo[l][r] = eval(a[e], dxi);
+        }
+        double B[KM - 1][KM - 1];
+        for (int e = 0; e < k - 1; e++) for (int f = 0; f < k - 1; f++) B[e][f] = 0.0;
+        Poly da[KM - 1];
+        for (int e = 0; e < k - 1; e++) da[e] = a[e];
+        double w = dxi;
+        for (int ord = 1; ord <= k - 1; ord++) {
+            for (int e = 0; e < k - 1; e++) da[e] = deriv(da[e]);
+            for (int e = 0; e < k - 1; e++) for (int f = 0; f < k - 1; f++) B[e][f] += w * int_prod(da[e], da[f], dxi);
+            w *= dxi * dxi;
+        }
+        int n = 0;
+        for (int r = 0; r < k - 1; r++) for (int r2 = r; r2 < k - 1; r2++) {
+            const int e = k - 2 - r, f = k - 2 - r2;
+            bto[l][n++] = (r == r2) ? B[e][e] : 2.0 * B[e][f];
+        }
+    }
+    Poly cbig[2 * KM];
+    cell_weights(X, 2 * k - 1, cbig);
+    for (int side = 0; side < 2; side++) {
+        const double xe = side == 0 ? 0.0 : dxi;
+        double* dd = side == 0 ? dLo : dRo;
+        for (int l = k - 1; l >= 0; l--) {
+            const int g = k - 1 - l;
+            double rhs = eval(cbig[g], xe);
+            for (int l2 = k - 1; l2 > l; l2--) rhs -= dd[l2] * eval(cw[l2][g - (k - 1 - l2)], xe);
+            dd[l] = rhs / eval(cw[l][0], xe);
+        }
+    }
+}
+}  // namespace wgen
+
 // ---- WENO tables: s_compute_weno_coefficients, m_weno.fpp:196-215 (order 3), :233-341 (order 5) -----
 static void weno_tables(const mfc5_handle* h, int d, std::vector<double> (&tab)[5], int& uniform) {
     const int s = h->s[d], b = h->b, pn = h->pn, ns = h->ns;
@@ -301,7 +406,7 @@ static void weno_tables(const mfc5_handle* h, int d, std::vector<double> (&tab)[
     tab[1].assign((size_t)nslot * ns * pr, 0.0);  // cR
     tab[2].assign((size_t)nslot * ns, 0.0);       // dL
     tab[3].assign((size_t)nslot * ns, 0.0);       // dR
-    tab[4].assign((size_t)nslot * ns * 3, 0.0);   // beta
+    tab[4].assign((size_t)nslot * ns * (pn == 3 ? 6 : 3), 0.0);   // beta (order 7: 6 entries per stencil)
     const double* x = h->scb[d].data() + 1 + b;
     auto q2 = [](double v) { return v * v; };
     auto CL = [&](int j, int q, int r) -> double& { return tab[0][((size_t)(j + b) * ns + q) * pr + r]; };
@@ -385,6 +490,21 @@ static void weno_tables(const mfc5_handle* h, int d, std::vector<double> (&tab)[
             }
         }
     }
+    if (h->P.weno_order == 7) {
+        for (int j = -b + pn; j <= s + b - pn; j++) {
+            double xb[8], cl[wgen::KM][wgen::KM - 1], cr[wgen::KM][wgen::KM - 1], dl[wgen::KM], dr[wgen::KM], bt[wgen::KM][6];
+            for (int m = 0; m < 8; m++) xb[m] = x[j - 4 + m];
+            wgen::tables(4, xb, cl, cr, dl, dr, bt);
+            for (int q = 0; q < 4; q++) {
+                for (int r = 0; r < 3; r++) { CL(j, q, r) = cl[q][r]; CR(j, q, r) = cr[q][r]; }
+                // the reference numbers the ideal weights of order 7 from the LEFTMOST stencil (d_cb(0) = 1/35 on a uniform grid)
+                // while poly_coef / beta_coef keep the rightmost-first index: d(q) belongs to stencil 3 - q
+                DL(q, j) = dl[3 - q];
+                DR(q, j) = dr[3 - q];
+                for (int r = 0; r < 6; r++) tab[4][((size_t)(j + b) * ns + q) * 6 + r] = bt[q][r];
+            }
+        }
+    }
     uniform = 1;  // m_weno.fpp:869-879
     if (s > 0) {
         const double h0 = (x[s] - x[0]) / (double)s;
@@ -458,12 +578,13 @@ extern "C" int mfc5_finalize_setup(mfc5_handle* h) {
     // weno_eps large enough that products of four smoothness indicators cannot underflow
     D.low_mach = h->P.low_Mach;
     D.alt_ss = h->P.alt_soundspeed;
-    D.teno = h->P.teno; D.teno_ct = h->P.teno_CT; D.mp_weno = h->P.mp_weno;
+    D.teno = h->P.teno; D.teno_ct = h->P.teno_CT; D.mp_weno = h->P.mp_weno; D.wenoz_q = h->P.wenoz_q;
     D.int_comp = h->P.int_comp; D.ic_eps = h->P.ic_eps; D.ic_beta = h->P.ic_beta;
     D.ic_cosh = std::cosh(h->P.ic_beta); D.ic_tanh = std::tanh(h->P.ic_beta);
     D.muscl = h->P.muscl_order; D.muscl_lim = h->P.muscl_lim; D.muscl_eps = h->P.muscl_eps;
     D.fast = h->P.fast_math && h->P.wave_speeds == 1 && !h->P.null_weights && h->P.weno_eps >= 1e-30 && h->P.low_Mach == 0 &&
-             !h->P.alt_soundspeed && h->P.riemann_solver != 5 && h->P.muscl_order == 0 && !h->P.teno && !h->P.mp_weno && h->P.int_comp == 0;
+             !h->P.alt_soundspeed && h->P.riemann_solver != 5 && h->P.muscl_order == 0 && !h->P.teno && !h->P.mp_weno && h->P.int_comp == 0 &&
+             h->P.weno_order != 7;
     if (getenv("MFC5_NO_FAST")) D.fast = 0;
     D.sy = h->px; D.sz = h->px * h->ey; D.fs = h->fs;
     D.base = h->ox + h->oy * D.sy + h->oz * D.sz;
@@ -486,7 +607,7 @@ extern "C" int mfc5_finalize_setup(mfc5_handle* h) {
             std::vector<double> rows((size_t)nslot * MFC5_TAB, 0.0);
             for (int sl = 0; sl < nslot; sl++) {
                 double* r = rows.data() + (size_t)sl * MFC5_TAB;
-                for (int q = 0; q < ns; q++) {
+                for (int q = 0; q < ns && h->pn < 3; q++) {   // (order 7 runs the reference-order kernels: its rows only carry ds)
                     for (int k = 0; k < pr && h->pn > 0; k++) {
                         r[0 + q * pr + k] = tab[0][((size_t)sl * ns + q) * pr + k];
                         r[6 + q * pr + k] = tab[1][((size_t)sl * ns + q) * pr + k];
@@ -831,10 +952,11 @@ static int launch_sweep(mfc5_handle* h, const DevP& D0, int dir, bool* halo_pend
     const bool x_shuffle = dir == 0 && !(D.x_march && (long long)(h->s[1] + 1) * (h->s[2] + 1) >= 4096 && h->nd >= 2);
     if (*halo_pending && x_shuffle) {
         const int nx = h->s[0] + 1, segs = (nx + MFC5_XW - 1) / MFC5_XW;
-        // segment g reads cells [30 g - 3, min(30 g + 32, m + 3)]: interior iff that range is within [0, m]
+        // segment g reads cells [30 g - 1 - w, min(30 g + 30 + w, m + 1 + w)], w = 2 (3 at order 7): interior iff that range is within [0, m]
+        const int wh = h->pn == 3 ? 3 : 2;
         int lo = 0, hi = segs;  // interior segments [lo, hi)
-        while (lo < segs && MFC5_XW * lo - 3 < 0) lo++;
-        while (hi > lo && std::min(MFC5_XW * (hi - 1) + 32, h->s[0] + 3) > h->s[0]) hi--;
+        while (lo < segs && MFC5_XW * lo - 1 - wh < 0) lo++;
+        while (hi > lo && std::min(MFC5_XW * (hi - 1) + 30 + wh, h->s[0] + 1 + wh) > h->s[0]) hi--;
         if (hi > lo) {
             D.xseg_lo = lo; D.xseg_n = hi - lo;
             if (launch_sweep_raw(h, D, 0)) return -1;

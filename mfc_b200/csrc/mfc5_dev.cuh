@@ -46,6 +46,7 @@ struct DevP {
     int low_mach;      // 0 / 1 / 2, inline_riemann.fpp:71-93 (reference-order kernels only)
     int teno;          // TENO5 weights (m_weno.fpp:1167-1187), cut-off teno_ct (reference-order kernels only)
     double teno_ct;
+    double wenoz_q;    // WENO-Z power at order 7 (m_weno.fpp:1381-1389)
     int mp_weno;       // monotonicity-preserving bounds on the WENO5 edge values (m_weno.fpp:1495-1601; reference-order kernels only)
     int muscl, muscl_lim;  // MUSCL reconstruction order (0 = WENO) and limiter, m_muscl.fpp (reference-order kernels only)
     double muscl_eps;
@@ -534,6 +535,104 @@ __device__ __forceinline__ void weno_edges(const DevP& P, const DirTables& T, in
             if (side == 0) eL = val; else eR = val;
         }
         if ((WV < 0) && P.mp_weno) mp_limit(f0, f1, f2, f3, f4, eL, eR);  // m_weno.fpp:1241-1243
+    }
+}
+
+// WENO7 / TENO7 reconstruction of one variable in one cell (reference-order only): s_weno, m_weno.fpp:1248-1490.
+// f[0..6] = v(j-3 .. j+3).  Tables: cL / cR(stencil, r) and beta(stencil, 0..5) with stencil 0 the rightmost one; the ideal
+// weights d(q), the polynomials and the smoothness indicators are numbered from the leftmost one (m_weno.fpp:362-851).
+// Same operation order as oracle/mfc5_oracle.c weno7_cell.
+__device__ __forceinline__ void weno7_edges(const DevP& P, const DirTables& T, int slot, const double (&f)[7], double& eL, double& eR) {
+    const double eps = P.eps;
+    const double vm3 = f[0], vm2 = f[1], vm1 = f[2], vp0 = f[3], vp1 = f[4], vp2 = f[5], vp3 = f[6];
+    double poly[5], beta[5], alpha[5] = {0, 0, 0, 0, 0}, omega[5], delta[5] = {1, 1, 1, 1, 1}, tau = 0.0;
+    if (!P.teno) {
+        const double* dl = T.dL + slot * 4;
+        const double* dr = T.dR + slot * 4;
+        const double* cl = T.cL + slot * 12;
+        const double* cr = T.cR + slot * 12;
+        const double* bt = T.bt + slot * 24;
+        const double e2 = vp3 - vp2, e1 = vp2 - vp1, e0 = vp1 - vp0, em1 = vp0 - vm1, em2 = vm1 - vm2, em3 = vm2 - vm3;
+        beta[3] = __ldg(bt + 0) * e2 * e2 + __ldg(bt + 1) * e2 * e1 + __ldg(bt + 2) * e2 * e0 + __ldg(bt + 3) * e1 * e1 + __ldg(bt + 4) * e1 * e0 + __ldg(bt + 5) * e0 * e0 + eps;
+        beta[2] = __ldg(bt + 6) * e1 * e1 + __ldg(bt + 7) * e1 * e0 + __ldg(bt + 8) * e1 * em1 + __ldg(bt + 9) * e0 * e0 + __ldg(bt + 10) * e0 * em1 + __ldg(bt + 11) * em1 * em1 + eps;
+        beta[1] = __ldg(bt + 12) * e0 * e0 + __ldg(bt + 13) * e0 * em1 + __ldg(bt + 14) * e0 * em2 + __ldg(bt + 15) * em1 * em1 + __ldg(bt + 16) * em1 * em2 + __ldg(bt + 17) * em2 * em2 + eps;
+        beta[0] = __ldg(bt + 18) * em1 * em1 + __ldg(bt + 19) * em1 * em2 + __ldg(bt + 20) * em1 * em3 + __ldg(bt + 21) * em2 * em2 + __ldg(bt + 22) * em2 * em3 + __ldg(bt + 23) * em3 * em3 + eps;
+#pragma unroll
+        for (int side = 0; side < 2; side++) {
+            const double* cc = side == 0 ? cl : cr;
+            const double* dd = side == 0 ? dl : dr;
+            poly[3] = vp0 + __ldg(cc + 0) * e2 + __ldg(cc + 1) * e1 + __ldg(cc + 2) * e0;
+            poly[2] = vp0 + __ldg(cc + 3) * e1 + __ldg(cc + 4) * e0 + __ldg(cc + 5) * em1;
+            poly[1] = vp0 + __ldg(cc + 6) * e0 + __ldg(cc + 7) * em1 + __ldg(cc + 8) * em2;
+            poly[0] = vp0 + __ldg(cc + 9) * em1 + __ldg(cc + 10) * em2 + __ldg(cc + 11) * em3;
+            double d4[4];
+#pragma unroll
+            for (int q = 0; q < 4; q++) d4[q] = __ldg(dd + q);
+            if (P.wv == 1) {
+#pragma unroll
+                for (int q = 0; q < 4; q++) alpha[q] = d4[q] / (beta[q] * beta[q]);
+                const double sum = alpha[0] + alpha[1] + alpha[2] + alpha[3];
+#pragma unroll
+                for (int q = 0; q < 4; q++) omega[q] = alpha[q] / sum;
+#pragma unroll
+                for (int q = 0; q < 4; q++)
+                    alpha[q] = (d4[q] * (1.0 + d4[q] - 3.0 * omega[q]) + omega[q] * omega[q]) * (omega[q] / (d4[q] * d4[q] + omega[q] * (1.0 - 2.0 * d4[q])));
+            } else if (P.wv == 2) {
+                if (side == 0) tau = fabs(beta[3] - beta[0]);
+#pragma unroll
+                for (int q = 0; q < 4; q++) alpha[q] = d4[q] * (1.0 + pow(tau / beta[q], P.wenoz_q));
+            } else {
+#pragma unroll
+                for (int q = 0; q < 4; q++) alpha[q] = d4[q] / (beta[q] * beta[q]);
+            }
+            const double sum = alpha[0] + alpha[1] + alpha[2] + alpha[3];
+#pragma unroll
+            for (int q = 0; q < 4; q++) omega[q] = alpha[q] / sum;
+            const double val = omega[0] * poly[0] + omega[1] * poly[1] + omega[2] * poly[2] + omega[3] * poly[3];
+            if (side == 0) eL = val; else eR = val;
+        }
+        return;
+    }
+    // TENO7 (Fu et al. 2016; Fu & Tang 2019): five uniform-grid stencils, m_weno.fpp:1303-1313,1355-1372,1427-1456
+    const double dLt[5] = {18.0 / 35.0, 3.0 / 35.0, 9.0 / 35.0, 1.0 / 35.0, 4.0 / 35.0};
+    const double dRt[5] = {18.0 / 35.0, 9.0 / 35.0, 3.0 / 35.0, 4.0 / 35.0, 1.0 / 35.0};
+    beta[0] = 13.0 / 12.0 * sq(vm1 - 2.0 * vp0 + vp1) + sq(vm1 - vp1) / 4.0 + eps;
+    beta[1] = 13.0 / 12.0 * sq(vp0 - 2.0 * vp1 + vp2) + sq(3.0 * vp0 - 4.0 * vp1 + vp2) / 4.0 + eps;
+    beta[2] = 13.0 / 12.0 * sq(vm2 - 2.0 * vm1 + vp0) + sq(vm2 - 4.0 * vm1 + 3.0 * vp0) / 4.0 + eps;
+    beta[3] = (vp0 * (2107.0 * vp0 - 9402.0 * vp1 + 7042.0 * vp2 - 1854.0 * vp3) + vp1 * (11003.0 * vp1 - 17246.0 * vp2 + 4642.0 * vp3) +
+               vp2 * (7043.0 * vp2 - 3882.0 * vp3) + vp3 * (547.0 * vp3)) / 240.0 + eps;
+    beta[4] = (vm3 * (547.0 * vm3 - 3882.0 * vm2 + 4642.0 * vm1 - 1854.0 * vp0) + vm2 * (7043.0 * vm2 - 17246.0 * vm1 + 7042.0 * vp0) +
+               vm1 * (11003.0 * vm1 - 9402.0 * vp0) + vp0 * (2107.0 * vp0)) / 240.0 + eps;
+#pragma unroll
+    for (int side = 0; side < 2; side++) {
+        const double* dd = side == 0 ? dLt : dRt;
+        if (side == 0) {
+            poly[0] = (2.0 * vm1 + 5.0 * vp0 - 1.0 * vp1) / 6.0;
+            poly[1] = (11.0 * vp0 - 7.0 * vp1 + 2.0 * vp2) / 6.0;
+            poly[2] = (-1.0 * vm2 + 5.0 * vm1 + 2.0 * vp0) / 6.0;
+            poly[3] = (25.0 * vp0 - 23.0 * vp1 + 13.0 * vp2 - 3.0 * vp3) / 12.0;
+            poly[4] = (1.0 * vm3 - 5.0 * vm2 + 13.0 * vm1 + 3.0 * vp0) / 12.0;
+            tau = fabs(beta[4] - beta[3]);
+#pragma unroll
+            for (int q = 0; q < 5; q++) { alpha[q] = 1.0 + tau / beta[q]; alpha[q] = (alpha[q] * alpha[q] * alpha[q]) * (alpha[q] * alpha[q] * alpha[q]); }
+            const double sum = alpha[0] + alpha[1] + alpha[2] + alpha[3] + alpha[4];
+#pragma unroll
+            for (int q = 0; q < 5; q++) { omega[q] = alpha[q] / sum; delta[q] = omega[q] < P.teno_ct ? 0.0 : 1.0; }
+        } else {
+            poly[0] = (-1.0 * vm1 + 5.0 * vp0 + 2.0 * vp1) / 6.0;
+            poly[1] = (2.0 * vp0 + 5.0 * vp1 - 1.0 * vp2) / 6.0;
+            poly[2] = (2.0 * vm2 - 7.0 * vm1 + 11.0 * vp0) / 6.0;
+            poly[3] = (3.0 * vp0 + 13.0 * vp1 - 5.0 * vp2 + 1.0 * vp3) / 12.0;
+            poly[4] = (-3.0 * vm3 + 13.0 * vm2 - 23.0 * vm1 + 25.0 * vp0) / 12.0;
+        }
+#pragma unroll
+        for (int q = 0; q < 5; q++) alpha[q] = delta[q] * dd[q];
+        const double sum = alpha[0] + alpha[1] + alpha[2] + alpha[3] + alpha[4];
+#pragma unroll
+        for (int q = 0; q < 5; q++) omega[q] = alpha[q] / sum;
+        double val = omega[0] * poly[0] + omega[1] * poly[1] + omega[2] * poly[2] + omega[3] * poly[3];
+        val = val + omega[4] * poly[4];
+        if (side == 0) eL = val; else eR = val;
     }
 }
 

@@ -76,7 +76,8 @@ inline int march_chunk(const DevP& P, int dir, int blocks_per_sm, int max_chunk)
 
 template <int NF, int ND, int DIR, int WO, int WV, int RS, int FAST>
 inline bool launch_march(const DevP& P0, cudaStream_t st) {
-    constexpr int bps = (2 * NF + ND + 1 <= 8) ? MFC5_MARCH_MINB : 1;  // resident blocks per SM the kernel is built for
+    // resident blocks per SM the kernel is built for; one when two rings do not fit (order 7 with 8 variables)
+    const int bps = ((2 * NF + ND + 1 <= 8) && 2 * (march_smem_bytes<NF, ND, WO>(4) + 1024) <= 227 * 1024) ? MFC5_MARCH_MINB : 1;
     auto kern = k_sweep_march<NF, ND, DIR, WO, WV, RS, FAST>;
     // the attribute is per device (a process may hold handles on several): once per (kernel, device ordinal)
     static bool attr_done[64] = {};
@@ -93,6 +94,7 @@ inline bool launch_march(const DevP& P0, cudaStream_t st) {
     // longest chunk whose table rows still let `bps` blocks share the 227 KB of an SM
     const long long budget = (227LL * 1024 - bps * 1024) / bps - (long long)march_smem_bytes<NF, ND, WO>(-2);
     const int max_chunk = (int)std::max<long long>(4, budget / (MFC5_TAB * (long long)sizeof(double)) - 2);
+    if (march_smem_bytes<NF, ND, WO>(4) > 226 * 1024) return false;   // does not fit at all
     if (P.chunk <= 0) P.chunk = march_chunk(P, DIR, bps, max_chunk);
     P.chunk = std::min(P.chunk, max_chunk);
     const long long lanes_blocks = (march_pencils(P, DIR) + MFC5_MARCH_THREADS - 1) / MFC5_MARCH_THREADS;
@@ -179,6 +181,13 @@ inline bool launch_sweep_generic(const DevP& P, int dir, cudaStream_t st) {
         }
     }
 #endif
+    if (P.wo == 7) {   // seven-point window: its own instantiation (reference-order arithmetic, run-time variant / solver)
+        switch (P.nd) {
+        case 1: return launch_sweep_t<NF, 1, 7, -1, -1, 0>(P, dir, st);
+        case 2: return launch_sweep_t<NF, 2, 7, -1, -1, 0>(P, dir, st);
+        case 3: return launch_sweep_t<NF, 3, 7, -1, -1, 0>(P, dir, st);
+        }
+    }
     switch (P.nd) {
     case 1: return launch_sweep_t<NF, 1, -1, -1, -1, 0>(P, dir, st);
     case 2: return launch_sweep_t<NF, 2, -1, -1, -1, 0>(P, dir, st);

@@ -517,6 +517,8 @@ __global__ void __launch_bounds__(128, MFC5_X_MINB) k_sweep_x(const __grid_const
     constexpr int N = S::N;
     constexpr int XT = 40;
     constexpr int NV = MFC5_WENO_NV;
+    constexpr int PNX = (WO == 7) ? 3 : 2;   // half-width of the staged stencil window (the generic kernels reserve the WENO5 one)
+    constexpr int FW = 2 * PNX + 1;
     constexpr int NB = (MFC5_X_RPB > 1 && N <= 8) ? 2 : 1;  // window buffers per warp (static shared memory: 48 KB)
     const int lane = threadIdx.x & 31;
     const int w = threadIdx.x >> 5, nw = blockDim.x >> 5;
@@ -538,16 +540,16 @@ __global__ void __launch_bounds__(128, MFC5_X_MINB) k_sweep_x(const __grid_const
     // window cells of this lane (clamped to the ghost region), through the ghost modes of the x boundaries (DevP::gmode)
     bool fa, fb;
     const GhostMap gmap(P, 0);
-    const int ca = gmap.src(min(i0 - 3 + lane, hi), fa), cb = gmap.src(min(i0 - 3 + 32 + lane, hi), fb);
+    const int ca = gmap.src(min(i0 - 1 - PNX + lane, hi), fa), cb = gmap.src(min(i0 - 1 - PNX + 32 + lane, hi), fb);
     const bool any_flip = (P.gmode[0][0] == MFC5_GM_MIRROR) | (P.gmode[0][1] == MFC5_GM_MIRROR);   // kernel-uniform
-    using ix = typename SweepIdx<(WO >= 0)>::type;  // 32-bit element indices in the case-optimised kernels (k_sweep_march)
+    using ix = typename SweepIdx<(WO >= 0 && FAST)>::type;  // 32-bit element indices in the case-optimised kernels (k_sweep_march)
     const ix fs = (ix)P.fs;
     auto load_window = [&](int buf, int jj) {
         const ix rb = (ix)P.base + (ix)jj * (ix)P.sy + (ix)k * (ix)P.sz;
 #pragma unroll
         for (int v = 0; v < N; v++) {
             cp_async8(&sx[w][buf][v][lane], P.prim + (ix)((ix)v * fs + rb + (ix)ca));
-            if (lane < 4) cp_async8(&sx[w][buf][v][32 + lane], P.prim + (ix)((ix)v * fs + rb + (ix)cb));
+            if (lane < 2 * PNX) cp_async8(&sx[w][buf][v][32 + lane], P.prim + (ix)((ix)v * fs + rb + (ix)cb));
         }
         cp_async_commit();
     };
@@ -579,7 +581,7 @@ __global__ void __launch_bounds__(128, MFC5_X_MINB) k_sweep_x(const __grid_const
         double(*my)[XT] = sx[w][buf];
         if (any_flip) {   // reflective wall: the mirrored cells carry -u_x
             if (fa) my[S::IM][lane] = -my[S::IM][lane];
-            if (lane < 4 && fb) my[S::IM][32 + lane] = -my[S::IM][32 + lane];
+            if (lane < 2 * PNX && fb) my[S::IM][32 + lane] = -my[S::IM][32 + lane];
             __syncwarp();
         }
         const long long row = j + (long long)(P.s[1] + 1) * k;
@@ -589,15 +591,20 @@ __global__ void __launch_bounds__(128, MFC5_X_MINB) k_sweep_x(const __grid_const
         // warp shuffle; edge states wait in shared memory for the Riemann solve
 #pragma unroll 1
         for (int v0 = 0; v0 < N; v0 += NV) {
-            double f[NV][5], l[NV], r[NV];
+            double f[NV][FW], l[NV], r[NV];
             int vv[NV];
 #pragma unroll
             for (int u = 0; u < NV; u++) {
                 vv[u] = min(v0 + u, N - 1);
 #pragma unroll
-                for (int q = 0; q < 5; q++) f[u][q] = my[vv[u]][lane + q];
+                for (int q = 0; q < FW; q++) f[u][q] = my[vv[u]][lane + q];
             }
-            weno_edges_nv<WO, WV, FAST, NV>(P, T, slot, xrow, f, l, r);
+            if constexpr (WO == 7) {
+#pragma unroll
+                for (int u = 0; u < NV; u++) weno7_edges(P, T, slot, f[u], l[u], r[u]);
+            } else {
+                weno_edges_nv<WO, WV, FAST, NV>(P, T, slot, xrow, f, l, r);
+            }
 #pragma unroll
             for (int u = 0; u < NV; u++) {
                 myR[vv[u]][lane] = r[u];
@@ -723,7 +730,7 @@ __global__ void __launch_bounds__(MFC5_MARCH_THREADS, (2 * NF + ND + 1 <= 8) ? M
     // element indices into the field arrays: 32-bit (one IMAD.WIDE per access, the per-variable index shared by all arrays)
     // in the case-optimised kernels, whose launcher checks that N * field size fits; 64-bit in the generic ones.  Plane
     // numbers below zero wrap around in unsigned arithmetic and come out right because the final index is non-negative.
-    using ix = typename SweepIdx<(WO >= 0)>::type;
+    using ix = typename SweepIdx<(WO >= 0 && FAST)>::type;
     const ix fs = (ix)P.fs;
     const ix sa = (DIR == 0) ? (ix)P.sy : (ix)1;
     const ix sb = (DIR == 2) ? (ix)P.sy : (ix)P.sz;
@@ -790,18 +797,23 @@ __global__ void __launch_bounds__(MFC5_MARCH_THREADS, (2 * NF + ND + 1 <= 8) ? M
             const RowAoS mrow{srow + (cc - (c0 - 1)) * MFC5_TAB};
 #pragma unroll 1
             for (int v0 = 0; v0 < N; v0 += NV) {
-                double f[NV][5], l[NV], r[NV];
+                constexpr int FW = (PN == 3) ? 7 : 5, FC = FW / 2;   // f[u][FC + k] = v(cc + k)
+                double f[NV][FW], l[NV], r[NV];
                 int vv[NV];
 #pragma unroll
                 for (int u = 0; u < NV; u++) {
                     vv[u] = min(v0 + u, N - 1);
 #pragma unroll
-                    for (int k = 0; k < 5; k++) f[u][k] = 0.0;
-                    f[u][2] = ring[off[PN] + vv[u] * NT];
-                    if (PN >= 1) { f[u][1] = ring[off[PN - 1] + vv[u] * NT]; f[u][3] = ring[off[PN + (PN >= 1 ? 1 : 0)] + vv[u] * NT]; }
-                    if (PN >= 2) { f[u][0] = ring[off[0] + vv[u] * NT]; f[u][4] = ring[off[R - 1] + vv[u] * NT]; }
+                    for (int k = 0; k < FW; k++) f[u][k] = 0.0;
+#pragma unroll
+                    for (int k = 0; k < R; k++) f[u][FC - PN + k] = ring[off[k] + vv[u] * NT];
                 }
-                weno_edges_nv<WO, WV, FAST, NV>(P, T, cc + P.b, mrow, f, l, r);
+                if constexpr (WO == 7) {
+#pragma unroll
+                    for (int u = 0; u < NV; u++) weno7_edges(P, T, cc + P.b, f[u], l[u], r[u]);
+                } else {
+                    weno_edges_nv<WO, WV, FAST, NV>(P, T, cc + P.b, mrow, f, l, r);
+                }
 #pragma unroll
                 for (int u = 0; u < NV; u++) { sEL[vv[u] * NT + tid] = l[u]; sERc[vv[u] * NT] = r[u]; }
             }
@@ -941,11 +953,14 @@ __global__ void __launch_bounds__(MFC5_MARCH_THREADS, (2 * NF + ND + 1 <= 8) ? M
 #ifndef MFC5_M2_NV
 #define MFC5_M2_NV MFC5_WENO_NV   // variables per iteration of the rolled WENO loop
 #endif
+#ifndef MFC5_M2_FPS
+#define MFC5_M2_FPS 0       // 1: the flux of the previous face crosses iterations through shared memory instead of 16 registers + their copies
+#endif
 
 template <int NF, int ND, int WO>
 inline size_t march2_smem_bytes(int chunk) {
     constexpr int R = 2 * ((WO - 1) / 2) + 1;
-    return ((size_t)(R + 2) * (2 * NF + ND + 1) * MFC5_M2_THREADS + (MFC5_M2_TABS ? (size_t)(chunk + 2) * MFC5_TAB : 0)) * sizeof(double);
+    return ((size_t)(R + 2 + MFC5_M2_FPS) * (2 * NF + ND + 1) * MFC5_M2_THREADS + (MFC5_M2_TABS ? (size_t)(chunk + 2) * MFC5_TAB : 0)) * sizeof(double);
 }
 
 // cons -> prim of one cell with reciprocals + residual-corrected quotients (same formulas and order as cons2prim_cell)
@@ -1006,7 +1021,8 @@ __global__ void __launch_bounds__(MFC5_M2_THREADS, MFC5_M2_MINB) k_march2(const 
     extern __shared__ double smem[];
     double* ring = smem;                   // [NSLOT][N][NT]: R window planes + the right-edge states of the previous cell
     double* sEL = smem + NSLOT * N * NT;   // [N][NT] left-edge states of the cell reconstructed in this iteration
-    double* srow = sEL + N * NT;           // [chunk + 2][MFC5_TAB] table rows of cells c0-1 .. c1+1
+    double* sFp = sEL + N * NT;            // [N][NT] (MFC5_M2_FPS) flux of the previous face
+    double* srow = sFp + MFC5_M2_FPS * N * NT;   // [chunk + 2][MFC5_TAB] table rows of cells c0-1 .. c1+1
     const int tid = threadIdx.x;
     const int s = P.s[DIR];
     const int c0 = blockIdx.y * P.chunk;
@@ -1060,9 +1076,9 @@ __global__ void __launch_bounds__(MFC5_M2_THREADS, MFC5_M2_MINB) k_march2(const 
     cp_async_commit();
     int tail = 0;  // slot of the oldest plane of the window (cc - PN)
 
-    double Fp[N], Fsp[NF];  // flux of the previous face
+    double Fp[MFC5_M2_FPS ? 1 : N], Fsp[NF];  // flux of the previous face
 #pragma unroll
-    for (int v = 0; v < N; v++) Fp[v] = 0.0;
+    for (int v = 0; v < (MFC5_M2_FPS ? 1 : N); v++) Fp[v] = 0.0;
 #pragma unroll
     for (int f = 0; f < NF; f++) Fsp[f] = 0.0;
 
@@ -1120,12 +1136,12 @@ __global__ void __launch_bounds__(MFC5_M2_THREADS, MFC5_M2_MINB) k_march2(const 
                 load_plane(slR, cc + 1 + PN);
                 cp_async_commit();
             }
-#if !MFC5_M2_LATE
+#if MFC5_M2_LATE != 1
             double rin[N], q1in[N], q2in[N], acoef[NF];
             if (fin) {
 #pragma unroll
                 for (int v = 0; v < N; v++) rin[v] = (DIR == 0) ? 0.0 : P.rhs[(ix)((ix)v * fs + c)];
-                if (rk) {
+                if (rk && MFC5_M2_LATE == 0) {
 #pragma unroll
                     for (int v = 0; v < N; v++) q1in[v] = __ldg(P.q1 + (ix)((ix)v * fs + c));
 #pragma unroll
@@ -1141,7 +1157,15 @@ __global__ void __launch_bounds__(MFC5_M2_THREADS, MFC5_M2_MINB) k_march2(const 
             if (P.cbc_on[DIR][0] | P.cbc_on[DIR][1]) cbc_override<NF, ND, DIR>(P, face, t, plane, F, Fs);
             if (fin) {
                 const double inv_ds = MFC5_M2_TABS ? srow[(cc - 1 - (c0 - 1)) * MFC5_TAB + 46] : __ldg(T.tab + (long long)(cc - 1 + P.b) * MFC5_TAB + 46);
-#if MFC5_M2_LATE
+#if MFC5_M2_LATE == 2   // rhs and the alpha coefficients early, q1 / q2 after the Riemann solve
+                if (rk) {
+#pragma unroll
+                    for (int v = 0; v < N; v++) q1in[v] = __ldg(P.q1 + (ix)((ix)v * fs + c));
+#pragma unroll
+                    for (int v = 0; v < N; v++) q2in[v] = (P.rk1 != 0.0) ? __ldg(P.q2 + (ix)((ix)v * fs + c)) : 0.0;
+                }
+#endif
+#if MFC5_M2_LATE == 1
                 double rin[N], q1in[N], q2in[N], acoef[NF];
 #pragma unroll
                 for (int v = 0; v < N; v++) rin[v] = (DIR == 0) ? 0.0 : P.rhs[(ix)((ix)v * fs + c)];
@@ -1157,8 +1181,9 @@ __global__ void __launch_bounds__(MFC5_M2_THREADS, MFC5_M2_MINB) k_march2(const 
                 double r[N];
 #pragma unroll
                 for (int v = 0; v < N; v++) {
-                    if (DIR == 0) r[v] = inv_ds * (Fp[v] - F[v]);
-                    else r[v] = rin[v] + inv_ds * (Fp[v] - F[v]);
+                    const double fp = MFC5_M2_FPS ? sFp[v * NT + tid] : Fp[MFC5_M2_FPS ? 0 : v];
+                    if (DIR == 0) r[v] = inv_ds * (fp - F[v]);
+                    else r[v] = rin[v] + inv_ds * (fp - F[v]);
                 }
 #pragma unroll
                 for (int f = 0; f < NF; f++) {
@@ -1183,7 +1208,10 @@ __global__ void __launch_bounds__(MFC5_M2_THREADS, MFC5_M2_MINB) k_march2(const 
                 }
             }
 #pragma unroll
-            for (int v = 0; v < N; v++) Fp[v] = F[v];
+            for (int v = 0; v < N; v++) {
+                if (MFC5_M2_FPS) sFp[v * NT + tid] = F[v];
+                else Fp[MFC5_M2_FPS ? 0 : v] = F[v];
+            }
 #pragma unroll
             for (int f = 0; f < NF; f++) Fsp[f] = Fs[f];
         }

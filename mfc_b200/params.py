@@ -125,25 +125,26 @@ def params_from_case(case, device=0, fast_math=1, oracle_only=False):
         P.weno_order = 2 * P.muscl_order + 1   # same stencil window / buffer geometry as the WENO of that width
     else:
         P.weno_order = int(case["weno_order"])
-        if P.weno_order not in (1, 3, 5) and not (oracle_only and P.weno_order == 7):
-            # weno_order = 7: restated in the CPU oracle and pinned by the reference's goldens (tests/test_oracle_next.py); the CUDA
-            # kernels do not have it yet, so the product path rejects it
-            raise UnsupportedCase("weno_order must be 1, 3 or 5")
+        if P.weno_order not in (1, 3, 5, 7):   # toolchain/mfc/case_validator.py:401
+            raise UnsupportedCase("weno_order must be 1, 3, 5, or 7")
     P.mapped_weno = _logical(case.get("mapped_weno", "F"))
     P.wenoz = _logical(case.get("wenoz", "F"))
     P.null_weights = _logical(case.get("null_weights", "F"))
     P.teno = _logical(case.get("teno", "F"))
     if P.teno:  # toolchain/mfc/case_validator.py:942-966
         if P.muscl_order > 0 or P.weno_order not in (5, 7):
-            raise UnsupportedCase("teno is available for weno_order = 5 on this path (the reference: 5 or 7)")
+            raise UnsupportedCase("teno requires weno_order = 5 or 7")
         if P.mapped_weno or P.wenoz:
             raise UnsupportedCase("Only one of mapped_weno, wenoz, or teno can be set to true")
         if "teno_CT" not in case or float(case["teno_CT"]) <= 0:
             raise UnsupportedCase("teno requires teno_CT to be set. A typical value is 1e-6")
         P.teno_CT = float(case["teno_CT"])
     P.wenoz_q = float(case.get("wenoz_q", 1.0) or 1.0)
-    if P.wenoz and P.weno_order == 7 and "wenoz_q" not in case:  # toolchain/mfc/case_validator.py: wenoz_q required for order 7
-        raise UnsupportedCase("wenoz at weno_order = 7 requires wenoz_q")
+    if P.wenoz and P.weno_order == 7:  # toolchain/mfc/case_validator.py:959-960
+        if "wenoz_q" not in case:
+            raise UnsupportedCase("wenoz at 7th order requires wenoz_q to be set (should be 2, 3, or 4)")
+        if P.wenoz_q not in (2.0, 3.0, 4.0):
+            raise UnsupportedCase("wenoz_q must be either 2, 3, or 4")
     P.mp_weno = _logical(case.get("mp_weno", "F"))
     if P.mp_weno and (P.muscl_order > 0 or P.weno_order != 5):  # toolchain/mfc/case_validator.py:967
         raise UnsupportedCase("mp_weno requires weno_order = 5")
@@ -229,6 +230,11 @@ def check_params(P):
     need = 5 * P.recon_order   # num_stcls_min * weno_order (or muscl_order), order 1 included: m_checker.fpp:52-90
     if P.muscl_order > 0 and any(-12 <= P.bc[d][s] <= -5 for d in range(P.num_dims) for s in range(2)):
         raise UnsupportedCase("characteristic boundary conditions with MUSCL reconstruction are outside the hot path")
+    if P.weno_order == 7 and P.muscl_order == 0:
+        if any(-12 <= P.bc[d][s] <= -5 for d in range(P.num_dims) for s in range(2)):
+            raise UnsupportedCase("characteristic boundary conditions at weno_order = 7 are outside the hot path (the reference's CBC tables stop at order 5)")
+        if P.int_comp != 0 or P.null_weights:
+            raise UnsupportedCase("int_comp / null_weights at weno_order = 7 are outside the hot path")
     for s, name in ((P.m, "m"), (P.n, "n"), (P.p, "p")):
         if s > 0 and s + 1 < need:
             raise UnsupportedCase(f"{name}+1 must be >= num_stcls_min*weno_order = {need}")

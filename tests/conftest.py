@@ -27,3 +27,22 @@ def pytest_collection_modifyitems(config, items):
     for it in items:
         if "gpu" in it.keywords:
             it.add_marker(skip)
+
+
+@pytest.hookimpl(tryfirst=True)
+def pytest_cmdline_main(config):
+    """CPU suite (no CUDA device): spread the oracle-vs-golden cases over a few worker processes (pytest-xdist, if installed and
+    not already requested) so that the whole `-m "not gpu"` run stays within a few minutes.  On a GPU box the suite runs
+    in-process, one CUDA context."""
+    if getattr(config.option, "numprocesses", None) not in (None, 0) or os.environ.get("MFC5_TEST_SERIAL"):
+        return None
+    if not config.pluginmanager.hasplugin("xdist"):
+        return None
+    try:
+        import torch
+        if torch.cuda.is_available():
+            return None
+    except Exception:
+        pass
+    config.option.numprocesses = min(4, max(1, (os.cpu_count() or 2) // 2))
+    return None

@@ -66,7 +66,7 @@ def test_no_cpu_fallback_without_device():
 def test_out_of_envelope_cases_are_rejected():
     from golden_util import CASES
     base = dict(CASES["2AB32975"]["params"])
-    for key, val in (("viscous", "T"), ("bubbles_euler", "T"), ("model_eqns", 3), ("riemann_solver", 4), ("weno_order", 7),
+    for key, val in (("viscous", "T"), ("bubbles_euler", "T"), ("model_eqns", 3), ("riemann_solver", 4), ("weno_order", 9),
                      ("igr", "T"), ("alt_soundspeed", "T"), ("low_Mach", 3), ("cont_damage", "T")):
         with pytest.raises(UnsupportedCase):  # (alt_soundspeed: the base case has one fluid)
             params_from_case(dict(base, **{key: val}))

@@ -1,11 +1,12 @@
-"""Features the CPU oracle already has and the CUDA library does not yet -- the checker waiting for those
-kernels; the product path (``params_from_case`` without ``oracle_only``, ``mfc5_create``) rejects them.
+"""Oracle-side checks of the newest features.
 
-* weno_order = 7: WENO7-JS / -M / -Z with wenoz_q, TENO7 (m_weno.fpp:362-851,1248-1490), pinned by the reference's 13 order-7
-  goldens and its 7th-order convergence cases.  The tables are not transcribed from the reference's ~500 lines of closed forms
-  but built by the general construction those come from (oracle/mfc5_oracle.c g_weno_tables), which reproduces the transcribed
-  WENO5 tables to 1e-13 on stretched grids (first test).
-* int_comp = 2: MTHINC (m_thinc.fpp:28-291,323-355), pinned by the reference's 5 goldens.
+* weno_order = 7: WENO7-JS / -M / -Z with wenoz_q, TENO7 (m_weno.fpp:362-851,1248-1490).  In the CUDA library since round 2 (its 13
+  goldens run with every other golden in tests/test_oracle_golden.py and tests/test_gpu_parity.py); here: the table construction.
+  The tables are not transcribed from the reference's ~500 lines of closed forms but built by the general construction those
+  come from (oracle/mfc5_oracle.c g_weno_tables; mfc_b200/csrc/mfc5.cu wgen::tables), which reproduces the transcribed WENO5
+  tables to 1e-13 on stretched grids (first test), and the reference's 7th-order convergence case.
+* int_comp = 2: MTHINC (m_thinc.fpp:28-291,323-355): the CPU oracle only so far, pinned by the reference's 5 goldens; the product
+  path (``params_from_case`` without ``oracle_only``, ``mfc5_create``) rejects it.
 """
 import ctypes as C
 import math
@@ -44,7 +45,7 @@ def test_general_construction_reproduces_weno5_tables(uuid):
         assert 0.0 <= L.orc_selftest_weno_generic(o.h, d) <= 1e-12
 
 
-def test_product_path_rejects_order_7():
+def test_product_path_rejects_mthinc():
     case = next(iter(ORACLE_ONLY.values()))["params"]
     with pytest.raises(UnsupportedCase):
         params_from_case(case)
