@@ -37,7 +37,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
-    ap.add_argument("--case", default="3D_performance_test", choices=["3D_performance_test", "5eq_rk3_weno3_hllc", "3D_shockdroplet"])
+    ap.add_argument("--case", default="3D_performance_test", choices=["3D_performance_test", "5eq_rk3_weno3_hllc", "3D_shockdroplet", "2D_shockbubble", "1D_sodshocktube"])
     ap.add_argument("--m", type=int, default=200, help="cells-1 per direction per GPU (3D_performance_test)")
     ap.add_argument("--riemann", default="hllc", choices=["hllc", "hll"])
     ap.add_argument("--gbpp", type=int, default=16, help="5eq_rk3_weno3_hllc: the reference's --gbpp")
@@ -45,6 +45,8 @@ def parse():
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-other-configs", action="store_true", help="skip BASELINE.json's other configurations (C1 .. C4, HLL variant, strong scaling)")
+    ap.add_argument("--other-budget", type=float, default=150.0, help="seconds the other configurations may take in total")
     ap.add_argument("--cpu-steps", type=int, default=2)
     return ap.parse_args()
 
@@ -62,6 +64,12 @@ def build_case(args, nranks):
     elif args.case == "5eq_rk3_weno3_hllc":
         case = cases.bench_5eq_weno3_hllc(gbpp=args.gbpp, riemann=args.riemann)
         name = f"benchmarks/5eq_rk3_weno3_{args.riemann} --gbpp {args.gbpp}: {case['m'] + 1}x{case['n'] + 1}x{case['p'] + 1} cells/GPU, WENO3-M"
+    elif args.case == "2D_shockbubble":
+        case = cases.shockbubble_2d()
+        name = f"examples/2D_shockbubble {case['m'] + 1}x{case['n'] + 1} cells, air/helium, WENO5-M, HLLC"
+    elif args.case == "1D_sodshocktube":
+        case = cases.sod_1d()
+        name = f"examples/1D_sodshocktube {case['m'] + 1} cells, WENO5-M, HLLC"
     else:
         case = cases.shockdroplet_3d(**(dict(weno_order=5, mapped_weno="F", wenoz="T") if args.weno5z else {}))
         name = "examples/3D_shockdroplet 201x101x101 " + ("WENO5-Z override" if args.weno5z else "WENO3-M as shipped") + ", HLLC"
@@ -211,6 +219,93 @@ def multi_gpu_parity(args, rank, world, local_rank):
     return {"what": "decomposed run == single-GPU run of the same global case, 3D_performance_test at 60^3 cells per GPU, %d RK3 steps" % nsteps,
             "cells_global": int((case["m"] + 1) * (case["n"] + 1) * (case["p"] + 1)), "proc_grid": list(dims), "max_rel": worst, "tol": 1e-12,
             "ok": bool(worst <= 1e-12 and moved > 0.0), "state_change": moved, "kernel_launches_per_rank": int(launches)}
+
+
+def time_config(sargs, rank, world, local_rank, steps, warmup, peak):
+    """Device-resident time per RK3 step of one more configuration (same timing rules as the headline: warm-up, CUDA events on
+    the library's compute stream, barrier + synchronise on both sides, max over ranks).  Collective: every rank calls it."""
+    import torch
+    import torch.distributed as dist
+    from mfc_b200 import lib
+    from mfc_b200.lib import Mfc5
+    t_setup = time.time()
+    case, dims, name = build_case(sargs, world)
+    blk, lcase, P, cbs, gws, cons = setup_rank(case, rank, world, dims)
+    P.device = local_rank
+    g = Mfc5(P, cbs, ghost_widths=gws)
+    if world > 1:
+        uid = [lib.nccl_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        g.comm_init(uid[0], rank, world)
+    g.set_cons(cons)
+    del cons
+    stream = torch.cuda.ExternalStream(g.compute_stream, device=torch.device("cuda", local_rank))
+    dt = float(case["dt"])
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        g.sync()
+    barrier()
+    g.steps(dt, warmup)
+    barrier()
+    l0 = g.kernel_launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    g.steps(dt, steps)
+    e1.record(stream)
+    barrier()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        tt = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms = float(tt.item())
+    launches = g.kernel_launches - l0
+    nan_count = g.reduce(2)
+    graph_state = g.graph_state
+    N, ns, nd = g.N, P.time_stepper, P.num_dims
+    g.close()
+    ms_step = ms / steps
+    ncell_loc = (P.m + 1) * (P.n + 1) * (P.p + 1)
+    ncell_glb = (case["m"] + 1) * (case["n"] + 1) * (case["p"] + 1)
+    stage_bytes = (12 if nd == 3 else 9 if nd == 2 else 6) * N * 8
+    ach = stage_bytes * ncell_loc / (ms_step * 1e-3 / ns) / 1e9
+    return {"workload": name, "cells_per_gpu": ncell_loc, "cells_global": ncell_glb, "sys_size": N, "proc_grid": list(dims), "steps": steps,
+            "warmup": warmup, "ms_per_step": ms_step, "value": grind(ms_step * 1e-3 / ns, (case["m"], case["n"], case["p"]), N),
+            "unit": "ns/gp/eq/rhs", "cells_steps_per_s": ncell_glb / (ms_step * 1e-3),
+            "roofline_stage": {"achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "algorithmic_bytes_per_cell_per_stage": stage_bytes},
+            "gpu_launches": int(launches), "graph_replay": graph_state, "nan_count": nan_count, "setup_s": round(time.time() - t_setup - ms * 1e-3, 1)}
+
+
+def other_configs(args, rank, world, local_rank, peak, budget_s):
+    """BASELINE.json's other configurations, timed device-resident after the headline measurement (parity for each of them is the
+    test suite's job: tests/test_gpu_parity.py).  N = 1: C1 .. C4 and the HLL variant of C5; N > 1: the strong-scaling case
+    (C4, fixed global size over N GPUs) and the HLL variant of the weak-scaling case."""
+    mk = lambda **kw: argparse.Namespace(**dict(vars(args), **kw))
+    if world == 1:
+        plan = [("C5_hll", mk(case="3D_performance_test", riemann="hll", scaling="weak"), 10, 3),
+                ("C4_shockdroplet_weno5z", mk(case="3D_shockdroplet", weno5z=True, riemann="hllc"), 50, 5),
+                ("C4_shockdroplet_as_shipped", mk(case="3D_shockdroplet", weno5z=False, riemann="hllc"), 50, 5),
+                ("C2_shockbubble_2d", mk(case="2D_shockbubble", riemann="hllc"), 100, 10),
+                ("C1_sodshocktube_1d", mk(case="1D_sodshocktube", riemann="hllc"), 200, 20),
+                ("C3_5eq_rk3_weno3_hllc_gbpp180", mk(case="5eq_rk3_weno3_hllc", gbpp=180, riemann="hllc"), 5, 3)]
+    else:
+        plan = [("C5_hll_weak", mk(case="3D_performance_test", riemann="hll", scaling="weak"), 10, 3),
+                ("C4_strong_weno5z", mk(case="3D_shockdroplet", weno5z=True, riemann="hllc", scaling="strong"), 100, 10),
+                ("C4_strong_as_shipped", mk(case="3D_shockdroplet", weno5z=False, riemann="hllc", scaling="strong"), 100, 10)]
+    out, t0 = {}, time.time()
+    for key, sargs, steps, warm in plan:
+        import torch
+        flag = torch.tensor([1.0 if time.time() - t0 < budget_s else 0.0], device="cuda")
+        if world > 1:
+            import torch.distributed as dist
+            dist.broadcast(flag, src=0)   # one decision for all ranks
+        if flag.item() == 0.0:
+            out[key] = {"skipped": "time budget of the default run (%d s) used up" % budget_s}
+            continue
+        out[key] = time_config(sargs, rank, world, local_rank, steps, warm, peak)
+    return out
 
 
 def cpu_arm(case, P, cbs, cons, nsteps, warm):
@@ -428,12 +523,6 @@ def main():
                "at_case_save_cadence": {"steps_per_save": nsave, "ms_per_step": ta * 1e3,
                                         "value": grind(ta / ns, (case["m"], case["n"], case["p"]), N), "unit": "ns/gp/eq/rhs"}}
 
-    if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
-
-    # ---- roofline of the dominant kernel (algorithmic bytes: SURVEY.md 8d / DESIGN.md)
     peaks = {}
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -442,10 +531,27 @@ def main():
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "MEASURED_PEAKS.json hbm_gbs (measured)" if "hbm_gbs" in peaks else "B200_PROFILING.md fallback 6650 GB/s"
+
+    # ---- BASELINE.json's other configurations (collective: every rank takes part)
+    others = None
+    if not args.no_other_configs and args.case == "3D_performance_test" and args.riemann == "hllc" and args.scaling == "weak":
+        others = other_configs(args, rank, world, local_rank, peak, args.other_budget)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (algorithmic bytes: SURVEY.md 8d / DESIGN.md)
     nd = P.num_dims
     last = ["sweep_x", "sweep_y", "sweep_z"][nd - 1]
     alg = {"cons2prim": 2 * N * 8, "sweep_x": 2 * N * 8, "sweep_y": 3 * N * 8, "sweep_z": 3 * N * 8}
     alg[last] = (5 if nd > 1 else 4) * N * 8  # prim + rhs + q1 + q2 read, q written (1-D: no rhs read)
+    fused_c2p = "cons2prim" not in prof or prof["cons2prim"][1] == 0
+    if fused_c2p:
+        # case-optimised path: the RK-fused last sweep also writes the next stage's primitive variables (over the rhs entries it
+        # has consumed), which replaces the separate cons -> prim pass (N read + N written): one more N written here
+        alg[last] += N * 8
     kern = {}
     for k, (kms, nl) in prof.items():
         if nl == 0:
@@ -461,6 +567,11 @@ def main():
     roof = {"bound": "hbm", "kernel": dom, "achieved": kern[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s",
             "frac": kern[dom]["achieved_gbs"] / peak, "traffic": None, "peak_source": peak_src,
             "algorithmic_bytes_per_cell": alg[dom], "share_of_step": kern[dom]["ms_per_step"] / sum(v["ms_per_step"] for v in kern.values())}
+    if fused_c2p and dom == last:
+        s5 = (5 if nd > 1 else 4) * N * 8
+        roof["algorithmic_bytes_note"] = ("%d B/cell = SURVEY 8(d)'s last sweep with RK (%d B) + the N doubles of the cons->prim pass's output, which this "
+                                          "kernel writes instead of a separate pass (whose N doubles of input are no longer read at all)" % (alg[dom], s5))
+        roof["frac_at_survey_bytes"] = s5 * ncell_loc / (kern[dom]["ms_per_pass"] * 1e-3) / 1e9 / peak
     stage_bytes = (12 if nd == 3 else 9 if nd == 2 else 6) * N * 8
     t_stage = ms_step * 1e-3 / ns
     roof_stage = {"achieved": stage_bytes * ncell_loc / t_stage / 1e9, "peak": peak, "unit": "GB/s",
@@ -506,6 +617,8 @@ def main():
     }
     if parity is not None:
         out["parity_check"] = parity
+    if others is not None:
+        out["other_configs"] = others
     out["graph_replay"] = graph_state
     if fp64 is not None:
         out["roofline_fp64"] = fp64

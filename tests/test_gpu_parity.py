@@ -220,6 +220,64 @@ def test_100_rk3_steps_within_1e10(name):
     g.close()
 
 
+def _acceptance_cases():
+    from mfc_b200 import cases
+    return {
+        # examples/3D_shockdroplet/case.py at its own size (201 x 101 x 101 cells, stretched grid), as shipped and with the north
+        # star's WENO5-Z override
+        "C4_full_weno3m": cases.shockdroplet_3d(ny=100, steps=100),
+        "C4_full_weno5z": cases.shockdroplet_3d(ny=100, weno_order=5, mapped_weno="F", wenoz="T", steps=100),
+        # examples/3D_performance_test at the bench size (201^3): ~5 minutes of oracle time on 16 cores, so only on request
+        "C5_full_weno5m": cases.perf_test_3d(m=200, steps=100),
+    }
+
+
+@pytest.mark.parametrize("name", ["C4_full_weno3m", "C4_full_weno5z", "C5_full_weno5m"])
+def test_full_size_100_rk3_steps_within_1e10(name):
+    """The north star's acceptance bar AT THE STATED SIZES: 100 RK3 steps of the case file's own grid, product build (case-optimised
+    kernels, CUDA-graph replay) against the oracle, max relative error of every conserved variable <= 1e-10.  The result line
+    is appended to gpurun_out/acceptance.log (kept under profiles/).  C5 at 201^3 costs ~5 minutes of oracle time and runs when
+    MFC5_ACCEPTANCE=1 (tools/gpu_accept.sh)."""
+    import os
+    import time
+    from mfc_b200 import pre_process
+    from mfc_b200.lib import Mfc5
+    from mfc_b200.params import params_from_case
+    from oracle_lib import Oracle
+    if name.startswith("C5") and not os.environ.get("MFC5_ACCEPTANCE"):
+        pytest.skip("set MFC5_ACCEPTANCE=1 (about 5 minutes of oracle time on 16 cores)")
+    case = dict(_acceptance_cases()[name], t_step_stop=100, t_step_save=100)
+    P = params_from_case(case)
+    cbs, ccs = pre_process.generate_grid(case)
+    _, cons = pre_process.initial_condition(case, ccs)
+    g = Mfc5(P, cbs)
+    o = Oracle(P, cbs, omp=True)
+    g.set_cons(cons)
+    o.set_cons(cons)
+    dt = float(case["dt"])
+    t0 = time.time()
+    g.steps(dt, 100)
+    g.sync()
+    t1 = time.time()
+    for _ in range(100):
+        o.step(dt)
+    t2 = time.time()
+    a, b = g.get_cons(), o.get_cons()
+    g.close()
+    assert not np.isnan(a).any() and not np.array_equal(b, cons)
+    errs = [float(np.max(np.abs(a[v] - b[v])) / (np.max(np.abs(b[v])) + 1e-300)) for v in range(a.shape[0])]
+    line = (f"{name}: cells {cons.shape[3]}x{cons.shape[2]}x{cons.shape[1]}, 100 RK3 steps, max rel err per variable "
+            + " ".join(f"{e:.2e}" for e in errs) + f"; GPU {t1 - t0:.2f} s, oracle ({os.cpu_count()} threads) {t2 - t1:.1f} s")
+    print(line)
+    try:
+        os.makedirs("gpurun_out", exist_ok=True)
+        with open("gpurun_out/acceptance.log", "a") as f:
+            f.write(line + "\n")
+    except OSError:
+        pass
+    assert max(errs) <= 1e-10, line
+
+
 # ---- BASELINE.json's full size (examples/3D_performance_test, 201^3 cells): one step against the oracle, and the
 # ---- size-independent properties of the scheme ----------------------------------------------------------------------
 def _full_size_c5(fast, strict, **over):
