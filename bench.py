@@ -421,7 +421,12 @@ def main():
     ncell_loc = (P.m + 1) * (P.n + 1) * (P.p + 1)
     ncell_glb = (case["m"] + 1) * (case["n"] + 1) * (case["p"] + 1)
 
-    # pinned host state (the caller's q_cons_vf arrays)
+    # pinned host state (the caller's q_cons_vf arrays); with several ranks on the node each one first moves next to its GPU,
+    # as the reference's MPI launcher binds its ranks (mfc_b200/affinity.py)
+    affinity = None
+    if world > 1 and not os.environ.get("MFC5_NO_BIND"):
+        from mfc_b200.affinity import bind_to_gpu
+        affinity = bind_to_gpu(local_rank, world)
     host = torch.empty(g.shape, dtype=torch.float64, pin_memory=True)
     hq = host.numpy()
     hq[...] = cons
@@ -520,6 +525,7 @@ def main():
         e2e = {"value": grind(te / ns, (case["m"], case["n"], case["p"]), N), "unit": "ns/gp/eq/rhs", "h2d_bytes_per_step": nbytes,
                "d2h_bytes_per_step": nbytes, "ms_per_step": te * 1e3, "timer": "host wall clock around upload + s_tvd_rk + download, synchronised both sides",
                "note": "worst case: the whole conservative state crosses PCIe both ways every step; the reference (and this library) keep it resident between saves",
+               "pcie_gbs_per_direction": 2 * nbytes / max(te - ms_step * 1e-3, 1e-9) / 1e9 / 2, "rank_affinity": affinity,
                "at_case_save_cadence": {"steps_per_save": nsave, "ms_per_step": ta * 1e3,
                                         "value": grind(ta / ns, (case["m"], case["n"], case["p"]), N), "unit": "ns/gp/eq/rhs"}}
 

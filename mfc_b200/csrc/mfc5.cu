@@ -108,10 +108,10 @@ struct mfc5_handle {
     int fuse_c2p = 0;
     int cur = 0;
     // host grid (ghosted): scb[d][i + 1 + b], ds[d][i + b]
-    std::vector<double> scb[3], ds[3];
+    std::vector<double> scb[3], ds[3], scc[3];   // (scc: cell centres, [i + b])
     bool grid_set[3] = {false, false, false};
     bool setup = false;
-    double* d_tab[3][9] = {};  // cL cR dL dR bt ds + combined rows + their transpose + x-segment layout
+    double* d_tab[3][10] = {};  // cL cR dL dR bt ds + combined rows + their transpose + x-segment layout + cell centres
     int uniform[3] = {1, 1, 1};
     CbcCoef cbc[3][2];
     double* d_cbcbuf[3][2] = {};
@@ -211,6 +211,20 @@ extern "C" int mfc5_create(const mfc5_params* p, mfc5_handle** out) {
     h->pn = (p->weno_order - 1) / 2;
     h->ns = h->pn + 1;
     h->b = h->pn + 2;  // m_helper_basic.fpp:127-132
+    if (p->viscous && p->muscl_order == 0) h->b = 2 * h->pn + 2;   // viscous WENO: 2 weno_polyn + 2
+    if (p->viscous) {
+        const char* why = nullptr;
+        if (p->muscl_order > 0) why = "viscous: not available with MUSCL reconstruction";
+        else if (p->riemann_solver == 5) why = "viscous: not available with the Lax-Friedrichs solver";
+        else if (p->weno_Re_flux) why = "viscous: weno_Re_flux = T is not available (finite-difference gradients, weno_Re_flux = F, are)";
+        else if (p->weno_order == 7) why = "viscous: not available at weno_order = 7";
+        bool any = false;
+        for (int f = 0; f < p->num_fluids; f++) any = any || p->fluid_Re[f][0] > 0 || p->fluid_Re[f][1] > 0;
+        if (!why && !any) why = "viscous = T needs at least one fluid_pp(i)%Re(1) or %Re(2)";
+        for (int d = 0; d < h->nd && !why; d++)
+            if (p->bc[d][0] >= 0 || p->bc[d][1] >= 0) why = "viscous: processor boundaries are not available (the gradients read edge / corner ghost cells)";
+        if (why) { delete h; return fail(why); }
+    }
     for (int d = 0; d < h->nd; d++)
         for (int sd = 0; sd < 2; sd++)
             if (is_cbc(p->bc[d][sd]) && (p->weno_order == 1 || p->weno_order == 7 || p->muscl_order > 0)) {
@@ -254,7 +268,7 @@ extern "C" int mfc5_destroy(mfc5_handle* h) {
     for (int i = 0; i < 4; i++) if (h->gexec[i]) cudaGraphExecDestroy(h->gexec[i]);
     cudaFree(h->d_prim[0]); if (!h->alias) cudaFree(h->d_prim[1]); cudaFree(h->d_rhs); cudaFree(h->d_red); cudaFree(h->d_red_all);
     for (int d = 0; d < 3; d++) {
-        for (int k = 0; k < 9; k++) cudaFree(h->d_tab[d][k]);
+        for (int k = 0; k < 10; k++) cudaFree(h->d_tab[d][k]);
         for (int k = 0; k < 2; k++) { cudaFree(h->d_cbcbuf[d][k]); cudaFree(h->d_dirich[d][k]); cudaFree(h->d_send[d][k]); cudaFree(h->d_recv[d][k]); }
     }
     for (auto& ev : h->ev_stage) cudaEventDestroy(ev);
@@ -289,6 +303,12 @@ extern "C" int mfc5_set_grid(mfc5_handle* h, int d, const double* s_cb, const do
     }
     for (int i = 1; i <= b; i++) cb[-1 - i] = cb[-i] - w[-i];
     for (int i = 1; i <= b; i++) cb[s + i] = cb[s + i - 1] + w[s + i];
+    // cell centres: m_start_up.fpp:191 and the ghost recurrence of s_populate_grid_bc_direction (m_boundary_common.fpp:449-465)
+    h->scc[d].assign(s + 1 + 2 * b, 0.0);
+    double* cc = h->scc[d].data() + b;
+    for (int i = 0; i <= s; i++) cc[i] = cb[i - 1] + w[i] / 2.0;
+    for (int i = 1; i <= b; i++) cc[-i] = cc[1 - i] - (w[1 - i] + w[-i]) / 2.0;
+    for (int i = 1; i <= b; i++) cc[s + i] = cc[s + i - 1] + (w[s + i - 1] + w[s + i]) / 2.0;
     h->grid_set[d] = true;
     h->setup = false;
     return 0;
@@ -582,10 +602,20 @@ extern "C" int mfc5_finalize_setup(mfc5_handle* h) {
     D.int_comp = h->P.int_comp; D.ic_eps = h->P.ic_eps; D.ic_beta = h->P.ic_beta;
     D.ic_cosh = std::cosh(h->P.ic_beta); D.ic_tanh = std::tanh(h->P.ic_beta);
     D.muscl = h->P.muscl_order; D.muscl_lim = h->P.muscl_lim; D.muscl_eps = h->P.muscl_eps;
-    D.fast = h->P.fast_math && h->P.wave_speeds == 1 && !h->P.null_weights && h->P.weno_eps >= 1e-30 && h->P.low_Mach == 0 &&
+    // fast: division-light WENO and flux-difference arithmetic; fast_riem: the division-light Riemann solve as well.  wave_speeds = 2
+    // and low_Mach are Riemann-only features: they keep the fast reconstruction and take the reference-order solve (generic kernels)
+    D.fast = h->P.fast_math && !h->P.null_weights && h->P.weno_eps >= 1e-30 &&
              !h->P.alt_soundspeed && h->P.riemann_solver != 5 && h->P.muscl_order == 0 && !h->P.teno && !h->P.mp_weno && h->P.int_comp == 0 &&
-             h->P.weno_order != 7;
+             h->P.weno_order != 7 && !h->P.viscous;
     if (getenv("MFC5_NO_FAST")) D.fast = 0;
+    D.fast_riem = D.fast && h->P.wave_speeds == 1 && h->P.low_Mach == 0;
+    if (getenv("MFC5_NO_FAST_WENO_ONLY") && !D.fast_riem) D.fast = 0;   // (A/B knob: the round-1 behaviour for these cases)
+    D.viscous = h->P.viscous;
+    for (int i = 0; i < 2; i++) {   // Re_size / Re_idx / Res_gs, m_global_parameters.fpp:781-812
+        D.re_size[i] = 0;
+        for (int f = 0; f < h->nf && h->P.viscous; f++)
+            if (h->P.fluid_Re[f][i] > 0) { D.re_idx[i][D.re_size[i]] = f; D.res[i][D.re_size[i]] = h->P.fluid_Re[f][i]; D.re_size[i]++; }
+    }
     D.sy = h->px; D.sz = h->px * h->ey; D.fs = h->fs;
     D.base = h->ox + h->oy * D.sy + h->oz * D.sz;
     D.eps = h->P.weno_eps;
@@ -600,6 +630,8 @@ extern "C" int mfc5_finalize_setup(mfc5_handle* h) {
         h->uniform[d] = uni;
         for (int k = 0; k < 5; k++) if (upload(&h->d_tab[d][k], tab[k])) return -1;
         if (upload(&h->d_tab[d][5], h->ds[d])) return -1;
+        if (upload(&h->d_tab[d][9], h->scc[d])) return -1;
+        D.T[d].cc = h->d_tab[d][9];
         D.T[d].cL = h->d_tab[d][0]; D.T[d].cR = h->d_tab[d][1]; D.T[d].dL = h->d_tab[d][2]; D.T[d].dR = h->d_tab[d][3];
         D.T[d].bt = h->d_tab[d][4]; D.T[d].ds = h->d_tab[d][5]; D.T[d].uniform = uni;
         {   // combined rows for the division-light kernels (layout: DirTables::tab)
@@ -1045,6 +1077,20 @@ static int run_stage(mfc5_handle* h, const double* q1, const double* q2, double*
         return 0;
     };
     bool side_pending = false;
+    if (h->P.viscous) {
+        // the velocity gradients of the viscous fluxes read edge / corner ghost cells: fill in the reference's order (x, then y
+        // over the x ghosts, then z over both), m_boundary_common.fpp:143-149; the CBC fluxes follow on the same stream
+        if (h->any_phys) {
+            if (seg_begin(h, MFC5_K_BC_FILL)) return -1;
+            const long long l0 = h->launches;
+            if (fill_full(h, D)) return -1;
+            const int nfill = (int)(h->launches - l0);
+            h->launches = l0;   // (seg_end counts them)
+            if (seg_end(h, nfill)) return -1;
+        }
+        if (faces(0, 2 * h->nd, false, any_cbc_x || any_cbc_yz, h->st)) return -1;
+        any_phys_x = any_phys_yz = any_cbc_x = any_cbc_yz = false;
+    }
     if (h->nd > 1 && (any_phys_yz || any_cbc_yz)) {
         if (h->use_side_stream) {
             if (!h->any_nb) CK(cudaEventRecord(h->ev_prim, h->st));

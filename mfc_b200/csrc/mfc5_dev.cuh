@@ -23,6 +23,7 @@ struct DirTables {
     const double* dR;  // [slot][q]     d_cbR
     const double* bt;  // [slot][q][3]  beta_coef
     const double* ds;  // cell widths, index i in [-b, s+b] -> slot (i + b)
+    const double* cc;  // cell centres, same indexing (viscous path only: finite-difference velocity gradients)
     // the same numbers as one row of MFC5_TAB doubles per slot (one base pointer, immediate offsets),
     // plus the ideal-weight terms of the WENO-M map; used by the division-light kernels:
     //   [0,6) cL  [6,12) cR  [12,15) dL  [15,18) dR  [18,27) beta
@@ -43,6 +44,7 @@ struct DevP {
     int nd, nf, N, b, pn, ns;
     int wo, wv, rs;    // weno_order; variant 0 JS / 1 M / 2 Z; riemann_solver 1 HLL / 2 HLLC
     int hll_u, avg, ws, mpp, mixerr, fast;
+    int fast_riem;     // fast: division-light WENO + finish; fast_riem: also the division-light Riemann solve (wave_speeds = 1, no low_Mach)
     int low_mach;      // 0 / 1 / 2, inline_riemann.fpp:71-93 (reference-order kernels only)
     int teno;          // TENO5 weights (m_weno.fpp:1167-1187), cut-off teno_ct (reference-order kernels only)
     double teno_ct;
@@ -55,6 +57,9 @@ struct DevP {
     int bf_on;         // body forces after the RK update of this stage (m_time_steppers.fpp:533): accelerations bf_a (0 where off)
     double bf_a[3], bf_ldt;  // bf_ldt = rk_coef(s,3) * dt / rk_coef(s,4)
     int alt_ss;        // alt_soundspeed: Wood sound speed + K div(u) term (reference-order kernels only)
+    // viscous stresses (reference-order kernels only): Re_size / Re_idx / Res_gs of m_global_parameters.fpp:781-812
+    int viscous, re_size[2], re_idx[2][MFC5_MAX_FLUIDS];
+    double res[2][MFC5_MAX_FLUIDS];
     long long sy, sz, fs, base;  // strides (x stride = 1), field size, offset of cell (0,0,0)
     double eps;
     double gam[MFC5_MAX_FLUIDS], pinf[MFC5_MAX_FLUIDS], qv[MFC5_MAX_FLUIDS];
@@ -891,8 +896,95 @@ __device__ __forceinline__ void riemann_face_fast(const DevP& P, double* qL, dou
 // averages: src/simulation/include/inline_riemann.fpp:1-30
 // F[0..N) fluxes; Fs[0] face-normal velocity (u-interface modes) or Fs[0..NF) interface alphas (HLL method 1)
 // -------------------------------------------------------------------------------------------------
+// -------------------------------------------------------------------------------------------------
+// Viscous stresses (viscous = T, weno_Re_flux = F; reference-order kernels only).
+// What the Riemann solver exports for the viscous source flux of its face: the interface velocities vel_src_rsx_vf
+// (hllc.fpp:1317-1322; the HLL solver never writes them: zero) and the interface Reynolds numbers Re_avg_rsx_vf
+// (hllc.fpp:975-977,1073-1080; hll.fpp:205-207,340-347).
+// -------------------------------------------------------------------------------------------------
+struct VisFace {
+    double vel_src[3];
+    double re_avg[2];
+};
+
+// s_compute_interface_reynolds, m_riemann_state.fpp:1062-1090
+template <int NF>
+__device__ __forceinline__ void interface_reynolds(const DevP& P, const double* alpha, double* Re) {
+#pragma unroll
+    for (int i = 0; i < 2; i++) {
+        Re[i] = -1.e6;  // dflt_real
+        if (P.re_size[i] > 0) Re[i] = 0.0;
+        for (int q = 0; q < P.re_size[i]; q++) {
+            double a = 0.0;
+#pragma unroll
+            for (int f = 0; f < NF; f++) if (f == P.re_idx[i][q]) a = alpha[f];
+            Re[i] = a / P.res[i][q] + Re[i];
+        }
+        Re[i] = 1.0 / fmax(Re[i], MFC5_SGM_EPS);
+    }
+}
+
+// Viscous source flux of the momentum and energy equations on the face between cell c (coordinates idx[]) and its neighbour
+// c + e_DIR: s_compute_cartesian_viscous_source_flux m_riemann_state.fpp:805-975 with s_calculate_shear / bulk_stress_tensor
+// (:978-1031), fed by the finite-difference cell-boundary velocity gradients of s_get_viscous (m_viscous.fpp:515-830).
+// The solver averages the RIGHT-boundary gradient field of cell c and the LEFT-boundary one of cell c + e_DIR (argument swap,
+// m_rhs.fpp:1031-1033); both are the same expression of the cell-centre velocities, evaluated here from the primitive
+// variables themselves (read through L1 / L2):
+//   along DIR      (v(c + e) - v(c)) / (cc(j + 1) - cc(j))
+//   along dd != DIR 0.25 (L(c + e) + R(c + e) + L(c) + R(c)),  L(x) = (v(x) - v(x - e_dd)) / (cc - cc'),  R(x) = (v(x + e_dd) - v(x)) / (cc' - cc)
+// Fv[0 .. ND-1]: momentum components, Fv[ND]: energy.
+template <int NF, int ND, int DIR>
+__device__ __forceinline__ void viscous_face(const DevP& P, long long c, const int* idx, const VisFace& vo, double* Fv) {
+    constexpr int IM = NF;
+    const long long strd[3] = {1, P.sy, P.sz};
+    const long long sd = strd[DIR];
+    double vga[ND][ND];
+#pragma unroll
+    for (int a = 0; a < ND; a++) {
+        const double* v = P.prim + (long long)(IM + a) * P.fs;
+#pragma unroll
+        for (int dd = 0; dd < ND; dd++) {
+            const double* cc = P.T[dd].cc + P.b;
+            const int jj = idx[dd];
+            double g;
+            if (dd == DIR) {
+                g = (__ldg(v + c + sd) - __ldg(v + c)) / (cc[jj + 1] - cc[jj]);
+            } else {
+                const long long st = strd[dd];
+                const double hL = cc[jj] - cc[jj - 1], hR = cc[jj + 1] - cc[jj];
+                const double L1 = (__ldg(v + c + sd) - __ldg(v + c + sd - st)) / hL, R1 = (__ldg(v + c + sd + st) - __ldg(v + c + sd)) / hR;
+                const double L0 = (__ldg(v + c) - __ldg(v + c - st)) / hL, R0 = (__ldg(v + c + st) - __ldg(v + c)) / hR;
+                g = 25.e-2 * (L1 + R1 + L0 + R0);
+            }
+            vga[a][dd] = 0.5 * (g + g);
+        }
+    }
+    double div = 0.0;
+#pragma unroll
+    for (int a = 0; a < ND; a++) div = div + vga[a][a];
+#pragma unroll
+    for (int a = 0; a <= ND; a++) Fv[a] = 0.0;   // s_initialize_riemann_solver, m_riemann_state.fpp:440-450
+    if (P.re_size[0] > 0) {   // shear_stress
+#pragma unroll
+        for (int a = 0; a < ND; a++) {
+            double tau = (vga[a][DIR] + vga[DIR][a]) / vo.re_avg[0];
+            if (a == DIR) tau = tau - (2.0 / 3.0) * div / vo.re_avg[0];
+            Fv[a] = Fv[a] - tau;
+            Fv[ND] = Fv[ND] - vo.vel_src[a] * tau;
+        }
+    }
+    if (P.re_size[1] > 0) {   // bulk_stress
+#pragma unroll
+        for (int a = 0; a < ND; a++) {
+            const double tau = (a == DIR) ? div / vo.re_avg[1] : 0.0;
+            Fv[a] = Fv[a] - tau;
+            Fv[ND] = Fv[ND] - vo.vel_src[a] * tau;
+        }
+    }
+}
+
 template <int NF, int ND, int DIR, int RS>
-__device__ __forceinline__ void riemann_face(const DevP& P, double* qL, double* qR, double* F, double* Fs) {
+__device__ __forceinline__ void riemann_face(const DevP& P, double* qL, double* qR, double* F, double* Fs, VisFace* vo = nullptr) {
     constexpr int IM = NF, IE = NF + ND, IA = NF + ND + 1;
     const int rs = (RS < 0) ? P.rs : RS;
     double vel_L_rms = 0.0, vel_R_rms = 0.0;
@@ -979,6 +1071,13 @@ __device__ __forceinline__ void riemann_face(const DevP& P, double* qL, double* 
     const double H_R = (E_R + pres_R) / rho_R;
     const double c_L = sound_speed(P, pres_L, rho_L, gamma_L, H_L, adv_L, vel_L_rms, qv_L);
     const double c_R = sound_speed(P, pres_R, rho_R, gamma_R, H_R, adv_R, vel_R_rms, qv_R);
+    if (vo) {
+        double Re_L[2], Re_R[2];
+        interface_reynolds<NF>(P, adv_L, Re_L);
+        interface_reynolds<NF>(P, adv_R, Re_R);
+#pragma unroll
+        for (int q = 0; q < 2; q++) vo->re_avg[q] = 2.0 / (1.0 / Re_L[q] + 1.0 / Re_R[q]);
+    }
     // low Mach corrections, inline_riemann.fpp:71-93 (hllc.fpp:1084-1086,1137-1141; hll.fpp:400-404)
     double zcoef = 0.0;
     if (P.low_mach != 0) zcoef = fmin(1.0, fmax(sqrt(vel_L_rms) / c_L, sqrt(vel_R_rms) / c_R));
@@ -1062,7 +1161,18 @@ __device__ __forceinline__ void riemann_face(const DevP& P, double* qL, double* 
         for (int f = 0; f < NF; f++)
             F[IA + f] = xi_M * qL[IA + f] * (uL + s_M * xi_L_m1) + xi_P * qR[IA + f] * (uR + s_P * xi_R_m1);
         Fs[0] = xi_M * (uL + s_M * xi_L_m1) + xi_P * (uR + s_P * xi_R_m1);
+        if (vo) {
+#pragma unroll
+            for (int a = 0; a < ND; a++) {
+                const double flg = (a == DIR) ? 1.0 : 0.0;
+                vo->vel_src[a] = xi_M * (qL[IM + a] + flg * s_M * xi_L_m1) + xi_P * (qR[IM + a] + flg * s_P * xi_R_m1);
+            }
+        }
     } else {
+        if (vo) {
+#pragma unroll
+            for (int a = 0; a < ND; a++) vo->vel_src[a] = 0.0;
+        }
 #pragma unroll
         for (int f = 0; f < NF; f++)
             F[f] = (s_M * arho_R[f] * uR - s_P * arho_L[f] * uL + s_M * s_P * (arho_L[f] - arho_R[f])) / (s_M - s_P);

@@ -14,7 +14,7 @@ inline bool opt_config(const DevP& P) {
     return false;
 #else
     if (getenv("MFC5_NO_OPT")) return false;
-    if (P.nf != 2 || P.nd != 3 || !P.fast) return false;
+    if (P.nf != 2 || P.nd != 3 || !P.fast || !P.fast_riem) return false;
     if ((unsigned long long)P.fs * (unsigned long long)(2 * P.nf + P.nd + 1) >= (1ull << 32)) return false;  // 32-bit field indices
     for (int d = 0; d < 3; d++)
         for (int sd = 0; sd < 2; sd++)

@@ -197,16 +197,13 @@ struct CbcCoef {
     int grcbc_in, grcbc_out, grcbc_vel_out;
 };
 
-// the characteristic-BC faces face0 .. of the block in ONE launch (face = 2 * direction + side); Kall[6] in HBM
-template <int NF, int ND>
-__global__ void __launch_bounds__(128) k_cbc(const __grid_constant__ DevP P, const CbcCoef* __restrict__ Kall, int face0) {
+// one plane point of the face (direction d, compile-time: every velocity-component index below is a constant, so the layer and
+// flux arrays stay in registers)
+template <int NF, int ND, int d>
+__device__ __forceinline__ void cbc_point(const DevP& P, const CbcCoef& K, const int side) {
     using S = Shape<NF, ND>;
     constexpr int N = S::N;
-    const int face = blockIdx.y + face0;
-    const int d = face >> 1, side = face & 1;
-    if (d >= ND || !P.cbc_on[d][side]) return;
-    const CbcCoef& K = Kall[face];
-    const int t1 = d == 0 ? 1 : 0, t2 = d == 2 ? 1 : 2;
+    constexpr int t1 = d == 0 ? 1 : 0, t2 = d == 2 ? 1 : 2;
     const int n1 = P.s[t1] + 1, n2 = P.s[t2] + 1;
     const long long plane = (long long)n1 * n2;
     const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
@@ -219,17 +216,24 @@ __global__ void __launch_bounds__(128) k_cbc(const __grid_constant__ DevP P, con
     const double sgn = side == 0 ? 1.0 : -1.0;
     const bool hll1 = (P.rs == 1 && !P.hll_u);
     const int nface = P.nface;
-    int didx[3];
-    didx[0] = d;
-    if (d == 0) { didx[1] = 1; didx[2] = 2; } else if (d == 1) { didx[1] = 0; didx[2] = 2; } else { didx[1] = 0; didx[2] = 1; }
+    constexpr int didx[3] = {d, d == 0 ? 1 : 0, d == 2 ? 1 : 2};
 
-    double q[6][N], Fc[4][N], Fsc[4][NF];
-    for (int jl = 0; jl <= b; jl++) {
-        const long long c = base + sd * (side == 0 ? jl : s - jl);
-        for (int v = 0; v < N; v++) q[jl][v] = P.prim[v * P.fs + c];
-        q[jl][S::IM + d] = q[jl][S::IM + d] * sgn;
+    double q[7][N], Fc[4][N], Fsc[4][NF];   // layers 0 .. buff_size (<= 6: viscous WENO5)
+#pragma unroll
+    for (int jl = 0; jl < 7; jl++) {
+        if (jl <= b) {
+            const long long c = base + sd * (side == 0 ? jl : s - jl);
+#pragma unroll
+            for (int v = 0; v < N; v++) q[jl][v] = P.prim[v * P.fs + c];
+            q[jl][S::IM + d] = q[jl][S::IM + d] * sgn;
+        } else {
+#pragma unroll
+            for (int v = 0; v < N; v++) q[jl][v] = 0.0;
+        }
     }
-    for (int jl = 0; jl <= 3 && jl <= b; jl++) {
+#pragma unroll
+    for (int jl = 0; jl <= 3; jl++) {
+        if (jl > b) break;
         double arho[NF], alf[NF], vel[3] = {0, 0, 0}, vsum = 0, rho, gam, pinf, qv;
         for (int f = 0; f < NF; f++) { arho[f] = q[jl][f]; alf[f] = q[jl][S::IA + f]; }
         for (int a = 0; a < ND; a++) vel[a] = q[jl][S::IM + a];
@@ -274,7 +278,9 @@ __global__ void __launch_bounds__(128) k_cbc(const __grid_constant__ DevP P, con
     const double c = sound_speed(P, pres, rho, gam, H, adv, vel_K_sum, qv);
     double darho_ds[NF], dvel_ds[3] = {0, 0, 0}, dpres_ds = 0, dadv_ds[NF];
     for (int f = 0; f < NF; f++) { darho_ds[f] = 0; dadv_ds[f] = 0; }
-    for (int jl = 0; jl <= b; jl++) {
+#pragma unroll
+    for (int jl = 0; jl < 7; jl++) {
+        if (jl > b) break;
         for (int f = 0; f < NF; f++) darho_ds[f] = q[jl][f] * K.fd[jl] + darho_ds[f];
         for (int a = 0; a < ND; a++) dvel_ds[a] = q[jl][S::IM + a] * K.fd[jl] + dvel_ds[a];
         dpres_ds = q[jl][S::IE] * K.fd[jl] + dpres_ds;
@@ -363,11 +369,26 @@ __global__ void __launch_bounds__(128) k_cbc(const __grid_constant__ DevP P, con
     // store with the sign conventions of s_finalize_cbc; slot jl+1, comp-major, plane-minor
     double* out = P.cbcbuf[d][side];
     const int ncomp = P.ncbc_comp;
-    for (int jl = -1; jl <= nface - 1; jl++) {
+#pragma unroll
+    for (int jl = -1; jl <= 1; jl++) {
+        if (jl > nface - 1) break;
+#pragma unroll
         for (int v = 0; v < N; v++) out[((long long)(jl + 1) * ncomp + v) * plane + t] = fl[jl + 1][v] * (v == S::IM + d ? 1.0 : sgn);
         if (hll1) for (int f = 0; f < NF; f++) out[((long long)(jl + 1) * ncomp + N + f) * plane + t] = fsl[jl + 1][f];
         else out[((long long)(jl + 1) * ncomp + N) * plane + t] = fsl[jl + 1][0] * sgn;
     }
+}
+
+// the characteristic-BC faces face0 .. of the block in ONE launch (face = 2 * direction + side); Kall[6] in HBM
+template <int NF, int ND>
+__global__ void __launch_bounds__(128) k_cbc(const __grid_constant__ DevP P, const CbcCoef* __restrict__ Kall, int face0) {
+    const int face = blockIdx.y + face0;
+    const int d = face >> 1, side = face & 1;
+    if (d >= ND || !P.cbc_on[d][side]) return;
+    const CbcCoef& K = Kall[face];
+    if (d == 0) cbc_point<NF, ND, 0>(P, K, side);
+    else if (d == 1) cbc_point<NF, ND, (ND > 1 ? 1 : 0)>(P, K, side);
+    else cbc_point<NF, ND, (ND > 2 ? 2 : 0)>(P, K, side);
 }
 
 // -------------------------------------------------------------------------------------------------
@@ -410,7 +431,7 @@ __device__ __forceinline__ void store_next_prim(const DevP& P, long long c, cons
 
 template <int NF, int ND, int DIR, int FAST, class ix = long long>
 __device__ __forceinline__ void finish_cell(const DevP& P, ix c, double ds, double inv_ds_tab, const double* Fp, const double* Fsp,
-                                            const double* Fc, const double* Fsc) {
+                                            const double* Fc, const double* Fsc, const double* Fvp = nullptr, const double* Fvc = nullptr) {
     const double inv_ds = FAST ? inv_ds_tab : 1.0 / ds;  // FAST: 1/ds from the table (host division, correctly rounded like the reference's)
     using S = Shape<NF, ND>;
     const ix fs = (ix)P.fs;
@@ -436,6 +457,10 @@ __device__ __forceinline__ void finish_cell(const DevP& P, ix c, double ds, doub
         const double K = k_term(P, __ldg(P.prim + (ix)((ix)S::IE * fs + c)), __ldg(P.prim + (ix)((ix)S::IA * fs + c)), __ldg(P.prim + (ix)((ix)(S::IA + NF - 1) * fs + c)));
         r[S::IA] = r[S::IA] + K * inv_ds * (Fsc[0] - Fsp[0]);
         r[S::IA + NF - 1] = r[S::IA + NF - 1] - K * inv_ds * (Fsc[0] - Fsp[0]);
+    }
+    if (!FAST && Fvp) {   // viscous source fluxes, s_compute_additional_physics_rhs m_rhs.fpp:1762-1770 (after the advection source terms)
+#pragma unroll
+        for (int a = 0; a <= ND; a++) r[S::IM + a] = r[S::IM + a] + inv_ds * (Fvp[a] - Fvc[a]);
     }
     if (DIR == ND - 1 && P.do_rk) {
         double qn[S::N];
@@ -638,14 +663,24 @@ __global__ void __launch_bounds__(128, MFC5_X_MINB) k_sweep_x(const __grid_const
 #pragma unroll
             for (int v = 0; v < N; v++) qR[v] = eR[v];
         }
-        double F[N], Fs[NF];
+        double F[N], Fs[NF], Fv[FAST ? 1 : ND + 1], Fvp[FAST ? 1 : ND + 1];
 #pragma unroll
         for (int f = 0; f < NF; f++) Fs[f] = 0.0;
+#pragma unroll
+        for (int a = 0; a < (FAST ? 1 : ND + 1); a++) Fv[a] = 0.0;
 #ifdef MFC5_DEBUG_SPLIT   // accuracy bisection builds: 1 = reference-order Riemann solve with the fast WENO
         if (FAST && MFC5_DEBUG_SPLIT != 1) riemann_face_fast<NF, ND, 0, RS>(P, eR, qR, F, Fs);
 #else
-        if (FAST) riemann_face_fast<NF, ND, 0, RS>(P, eR, qR, F, Fs);
+        // division-light Riemann solve; the generic kernels (RS < 0) take the reference-order one under the fast WENO when the
+        // case asks for what only it implements (wave_speeds = 2, low_Mach): DevP::fast_riem
+        if (FAST && (RS >= 0 || P.fast_riem)) riemann_face_fast<NF, ND, 0, RS>(P, eR, qR, F, Fs);
 #endif
+        else if (!FAST && P.viscous) {   // the face between my cell i and cell i + 1 (lanes beyond m: never finished, loads clamped)
+            VisFace vo;
+            riemann_face<NF, ND, 0, RS>(P, eR, qR, F, Fs, &vo);
+            const int idx[3] = {min(i, P.s[0]), j, k};
+            viscous_face<NF, ND, 0>(P, (long long)P.base + idx[0] + (long long)j * P.sy + (long long)k * P.sz, idx, vo, Fv);
+        }
         else riemann_face<NF, ND, 0, RS>(P, eR, qR, F, Fs);
         if (P.cbc_on[0][0] | P.cbc_on[0][1]) cbc_override<NF, ND, 0>(P, i, row, rows, F, Fs);
         double Fp[N], Fsp[NF];
@@ -653,8 +688,13 @@ __global__ void __launch_bounds__(128, MFC5_X_MINB) k_sweep_x(const __grid_const
         for (int v = 0; v < N; v++) Fp[v] = __shfl_up_sync(0xffffffffu, F[v], 1);
 #pragma unroll
         for (int f = 0; f < NF; f++) Fsp[f] = __shfl_up_sync(0xffffffffu, Fs[f], 1);
+        const bool visc = !FAST && P.viscous;   // kernel-uniform
+        if (visc) {
+#pragma unroll
+            for (int a = 0; a < (FAST ? 1 : ND + 1); a++) Fvp[a] = __shfl_up_sync(0xffffffffu, Fv[a], 1);
+        }
         if (lane >= 1 && lane <= MFC5_XW && i <= P.s[0]) {
-            finish_cell<NF, ND, 0, FAST, ix>(P, rowbase + (ix)i, ds_i, FAST ? xrow[46] : 0.0, Fp, Fsp, F, Fs);
+            finish_cell<NF, ND, 0, FAST, ix>(P, rowbase + (ix)i, ds_i, FAST ? xrow[46] : 0.0, Fp, Fsp, F, Fs, visc ? Fvp : nullptr, Fv);
         }
         __syncwarp();  // the window buffer and the edge arrays are rewritten by the next rows
     }
@@ -757,6 +797,11 @@ __global__ void __launch_bounds__(MFC5_MARCH_THREADS, (2 * NF + ND + 1 <= 8) ? M
     for (int v = 0; v < N; v++) Fp[v] = 0.0;
 #pragma unroll
     for (int f = 0; f < NF; f++) Fsp[f] = 0.0;
+    constexpr int NVIS = FAST ? 1 : ND + 1;
+    double Fvp[NVIS];       // viscous source flux of the previous face (reference-order kernels, viscous = T)
+#pragma unroll
+    for (int q = 0; q < NVIS; q++) Fvp[q] = 0.0;
+    const bool visc = !FAST && P.viscous;
 
     constexpr int NV = MFC5_WENO_NV;
     for (int cc = c0 - 1; cc <= c1 + 1; cc++) {
@@ -858,11 +903,13 @@ __global__ void __launch_bounds__(MFC5_MARCH_THREADS, (2 * NF + ND + 1 <= 8) ? M
 #pragma unroll
                 for (int f = 0; f < NF; f++) acoef[f] = __ldg(P.prim + (ix)((ix)(alpha_iface ? (S::IM + DIR) : (S::IA + f)) * fs + c));
             }
-            double qL[N], eL[N], F[N], Fs[NF];
+            double qL[N], eL[N], F[N], Fs[NF], Fv[NVIS];
 #pragma unroll
             for (int v = 0; v < N; v++) { qL[v] = sERp[v * NT]; eL[v] = sEL[v * NT + tid]; }
 #pragma unroll
             for (int f = 0; f < NF; f++) Fs[f] = 0.0;
+#pragma unroll
+            for (int q = 0; q < NVIS; q++) Fv[q] = 0.0;
             if (P.bc[DIR][0] == MFC5_BC_RIEMANN_EXTRAP && face == -1) {  // m_riemann_state.fpp:149-206
 #pragma unroll
                 for (int v = 0; v < N; v++) qL[v] = eL[v];
@@ -874,8 +921,17 @@ __global__ void __launch_bounds__(MFC5_MARCH_THREADS, (2 * NF + ND + 1 <= 8) ? M
 #ifdef MFC5_DEBUG_SPLIT
             if (FAST && MFC5_DEBUG_SPLIT != 1) riemann_face_fast<NF, ND, DIR, RS>(P, qL, eL, F, Fs);
 #else
-            if (FAST) riemann_face_fast<NF, ND, DIR, RS>(P, qL, eL, F, Fs);
+            if (FAST && (RS >= 0 || P.fast_riem)) riemann_face_fast<NF, ND, DIR, RS>(P, qL, eL, F, Fs);
 #endif
+            else if (visc) {   // face cc-1: between cells cc-1 and cc of my pencil
+                VisFace vo;
+                riemann_face<NF, ND, DIR, RS>(P, qL, eL, F, Fs, &vo);
+                int idx[3];
+                idx[DIR] = cc - 1;
+                idx[DIR == 0 ? 1 : 0] = a;
+                idx[DIR == 2 ? 1 : 2] = bb;
+                viscous_face<NF, ND, DIR>(P, (long long)c, idx, vo, Fv);
+            }
             else riemann_face<NF, ND, DIR, RS>(P, qL, eL, F, Fs);
             if (P.cbc_on[DIR][0] | P.cbc_on[DIR][1]) cbc_override<NF, ND, DIR>(P, face, t, plane, F, Fs);
             if (fin) {
@@ -896,6 +952,10 @@ __global__ void __launch_bounds__(MFC5_MARCH_THREADS, (2 * NF + ND + 1 <= 8) ? M
                     r[S::IA] = r[S::IA] + K * inv_ds * (Fs[0] - Fsp[0]);
                     r[S::IA + NF - 1] = r[S::IA + NF - 1] - K * inv_ds * (Fs[0] - Fsp[0]);
                 }
+                if (visc) {   // s_compute_additional_physics_rhs, m_rhs.fpp:1762-1770,1847-1855,1939-1947
+#pragma unroll
+                    for (int q = 0; q < NVIS; q++) r[S::IM + q] = r[S::IM + q] + inv_ds * (Fvp[q] - Fv[q]);
+                }
                 if (rk) {
 #pragma unroll
                     for (int v = 0; v < N; v++) {
@@ -915,6 +975,8 @@ __global__ void __launch_bounds__(MFC5_MARCH_THREADS, (2 * NF + ND + 1 <= 8) ? M
             for (int v = 0; v < N; v++) Fp[v] = F[v];
 #pragma unroll
             for (int f = 0; f < NF; f++) Fsp[f] = Fs[f];
+#pragma unroll
+            for (int q = 0; q < NVIS; q++) Fvp[q] = Fv[q];
         }
         tail = tail + 1;
         if (tail >= NSLOT) tail = 0;
@@ -1253,6 +1315,17 @@ __global__ void __launch_bounds__(256) k_reduce(const __grid_constant__ DevP P, 
         double icfl;
         if (ND == 1) icfl = (dt / P.T[0].ds[i + P.b]) * (fabs(vel[0]) + cs);
         else icfl = dt / dtl;
+        if (P.viscous) {   // viscous limit of s_compute_dt_from_cfl (m_sim_helpers.fpp:214-227) with the mixture Reynolds numbers of
+            // s_convert_species_to_mixture_variables_kernel (m_variables_conversion.fpp:256-268; alpha after the limiter)
+            double Re[2];
+            interface_reynolds<NF>(P, alf, Re);
+            double dsm = P.T[0].ds[i + P.b];
+            if (ND > 1) dsm = fmin(dsm, P.T[1].ds[j + P.b]);
+            if (ND > 2) dsm = fmin(dsm, P.T[2].ds[k + P.b]);
+            const double inv0 = (ND == 2) ? (1.0 / Re[0]) / rho : 1.0 / (rho * Re[0]);
+            const double inv1 = (ND == 2) ? (1.0 / Re[1]) / rho : 1.0 / (rho * Re[1]);
+            dtl = fmin(dtl, (dsm * dsm) / fmax(inv0, inv1));
+        }
         if (icfl != icfl) nans++;
         icfl_max = fmax(icfl_max, icfl);
         dtl_min = fmin(dtl_min, dtl);

@@ -47,6 +47,8 @@ class Mfc5Params(C.Structure):
         ("bf_k", C.c_double * 3), ("bf_w", C.c_double * 3), ("bf_p", C.c_double * 3), ("bf_g", C.c_double * 3),
         ("int_comp", C.c_int), ("reserved4", C.c_int), ("ic_eps", C.c_double), ("ic_beta", C.c_double),
         ("wenoz_q", C.c_double),
+        ("viscous", C.c_int), ("weno_Re_flux", C.c_int), ("weno_avg", C.c_int), ("reserved5", C.c_int),
+        ("fluid_Re", (C.c_double * 2) * MAX_FLUIDS),
     ]
 
     @property
@@ -62,6 +64,8 @@ class Mfc5Params(C.Structure):
         # src/common/m_helper_basic.fpp:127-135 (inviscid WENO: weno_polyn + 2; MUSCL: muscl_polyn + 2 = muscl_order + 2)
         if self.muscl_order > 0:
             return self.muscl_order + 2
+        if self.viscous:   # 2 * weno_polyn + 2
+            return (self.weno_order - 1) + 2
         return (self.weno_order - 1) // 2 + 2
 
     @property
@@ -88,7 +92,7 @@ def _val(case, key, default=None):
 
 
 _UNSUPPORTED_TRUE = [
-    "viscous", "surface_tension", "bubbles_euler", "bubbles_lagrange", "qbmm", "hypoelasticity",
+    "surface_tension", "bubbles_euler", "bubbles_lagrange", "qbmm", "hypoelasticity",
     "hyperelasticity", "mhd", "relativity", "chemistry", "igr", "ib", "cyl_coord", "acoustic_source", "relax",
     "cont_damage", "hyper_cleaning",
 ]
@@ -195,6 +199,27 @@ def params_from_case(case, device=0, fast_math=1, oracle_only=False):
         P.fluid_gamma[f] = float(case[f"fluid_pp({f + 1})%gamma"])
         P.fluid_pi_inf[f] = float(case.get(f"fluid_pp({f + 1})%pi_inf", 0.0))
         P.fluid_qv[f] = float(case.get(f"fluid_pp({f + 1})%qv", 0.0))
+    # viscous stresses (m_viscous.fpp; Re_size / Re_idx m_global_parameters.fpp:781-812): Newtonian fluids, Cartesian grids
+    P.viscous = _logical(case.get("viscous", "F"))
+    P.weno_Re_flux = _logical(case.get("weno_Re_flux", "F"))
+    P.weno_avg = _logical(case.get("weno_avg", "F"))
+    if P.viscous:
+        if P.muscl_order > 0:
+            raise UnsupportedCase("viscous with MUSCL reconstruction is outside the hot path")
+        if P.riemann_solver == 5:
+            raise UnsupportedCase("viscous with the Lax-Friedrichs solver (its own stress formulas, m_riemann_solver_lf.fpp:359-680) is outside the hot path")
+        if P.weno_Re_flux:
+            raise UnsupportedCase("weno_Re_flux = T (WENO-reconstructed velocity gradients) is outside the hot path; weno_Re_flux = F is available")
+        if P.weno_order == 7:
+            raise UnsupportedCase("viscous at weno_order = 7 is outside the hot path")
+        for f in range(P.num_fluids):
+            for i in range(2):
+                key = f"fluid_pp({f + 1})%Re({i + 1})"
+                P.fluid_Re[f][i] = float(case.get(key, -1.0e6))   # dflt_real
+            if _logical(case.get(f"fluid_pp({f + 1})%non_newtonian", "F")):
+                raise UnsupportedCase("non-Newtonian viscosity is outside the hot path")
+        if not any(P.fluid_Re[f][i] > 0 for f in range(P.num_fluids) for i in range(2)):
+            raise UnsupportedCase("viscous = T needs at least one fluid_pp(i)%Re(1) or %Re(2)")   # toolchain/mfc/case_validator.py
     ic = _val(case, "int_comp", 0)
     ic = (1 if _logical(ic) else 0) if isinstance(ic, str) and ic.strip().upper() in ("T", "F") else int(ic or 0)
     if ic not in (0, 1) and not (oracle_only and ic == 2):

@@ -39,6 +39,14 @@ struct orc_state {
     double* dirich[3][2];
     /* MTHINC (int_comp = 2): unit normal and interface position per cell, m_thinc.fpp:36-38 */
     double *mth_n[3], *mth_d;
+    /* viscous stresses (m_viscous.fpp, m_riemann_state.fpp:805-1031): cell centres scc[d][i], i in [-b, s+b]; velocity-gradient
+     * fields at the cell boundaries dqL / dqR[derivative direction][face-normal direction] (nd velocity components each, the
+     * reference's dqL_prim_d<x|y|z>_n(normal)%vf(mom)); interface Reynolds numbers and velocities exported by the Riemann solver
+     * (Re_avg_rsx_vf, vel_src_rsx_vf); viscous source flux of the momentum and energy equations (flux_src_n(dir)%vf(mom..E)) */
+    double *scc_store[3], *scc[3];
+    double *dqL[3][3], *dqR[3][3], *re_avg, *vel_src, *fvis;
+    int re_size[2], re_idx[2][MAXF];
+    double res[2][MAXF];
 };
 
 static inline long IDX(const orc_state* S, int i, int j, int k) {
@@ -117,8 +125,9 @@ orc_state* orc_create(const mfc5_params* P) {
     if (P->muscl_order > 0) S->P.weno_order = 2 * P->muscl_order + 1; /* stencil / buffer geometry: buff_size = muscl_order + 2 */
     S->polyn = (S->P.weno_order - 1) / 2;
     S->ns = S->polyn + 1;
-    /* buff_size = weno_polyn + 2 for inviscid WENO: src/common/m_helper_basic.fpp:127-132 */
+    /* buff_size = weno_polyn + 2 for inviscid WENO, 2 weno_polyn + 2 with viscous: src/common/m_helper_basic.fpp:127-135 */
     S->b = S->polyn + 2;
+    if (P->viscous && P->muscl_order == 0) S->b = 2 * S->polyn + 2;
     for (int d = 0; d < 3; d++) {
         S->off[d] = (d < S->nd) ? S->b : 0;
         S->ext[d] = S->s[d] + 1 + 2 * S->off[d];
@@ -130,6 +139,20 @@ orc_state* orc_create(const mfc5_params* P) {
     S->q1 = (double*)calloc(1, nb); S->q2 = (double*)calloc(1, nb); S->prim = (double*)calloc(1, nb);
     S->rhs = (double*)calloc(1, nb); S->vL = (double*)calloc(1, nb); S->vR = (double*)calloc(1, nb);
     S->flux = (double*)calloc(1, nb); S->fsrc = (double*)calloc(1, (size_t)MAXF * S->fsz * sizeof(double));
+    if (P->viscous) {
+        /* Re_size / Re_idx / Res: m_global_parameters.fpp:781-812, m_variables_conversion.fpp:315-322 */
+        for (int i = 0; i < 2; i++) {
+            S->re_size[i] = 0;
+            for (int f = 0; f < S->nf; f++)
+                if (P->fluid_Re[f][i] > 0) { S->re_idx[i][S->re_size[i]] = f; S->res[i][S->re_size[i]] = P->fluid_Re[f][i]; S->re_size[i]++; }
+        }
+        size_t nv = (size_t)S->nd * S->fsz * sizeof(double);
+        for (int dd = 0; dd < S->nd; dd++)
+            for (int n = 0; n < S->nd; n++) { S->dqL[dd][n] = (double*)calloc(1, nv); S->dqR[dd][n] = (double*)calloc(1, nv); }
+        S->re_avg = (double*)calloc(1, 2 * S->fsz * sizeof(double));
+        S->vel_src = (double*)calloc(1, 3 * S->fsz * sizeof(double));
+        S->fvis = (double*)calloc(1, (size_t)(S->nd + 1) * S->fsz * sizeof(double));
+    }
     return S;
 }
 
@@ -139,7 +162,9 @@ void orc_destroy(orc_state* S) {
         free(S->scb_store[d]); free(S->ds_store[d]);
         free(S->cL[d]); free(S->cR[d]); free(S->dL[d]); free(S->dR[d]); free(S->bt[d]); free(S->mth_n[d]);
     }
-    for (int d = 0; d < 3; d++) { free(S->dirich[d][0]); free(S->dirich[d][1]); }
+    for (int d = 0; d < 3; d++) { free(S->dirich[d][0]); free(S->dirich[d][1]); free(S->scc_store[d]); }
+    for (int dd = 0; dd < 3; dd++) for (int n = 0; n < 3; n++) { free(S->dqL[dd][n]); free(S->dqR[dd][n]); }
+    free(S->re_avg); free(S->vel_src); free(S->fvis);
     free(S->q1); free(S->q2); free(S->prim); free(S->rhs); free(S->vL); free(S->vR); free(S->flux); free(S->fsrc); free(S->mth_d);
     free(S);
 }
@@ -177,6 +202,14 @@ void orc_set_grid(orc_state* S, int d, const double* s_cb_in, const double* gbeg
     }
     for (int i = 1; i <= b; i++) cb[-1 - i] = cb[-i] - w[-i];
     for (int i = 1; i <= b; i++) cb[s + i] = cb[s + i - 1] + w[s + i];
+    /* cell centres: interior m_start_up.fpp:191, ghosts by the recurrence of s_populate_grid_bc_direction
+     * (m_boundary_common.fpp:449-465) */
+    S->scc_store[d] = (double*)calloc((size_t)(s + 1 + 2 * b), sizeof(double));
+    double* cc = S->scc_store[d] + b;
+    S->scc[d] = cc;
+    for (int i = 0; i <= s; i++) cc[i] = cb[i - 1] + w[i] / 2.0;
+    for (int i = 1; i <= b; i++) cc[-i] = cc[1 - i] - (w[1 - i] + w[-i]) / 2.0;
+    for (int i = 1; i <= b; i++) cc[s + i] = cc[s + i - 1] + (w[s + i - 1] + w[s + i]) / 2.0;
 }
 
 /* ---------------------------------------------------------------------------------------------
@@ -1123,6 +1156,7 @@ static void weno_dir(orc_state* S, int d) {
  * HLL : m_riemann_solver_hll.fpp:128-576.
  * Averages: include/inline_riemann.fpp:1-30.
  * ------------------------------------------------------------------------------------------- */
+static void interface_reynolds(const orc_state* S, const double* alpha, double* Re);
 static void riemann_dir(orc_state* S, int d) {
     int nf = S->nf, nd = S->nd;
     long sd = S->stride[d];
@@ -1285,7 +1319,7 @@ static void riemann_dir(orc_state* S, int d) {
                     if (hllc) pcorr = rho_L * rho_R * (s_L - uL) * (s_R - uR) * (uR - uL) / (rho_R * (s_R - uR) - rho_L * (s_L - uL)) * (zcoef - 1.0);
                     else pcorr = -(s_P - s_M) * (rho_L + rho_R) / 8.0 * (zcoef - 1.0);
                 }
-                double F[MAXN], Fsrc[MAXF];
+                double F[MAXN], Fsrc[MAXF], Vsrc[3] = {0.0, 0.0, 0.0};
                 for (int f = 0; f < MAXF; f++) Fsrc[f] = 0.0;
                 if (hllc) {
                     double xi_L = (s_L - uL) / dmin(s_L - s_S, -SGM_EPS);
@@ -1311,6 +1345,10 @@ static void riemann_dir(orc_state* S, int d) {
                         F[S->iadv + f] = xi_M * qL[S->iadv + f] * (uL + s_M * xi_L_m1) + xi_P * qR[S->iadv + f] * (uR + s_P * xi_R_m1);
                     /* vel_src for the normal direction -> flux_src(adv%beg): hllc.fpp:1319-1332 */
                     Fsrc[0] = xi_M * (uL + 1.0 * s_M * xi_L_m1) + xi_P * (uR + 1.0 * s_P * xi_R_m1);
+                    for (int a = 0; a < nd; a++) {
+                        double flg = (a == d) ? 1.0 : 0.0;
+                        Vsrc[a] = xi_M * (vel_L[a] + flg * s_M * xi_L_m1) + xi_P * (vel_R[a] + flg * s_P * xi_R_m1);
+                    }
                 } else {
                     for (int f = 0; f < nf; f++)
                         F[f] = (s_M * arho_R[f] * uR - s_P * arho_L[f] * uL + s_M * s_P * (arho_L[f] - arho_R[f])) / (s_M - s_P);
@@ -1345,6 +1383,148 @@ static void riemann_dir(orc_state* S, int d) {
                 }
                 for (int v = 0; v < S->N; v++) S->flux[v * S->fsz + c] = F[v];
                 for (int f = 0; f < nf; f++) S->fsrc[f * S->fsz + c] = Fsrc[f];
+                if (P->viscous) {
+                    /* Re_avg_rsx_vf: hllc.fpp:975-977,1073-1080 (alpha_L / alpha_R: the pre-limiter loads); hll.fpp:205-207,340-347 (its
+                     * limited copies).  vel_src_rsx_vf: hllc.fpp:1317-1322; the HLL solver never writes it (zero as allocated) */
+                    double Re_L[2], Re_R[2];
+                    interface_reynolds(S, adv_L, Re_L);
+                    interface_reynolds(S, adv_R, Re_R);
+                    for (int q = 0; q < 2; q++) S->re_avg[q * S->fsz + c] = 2.0 / (1.0 / Re_L[q] + 1.0 / Re_R[q]);
+                    for (int a = 0; a < nd; a++) S->vel_src[a * S->fsz + c] = Vsrc[a];
+                }
+            }
+}
+
+/* ---------------------------------------------------------------------------------------------
+ * Viscous stresses, velocity gradients at the cell boundaries by finite differences (weno_Re_flux = F):
+ * s_get_viscous m_viscous.fpp:515-830.  For the derivative along dd:
+ *   normal faces   dqL_dd_n(dd)(c) = (v(c) - v(c - e_dd)) / (cc(c) - cc(c - 1)),   dqR_dd_n(dd)(c) = (v(c + e_dd) - v(c)) / (cc(c + 1) - cc(c))
+ *   faces along n  dqL_dd_n(n)(c)  = 0.25 (L(c) + R(c) + L(c - e_n) + R(c - e_n)),  dqR_dd_n(n)(c)  = 0.25 (L(c + e_n) + R(c + e_n) + L(c) + R(c))
+ * with L / R = dqL / dqR_dd_n(dd), over the reference's index ranges (the whole buffered box minus the cells whose stencil
+ * would leave it).
+ * ------------------------------------------------------------------------------------------- */
+static void viscous_gradients_fd(orc_state* S) {
+    const int nd = S->nd;
+    int lo[3] = {0, 0, 0}, hi[3] = {S->s[0], S->s[1], S->s[2]};
+    for (int e = 0; e < nd; e++) { lo[e] = -S->b; hi[e] = S->s[e] + S->b; }
+    for (int dd = 0; dd < nd; dd++) {
+        const long sd = S->stride[dd];
+        const double* cc = S->scc[dd];
+        for (int side = 0; side < 2; side++) {   /* 0: dqL (backward), 1: dqR (forward) */
+            int l2[3] = {lo[0], lo[1], lo[2]}, h2[3] = {hi[0], hi[1], hi[2]};
+            if (side == 0) l2[dd] = lo[dd] + 1; else h2[dd] = hi[dd] - 1;
+            double* out = side == 0 ? S->dqL[dd][dd] : S->dqR[dd][dd];
+#pragma omp parallel for collapse(2)
+            for (int k = l2[2]; k <= h2[2]; k++)
+                for (int j = l2[1]; j <= h2[1]; j++)
+                    for (int i = l2[0]; i <= h2[0]; i++) {
+                        const int ijk[3] = {i, j, k};
+                        const int jc = ijk[dd];
+                        const long c = IDX(S, i, j, k);
+                        for (int a = 0; a < nd; a++) {
+                            const double* v = S->prim + (S->imom + a) * S->fsz;
+                            if (side == 0) out[a * S->fsz + c] = (v[c] - v[c - sd]) / (cc[jc] - cc[jc - 1]);
+                            else out[a * S->fsz + c] = (v[c + sd] - v[c]) / (cc[jc + 1] - cc[jc]);
+                        }
+                    }
+        }
+    }
+    for (int dd = 0; dd < nd; dd++)
+        for (int n = 0; n < nd; n++) {
+            if (n == dd) continue;
+            const long sn = S->stride[n];
+            const double *L = S->dqL[dd][dd], *R = S->dqR[dd][dd];
+            for (int side = 0; side < 2; side++) {
+                int l2[3] = {lo[0], lo[1], lo[2]}, h2[3] = {hi[0], hi[1], hi[2]};
+                l2[dd] = lo[dd] + 1; h2[dd] = hi[dd] - 1;
+                if (side == 0) l2[n] = lo[n] + 1; else h2[n] = hi[n] - 1;
+                double* out = side == 0 ? S->dqL[dd][n] : S->dqR[dd][n];
+#pragma omp parallel for collapse(2)
+                for (int k = l2[2]; k <= h2[2]; k++)
+                    for (int j = l2[1]; j <= h2[1]; j++)
+                        for (int i = l2[0]; i <= h2[0]; i++) {
+                            const long c = IDX(S, i, j, k);
+                            for (int a = 0; a < nd; a++) {
+                                const long o = a * S->fsz + c;
+                                double t;
+                                if (side == 0) t = (L[o] + R[o] + L[o - sn] + R[o - sn]);
+                                else t = (L[o + sn] + R[o + sn] + L[o] + R[o]);
+                                out[o] = 25.e-2 * t;
+                            }
+                        }
+            }
+        }
+}
+
+/* s_compute_interface_reynolds, m_riemann_state.fpp:1062-1090 */
+static void interface_reynolds(const orc_state* S, const double* alpha, double* Re) {
+    for (int i = 0; i < 2; i++) {
+        Re[i] = -1.e6; /* dflt_real */
+        if (S->re_size[i] > 0) Re[i] = 0.0;
+        for (int q = 0; q < S->re_size[i]; q++) Re[i] = alpha[S->re_idx[i][q]] / S->res[i][q] + Re[i];
+        Re[i] = 1.0 / dmax(Re[i], SGM_EPS);
+    }
+}
+
+/* s_compute_cartesian_viscous_source_flux, m_riemann_state.fpp:805-975 (+ s_calculate_shear / bulk_stress_tensor :978-1031),
+ * on faces -1..s of direction d after the Riemann solve of that direction.  The solver's "L" gradients are the RIGHT cell-boundary
+ * fields of cell j and its "R" gradients the LEFT ones of cell j+1 (argument swap at m_rhs.fpp:1031-1033). */
+static void viscous_source_flux(orc_state* S, int d) {
+    const int nd = S->nd;
+    const long sd = S->stride[d];
+    int lo[3] = {0, 0, 0}, hi[3] = {S->s[0], S->s[1], S->s[2]};
+    lo[d] = -1;
+    const int shear = S->re_size[0] > 0, bulk = S->re_size[1] > 0;
+#pragma omp parallel for collapse(2)
+    for (int k = lo[2]; k <= hi[2]; k++)
+        for (int j = lo[1]; j <= hi[1]; j++)
+            for (int i = lo[0]; i <= hi[0]; i++) {
+                const long c = IDX(S, i, j, k);
+                double vga[3][3], tau[3][3];
+                for (int a = 0; a < 3; a++) for (int e = 0; e < 3; e++) vga[a][e] = 0.0;
+                for (int a = 0; a < nd; a++)
+                    for (int dd = 0; dd < nd; dd++)
+                        vga[a][dd] = 0.5 * (S->dqR[dd][d][a * S->fsz + c] + S->dqL[dd][d][a * S->fsz + c + sd]);
+                double div = 0.0;
+                for (int a = 0; a < nd; a++) div = div + vga[a][a];
+                const double Re_shear = S->re_avg[c], Re_bulk = S->re_avg[S->fsz + c];
+                double fs[4] = {0.0, 0.0, 0.0, 0.0}; /* flux_src of mom(1..nd), E; initialised to zero (s_initialize_riemann_solver :440-450) */
+                if (shear) {
+                    for (int a = 0; a < nd; a++)
+                        for (int e = 0; e < nd; e++) {
+                            tau[a][e] = (vga[e][a] + vga[a][e]) / Re_shear;
+                            if (a == e) tau[a][e] = tau[a][e] - (2.0 / 3.0) * div / Re_shear;
+                        }
+                    for (int a = 0; a < nd; a++) {
+                        fs[a] = fs[a] - tau[d][a];
+                        fs[nd] = fs[nd] - S->vel_src[a * S->fsz + c] * tau[d][a];
+                    }
+                }
+                if (bulk) {
+                    for (int a = 0; a < nd; a++) for (int e = 0; e < nd; e++) tau[a][e] = 0.0;
+                    for (int a = 0; a < nd; a++) tau[a][a] = div / Re_bulk;
+                    for (int a = 0; a < nd; a++) {
+                        fs[a] = fs[a] - tau[d][a];
+                        fs[nd] = fs[nd] - S->vel_src[a * S->fsz + c] * tau[d][a];
+                    }
+                }
+                for (int a = 0; a <= nd; a++) S->fvis[a * S->fsz + c] = fs[a];
+            }
+}
+
+/* s_compute_additional_physics_rhs, m_rhs.fpp:1737-1960 (Cartesian, viscous): rhs(mom..E) += 1/ds (fvis(j-1) - fvis(j)) */
+static void viscous_rhs(orc_state* S, int d) {
+    const long sd = S->stride[d];
+#pragma omp parallel for collapse(2)
+    for (int k = 0; k <= S->s[2]; k++)
+        for (int j = 0; j <= S->s[1]; j++)
+            for (int i = 0; i <= S->s[0]; i++) {
+                const int ijk[3] = {i, j, k};
+                const long c = IDX(S, i, j, k);
+                for (int a = 0; a <= S->nd; a++) {
+                    const long v = (long)(S->imom + a) * S->fsz + c;
+                    S->rhs[v] = S->rhs[v] + 1.0 / S->ds[d][ijk[d]] * (S->fvis[a * S->fsz + c - sd] - S->fvis[a * S->fsz + c]);
+                }
             }
 }
 
@@ -1594,13 +1774,16 @@ static void flux_difference(orc_state* S, int d) {
 }
 
 void orc_sweeps(orc_state* S) {
+    if (S->P.viscous) viscous_gradients_fd(S); /* s_get_viscous, m_rhs.fpp:658-664 */
     if (S->P.int_comp == 2 && S->nd > 1) mthinc_normals(S);
     for (int d = 0; d < S->nd; d++) {
         weno_dir(S, d);
         riemann_dir(S, d);
+        if (S->P.viscous) viscous_source_flux(S, d); /* end of the Riemann solver, hllc.fpp:1548-1570 / hll.fpp:678-700 */
         for (int side = 0; side < 2; side++)
             if (is_cbc(S->P.bc[d][side])) cbc_dir_side(S, d, side);
         flux_difference(S, d);
+        if (S->P.viscous) viscous_rhs(S, d); /* s_compute_additional_physics_rhs, m_rhs.fpp:729-734 */
     }
 }
 

@@ -36,6 +36,8 @@ def pytest_cmdline_main(config):
     in-process, one CUDA context."""
     if getattr(config.option, "numprocesses", None) not in (None, 0) or os.environ.get("MFC5_TEST_SERIAL"):
         return None
+    if hasattr(config, "workerinput") or os.environ.get("PYTEST_XDIST_WORKER"):   # an xdist worker never spawns workers of its own
+        return None
     if not config.pluginmanager.hasplugin("xdist"):
         return None
     try:

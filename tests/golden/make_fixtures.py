@@ -24,7 +24,8 @@ REF = sys.argv[1] if len(sys.argv) > 1 else "/root/reference"
 
 # UUIDs inside the 5-eq / WENO{3,5}{JS,M,Z} / HLL|HLLC / RK3 envelope;
 # (weno_order = 7 and int_comp = 2 (MTHINC): the CPU oracle only so far, tests/test_oracle_next.py)
-# last lines: the f-4 widening (low_Mach = 1 / 2, tolerance 1e-10 by the reference's own rule; alt_soundspeed) and f-3 (elliptic smoothing, hard-coded profiles), Lax-Friedrichs, MUSCL
+# last line: viscous (finite-difference velocity gradients, weno_Re_flux = F)
+# before them: the f-4 widening (low_Mach = 1 / 2, tolerance 1e-10 by the reference's own rule; alt_soundspeed) and f-3 (elliptic smoothing, hard-coded profiles), Lax-Friedrichs, MUSCL
 UUIDS = """
 D79C3E6F 8A59E8E6 2AB32975 70DAE9E8 3AE495F4 5EC236F2 48CCE072 AED93D34 C5B79059 727F72ED A60691E7 3FC6FC4A
 2FD933A2 ED728400 9D92767D 63CD6ADF
@@ -62,6 +63,7 @@ AFE4994E 66CB22E3 7B21681C CB76A5E1 96AF00B3 9DAC4DDC F5512823 F28381D9 0288BDAD
 09DDCC0C 1A78D4CC 126FF74F 290C3BA8 9730B2DF 5DAB50B2 4912EFF1 B2AEF240 1929BEC7 55A51767
 EBBC93BD F1CF01C4 DC97B66D 4111B2ED
 4201674B 342686E8 DEA0A0D6 AE02324F E21940B3 121D4ECA
+8EAC3DA7 C79E1D3C CD6DC908 9CB03CEF 0A022883 1C0780C8 70EC99CE
 """.split()
 
 

@@ -14,6 +14,7 @@ with open(os.path.join(GOLD, "cases.json")) as _f:
     _ALL = json.load(_f)
 # MTHINC (int_comp = 2) exists in the CPU oracle only so far (tests/test_oracle_next.py); every other list of cases is the product's
 ORACLE_ONLY = {u: c for u, c in _ALL.items() if str(c["params"].get("int_comp", 0)) in ("2", "mthinc")}
+VISCOUS = sorted(u for u, c in _ALL.items() if str(c["params"].get("viscous", "F")) == "T" and u not in ORACLE_ONLY)
 ORDER7 = sorted(u for u, c in _ALL.items() if int(c["params"].get("weno_order", 0) or 0) == 7)
 CASES = {u: c for u, c in _ALL.items() if u not in ORACLE_ONLY}
 

@@ -43,7 +43,7 @@ def _check_golden(uuid, case_dir):
         assert ok, (uuid, key, amax, worst)
 
 
-@pytest.mark.parametrize("uuid", ["2AB32975", "BCA926AC", "05D092C5", "A0B82851", "04E1CB26", "B49877F3", "A078904B", "C9E0B721", "8370A3D9", "10041BB7", "B54BB9D8", "121D4ECA"])
+@pytest.mark.parametrize("uuid", ["2AB32975", "BCA926AC", "05D092C5", "A0B82851", "04E1CB26", "B49877F3", "A078904B", "C9E0B721", "8370A3D9", "10041BB7", "B54BB9D8", "121D4ECA", "1C0780C8", "70EC99CE"])
 def test_cli_matches_golden(uuid, tmp_path):
     out = _run_cli(dict(CASES[uuid]["params"]), str(tmp_path))
     _check_golden(uuid, str(tmp_path))

@@ -11,7 +11,7 @@ against the reference's golden files.
 import numpy as np
 import pytest
 
-from golden_util import CASES, ORDER7, compare, golden, golden_field, setup_case
+from golden_util import CASES, ORDER7, VISCOUS, compare, golden, golden_field, setup_case
 from mfc_b200 import driver
 
 pytestmark = pytest.mark.gpu
@@ -97,6 +97,26 @@ def test_order7_strict_vs_oracle(uuid):
         assert np.max(np.abs(a - b)) <= 1e-13 * np.max(np.abs(b))
     else:
         np.testing.assert_array_equal(a, b)
+
+
+@pytest.mark.parametrize("uuid", [u for u in VISCOUS if u in SINGLE])
+def test_viscous_strict_vs_oracle(uuid):
+    """viscous = T (finite-difference velocity gradients at the cell boundaries, m_viscous.fpp:515-830; viscous source flux
+    m_riemann_state.fpp:805-1031; buff_size = 2 weno_polyn + 2): RHS of the initial state and the state after 10 steps, strict
+    build vs oracle, bit for bit (1-D, 2-D, 3-D; one and two fluids)."""
+    case, P, cbs, cons, dbuf, g = _gpu(uuid, strict=True)
+    assert g.b == 2 * ((P.weno_order - 1) // 2) + 2
+    o = _oracle(P, cbs, cons, dbuf)
+    g.compute_rhs()
+    o.compute_rhs()
+    np.testing.assert_array_equal(g.get_rhs(), o.get_rhs())
+    dt = float(case["dt"])
+    for _ in range(10):
+        g.step(dt)
+        o.step(dt)
+    a, b = g.get_cons(), o.get_cons()
+    assert not np.array_equal(b, cons)
+    np.testing.assert_array_equal(a, b)
 
 
 @pytest.mark.parametrize("fast", [1, 0])

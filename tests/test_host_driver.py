@@ -225,7 +225,20 @@ class OracleCfl(OracleState):
         H = (E + p) / rho
         c = np.sqrt((H - 0.5 * vs) / g)
         dts = [self._ds[a] / (np.abs(vel[a]) + c) for a in range(nd)]
-        return float(np.min(np.minimum.reduce(dts)))
+        dtl = np.minimum.reduce(dts)
+        if P.viscous:   # viscous limit, s_compute_dt_from_cfl m_sim_helpers.fpp:214-227 with the mixture Reynolds numbers of
+            # s_convert_species_to_mixture_variables_kernel (m_variables_conversion.fpp:256-268)
+            inv = []
+            for i in range(2):
+                idx = [f for f in range(nf) if P.fluid_Re[f][i] > 0]
+                if idx:
+                    Re = 1.0 / np.maximum(sum(alf[f] / P.fluid_Re[f][i] for f in idx), 1e-16)
+                else:
+                    Re = np.full_like(rho, -1.0e6)
+                inv.append(1.0 / (rho * Re) if nd != 2 else (1.0 / Re) / rho)
+            dsm = np.minimum.reduce([self._ds[a] + 0.0 * rho for a in range(nd)])
+            dtl = np.minimum(dtl, dsm ** 2.0 / np.maximum(inv[0], inv[1]))
+        return float(np.min(dtl))
 
 
 def _make_cfl_oracle(P, cbs, gws, dirichlet):
@@ -254,7 +267,7 @@ def test_cfl_driven_time_stepping(tmp_path):
     assert any(l.startswith(" [  0%] Time ") for l in lines)
 
 
-@pytest.mark.parametrize("uuid", ["A078904B", "B54BB9D8", "AE02324F", "121D4ECA"])
+@pytest.mark.parametrize("uuid", ["A078904B", "B54BB9D8", "AE02324F", "121D4ECA", "70EC99CE"])
 def test_cfl_driven_goldens(uuid, tmp_path):
     """Reference goldens of CFL-driven runs through the driver loop: A078904B (2-D Kelvin-Helmholtz example, HLL, hard-coded
     profile 207; every D/ file of every save, selected by simulated time) and B54BB9D8 (3-D body forces with cfl_adap_dt:

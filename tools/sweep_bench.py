@@ -13,9 +13,21 @@ ap.add_argument("--riemann", default="hllc")
 ap.add_argument("--gbpp", type=int, default=16)
 ap.add_argument("--weno5z", action="store_true")
 ap.add_argument("--steps", type=int, default=5)
+ap.add_argument("--set", action="append", default=[], metavar="KEY=VALUE", help="override a case parameter (e.g. wave_speeds=2, low_Mach=1)")
 a = ap.parse_args()
 args = argparse.Namespace(case=a.case, m=a.m, riemann=a.riemann, gbpp=a.gbpp, weno5z=a.weno5z, scaling="weak")
 case, dims, name = bench.build_case(args, 1)
+for kv in a.set:
+    k, v = kv.split("=", 1)
+    try:
+        v = int(v)
+    except ValueError:
+        try:
+            v = float(v)
+        except ValueError:
+            pass
+    case[k] = v
+    name += f" [{k}={v}]"
 blk, lcase, P, cbs, gws, cons = bench.setup_rank(case, 0, 1, dims)
 g = Mfc5(P, cbs)
 g.set_cons(cons)
