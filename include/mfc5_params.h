@@ -98,12 +98,11 @@ typedef struct mfc5_params {
      * fluids after WENO or MUSCL); ic_eps / ic_beta default to 1e-4 / 1.6 (m_constants.fpp:53-54) */
     int int_comp, reserved4;
     double ic_eps, ic_beta;
-    /* WENO-Z power of order 7, alpha = d (1 + (tau / beta)^wenoz_q) (m_weno.fpp:1381-1389); the CPU oracle only so far: the CUDA
-     * library rejects weno_order = 7 */
+    /* WENO-Z power of order 7, alpha = d (1 + (tau / beta)^wenoz_q) (m_weno.fpp:1381-1389) */
     double wenoz_q;
     /* viscous stresses (src/simulation/m_viscous.fpp, m_riemann_state.fpp:805-1031): fluid_Re[k][0] = fluid_pp(k)%Re(1)
      * (shear), [k][1] = %Re(2) (bulk); a value <= 0 means "not set" (the reference's dflt_real).  weno_Re_flux = 0: velocity gradients
-     * at the cell boundaries by finite differences (m_viscous.fpp:515-830); 1: WENO-reconstructed (CPU oracle only).  With viscous the
+     * at the cell boundaries by finite differences (m_viscous.fpp:515-830); 1: WENO-reconstructed -- rejected by mfc5_create.  With viscous the
      * ghost region is 2 weno_polyn + 2 cells wide (m_helper_basic.fpp:127-132). */
     int viscous, weno_Re_flux, weno_avg, reserved5;
     double fluid_Re[MFC5_MAX_FLUIDS][2];

@@ -9,6 +9,15 @@ for p in (ROOT, os.path.join(ROOT, "tests")):
         sys.path.insert(0, p)
 
 
+# pytest-xdist workers: the 3-D oracle cases use the OpenMP build, and W workers x (all cores) spinning OpenMP threads
+# oversubscribe the box several times over (measured: load average 30 on 8 cores, the suite three times slower).  Each worker
+# gets its share of the cores and passive waiting; set before libgomp is loaded (the oracle is dlopen'ed by the first test).
+if os.environ.get("PYTEST_XDIST_WORKER"):
+    _nw = max(1, int(os.environ.get("PYTEST_XDIST_WORKER_COUNT", "4") or 4))
+    os.environ.setdefault("OMP_NUM_THREADS", str(max(1, (os.cpu_count() or _nw) // _nw)))
+    os.environ.setdefault("OMP_WAIT_POLICY", "passive")
+
+
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
     config.addinivalue_line("markers", "slow: long-running CPU test")
