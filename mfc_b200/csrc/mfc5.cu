@@ -602,14 +602,14 @@ extern "C" int mfc5_finalize_setup(mfc5_handle* h) {
     D.int_comp = h->P.int_comp; D.ic_eps = h->P.ic_eps; D.ic_beta = h->P.ic_beta;
     D.ic_cosh = std::cosh(h->P.ic_beta); D.ic_tanh = std::tanh(h->P.ic_beta);
     D.muscl = h->P.muscl_order; D.muscl_lim = h->P.muscl_lim; D.muscl_eps = h->P.muscl_eps;
-    // fast: division-light WENO and flux-difference arithmetic; fast_riem: the division-light Riemann solve as well.  wave_speeds = 2
-    // and low_Mach are Riemann-only features: they keep the fast reconstruction and take the reference-order solve (generic kernels)
+    // fast: division-light arithmetic (WENO, Riemann solve, flux difference); fast_riem: the subset the case-optimised kernels are
+    // compiled for.  wave_speeds = 2 and low_Mach are Riemann-only features: division-light too, in the generic kernels
     D.fast = h->P.fast_math && !h->P.null_weights && h->P.weno_eps >= 1e-30 &&
              !h->P.alt_soundspeed && h->P.riemann_solver != 5 && h->P.muscl_order == 0 && !h->P.teno && !h->P.mp_weno && h->P.int_comp == 0 &&
              h->P.weno_order != 7 && !h->P.viscous;
     if (getenv("MFC5_NO_FAST")) D.fast = 0;
     D.fast_riem = D.fast && h->P.wave_speeds == 1 && h->P.low_Mach == 0;
-    if (getenv("MFC5_NO_FAST_WENO_ONLY") && !D.fast_riem) D.fast = 0;   // (A/B knob: the round-1 behaviour for these cases)
+    if (getenv("MFC5_NO_FAST_EXT") && !D.fast_riem) D.fast = 0;   // (A/B knob: the round-1 behaviour for these cases)
     D.viscous = h->P.viscous;
     for (int i = 0; i < 2; i++) {   // Re_size / Re_idx / Res_gs, m_global_parameters.fpp:781-812
         D.re_size[i] = 0;

@@ -44,7 +44,7 @@ struct DevP {
     int nd, nf, N, b, pn, ns;
     int wo, wv, rs;    // weno_order; variant 0 JS / 1 M / 2 Z; riemann_solver 1 HLL / 2 HLLC
     int hll_u, avg, ws, mpp, mixerr, fast;
-    int fast_riem;     // fast: division-light WENO + finish; fast_riem: also the division-light Riemann solve (wave_speeds = 1, no low_Mach)
+    int fast_riem;     // fast && wave_speeds = 1 && no low_Mach: what the case-optimised kernels (compile-time solver, EXT = false) cover
     int low_mach;      // 0 / 1 / 2, inline_riemann.fpp:71-93 (reference-order kernels only)
     int teno;          // TENO5 weights (m_weno.fpp:1167-1187), cut-off teno_ct (reference-order kernels only)
     double teno_ct;
@@ -737,10 +737,13 @@ __device__ __forceinline__ double k_term(const DevP& P, double pres, double alph
 }
 
 // -------------------------------------------------------------------------------------------------
-// Division-light Riemann solve (product build, wave_speeds = 1 only; the host dispatch guarantees it).
+// Division-light Riemann solve (product build).
 // Same formulas as riemann_face below; differences: reciprocals instead of divisions, and for HLLC only
 // the star state on the upwind side of the contact is evaluated (the reference evaluates both and
 // multiplies one by xi_M / xi_P = 0; identical unless the discarded side is non-finite).
+// EXT (the generic kernels, run-time solver): also the pressure-velocity wave-speed estimates (wave_speeds = 2,
+// hllc.fpp:1041-1066,1104-1119 / hll.fpp:352-396) and the low-Mach corrections (low_Mach = 1 / 2, inline_riemann.fpp:71-93);
+// the case-optimised kernels are only dispatched for wave_speeds = 1 without low_Mach (DevP::fast_riem) and compile them out.
 // -------------------------------------------------------------------------------------------------
 // min / max by one comparison and a select (DSETP + 2 SEL).  fmin / fmax carry IEEE NaN handling that costs ~6 more
 // integer-pipe instructions each, and every non-FP64 instruction takes an issue slot from the FP64 pipe;
@@ -762,7 +765,7 @@ __device__ __forceinline__ double sel_max(double a, double b) {
 }
 #endif
 
-template <int NF, int ND, int DIR, int RS>
+template <int NF, int ND, int DIR, int RS, bool EXT = (RS < 0)>
 __device__ __forceinline__ void riemann_face_fast(const DevP& P, double* qL, double* qR, double* F, double* Fs) {
     constexpr int IM = NF, IE = NF + ND, IA = NF + ND + 1;
     const int rs = (RS < 0) ? P.rs : RS;
@@ -822,26 +825,99 @@ __device__ __forceinline__ void riemann_face_fast(const DevP& P, double* qL, dou
     double c_R = (H_R - 5.e-1 * vel_R_rms - qv_R * irho_R) * igam_R;
     c_L = (P.mixerr && c_L < 0.0) ? 100.0 * MFC5_SGM_EPS : sqrt(c_L);
     c_R = (P.mixerr && c_R < 0.0) ? 100.0 * MFC5_SGM_EPS : sqrt(c_R);
+    // low-Mach corrections (EXT): zcoef; low_Mach = 2 replaces the face-normal velocities of the HLLC solve's local copies
+    double zcoef = 0.0;
+    if (EXT && P.low_mach != 0) {
+        double icL, icR;
+        rcp_nr2(c_L, c_R, icL, icR);
+        zcoef = sel_min(1.0, sel_max(sqrt(vel_L_rms) * icL, sqrt(vel_R_rms) * icR));
+        if (rs == 2 && P.low_mach == 2) {
+            const double a = qL[IM + DIR], b = qR[IM + DIR];
+            qL[IM + DIR] = 5.e-1 * ((a + b) + zcoef * (a - b));
+            qR[IM + DIR] = 5.e-1 * ((a + b) + zcoef * (b - a));
+        }
+    }
     const double uL = qL[IM + DIR], uR = qR[IM + DIR];
-    const double s_L = sel_min(uL - c_L, uR - c_R);
-    const double s_R = sel_max(uR + c_R, uL + c_L);
+    double s_L, s_R, s_S_ws2 = 0.0;
+    const bool ws2 = EXT && P.ws != 1;
+    if (!ws2) {
+        s_L = sel_min(uL - c_L, uR - c_R);
+        s_R = sel_max(uR + c_R, uL + c_L);
+    } else {   // pressure-velocity estimates; Roe (avg_state = 1) or arithmetic averages, inline_riemann.fpp:1-30
+        double rho_avg, vel_avg_rms, H_avg, gamma_avg, qv_avg;
+        if (P.avg == 1) {
+            const double sl = sqrt(rho_L), sr = sqrt(rho_R);
+            const double iw = rcp_nr(sl + sr);
+            rho_avg = sqrt(rho_L * rho_R);
+            H_avg = div_r(sl * H_L + sr * H_R, sl + sr, iw);
+            gamma_avg = div_r(sl * gamma_L + sr * gamma_R, sl + sr, iw);
+            const double w = sl + sr;
+            vel_avg_rms = div_r(sq(sl * qL[IM] + sr * qR[IM]), w * w, rcp_nr(w * w));  // component 1 only, inline_riemann.fpp:28
+            qv_avg = div_r(sl * qv_L + sr * qv_R, sl + sr, iw);
+        } else {
+            rho_avg = 5.e-1 * (rho_L + rho_R);
+            vel_avg_rms = 0.0;
+#pragma unroll
+            for (int a = 0; a < ND; a++) vel_avg_rms = vel_avg_rms + sq(5.e-1 * (qL[IM + a] + qR[IM + a]));
+            H_avg = 5.e-1 * (H_L + H_R);
+            gamma_avg = 5.e-1 * (gamma_L + gamma_R);
+            qv_avg = 5.e-1 * (qv_L + qv_R);
+        }
+        double ira, iga;
+        rcp_nr2(rho_avg, gamma_avg, ira, iga);
+        double c_avg = div_r(H_avg - 5.e-1 * vel_avg_rms - div_r(qv_avg, rho_avg, ira), gamma_avg, iga);
+        c_avg = (P.mixerr && c_avg < 0.0) ? 100.0 * MFC5_SGM_EPS : sqrt(c_avg);
+        const double pres_S = 5.e-1 * (pres_L + pres_R + rho_avg * c_avg * (uL - uR));
+        const double gL1 = 1.0 + gamma_L, gR1 = 1.0 + gamma_R;
+        double igL1, igR1, ipL, ipR;
+        rcp_nr2(gL1, gR1, igL1, igR1);
+        rcp_nr2(pres_L, pres_R, ipL, ipR);
+        const double dL = pres_L + div_r(pi_inf_L, gL1, igL1), dR = pres_R + div_r(pi_inf_R, gR1, igR1);
+        double idL, idR;
+        rcp_nr2(dL, dR, idL, idR);
+        const double Ms_L = sel_max(1.0, sqrt(1.0 + div_r(div_r(5.e-1 + gamma_L, gL1, igL1) * (div_r(pres_S, pres_L, ipL) - 1.0) * pres_L, dL, idL)));
+        const double Ms_R = sel_max(1.0, sqrt(1.0 + div_r(div_r(5.e-1 + gamma_R, gR1, igR1) * (div_r(pres_S, pres_R, ipR) - 1.0) * pres_R, dR, idR)));
+        s_L = uL - c_L * Ms_L;
+        s_R = uR + c_R * Ms_R;
+        const double rc = rho_avg * c_avg;
+        s_S_ws2 = 5.e-1 * ((uL + uR) + div_r(pres_L - pres_R, rc, rcp_nr(rc)));
+    }
     const double s_M = sel_min(s_L, 0.0), s_P = sel_max(s_R, 0.0);
+    // low_Mach = 1: pressure correction of the momentum and energy fluxes; (s_M / s_L)(s_P / s_R) is 1 on subsonic faces, else 0
+    double pcw = 0.0;
+    if (EXT && P.low_mach == 1) {
+        double pcorr;
+        if (rs == 2) {
+            const double den = rho_R * (s_R - uR) - rho_L * (s_L - uL);
+            pcorr = div_r(rho_L * rho_R * (s_L - uL) * (s_R - uR) * (uR - uL), den, rcp_nr(den)) * (zcoef - 1.0);
+        } else {
+            pcorr = -(s_P - s_M) * (rho_L + rho_R) * 0.125 * (zcoef - 1.0);
+        }
+        pcw = (s_M / s_L) * (s_P / s_R) * pcorr;
+    }
     if (rs == 2) {
         const double mL = rho_L * (s_L - uL), mR = rho_R * (s_R - uR);
         // s_S = A / B.  Its sign (which selects the upwind side) is known before the division, and
         // 1 / (s_K - s_S) = B / (s_K B - A): both reciprocals come out of one (rcp_nr2), in parallel
-        // with the one of s_K - u_K, instead of two dependent ones.
+        // with the one of s_K - u_K, instead of two dependent ones.  (wave_speeds = 2: s_S is given.)
         const double A = pres_R - pres_L + mL * uL - mR * uR, B = mL - mR;
-        const bool left = signbit(A) == signbit(B);  // xi_M = 1, xi_P = 0  (Fortran sign(0.5, s_S))
+        const bool left = ws2 ? !signbit(s_S_ws2) : (signbit(A) == signbit(B));  // xi_M = 1, xi_P = 0  (Fortran sign(0.5, s_S))
         const double* qK = left ? qL : qR;
         const double rho_K = left ? rho_L : rho_R, u_K = left ? uL : uR, p_K = left ? pres_L : pres_R, E_K = left ? E_L : E_R;
         const double s_K = left ? s_L : s_R, s_MP = left ? s_M : s_P;
-        double iB, iX;
-        rcp_nr2(B, fma(s_K, B, -A), iB, iX);
-        const double s_S = A * iB;
+        double s_S, iden_raw;
+        if (!ws2) {
+            double iB, iX;
+            rcp_nr2(B, fma(s_K, B, -A), iB, iX);
+            s_S = A * iB;
+            iden_raw = B * iX;
+        } else {
+            s_S = s_S_ws2;
+            iden_raw = rcp_nr(s_K - s_S);
+        }
         const double gap = s_K - s_S;  // the reference clamps it away from zero: min(., -eps) / max(., eps)
         const bool clamped = left ? !(gap < -MFC5_SGM_EPS) : !(gap > MFC5_SGM_EPS);
-        const double iden = clamped ? (left ? -1.0 / MFC5_SGM_EPS : 1.0 / MFC5_SGM_EPS) : B * iX;
+        const double iden = clamped ? (left ? -1.0 / MFC5_SGM_EPS : 1.0 / MFC5_SGM_EPS) : iden_raw;
         const double xi_K = (s_K - u_K) * iden;
         const double xi_K_m1 = (s_S - u_K) * iden;
         const double adv = fma(s_MP, xi_K_m1, u_K);  // u_K + s_MP (xi_K - 1)
@@ -853,6 +929,10 @@ __device__ __forceinline__ void riemann_face_fast(const DevP& P, double* qL, dou
             else F[IM + a] = rho_K * (qK[IM + a] * adv);
         }
         F[IE] = u_K * (E_K + p_K) + s_MP * (E_K * xi_K_m1 + xi_K * (s_S - u_K) * (rho_K * s_S + p_K * rcp_nr(s_K - u_K)));
+        if (EXT && P.low_mach == 1) {   // m_riemann_solver_hllc.fpp:1286-1305 (5-equation emission)
+            F[IM + DIR] = F[IM + DIR] + pcw;
+            F[IE] = F[IE] + pcw * s_S;
+        }
         Fs[0] = adv;
     } else {
         const double inv = rcp_nr(s_M - s_P);
@@ -866,6 +946,11 @@ __device__ __forceinline__ void riemann_face_fast(const DevP& P, double* qL, dou
                          smp * (rho_L * qL[IM + a] - rho_R * qR[IM + a])) * inv;
         }
         F[IE] = (s_M * uR * (E_R + pres_R) - s_P * uL * (E_L + pres_L) + smp * (E_L - E_R)) * inv;
+        if (EXT && P.low_mach == 1) {   // m_riemann_solver_hll.fpp:446-455,496-515
+#pragma unroll
+            for (int a = 0; a < ND; a++) F[IM + a] = F[IM + a] + pcw * (qR[IM + a] - qL[IM + a]);
+            F[IE] = F[IE] + pcw * (vel_R_rms - vel_L_rms) * 5.e-1;
+        }
         if (!P.hll_u) {
 #pragma unroll
             for (int f = 0; f < NF; f++) {

@@ -671,9 +671,7 @@ __global__ void __launch_bounds__(128, MFC5_X_MINB) k_sweep_x(const __grid_const
 #ifdef MFC5_DEBUG_SPLIT   // accuracy bisection builds: 1 = reference-order Riemann solve with the fast WENO
         if (FAST && MFC5_DEBUG_SPLIT != 1) riemann_face_fast<NF, ND, 0, RS>(P, eR, qR, F, Fs);
 #else
-        // division-light Riemann solve; the generic kernels (RS < 0) take the reference-order one under the fast WENO when the
-        // case asks for what only it implements (wave_speeds = 2, low_Mach): DevP::fast_riem
-        if (FAST && (RS >= 0 || P.fast_riem)) riemann_face_fast<NF, ND, 0, RS>(P, eR, qR, F, Fs);
+        if (FAST) riemann_face_fast<NF, ND, 0, RS>(P, eR, qR, F, Fs);
 #endif
         else if (!FAST && P.viscous) {   // the face between my cell i and cell i + 1 (lanes beyond m: never finished, loads clamped)
             VisFace vo;
@@ -921,7 +919,7 @@ __global__ void __launch_bounds__(MFC5_MARCH_THREADS, (2 * NF + ND + 1 <= 8) ? M
 #ifdef MFC5_DEBUG_SPLIT
             if (FAST && MFC5_DEBUG_SPLIT != 1) riemann_face_fast<NF, ND, DIR, RS>(P, qL, eL, F, Fs);
 #else
-            if (FAST && (RS >= 0 || P.fast_riem)) riemann_face_fast<NF, ND, DIR, RS>(P, qL, eL, F, Fs);
+            if (FAST) riemann_face_fast<NF, ND, DIR, RS>(P, qL, eL, F, Fs);
 #endif
             else if (visc) {   // face cc-1: between cells cc-1 and cc of my pencil
                 VisFace vo;
