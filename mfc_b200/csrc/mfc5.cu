@@ -989,6 +989,7 @@ static int launch_sweep(mfc5_handle* h, const DevP& D0, int dir, bool* halo_pend
         int lo = 0, hi = segs;  // interior segments [lo, hi)
         while (lo < segs && MFC5_XW * lo - 1 - wh < 0) lo++;
         while (hi > lo && std::min(MFC5_XW * (hi - 1) + 30 + wh, h->s[0] + 1 + wh) > h->s[0]) hi--;
+        D.xseg_hole = segs; D.xseg_hole_n = 0;
         if (hi > lo) {
             D.xseg_lo = lo; D.xseg_n = hi - lo;
             if (launch_sweep_raw(h, D, 0)) return -1;
@@ -996,13 +997,9 @@ static int launch_sweep(mfc5_handle* h, const DevP& D0, int dir, bool* halo_pend
         }
         CK(cudaStreamWaitEvent(h->st, h->ev_halo, 0));
         *halo_pending = false;
-        if (lo > 0) {
-            D.xseg_lo = 0; D.xseg_n = lo;
-            if (launch_sweep_raw(h, D, 0)) return -1;
-            nl++;
-        }
-        if (hi < segs) {
-            D.xseg_lo = hi; D.xseg_n = segs - hi;
+        if (lo > 0 || hi < segs) {   // both ends in ONE launch (one tail instead of two): the segment list minus the interior ones
+            D.xseg_lo = 0; D.xseg_n = segs - (hi - lo);
+            D.xseg_hole = lo; D.xseg_hole_n = hi - lo;
             if (launch_sweep_raw(h, D, 0)) return -1;
             nl++;
         }
@@ -1011,7 +1008,7 @@ static int launch_sweep(mfc5_handle* h, const DevP& D0, int dir, bool* halo_pend
             CK(cudaStreamWaitEvent(h->st, h->ev_halo, 0));
             *halo_pending = false;
         }
-        D.xseg_lo = 0; D.xseg_n = 0;
+        D.xseg_lo = 0; D.xseg_n = 0; D.xseg_hole = 1 << 30; D.xseg_hole_n = 0;
         if (launch_sweep_raw(h, D, dir)) return -1;
         nl++;
     }

@@ -82,7 +82,8 @@ struct DevP {
     double rk0, rk1, rk2, rk3, irk3, dt;
     int do_rk;
     int chunk;          // marching chunk length (<= 0: chosen per launch)
-    int xseg_lo, xseg_n;  // x kernel: this launch covers segments [xseg_lo, xseg_lo + xseg_n) (xseg_n = 0: all)
+    int xseg_lo, xseg_n;  // x kernel: this launch covers segments [xseg_lo, xseg_lo + xseg_n) (xseg_n = 0: all) ...
+    int xseg_hole, xseg_hole_n;  // ... of the segment list with [xseg_hole, xseg_hole + xseg_hole_n) taken out (the boundary launch: both ends in one grid)
     int x_march;        // x sweep with the marching kernel (lanes along y) instead of the warp-shuffle kernel
     // Ghost modes [direction][side] (case-optimised kernels): how a sweep loader obtains the primitive variables of a ghost
     // cell.  MEM: from memory (filled by k_bc_faces or the halo exchange); CLAMP / MIRROR / WRAP: straight from the interior

@@ -547,7 +547,8 @@ __global__ void __launch_bounds__(128, MFC5_X_MINB) k_sweep_x(const __grid_const
     constexpr int NB = (MFC5_X_RPB > 1 && N <= 8) ? 2 : 1;  // window buffers per warp (static shared memory: 48 KB)
     const int lane = threadIdx.x & 31;
     const int w = threadIdx.x >> 5, nw = blockDim.x >> 5;
-    const int seg = P.xseg_lo + (int)blockIdx.x;
+    int seg = P.xseg_lo + (int)blockIdx.x;
+    if (seg >= P.xseg_hole) seg += P.xseg_hole_n;
     const int k = blockIdx.z;
     const long long rows = (long long)(P.s[1] + 1) * (P.s[2] + 1);
     const int i0 = seg * MFC5_XW;
