@@ -249,10 +249,13 @@ def _acceptance_cases():
         "C4_full_weno5z": cases.shockdroplet_3d(ny=100, weno_order=5, mapped_weno="F", wenoz="T", steps=100),
         # examples/3D_performance_test at the bench size (201^3): ~5 minutes of oracle time on 16 cores, so only on request
         "C5_full_weno5m": cases.perf_test_3d(m=200, steps=100),
+        # examples/2D_shockbubble (300 x 100 cells) and examples/1D_sodshocktube (400 cells) as shipped
+        "C2_full": cases.shockbubble_2d(ny=100),
+        "C1_full": cases.sod_1d(),
     }
 
 
-@pytest.mark.parametrize("name", ["C4_full_weno3m", "C4_full_weno5z", "C5_full_weno5m"])
+@pytest.mark.parametrize("name", ["C4_full_weno3m", "C4_full_weno5z", "C5_full_weno5m", "C2_full", "C1_full"])
 def test_full_size_100_rk3_steps_within_1e10(name):
     """The north star's acceptance bar AT THE STATED SIZES: 100 RK3 steps of the case file's own grid, product build (case-optimised
     kernels, CUDA-graph replay) against the oracle, max relative error of every conserved variable <= 1e-10.  The result line
