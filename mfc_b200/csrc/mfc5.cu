@@ -221,8 +221,6 @@ extern "C" int mfc5_create(const mfc5_params* p, mfc5_handle** out) {
         bool any = false;
         for (int f = 0; f < p->num_fluids; f++) any = any || p->fluid_Re[f][0] > 0 || p->fluid_Re[f][1] > 0;
         if (!why && !any) why = "viscous = T needs at least one fluid_pp(i)%Re(1) or %Re(2)";
-        for (int d = 0; d < h->nd && !why; d++)
-            if (p->bc[d][0] >= 0 || p->bc[d][1] >= 0) why = "viscous: processor boundaries are not available (the gradients read edge / corner ghost cells)";
         if (why) { delete h; return fail(why); }
     }
     for (int d = 0; d < h->nd; d++)
@@ -822,7 +820,7 @@ extern "C" int mfc5_download_cons(mfc5_handle* h, double* const* q, int ghosted)
     return copy_fields(h, h->d_q[h->cur], nullptr, q, ghosted, false);
 }
 static int refresh_prim(mfc5_handle* h);
-static long long halo_count(const mfc5_handle* h, int d);
+static long long halo_count(const mfc5_handle* h, int d, bool full);
 extern "C" int mfc5_download_prim(mfc5_handle* h, double* const* q, int ghosted) {
     if (!h || !q) return fail("mfc5_download_prim: null argument");
     if (h->setup) {
@@ -885,12 +883,15 @@ static int seg_end(mfc5_handle* h, int nlaunch, cudaStream_t st = nullptr) {
 }
 
 // doubles in one packed halo face of direction d: b layers x transverse interior x N variables
-static long long halo_count(const mfc5_handle* h, int d) {
+// doubles per packed face of direction d; full: with the ghost layers of the directions before d (viscous path)
+static long long halo_count(const mfc5_handle* h, int d, bool full) {
     long long n = (long long)h->N * h->b;
     for (int e = 0; e < 3; e++)
-        if (e != d) n *= (h->s[e] + 1);
+        if (e != d) n *= (h->s[e] + 1 + ((full && e < d) ? 2 * h->b : 0));
     return n;
 }
+// buffer size: the larger of the two layouts when the case can take the viscous path
+static size_t halo_bytes(const mfc5_handle* h, int d) { return (size_t)halo_count(h, d, h->P.viscous != 0) * sizeof(double); }
 
 static unsigned faces_grid_x(const mfc5_handle* h, long long per_thread_items) {
     long long mx = 1;
@@ -933,7 +934,7 @@ static int exchange_halos(mfc5_handle* h, const DevP& D) {
             snd.buf[2 * d + sd] = rcv.buf[2 * d + sd] = nullptr;
             if (d >= h->nd || h->P.bc[d][sd] < 0) continue;
             if (!h->d_send[d][sd]) {
-                const size_t nb = (size_t)halo_count(h, d) * sizeof(double);
+                const size_t nb = halo_bytes(h, d);
                 CK(cudaMalloc(&h->d_send[d][sd], nb));
                 CK(cudaMalloc(&h->d_recv[d][sd], nb));
             }
@@ -948,7 +949,7 @@ static int exchange_halos(mfc5_handle* h, const DevP& D) {
     // per direction: send low face then high face, receive high then low, so that the pairing is also
     // right when both neighbours are the same rank (periodic direction split over 2 ranks)
     for (int d = 0; d < h->nd; d++) {
-        const size_t cnt = (size_t)halo_count(h, d);
+        const size_t cnt = (size_t)halo_count(h, d, false);
         for (int sd = 0; sd < 2; sd++)
             if (h->P.bc[d][sd] >= 0) NK(g_nccl.Send(h->d_send[d][sd], cnt, NCCL_FLOAT64, h->P.bc[d][sd], h->comm, sc));
         for (int sd = 1; sd >= 0; sd--)
@@ -958,6 +959,51 @@ static int exchange_halos(mfc5_handle* h, const DevP& D) {
     k_halo_faces<<<grid, 256, 0, sc>>>(D, rcv, 0);
     if (seg_end(h, 2, sc)) return -1;
     CK(cudaEventRecord(h->ev_halo, sc));
+    return 0;
+}
+
+// Viscous path: ghost cells INCLUDING edges and corners (the velocity gradients of a face read them), direction by direction
+// on the compute stream as s_populate_variables_buffers does (m_boundary_common.fpp:99-187): the physical fills of direction d
+// and its halo exchange both run over the ghost layers of the directions before d.
+static int fill_exchange_full(mfc5_handle* h, const DevP& D, int* nlaunch) {
+    int nl = 0;
+    for (int d = 0; d < h->nd; d++) {
+        const int t1 = d == 0 ? 1 : 0, t2 = d == 2 ? 1 : 2;
+        long long n1 = h->s[t1] + 1, n2 = h->s[t2] + 1;
+        if (t1 < d) n1 += 2 * h->b;
+        if (t2 < d && t2 < h->nd) n2 += 2 * h->b;
+        for (int sd = 0; sd < 2; sd++)
+            if (h->P.bc[d][sd] < 0) {
+                k_bc_fill<<<grid_for(n1 * n2 * h->N, 256), 256, 0, h->st>>>(D, d, sd, 1);
+                nl++;
+            }
+        if (h->P.bc[d][0] < 0 && h->P.bc[d][1] < 0) continue;
+        if (!h->comm) return fail("processor boundary (bc >= 0) but mfc5_comm_init was not called");
+        HaloBufs snd, rcv;
+        for (int f = 0; f < 6; f++) snd.buf[f] = rcv.buf[f] = nullptr;
+        for (int sd = 0; sd < 2; sd++) {
+            if (h->P.bc[d][sd] < 0) continue;
+            if (!h->d_send[d][sd]) {
+                CK(cudaMalloc(&h->d_send[d][sd], halo_bytes(h, d)));
+                CK(cudaMalloc(&h->d_recv[d][sd], halo_bytes(h, d)));
+            }
+            snd.buf[2 * d + sd] = h->d_send[d][sd];
+            rcv.buf[2 * d + sd] = h->d_recv[d][sd];
+        }
+        const size_t cnt = (size_t)halo_count(h, d, true);
+        const dim3 grid(grid_for((long long)cnt, 256), 2, 1);
+        k_halo_faces<<<grid, 256, 0, h->st>>>(D, snd, 1, 1, 2 * d);
+        NK(g_nccl.GroupStart());
+        for (int sd = 0; sd < 2; sd++)
+            if (h->P.bc[d][sd] >= 0) NK(g_nccl.Send(h->d_send[d][sd], cnt, NCCL_FLOAT64, h->P.bc[d][sd], h->comm, h->st));
+        for (int sd = 1; sd >= 0; sd--)
+            if (h->P.bc[d][sd] >= 0) NK(g_nccl.Recv(h->d_recv[d][sd], cnt, NCCL_FLOAT64, h->P.bc[d][sd], h->comm, h->st));
+        NK(g_nccl.GroupEnd());
+        k_halo_faces<<<grid, 256, 0, h->st>>>(D, rcv, 0, 1, 2 * d);
+        nl += 2;
+    }
+    CK(cudaGetLastError());
+    *nlaunch = nl;
     return 0;
 }
 
@@ -1041,7 +1087,7 @@ static int run_stage(mfc5_handle* h, const double* q1, const double* q2, double*
     }
     bool halo_pending = false;
     NvtxRange nv_comm("RHS-COMMUNICATION");
-    if (h->any_nb) {
+    if (h->any_nb && !h->P.viscous) {
         CK(cudaEventRecord(h->ev_prim, h->st));
         if (exchange_halos(h, D)) return -1;
         halo_pending = true;
@@ -1077,12 +1123,10 @@ static int run_stage(mfc5_handle* h, const double* q1, const double* q2, double*
     if (h->P.viscous) {
         // the velocity gradients of the viscous fluxes read edge / corner ghost cells: fill in the reference's order (x, then y
         // over the x ghosts, then z over both), m_boundary_common.fpp:143-149; the CBC fluxes follow on the same stream
-        if (h->any_phys) {
+        if (h->any_phys || h->any_nb) {
             if (seg_begin(h, MFC5_K_BC_FILL)) return -1;
-            const long long l0 = h->launches;
-            if (fill_full(h, D)) return -1;
-            const int nfill = (int)(h->launches - l0);
-            h->launches = l0;   // (seg_end counts them)
+            int nfill = 0;
+            if (fill_exchange_full(h, D, &nfill)) return -1;
             if (seg_end(h, nfill)) return -1;
         }
         if (faces(0, 2 * h->nd, false, any_cbc_x || any_cbc_yz, h->st)) return -1;
@@ -1345,7 +1389,7 @@ extern "C" int mfc5_comm_init(mfc5_handle* h, const char id_in[128], int rank, i
     for (int d = 0; d < h->nd; d++)
         for (int sd = 0; sd < 2; sd++)
             if (h->P.bc[d][sd] >= 0 && !h->d_send[d][sd]) {
-                const size_t nb = (size_t)halo_count(h, d) * sizeof(double);
+                const size_t nb = halo_bytes(h, d);
                 CK(cudaMalloc(&h->d_send[d][sd], nb));
                 CK(cudaMalloc(&h->d_recv[d][sd], nb));
             }

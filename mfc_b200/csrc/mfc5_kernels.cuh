@@ -1353,16 +1353,21 @@ struct HaloBufs {
     double* buf[6];
 };
 #ifdef MFC5_HOST_TU
-__global__ void __launch_bounds__(256) k_halo_faces(const __grid_constant__ DevP P, const __grid_constant__ HaloBufs B, int pack) {
-    const int d = blockIdx.y >> 1, side = blockIdx.y & 1;
+// full = 1 (viscous path): one direction per launch (face0 = 2 d), transverse ranges of the directions BEFORE d widened by the
+// ghost layers, which those directions' fills / exchanges have already written -- edges and corners travel as in the reference's
+// x -> y -> z sequence (m_mpi_common.fpp:620-1065 called per direction from s_populate_variables_buffers)
+__global__ void __launch_bounds__(256) k_halo_faces(const __grid_constant__ DevP P, const __grid_constant__ HaloBufs B, int pack, int full = 0, int face0 = 0) {
+    const int face = blockIdx.y + face0;
+    const int d = face >> 1, side = face & 1;
     if (d >= P.nd || P.bc[d][side] < 0) return;
     int lo[3] = {0, 0, 0}, hi[3] = {P.s[0], P.s[1], P.s[2]};
+    if (full) for (int e = 0; e < d; e++) { lo[e] = -P.b; hi[e] = P.s[e] + P.b; }
     // pack: the b interior layers next to the face; unpack: the b ghost layers beyond it
     const int first = pack ? (side == 0 ? 0 : P.s[d] - P.b + 1) : (side == 0 ? -P.b : P.s[d] + 1);
     lo[d] = first; hi[d] = first + P.b - 1;
     const int n0 = hi[0] - lo[0] + 1, n1 = hi[1] - lo[1] + 1, n2 = hi[2] - lo[2] + 1;
     const long long per = (long long)n0 * n1 * n2, tot = per * P.N;
-    double* buf = B.buf[blockIdx.y];
+    double* buf = B.buf[face];
     for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < tot; t += (long long)gridDim.x * blockDim.x) {
         const int v = (int)(t / per);
         long long r = t % per;

@@ -100,3 +100,35 @@ def test_decomposed_equals_single_gpu(world):
         for v in range(a.shape[0]):
             err = np.abs(a[v] - ref[v]).max() / (np.abs(full[v]).max() + 1e-300)
             assert err <= 1e-12, f"rank {r} var {v + 1}: {err:.3e}"
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_viscous_decomposed_equals_single_gpu(world):
+    """viscous = T on processor boundaries: the velocity gradients of a face read edge / corner ghost cells, so the ghost region
+    is filled and exchanged direction by direction over the ghost layers of the earlier directions (x, then y over the x ghosts,
+    then z over both; m_boundary_common.fpp:99-187, m_mpi_common.fpp:620-1065).  The reference's 3-D two-fluid viscous test case
+    (1C0780C8: shear and bulk Reynolds numbers, uniform grid) on 50^3 cells, decomposed vs the single-GPU run, strict build: the
+    single-GPU strict build is itself bit-identical with the oracle (tests/test_gpu_parity.py::test_viscous_strict_vs_oracle)."""
+    _need(world)
+    from mfc_b200 import driver, pre_process
+    from mfc_b200.lib import Mfc5
+    from mfc_b200.params import params_from_case
+    case = dict(CASES["1C0780C8"]["params"], m=49, n=49, p=49, t_step_stop=5, t_step_save=5, parallel_io="T")
+    out = _run(case, world, strict=True)
+    P = params_from_case(case)
+    assert P.viscous == 1
+    cbs, ccs = pre_process.generate_grid(case)
+    _, cons = pre_process.initial_condition(case, ccs)
+    g = Mfc5(P, cbs, strict=True)
+    g.set_cons(cons)
+    driver.run(g, case)
+    full = g.get_cons()
+    g.close()
+    assert not np.array_equal(full, cons)
+    for r in range(world):
+        start, a, _ = out[r]
+        nz, ny, nx = a.shape[1:]
+        ref = full[:, start[2]:start[2] + nz, start[1]:start[1] + ny, start[0]:start[0] + nx]
+        for v in range(a.shape[0]):
+            err = np.abs(a[v] - ref[v]).max() / (np.abs(full[v]).max() + 1e-300)
+            assert err <= 1e-13, f"rank {r} var {v + 1}: {err:.3e}"
