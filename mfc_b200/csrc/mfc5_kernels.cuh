@@ -1014,6 +1014,10 @@ __global__ void __launch_bounds__(MFC5_MARCH_THREADS, (2 * NF + ND + 1 <= 8) ? M
 #ifndef MFC5_M2_NV
 #define MFC5_M2_NV MFC5_WENO_NV   // variables per iteration of the rolled WENO loop
 #endif
+#ifndef MFC5_M2_DIET
+#define MFC5_M2_DIET 0      // 1: fewer address / index instructions per iteration (running field pointers stepped by the field size, the
+                            // ghost map of the plane that enters next carried over from its prefetch); A/B in profiles/variants_r02.txt
+#endif
 #ifndef MFC5_M2_FPS
 #define MFC5_M2_FPS 0       // 1: the flux of the previous face crosses iterations through shared memory instead of 16 registers + their copies
 #endif
@@ -1118,15 +1122,29 @@ __global__ void __launch_bounds__(MFC5_M2_THREADS, MFC5_M2_MINB) k_march2(const 
     const GhostMap gmap(P, DIR);
 
     // plane pl of the primitive variables -> ring slot k (this thread's column)
-    auto load_plane = [&](int k, int pl) {
-        bool flip;
-        const int ps = gmap.src(min(max(pl, lo), hi), flip);
+    auto load_plane_src = [&](int k, int ps, bool flip) {
         const ix c = colbase + (ix)ps * sd;
+#if MFC5_M2_DIET
+        const double* pp = P.prim + c;
+        double* rp = ring + k * N * NT + tid;
+#pragma unroll
+        for (int v = 0; v < N; v++) {
+            if (v == S::IM + DIR && flip) *rp = -*pp;
+            else cp_async8(rp, pp);
+            pp += fs; rp += NT;
+        }
+#else
 #pragma unroll
         for (int v = 0; v < N; v++) {
             if (v == S::IM + DIR && flip) ring[(k * N + v) * NT + tid] = -P.prim[(ix)((ix)v * fs + c)];   // reflective wall: -u_n of the mirror cell
             else cp_async8(ring + (k * N + v) * NT + tid, P.prim + (ix)((ix)v * fs + c));
         }
+#endif
+    };
+    auto load_plane = [&](int k, int pl) {
+        bool flip;
+        const int ps = gmap.src(min(max(pl, lo), hi), flip);
+        load_plane_src(k, ps, flip);
     };
     auto pf_plane = [&](const double* arr, int pl) { prefetch_l2(arr + (ix)(pfbase + (ix)pl * sd)); };
 
@@ -1143,11 +1161,22 @@ __global__ void __launch_bounds__(MFC5_M2_THREADS, MFC5_M2_MINB) k_march2(const 
 #pragma unroll
     for (int f = 0; f < NF; f++) Fsp[f] = 0.0;
 
+#if MFC5_M2_DIET
+    bool pf_flip, nxt_flip = false;
+    int pf_ps = gmap.src(min(max(c0 + PN, lo), hi), pf_flip), nxt_ps = 0;   // plane cc + 1 + PN of the first iteration (cc = c0 - 1)
+#endif
     for (int cc = c0 - 1; cc <= c1 + 1; cc++) {
         cp_async_wait_all();  // the window of cell cc is complete
         {   // pull into L2 what the NEXT iteration will ask for
             bool flip;
+#if MFC5_M2_DIET
+            nxt_ps = pf_ps; nxt_flip = pf_flip;   // the plane this iteration loads (cc + 1 + PN) was mapped by the previous one's prefetch
+            pf_ps = gmap.src(min(max(cc + 2 + PN, lo), hi), pf_flip);
+            if (cc < c1) pf_plane(P.prim, pf_ps);
+            (void)flip;
+#else
             if (cc < c1) pf_plane(P.prim, gmap.src(min(max(cc + 2 + PN, lo), hi), flip));
+#endif
             if (cc >= c0 && cc <= c1) {   // the cell finished in the next iteration is cc
                 if (DIR != 0) pf_plane(P.rhs, cc);
                 if (rk) {
@@ -1194,12 +1223,31 @@ __global__ void __launch_bounds__(MFC5_M2_THREADS, MFC5_M2_MINB) k_march2(const 
 #pragma unroll
             for (int v = 0; v < N; v++) { qL[v] = ring[(slR * N + v) * NT + tid]; eL[v] = sEL[v * NT + tid]; }
             if (cc <= c1) {       // plane cc+1+PN enters the window in the slot the previous right edge has just left
+#if MFC5_M2_DIET
+                load_plane_src(slR, nxt_ps, nxt_flip);
+#else
                 load_plane(slR, cc + 1 + PN);
+#endif
                 cp_async_commit();
             }
 #if MFC5_M2_LATE != 1
             double rin[N], q1in[N], q2in[N], acoef[NF];
             if (fin) {
+#if MFC5_M2_DIET
+                {
+                    const double* pr = P.rhs + c;
+#pragma unroll
+                    for (int v = 0; v < N; v++) { rin[v] = (DIR == 0) ? 0.0 : *pr; pr += fs; }
+                }
+                if (rk && MFC5_M2_LATE == 0) {
+                    const double* p1 = P.q1 + c;
+#pragma unroll
+                    for (int v = 0; v < N; v++) { q1in[v] = __ldg(p1); p1 += fs; }
+                    const double* p2 = P.q2 + c;
+#pragma unroll
+                    for (int v = 0; v < N; v++) { q2in[v] = (P.rk1 != 0.0) ? __ldg(p2) : 0.0; p2 += fs; }
+                }
+#else
 #pragma unroll
                 for (int v = 0; v < N; v++) rin[v] = (DIR == 0) ? 0.0 : P.rhs[(ix)((ix)v * fs + c)];
                 if (rk && MFC5_M2_LATE == 0) {
@@ -1208,6 +1256,7 @@ __global__ void __launch_bounds__(MFC5_M2_THREADS, MFC5_M2_MINB) k_march2(const 
 #pragma unroll
                     for (int v = 0; v < N; v++) q2in[v] = (P.rk1 != 0.0) ? __ldg(P.q2 + (ix)((ix)v * fs + c)) : 0.0;
                 }
+#endif
 #pragma unroll
                 for (int f = 0; f < NF; f++) acoef[f] = __ldg(P.prim + (ix)((ix)(alpha_iface ? (S::IM + DIR) : (S::IA + f)) * fs + c));
             }
@@ -1255,6 +1304,25 @@ __global__ void __launch_bounds__(MFC5_M2_THREADS, MFC5_M2_MINB) k_march2(const 
 #pragma unroll
                     for (int v = 0; v < N; v++) r[v] = div_by_const(P.rk0 * q1in[v] + P.rk1 * q2in[v] + P.rk2 * P.dt * r[v], P.rk3, P.irk3);
                     if (P.bf_on) apply_body_forces<NF, ND>(P, r);
+#if MFC5_M2_DIET
+                    {
+                        double* po = P.qout + c;
+#pragma unroll
+                        for (int v = 0; v < N; v++) { *po = r[v]; po += fs; }
+                    }
+                    if (P.prim_next) {
+                        double pr[N];
+                        cons2prim_cell_fast<NF, ND>(P, r, pr);
+                        double* pn = P.prim_next + c;
+#pragma unroll
+                        for (int v = 0; v < N; v++) { *pn = pr[v]; pn += fs; }
+                    }
+                } else {
+                    double* po = P.rhs + c;
+#pragma unroll
+                    for (int v = 0; v < N; v++) { *po = r[v]; po += fs; }
+                }
+#else
 #pragma unroll
                     for (int v = 0; v < N; v++) P.qout[(ix)((ix)v * fs + c)] = r[v];
                     if (P.prim_next) {   // primitive variables of the new state for the next stage (over the consumed rhs entry)
@@ -1267,6 +1335,7 @@ __global__ void __launch_bounds__(MFC5_M2_THREADS, MFC5_M2_MINB) k_march2(const 
 #pragma unroll
                     for (int v = 0; v < N; v++) P.rhs[(ix)((ix)v * fs + c)] = r[v];
                 }
+#endif
             }
 #pragma unroll
             for (int v = 0; v < N; v++) {
