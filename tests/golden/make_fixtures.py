@@ -23,7 +23,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 REF = sys.argv[1] if len(sys.argv) > 1 else "/root/reference"
 
 # UUIDs inside the 5-eq / WENO{3,5}{JS,M,Z} / HLL|HLLC / RK3 envelope;
-# (weno_order = 7 and int_comp = 2 (MTHINC): the CPU oracle only so far, tests/test_oracle_next.py)
+# (int_comp = 2 (MTHINC): the CPU oracle only so far, tests/test_oracle_next.py)
 # last line: viscous (finite-difference velocity gradients, weno_Re_flux = F)
 # before them: the f-4 widening (low_Mach = 1 / 2, tolerance 1e-10 by the reference's own rule; alt_soundspeed) and f-3 (elliptic smoothing, hard-coded profiles), Lax-Friedrichs, MUSCL
 UUIDS = """
