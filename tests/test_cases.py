@@ -77,3 +77,20 @@ def test_elliptic_smoothing_is_conservative_filter():
     assert prim_s.shape == prim_0.shape and not np.array_equal(prim_s, prim_0)
     for v in range(prim_0.shape[0]):  # a convex filter cannot create new extrema
         assert prim_s[v].min() >= prim_0[v].min() - 1e-14 and prim_s[v].max() <= prim_0[v].max() + 1e-14
+
+
+def test_rank_affinity_helper_is_safe_without_a_gpu():
+    """mfc_b200/affinity.py (ranks next to their GPU before they allocate pinned memory): without NVML / a GPU it reports why it
+    did nothing and leaves the process's CPU mask alone."""
+    import os
+    from mfc_b200 import affinity
+    before = os.sched_getaffinity(0) if hasattr(os, "sched_getaffinity") else None
+    info = affinity.bind_to_gpu(0, 1)
+    assert info["gpu"] == 0 and "bound" in info and info["numa_nodes"] >= 1
+    if not info["bound"]:
+        assert "note" in info
+        if before is not None:
+            assert os.sched_getaffinity(0) == before
+    else:   # a GPU box: the mask is a non-empty subset of what the process was allowed
+        assert before is None or os.sched_getaffinity(0) <= before
+        os.sched_setaffinity(0, before)
