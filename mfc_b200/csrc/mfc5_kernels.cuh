@@ -380,8 +380,11 @@ __device__ __forceinline__ void cbc_point(const DevP& P, const CbcCoef& K, const
 }
 
 // the characteristic-BC faces face0 .. of the block in ONE launch (face = 2 * direction + side); Kall[6] in HBM
+#ifndef MFC5_CBC_MINB
+#define MFC5_CBC_MINB 3   // resident blocks per SM the register allocation aims at: 168 registers + 1 kB of spills; 1 / 3 / 4: x faces 25.7 / 21.5 / 27.6 us, y + z faces 39.5 / 30.0 / 28.4 us (profiles/variants_r02.txt)
+#endif
 template <int NF, int ND>
-__global__ void __launch_bounds__(128) k_cbc(const __grid_constant__ DevP P, const CbcCoef* __restrict__ Kall, int face0) {
+__global__ void __launch_bounds__(128, MFC5_CBC_MINB) k_cbc(const __grid_constant__ DevP P, const CbcCoef* __restrict__ Kall, int face0) {
     const int face = blockIdx.y + face0;
     const int d = face >> 1, side = face & 1;
     if (d >= ND || !P.cbc_on[d][side]) return;
