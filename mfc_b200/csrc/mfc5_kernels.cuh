@@ -28,6 +28,9 @@ __device__ __forceinline__ void cp_async8(double* sdst, const double* gsrc) {
     const unsigned sa = (unsigned)__cvta_generic_to_shared(sdst);
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sa), "l"(gsrc) : "memory");
 }
+__device__ __forceinline__ void cp_async16(double* sdst, const double* gsrc) {   // two consecutive doubles, both addresses 16-byte aligned
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(sdst)), "l"(gsrc) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 #ifdef MFC5_NO_PREFETCH
@@ -521,6 +524,10 @@ __device__ __forceinline__ void cbc_override(const DevP& P, int face, long long 
 #ifndef MFC5_X_RPB
 #define MFC5_X_RPB 4    // rows a warp handles in turn; measured 4: 0.818, 8: 0.823, 16: 0.838, 32: 0.887 ms (the next row's window is in flight while the current one is computed)
 #endif
+#ifndef MFC5_X_VEC
+#define MFC5_X_VEC 1    // 1: segments whose stencil window is contiguous in memory stage it with 16-byte cp.async (20 lanes x double2 per variable
+                        // and row instead of 36 8-byte copies); the window then starts one cell earlier, on a 16-byte boundary
+#endif
 #ifndef MFC5_X_STAB
 #define MFC5_X_STAB 1   // 1: the segment's WENO table tile is staged in shared memory once per block
 #endif
@@ -560,7 +567,7 @@ __global__ void __launch_bounds__(128, MFC5_X_MINB) k_sweep_x(const __grid_const
     const DirTables& T = P.T[0];
     const int slot = ic + P.b;
     // the warp's 36-cell window of every variable is staged in shared memory with cp.async; lane l reads cells l .. l+4
-    __shared__ double sx[4][NB][N][XT];
+    __shared__ __align__(16) double sx[4][NB][N][XT];
     __shared__ double sedge[4][2][N][32];  // per lane: right edge of my cell, left edge of cell +1 (spill space of the rolled loop)
     __shared__ __align__(16) double stab[(FAST && MFC5_X_STAB) ? MFC5_TAB * 32 : 32];
     double(*myR)[32] = sedge[w][0];
@@ -570,15 +577,29 @@ __global__ void __launch_bounds__(128, MFC5_X_MINB) k_sweep_x(const __grid_const
     bool fa, fb;
     const GhostMap gmap(P, 0);
     const int ca = gmap.src(min(i0 - 1 - PNX + lane, hi), fa), cb = gmap.src(min(i0 - 1 - PNX + 32 + lane, hi), fb);
+    // 16-byte staging: the window buffer holds cells i0 - 2 - PNX .. (shifted by SH = 1: i0 = 30 seg and interior cell 0 sits on a
+    // 128-byte boundary, so cell i0 - 4 is 16-byte aligned), 40 cells = 20 double2, when all of them are real memory cells of this
+    // row (block-uniform: not for segments that touch a folded boundary or the end of the ghost region)
+    constexpr int SH = (MFC5_X_VEC && PNX == 2) ? 1 : 0;
+    const int wstart = i0 - 1 - PNX - SH;
+    const bool vec = SH == 1 && wstart >= (P.gmode[0][0] == MFC5_GM_MEM ? -P.b : 0) &&
+                     wstart + 39 <= (P.gmode[0][1] == MFC5_GM_MEM ? hi : P.s[0]);
     const bool any_flip = (P.gmode[0][0] == MFC5_GM_MIRROR) | (P.gmode[0][1] == MFC5_GM_MIRROR);   // kernel-uniform
     using ix = typename SweepIdx<(WO >= 0 && FAST)>::type;  // 32-bit element indices in the case-optimised kernels (k_sweep_march)
     const ix fs = (ix)P.fs;
     auto load_window = [&](int buf, int jj) {
         const ix rb = (ix)P.base + (ix)jj * (ix)P.sy + (ix)k * (ix)P.sz;
+        if (vec) {
+            if (lane < 20) {
 #pragma unroll
-        for (int v = 0; v < N; v++) {
-            cp_async8(&sx[w][buf][v][lane], P.prim + (ix)((ix)v * fs + rb + (ix)ca));
-            if (lane < 2 * PNX) cp_async8(&sx[w][buf][v][32 + lane], P.prim + (ix)((ix)v * fs + rb + (ix)cb));
+                for (int v = 0; v < N; v++) cp_async16(&sx[w][buf][v][2 * lane], P.prim + (ix)((ix)v * fs + rb + (ix)(wstart + 2 * lane)));
+            }
+        } else {
+#pragma unroll
+            for (int v = 0; v < N; v++) {
+                cp_async8(&sx[w][buf][v][lane + SH], P.prim + (ix)((ix)v * fs + rb + (ix)ca));
+                if (lane < 2 * PNX) cp_async8(&sx[w][buf][v][32 + lane + SH], P.prim + (ix)((ix)v * fs + rb + (ix)cb));
+            }
         }
         cp_async_commit();
     };
@@ -609,8 +630,8 @@ __global__ void __launch_bounds__(128, MFC5_X_MINB) k_sweep_x(const __grid_const
         __syncwarp();
         double(*my)[XT] = sx[w][buf];
         if (any_flip) {   // reflective wall: the mirrored cells carry -u_x
-            if (fa) my[S::IM][lane] = -my[S::IM][lane];
-            if (lane < 2 * PNX && fb) my[S::IM][32 + lane] = -my[S::IM][32 + lane];
+            if (fa) my[S::IM][lane + SH] = -my[S::IM][lane + SH];
+            if (lane < 2 * PNX && fb) my[S::IM][32 + lane + SH] = -my[S::IM][32 + lane + SH];
             __syncwarp();
         }
         const long long row = j + (long long)(P.s[1] + 1) * k;
@@ -626,7 +647,7 @@ __global__ void __launch_bounds__(128, MFC5_X_MINB) k_sweep_x(const __grid_const
             for (int u = 0; u < NV; u++) {
                 vv[u] = min(v0 + u, N - 1);
 #pragma unroll
-                for (int q = 0; q < FW; q++) f[u][q] = my[vv[u]][lane + q];
+                for (int q = 0; q < FW; q++) f[u][q] = my[vv[u]][lane + q + SH];
             }
             if constexpr (WO == 7) {
 #pragma unroll
@@ -642,7 +663,7 @@ __global__ void __launch_bounds__(128, MFC5_X_MINB) k_sweep_x(const __grid_const
         }
         if (!FAST && WO < 0 && NF >= 2 && P.int_comp == 1) {  // THINC on my cell: my right edge, and my left edge = lane-1's qR
             double tl[4], tr[4];
-            const bool on = thinc_cell(P, my[S::IA][lane + 1], my[S::IA][lane + 2], my[S::IA][lane + 3], my[0][lane + 2], my[NF - 1][lane + 2], tl, tr);
+            const bool on = thinc_cell(P, my[S::IA][lane + 1 + SH], my[S::IA][lane + 2 + SH], my[S::IA][lane + 3 + SH], my[0][lane + 2 + SH], my[NF - 1][lane + 2 + SH], tl, tr);
             __syncwarp();
             if (on) {
                 const int vi[4] = {0, NF - 1, S::IA, S::IA + NF - 1};
