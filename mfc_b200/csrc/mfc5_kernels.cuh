@@ -568,10 +568,9 @@ __global__ void __launch_bounds__(128, MFC5_X_MINB) k_sweep_x(const __grid_const
     const int slot = ic + P.b;
     // the warp's 36-cell window of every variable is staged in shared memory with cp.async; lane l reads cells l .. l+4
     __shared__ __align__(16) double sx[4][NB][N][XT];
-    __shared__ double sedge[4][2][N][32];  // per lane: right edge of my cell, left edge of cell +1 (spill space of the rolled loop)
+    __shared__ __align__(16) double2 sedge[4][N][32];  // per lane: (.x right edge of my cell, .y left edge of cell +1): one 16-byte access each way (spill space of the rolled loop)
     __shared__ __align__(16) double stab[(FAST && MFC5_X_STAB) ? MFC5_TAB * 32 : 32];
-    double(*myR)[32] = sedge[w][0];
-    double(*myQ)[32] = sedge[w][1];
+    double2(*myE)[32] = sedge[w];
     const int hi = P.s[0] + P.b;
     // window cells of this lane (clamped to the ghost region), through the ghost modes of the x boundaries (DevP::gmode)
     bool fa, fb;
@@ -657,8 +656,7 @@ __global__ void __launch_bounds__(128, MFC5_X_MINB) k_sweep_x(const __grid_const
             }
 #pragma unroll
             for (int u = 0; u < NV; u++) {
-                myR[vv[u]][lane] = r[u];
-                myQ[vv[u]][lane] = __shfl_down_sync(0xffffffffu, l[u], 1);
+                myE[vv[u]][lane] = make_double2(r[u], __shfl_down_sync(0xffffffffu, l[u], 1));
             }
         }
         if (!FAST && WO < 0 && NF >= 2 && P.int_comp == 1) {  // THINC on my cell: my right edge, and my left edge = lane-1's qR
@@ -669,15 +667,15 @@ __global__ void __launch_bounds__(128, MFC5_X_MINB) k_sweep_x(const __grid_const
                 const int vi[4] = {0, NF - 1, S::IA, S::IA + NF - 1};
 #pragma unroll
                 for (int q = 0; q < 4; q++) {
-                    myR[vi[q]][lane] = tr[q];
-                    if (lane > 0) myQ[vi[q]][lane - 1] = tl[q];
+                    myE[vi[q]][lane].x = tr[q];
+                    if (lane > 0) myE[vi[q]][lane - 1].y = tl[q];
                 }
             }
             __syncwarp();
         }
         double eR[N], qR[N];
 #pragma unroll
-        for (int v = 0; v < N; v++) { eR[v] = myR[v][lane]; qR[v] = myQ[v][lane]; }
+        for (int v = 0; v < N; v++) { const double2 e = myE[v][lane]; eR[v] = e.x; qR[v] = e.y; }
         // BC -4 (Riemann extrapolation), m_riemann_state.fpp:149-206 (the case-optimised kernels are not dispatched for it)
         constexpr bool kExtrap = !(FAST && WO >= 0);
         if (kExtrap && P.bc[0][0] == MFC5_BC_RIEMANN_EXTRAP && i == -1) {
